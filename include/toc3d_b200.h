@@ -1,0 +1,179 @@
+/*
+ * toc3d_b200 — C-ABI of the B200-native (sm_100a) ToC3D image-backbone hot path.
+ *
+ * Drop-in boundary: the reference (DYZhang09/ToC3D) is pure Python/PyTorch and has
+ * no FFI of its own; every entry point below replaces the ATen call sequence of one
+ * reference call site (cited per function, paths under
+ * projects/mmdet3d_plugin/models/ of the reference tree).  The Python plugin
+ * toc3d_b200/backbone.py (registry names ToC3DEVAViT / EVA_ViT) binds these with
+ * ctypes; INTEGRATION.md shows the stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless noted;
+ *   - the caller owns all memory; the library allocates nothing that outlives a call;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), does
+ *     not synchronise, and is re-entrant per stream (CUDA-graph capturable);
+ *   - return value 0 = success; >0 = cudaError_t; <0 = argument error.  No C++
+ *     exception crosses the boundary; toc3d_last_error() returns the message;
+ *   - bf16 tensors are raw uint16 storage (nv_bfloat16); activations row-major.
+ */
+#ifndef TOC3D_B200_H_
+#define TOC3D_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TOC3D_B200_ABI_VERSION 1
+
+int toc3d_abi_version(void);
+/* Thread-local message of the last failing call ("" if none). Host pointer. */
+const char* toc3d_last_error(void);
+
+/* ------------------------------------------------------------------ GEMM (tcgen05 + TMA + TMEM)
+ * C[M,N] = A[M,K] * B[N,K]^T with bf16 operands and fp32 accumulation in TMEM, followed by a
+ * fused epilogue.  B has the nn.Linear weight layout ([out_features, in_features]).
+ * Replaces F.linear / nn.Linear / nn.Conv2d(k=s=16) at: eva_vit.py:97-99,113 (q/k/v/proj),
+ * eva_vit.py:45-49 (w1,w2,w3), eva_utils.py:284 (patch conv as im2col GEMM),
+ * toc3d_utils.py:122,127 (first-frame scorer MLP).
+ * Requirements: K % 8 == 0, lda % 8 == 0, ldb % 8 == 0, A/B 16-byte aligned.
+ */
+enum toc3d_epilogue_kind {
+  TOC3D_EPI_LINEAR = 0, /* out = act(acc + bias), bf16 or fp32                                   */
+  TOC3D_EPI_QKV_ROPE = 1, /* bf16 out = [rope(acc+bias)*q_scale | rope(acc) | acc+bias]           */
+  TOC3D_EPI_RESID = 2,  /* fp32 out[out_map[m]] = resid[resid_map[m]] + acc + bias               */
+  TOC3D_EPI_SWIGLU = 3  /* bf16 out[:, h] = silu(acc1+b1) * (acc2+b2), B rows interleaved 32/32  */
+};
+
+typedef struct toc3d_epilogue {
+  const float* bias;      /* [N] fp32 or NULL                                                   */
+  void* out;              /* output base (bf16 or fp32, see kind)                               */
+  int32_t ldo;            /* leading dimension of out, in elements                              */
+  int32_t out_f32;        /* LINEAR: 1 -> fp32 output, 0 -> bf16                                */
+  int32_t act;            /* LINEAR: 0 none, 1 GELU(erf), 2 ReLU                                */
+  /* RESID: row maps are int32 per GEMM row m (NULL = identity).
+   *   resid_map[m] >= 0 : residual row in `resid`;  -1 : zero residual;  -2 : out_alt row m
+   *   out_map[m]   >= 0 : destination row in `out`; -1 : row dropped;    -2 : out_alt row m
+   *   resid_mod > 0     : residual row = m % resid_mod (abs-pos broadcast over views)         */
+  const float* resid;
+  const int32_t* resid_map;
+  int32_t resid_mod;
+  const int32_t* out_map;
+  float* out_alt;         /* fp32 [M, ldo] packed side buffer (may alias out)                   */
+  /* QKV_ROPE: columns [0, rope_cols) are rotated (q then k), q columns [0, rope_cols/2) are
+   * also multiplied by q_scale.  Head dim is 64: 32 row-axis + 32 column-axis channels.
+   *   rope_rows[m]  table row of GEMM row m (NULL -> m % rope_slots)
+   *   cos_axis/sin_axis  fp32 [rope_ft, 16]: per-axis position x frequency tables
+   *                       (= freqs_cos[p * rope_ft, 0:32:2] of eva_utils.py:364-371)           */
+  const int32_t* rope_rows;
+  int32_t rope_slots;
+  int32_t rope_ft;
+  int32_t rope_cols;
+  float q_scale;
+  const float* cos_axis;
+  const float* sin_axis;
+} toc3d_epilogue;
+
+int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
+                    int32_t epilogue_kind, const toc3d_epilogue* epi /* host */, void* stream);
+
+/* ------------------------------------------------------------------ windowed attention
+ * softmax(q k^T) v per (window, head); q already rotated and scaled by the QKV epilogue.
+ * qkv bf16 [n_windows*seq_len, 3*C] (q | k | v), out bf16 [n_windows*seq_len, C]; head dim 64.
+ * Replaces eva_vit.py:109-111 and toc3d_eva_vit.py:509-511 (bmm, softmax, bmm). seq_len <= 1024.
+ */
+int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
+                           void* stream);
+
+/* ------------------------------------------------------------------ LayerNorm over gathered rows
+ * out_bf16[m] = LN(row(m)) * gamma + beta over C channels (C % 128 == 0, C <= 4096), m in [0,M).
+ *   row_map NULL: row(m) = x[m];  row_map[m] >= 0: x[row_map[m]];  -2: alt[m];
+ *   -1: pad slot -> pad_mode 0: output zeros (dense Block pads AFTER norm1, eva_vit.py:249-254)
+ *                   pad_mode 1: LN of a zero vector = beta (ToC3D block pads BEFORE norm1,
+ *                               toc3d_eva_vit.py:412-415 then :369)
+ * Replaces nn.LayerNorm at eva_vit.py:249,263; toc3d_eva_vit.py:371,379; toc3d_utils.py:99.
+ */
+int toc3d_layernorm_rows(const float* x, const int32_t* row_map, const float* alt, const float* gamma,
+                         const float* beta, void* out_bf16, int32_t M, int32_t C, float eps, int32_t pad_mode,
+                         void* stream);
+
+/* SwiGLU sub-LayerNorm (eva_vit.py:48, ffn_ln over the true hidden width `Hd`) on the padded bf16
+ * hidden buffer [M, ld]; columns >= Hd are written as zero.  In place allowed (out == h). */
+int toc3d_subln_bf16(const void* h, void* out, const float* gamma, const float* beta, int32_t M, int32_t Hd,
+                     int32_t ld, float eps, void* stream);
+
+/* ------------------------------------------------------------------ token selection
+ * Per-window stable top-k (toc3d_eva_vit.py:412-419 + toc3d_utils.py:131-144 with the
+ * tie-break pin "score descending, index ascending"): scores fp32 [V,H,W] are window-partitioned
+ * with pad value -1e6; for every window the ws*ws slots are ranked and split into the first
+ * k (slow) and the rest (fast), both in rank order.
+ * Outputs (any may be NULL): slow_idx int32 [nW,k], fast_idx int32 [nW,n-k] (slot indices, the
+ * values torch.sort returns), fast_score fp32 [nW,n-k],
+ *   tok_map  int32 [nW*(k+1)] packed row -> image row v*H*W+r*W+c | -1 (pad slot) | -2 (the
+ *            representative token, last row of each window),
+ *   rope_rows int32 [nW*(k+1)] RoPE table row (slot index; k for the representative token,
+ *            toc3d_eva_vit.py:434-435),
+ *   fast_map int32 [nW,n-k] image row of each fast token or -1.
+ * nW = V*ceil(H/ws)*ceil(W/ws); window order view-major, row, col (eva_utils.py:108-109).
+ */
+int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int32_t W, int32_t ws, int32_t k,
+                      int32_t* slow_idx, int32_t* fast_idx, float* fast_score, int32_t* tok_map,
+                      int32_t* rope_rows, int32_t* fast_map, void* stream);
+
+/* Image-level stable descending sort split (toc3d_utils.py:137-144): scores fp32 [B,N] ->
+ * keep_idx int64 [B,k], drop_idx int64 [B,N-k].  N <= 12288. */
+int toc3d_topk_split(const float* scores, int32_t B, int32_t N, int32_t k, int64_t* keep_idx, int64_t* drop_idx,
+                     void* stream);
+
+/* Representative token (toc3d_utils.py:65-70 merge_tokens on the gathered fast set,
+ * toc3d_eva_vit.py:424-427): rep[w] = sum_j (s_j / sum s) * x[fast_map[w,j]] (pad slots are zero
+ * vectors but their scores count).  Written to rep_out fp32 [nW,C] and to
+ * packed[(w*(k+1)+k)*C] when packed != NULL. */
+int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, const float* fast_score, int32_t nW,
+                            int32_t n_fast, int32_t k, int32_t C, float* rep_out, float* packed, void* stream);
+
+/* Fast-token update (toc3d_eva_vit.py:452-456): x[fast_map[w,j]] += packed[(w*(k+1)+k)] - rep[w],
+ * i.e. the representative token's attention + MLP residual deltas. */
+int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* packed, const float* rep, int32_t nW,
+                            int32_t n_fast, int32_t k, int32_t C, void* stream);
+
+/* ------------------------------------------------------------------ history-query scorer
+ * toc3d_utils.py:232-252 is linear in the token up to the LogSoftmax, so the query bank is
+ * folded once per frame into A[f] (2 x C) and c[f] (2):
+ *   A = scale * W_agg (2xQ) * queries[f] (QxCq) * W_in (CqxC),  c = scale * W_agg * queries * b_in + b_agg
+ * queries fp32 [Bf,Q,Cq]; w_in fp32 [Cq,C]; b_in [Cq]; w_agg [2,Q]; b_agg [2]; A_out [Bf,2,C]; c_out [Bf,2]. */
+int toc3d_score_fold_queries(const float* queries, const float* w_in, const float* b_in, const float* w_agg,
+                             const float* b_agg, float scale, int32_t Bf, int32_t Q, int32_t Cq, int32_t C,
+                             float* A_out, float* c_out, void* stream);
+
+/* Per token: logit = mask_in * (x . A[f]) + c[f]; pred = log_softmax(logit) (fp32 [V*N,2]);
+ * mask_out = softmax(pred + g)[0] (toc3d_utils.py:147, pin 2) with g = gumbel [V*N,2] or, when
+ * gumbel == NULL, -log(-log(u)) drawn on device from (seed, token index).
+ * mask_in NULL = all ones.  views_per_frame = V / Bf (repeat_interleave, toc3d_utils.py:240). */
+int toc3d_score_tokens(const float* x, const float* mask_in, const float* A, const float* c, int32_t V, int32_t N,
+                       int32_t C, int32_t views_per_frame, const float* gumbel, uint64_t seed, float* pred,
+                       float* score, float* mask_out, void* stream);
+
+/* Same tail for the first-frame scorer (toc3d_utils.py:114-129) whose logits come from the MLP
+ * GEMM chain: logits fp32 [M,2] -> pred, score, mask_out. */
+int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed, float* pred,
+                       float* score, float* mask_out, void* stream);
+
+/* ------------------------------------------------------------------ stem
+ * im2col for the 16x16/stride-16 patch conv (eva_utils.py:283-287): img fp32 NCHW [V,3,Hi,Wi] ->
+ * bf16 [V*(Hi/16)*(Wi/16), 768], column = c*256 + ky*16 + kx (= conv weight flattening). */
+int toc3d_im2col_patch16(const float* img, void* out_bf16, int32_t V, int32_t Hi, int32_t Wi, void* stream);
+
+/* Row-wise helpers used by the first-frame scorer and weight repacking. */
+int toc3d_cast_f32_to_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
+/* x[m,:] * mask[m] -> LN -> bf16 is toc3d_layernorm_rows on a pre-masked buffer; this masks. */
+int toc3d_mask_rows(const float* x, const float* mask, float* out, int32_t M, int32_t C, void* stream);
+/* Half-channel token mean (toc3d_utils.py:124-126): y bf16 [V,N,C] -> y[:, :, C/2:] = mean_n y[:, n, C/2:]. */
+int toc3d_global_half_mean(void* y_bf16, int32_t V, int32_t N, int32_t C, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TOC3D_B200_H_ */

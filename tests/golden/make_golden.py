@@ -1,0 +1,71 @@
+"""Generate tests/golden/*.pt from the UNMODIFIED reference (build container only).
+
+    python -m tests.golden.make_golden
+
+Each fixture holds the outputs of the real reference backbone (imported via
+tests/golden/ref_import.py with the two documented pins) on seeded synthetic
+inputs and weights that are a pure function of (seed, key) — see
+toc3d_b200/synthetic.py — so the oracle and the CUDA path can rebuild the
+identical inputs on the GPU box where /root/reference does not exist.
+"""
+import contextlib
+import io
+import os
+
+import torch
+
+from tests.golden.ref_import import load_reference
+from toc3d_b200.configs import CONFIGS, TINY
+from toc3d_b200.synthetic import make_gumbel, make_inputs, randomize_state_dict
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+# name -> (kind, cfg, hw, views, bias_std, prev_exists, seed, subsample)
+CASES = {
+    "tiny_prev": ("toc3d", TINY, (320, 800), 1, 0.1, True, 0, 1),
+    "tiny_first": ("toc3d", TINY, (160, 352), 1, 0.1, False, 1, 1),
+    "tiny_prev_small": ("toc3d", TINY, (160, 352), 2, 0.0, True, 2, 1),
+    "tiny_dense": ("dense", {k: v for k, v in TINY.items() if k in CONFIGS["eva_vit_l"][1]},
+                   (160, 352), 1, 0.1, True, 3, 1),
+    "vitl_faster_1view": ("toc3d", CONFIGS["toc3d_faster"][1], (320, 800), 1, 0.1, True, 4, 16),
+}
+
+
+def build_case(name):
+    kind, cfg, hw, views, bias_std, prev, seed, sub = CASES[name]
+    ns = load_reference()
+    cls = ns.ToC3DEVAViT if kind == "toc3d" else ns.EVA_ViT
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = cls(**cfg).eval()
+    sd = randomize_state_dict(m.state_dict(), seed=seed, bias_std=bias_std)
+    m.load_state_dict(sd)
+    inp = make_inputs(1, views, hw, seed=seed, pose="random")
+    inp["prev_exists"] = prev
+    N = (hw[0] // 16) * (hw[1] // 16)
+    gn = make_gumbel(views, N, seed=seed + 100)
+    ns.set_gumbel(gn)
+    with torch.no_grad():
+        r = m(**inp)
+    fx = dict(meta=dict(kind=kind, hw=list(hw), views=views, bias_std=bias_std, prev_exists=prev, seed=seed,
+                        subsample=sub, n_keys=len(sd), torch=str(torch.__version__)))
+    if kind == "dense":
+        fx["last_feat"] = r["last_feat"][:, ::sub].contiguous()
+    else:
+        fx["last_feat"] = r.img_feats["last_feat"][:, ::sub].contiguous()
+        fx["token_masks"] = [t.contiguous() for t in r.token_masks]
+        fx["keep_idx"] = [t.to(torch.int16) for t in r.keep_idx]
+        fx["drop_idx"] = [t.to(torch.int16) for t in r.drop_idx]
+        assert r.attn_scores is None
+    return fx
+
+
+def main():
+    for name in CASES:
+        fx = build_case(name)
+        path = os.path.join(HERE, name + ".pt")
+        torch.save(fx, path)
+        print(name, os.path.getsize(path) // 1024, "KiB", tuple(fx["last_feat"].shape))
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,340 @@
+"""Kernel-level parity (GPU): every C-ABI entry point against the CPU oracle / fp32 torch math
+on identical inputs.  Integer outputs must be bit-exact; bf16 tensor-core outputs carry the
+tolerance written next to each check."""
+import math
+
+import pytest
+import torch
+
+from oracle import toc3d_oracle as O
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def bf16_round(t):
+    return t.to(torch.bfloat16).float()
+
+
+def rel_err(a, b):
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+# ------------------------------------------------------------------------------------ GEMM
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (128, 256, 256), (200, 520, 192), (1000, 1024, 768),
+                                   (8640, 3072, 1024), (333, 1024, 2752), (6000, 256, 1024)])
+@pytest.mark.parametrize("f32", [False, True])
+def test_gemm_linear(lib, M, N, K, f32):
+    g = torch.Generator().manual_seed(M + N + K)
+    A = bf16_round(torch.randn(M, K, generator=g))
+    B = bf16_round(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ B.double().t() + bias.double()
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32 if f32 else torch.bfloat16)
+    lib.gemm(A.to(DEV).bfloat16(), B.to(DEV).bfloat16(), lib.EPI_LINEAR, bias=bias.to(DEV), out=out, out_f32=f32)
+    torch.cuda.synchronize()
+    got = out.float().cpu().double()
+    assert torch.isfinite(got).all()
+    tol = 2e-5 if f32 else 6e-3          # fp32 accumulate; bf16 output rounding 2^-8 relative
+    assert rel_err(got, ref) < tol, rel_err(got, ref)
+
+
+@pytest.mark.parametrize("act", [1, 2])
+def test_gemm_linear_act(lib, act):
+    g = torch.Generator().manual_seed(7)
+    M, N, K = 300, 512, 128
+    A = bf16_round(torch.randn(M, K, generator=g)); B = bf16_round(torch.randn(N, K, generator=g) * 0.1)
+    bias = torch.randn(N, generator=g)
+    pre = A @ B.t() + bias
+    ref = torch.nn.functional.gelu(pre) if act == 1 else torch.relu(pre)
+    out = torch.empty(M, N, device=DEV, dtype=torch.float32)
+    lib.gemm(A.to(DEV).bfloat16(), B.to(DEV).bfloat16(), lib.EPI_LINEAR, bias=bias.to(DEV), out=out, out_f32=True, act=act)
+    assert (out.cpu() - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("ft,use_rows", [(16, False), (20, False), (16, True), (20, True)])
+def test_gemm_qkv_rope(lib, ft, use_rows):
+    g = torch.Generator().manual_seed(ft)
+    heads, C, K = 4, 256, 128
+    n = ft * ft
+    nW = 3
+    seq = n if not use_rows else 101
+    M = nW * seq
+    A = bf16_round(torch.randn(M, K, generator=g)); Wt = bf16_round(torch.randn(3 * C, K, generator=g) * 0.1)
+    bias = torch.randn(3 * C, generator=g); bias[C:2 * C] = 0
+    cos, sin = O.rope_table(ft, 32, 16)
+    if use_rows:
+        rows = torch.stack([torch.randperm(n, generator=g)[:seq] for _ in range(nW)]).reshape(-1)
+        rows[seq - 1::seq] = seq - 1
+    else:
+        rows = torch.arange(M) % n
+    y = (A @ Wt.t() + bias).reshape(M, 3, heads, 64)
+    q = O.apply_rope(y[:, 0], cos[rows][:, None], sin[rows][:, None]) * 0.125
+    k = O.apply_rope(y[:, 1], cos[rows][:, None], sin[rows][:, None])
+    ref = torch.stack([q, k, y[:, 2]], dim=1).reshape(M, 3 * C)
+    cos_axis = cos.reshape(ft, ft, 64)[:, 0, 0:32:2].contiguous().to(DEV)
+    sin_axis = sin.reshape(ft, ft, 64)[:, 0, 0:32:2].contiguous().to(DEV)
+    out = torch.empty(M, 3 * C, device=DEV, dtype=torch.bfloat16)
+    lib.gemm(A.to(DEV).bfloat16(), Wt.to(DEV).bfloat16(), lib.EPI_QKV_ROPE, bias=bias.to(DEV), out=out,
+             rope_rows=rows.int().to(DEV) if use_rows else None, rope_slots=n, rope_ft=ft, rope_cols=2 * C,
+             q_scale=0.125, cos_axis=cos_axis, sin_axis=sin_axis)
+    assert rel_err(out.float().cpu(), ref) < 6e-3
+
+
+def test_gemm_resid_maps(lib):
+    g = torch.Generator().manual_seed(3)
+    M, N, K, R = 300, 256, 128, 500
+    A = bf16_round(torch.randn(M, K, generator=g)); Wt = bf16_round(torch.randn(N, K, generator=g) * 0.1)
+    bias = torch.randn(N, generator=g)
+    x = torch.randn(R, N, generator=g)
+    alt = torch.randn(M, N, generator=g)
+    perm = torch.randperm(R, generator=g)[:M].int()
+    rmap = perm.clone(); rmap[::7] = -1; rmap[5::11] = -2
+    omap = perm.clone(); omap[3::5] = -1; omap[5::11] = -2
+    acc = A @ Wt.t() + bias
+    ref_x, ref_alt = x.clone(), alt.clone()
+    for m in range(M):
+        r = x[rmap[m]] if rmap[m] >= 0 else (alt[m] if rmap[m] == -2 else torch.zeros(N))
+        if omap[m] >= 0:
+            ref_x[omap[m]] = r + acc[m]
+        elif omap[m] == -2:
+            ref_alt[m] = r + acc[m]
+    xd, altd = x.to(DEV), alt.to(DEV)
+    lib.gemm(A.to(DEV).bfloat16(), Wt.to(DEV).bfloat16(), lib.EPI_RESID, bias=bias.to(DEV), out=xd, resid=xd,
+             resid_map=rmap.to(DEV), out_map=omap.to(DEV), out_alt=altd)
+    assert (xd.cpu() - ref_x).abs().max().item() < 2e-4
+    assert (altd.cpu() - ref_alt).abs().max().item() < 2e-4
+    # identity maps + resid_mod (abs-pos broadcast)
+    pos = torch.randn(100, N, generator=g)
+    out = torch.empty(M, N, device=DEV)
+    lib.gemm(A.to(DEV).bfloat16(), Wt.to(DEV).bfloat16(), lib.EPI_RESID, bias=bias.to(DEV), out=out,
+             resid=pos.to(DEV), resid_mod=100)
+    assert (out.cpu() - (acc + pos[torch.arange(M) % 100])).abs().max().item() < 2e-4
+
+
+@pytest.mark.parametrize("M,Hd", [(257, 2730), (1000, 341)])
+def test_gemm_swiglu(lib, M, Hd):
+    from toc3d_b200.backbone import interleave_w12, hidden_pad
+    g = torch.Generator().manual_seed(Hd)
+    K = 128
+    Hp = hidden_pad(Hd)
+    A = bf16_round(torch.randn(M, K, generator=g))
+    w1 = bf16_round(torch.randn(Hd, K, generator=g) * 0.1); w2 = bf16_round(torch.randn(Hd, K, generator=g) * 0.1)
+    b1 = torch.randn(Hd, generator=g); b2 = torch.randn(Hd, generator=g)
+    ref = torch.nn.functional.silu(A @ w1.t() + b1) * (A @ w2.t() + b2)
+    W12, b12 = interleave_w12(w1, b1, w2, b2, Hp)
+    out = torch.full((M, Hp), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib.gemm(A.to(DEV).bfloat16(), W12.to(DEV).bfloat16(), lib.EPI_SWIGLU, bias=b12.to(DEV), out=out)
+    got = out.float().cpu()
+    assert rel_err(got[:, :Hd], ref) < 8e-3
+    assert (got[:, Hd:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------ attention
+@pytest.mark.parametrize("seq", [1, 64, 77, 129, 180, 256, 281, 400, 401])
+def test_window_attention(lib, seq):
+    g = torch.Generator().manual_seed(seq)
+    nW, heads = 5, 3
+    C = heads * 64
+    qkv = bf16_round(torch.randn(nW * seq, 3 * C, generator=g))
+    q, k, v = qkv.reshape(nW, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(nW * seq, C)
+    out = torch.full((nW * seq, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib.window_attention(qkv.to(DEV).bfloat16(), out, nW, seq, heads)
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2e-2, (got - ref).abs().max().item()   # P rounded to bf16, |v|~3
+
+
+# ------------------------------------------------------------------------------------ LayerNorm
+@pytest.mark.parametrize("C", [128, 1024])
+@pytest.mark.parametrize("pad_mode", [0, 1])
+def test_layernorm_rows(lib, C, pad_mode):
+    g = torch.Generator().manual_seed(C)
+    R, M = 300, 411
+    x = torch.randn(R, C, generator=g) * 3 + 1
+    alt = torch.randn(M, C, generator=g)
+    gam = torch.randn(C, generator=g); bet = torch.randn(C, generator=g)
+    rmap = torch.randint(0, R, (M,), generator=g).int(); rmap[::5] = -1; rmap[3::17] = -2
+    src = torch.zeros(M, C)
+    for m in range(M):
+        src[m] = x[rmap[m]] if rmap[m] >= 0 else (alt[m] if rmap[m] == -2 else 0)
+    ref = torch.nn.functional.layer_norm(src, (C,), gam, bet, 1e-6)
+    if pad_mode == 0:
+        ref[rmap == -1] = 0
+    out = torch.empty(M, C, device=DEV, dtype=torch.bfloat16)
+    lib.layernorm_rows(x.to(DEV), gam.to(DEV), bet.to(DEV), out, M, C, 1e-6, row_map=rmap.to(DEV), alt=alt.to(DEV),
+                       pad_mode=pad_mode)
+    assert (out.float().cpu() - bf16_round(ref)).abs().max().item() <= 0.04   # 1 bf16 ulp at |y|<8
+    out2 = torch.empty(R, C, device=DEV, dtype=torch.bfloat16)
+    lib.layernorm_rows(x.to(DEV), gam.to(DEV), bet.to(DEV), out2, R, C, 1e-6)
+    ref2 = torch.nn.functional.layer_norm(x, (C,), gam, bet, 1e-6)
+    assert (out2.float().cpu() - bf16_round(ref2)).abs().max().item() <= 0.04
+
+
+@pytest.mark.parametrize("Hd,ld", [(2730, 2752), (341, 352), (64, 64)])
+def test_subln(lib, Hd, ld):
+    g = torch.Generator().manual_seed(Hd)
+    M = 257
+    h = torch.zeros(M, ld); h[:, :Hd] = torch.randn(M, Hd, generator=g) * 2 + 0.3
+    h = bf16_round(h)
+    gam = torch.randn(Hd, generator=g); bet = torch.randn(Hd, generator=g)
+    ref = torch.nn.functional.layer_norm(h[:, :Hd], (Hd,), gam, bet, 1e-6)
+    gp = torch.zeros(ld); gp[:Hd] = gam; bp = torch.zeros(ld); bp[:Hd] = bet
+    out = torch.full((M, ld), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib.subln(h.to(DEV).bfloat16(), out, gp.to(DEV), bp.to(DEV), M, Hd, ld, 1e-6)
+    got = out.float().cpu()
+    assert (got[:, :Hd] - bf16_round(ref)).abs().max().item() <= 0.04
+    assert (got[:, Hd:] == 0).all()
+
+
+# ------------------------------------------------------------------------------------ selection
+def _adversarial_scores(V, H, W, kind, g):
+    s = -torch.rand(V, H, W, generator=g) * 5
+    if kind == "equal":
+        s[:] = -0.5
+    elif kind == "dups":
+        s = (s * 4).round() / 4
+    elif kind == "zeros":
+        s = torch.where(torch.rand(V, H, W, generator=g) < 0.5, torch.zeros(()), -torch.zeros(()))
+    elif kind == "ramp_up":
+        s = torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W) * 1e-3 - 10
+    elif kind == "ramp_down":
+        s = -torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W) * 1e-3
+    elif kind == "pads_tie":
+        s[:, ::2] = O.PAD_SCORE      # real tokens that tie with the pad value
+    return s
+
+
+@pytest.mark.parametrize("kind", ["random", "equal", "dups", "zeros", "ramp_up", "ramp_down", "pads_tie"])
+@pytest.mark.parametrize("H,W,ws,ratio", [(20, 50, 16, 0.7), (20, 50, 20, 0.5), (20, 50, 20, 0.4), (20, 50, 16, 0.3),
+                                          (50, 100, 16, 0.5), (50, 100, 20, 0.3), (7, 9, 16, 0.5)])
+def test_window_topk_bit_exact(lib, kind, H, W, ws, ratio):
+    g = torch.Generator().manual_seed(H * W + ws)
+    V = 3
+    s = _adversarial_scores(V, H, W, kind, g)
+    n = ws * ws
+    k = int(n * ratio)
+    sw, _ = O.window_partition(s[..., None], ws, pad_value=O.PAD_SCORE)
+    sw = sw.reshape(-1, n)
+    _, fast_s, slow_idx, fast_idx = O.sample(sw, ratio)
+    nW = sw.shape[0]
+    d = dict(slow_idx=torch.full((nW, k), -9, dtype=torch.int32, device=DEV),
+             fast_idx=torch.full((nW, n - k), -9, dtype=torch.int32, device=DEV),
+             fast_score=torch.zeros(nW, n - k, device=DEV),
+             tok_map=torch.full((nW * (k + 1),), -9, dtype=torch.int32, device=DEV),
+             rope_rows=torch.full((nW * (k + 1),), -9, dtype=torch.int32, device=DEV),
+             fast_map=torch.full((nW, n - k), -9, dtype=torch.int32, device=DEV))
+    lib.window_topk(s.to(DEV), V, H, W, ws, k, **d)
+    assert torch.equal(d["slow_idx"].cpu().long(), slow_idx)
+    assert torch.equal(d["fast_idx"].cpu().long(), fast_idx)
+    assert torch.equal(d["fast_score"].cpu(), fast_s)
+    # derived maps: slot -> image row
+    rows = torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W, 1)
+    rw, _ = O.window_partition(rows, ws, pad_value=-1.0)
+    rw = rw.reshape(nW, n).long()
+    tok = torch.cat([torch.gather(rw, 1, slow_idx), torch.full((nW, 1), -2)], 1).reshape(-1)
+    assert torch.equal(d["tok_map"].cpu().long(), tok)
+    rr = torch.cat([slow_idx, torch.full((nW, 1), k)], 1).reshape(-1)
+    assert torch.equal(d["rope_rows"].cpu().long(), rr)
+    assert torch.equal(d["fast_map"].cpu().long(), torch.gather(rw, 1, fast_idx))
+
+
+@pytest.mark.parametrize("kind", ["random", "equal", "dups", "zeros"])
+@pytest.mark.parametrize("N,ratio", [(1000, 0.7), (1000, 0.3), (5000, 0.5), (5000, 0.4), (63, 0.5)])
+def test_topk_split_bit_exact(lib, kind, N, ratio):
+    g = torch.Generator().manual_seed(N)
+    B = 6
+    s = _adversarial_scores(B, 1, N, kind, g).reshape(B, N)
+    k = int(N * ratio)
+    _, _, keep, drop = O.sample(s, ratio)
+    ki = torch.full((B, k), -9, dtype=torch.int64, device=DEV)
+    di = torch.full((B, N - k), -9, dtype=torch.int64, device=DEV)
+    lib.topk_split(s.to(DEV), B, N, k, ki, di)
+    assert torch.equal(ki.cpu(), keep) and torch.equal(di.cpu(), drop)
+
+
+def test_merge_and_fast_update(lib):
+    g = torch.Generator().manual_seed(11)
+    V, H, W, ws, C, ratio = 2, 20, 50, 16, 256, 0.7
+    n, k = ws * ws, int(ws * ws * ratio)
+    x = torch.randn(V, H, W, C, generator=g)
+    s = -torch.rand(V, H, W, generator=g) * 4
+    xw, _ = O.window_partition(x, ws); xw = xw.reshape(-1, n, C)
+    sw, _ = O.window_partition(s[..., None], ws, pad_value=O.PAD_SCORE); sw = sw.reshape(-1, n)
+    _, fast_s, slow_idx, fast_idx = O.sample(sw, ratio)
+    rep_ref = O.merge_tokens(O.batch_index_select(xw, fast_idx), fast_s)[:, 0]
+    nW, nf = sw.shape[0], n - k
+    fs = torch.empty(nW, nf, device=DEV); fm = torch.empty(nW, nf, dtype=torch.int32, device=DEV)
+    lib.window_topk(s.to(DEV), V, H, W, ws, k, fast_score=fs, fast_map=fm)
+    xd = x.reshape(-1, C).to(DEV).contiguous()
+    rep = torch.empty(nW, C, device=DEV); packed = torch.zeros(nW * (k + 1), C, device=DEV)
+    lib.merge_fast_tokens(xd, fm, fs, nW, nf, k, C, rep, packed)
+    assert (rep.cpu() - rep_ref).abs().max().item() < 1e-5 * max(1.0, rep_ref.abs().max().item())
+    assert torch.equal(packed.reshape(nW, k + 1, C)[:, k], rep)
+    # fast update: packed rep rows hold t2_rep
+    delta = torch.randn(nW, C, generator=g)
+    packed.reshape(nW, k + 1, C)[:, k] = rep + delta.to(DEV)
+    lib.fast_token_update(xd, fm, packed, rep, nW, nf, k, C)
+    out_w = xw.clone()
+    fi = fast_idx[..., None].expand(-1, -1, C)
+    out_w.scatter_(1, fi, torch.gather(xw, 1, fi) + delta[:, None])
+    ref = O.window_unpartition(out_w.reshape(-1, ws, ws, C), ws, (32, 64), (H, W)).reshape(-1, C)
+    assert (xd.cpu() - ref).abs().max().item() < 1e-5
+
+
+# ------------------------------------------------------------------------------------ scorer
+def test_scorer_fold_and_tokens(lib):
+    g = torch.Generator().manual_seed(5)
+    Bf, views, H, W, C, Q, Cq = 2, 3, 10, 22, 1024, 64, 256
+    V, N = Bf * views, H * W
+    p = {"score_predictor.0.input_proj.0.weight": torch.randn(Cq, C, generator=g) * 0.02,
+         "score_predictor.0.input_proj.0.bias": torch.randn(Cq, generator=g) * 0.1,
+         "score_predictor.0.aggregate.0.weight": torch.randn(2, Q, generator=g) * 0.1,
+         "score_predictor.0.aggregate.0.bias": torch.randn(2, generator=g) * 0.1}
+    x = torch.randn(V, H, W, C, generator=g) * 2
+    mask = torch.rand(V, H, W, 1, generator=g)
+    queries = torch.randn(Bf, Q, Cq, generator=g)
+    gn = -torch.log(-torch.log(torch.rand(V, N, 2, generator=g).clamp(1e-9, 1 - 1e-7)))
+    pred_ref = O.query_based_score(x, mask, queries, p, 0)
+    mask_ref = O.gumbel_mask(pred_ref, gn)[..., 0]
+    A = torch.empty(Bf, 2, C, device=DEV); c = torch.empty(Bf, 2, device=DEV)
+    lib.score_fold_queries(queries.to(DEV), p["score_predictor.0.input_proj.0.weight"].to(DEV),
+                           p["score_predictor.0.input_proj.0.bias"].to(DEV),
+                           p["score_predictor.0.aggregate.0.weight"].to(DEV),
+                           p["score_predictor.0.aggregate.0.bias"].to(DEV), Cq ** -0.5, A, c)
+    pred = torch.empty(V, N, 2, device=DEV); score = torch.empty(V, N, device=DEV); mo = torch.empty(V, N, device=DEV)
+    lib.score_tokens(x.to(DEV), mask.reshape(V, N).to(DEV).contiguous(), A, c, V, N, C, views, gn.to(DEV), 0, pred, score, mo)
+    assert (pred.cpu() - pred_ref).abs().max().item() < 2e-4       # fp32, re-associated (folded) product
+    assert torch.equal(score.cpu(), pred.cpu()[..., 0])
+    assert (mo.cpu() - mask_ref).abs().max().item() < 2e-4
+    # device-drawn noise: masks must lie in (0,1) and differ between seeds
+    m1 = torch.empty(V, N, device=DEV); m2 = torch.empty(V, N, device=DEV)
+    lib.score_tokens(x.to(DEV), None, A, c, V, N, C, views, None, 1, None, None, m1)
+    lib.score_tokens(x.to(DEV), None, A, c, V, N, C, views, None, 2, None, None, m2)
+    assert ((m1 > 0) & (m1 < 1)).all() and not torch.equal(m1, m2)
+
+
+def test_im2col_patch_embed(lib):
+    g = torch.Generator().manual_seed(9)
+    V, Hi, Wi, C = 2, 64, 96, 256
+    img = torch.randn(V, 3, Hi, Wi, generator=g)
+    p = {"patch_embed.proj.weight": bf16_round(torch.randn(C, 3, 16, 16, generator=g) * 0.05),
+         "patch_embed.proj.bias": torch.randn(C, generator=g)}
+    ref = O.patch_embed(bf16_round(img), p, 16).reshape(-1, C)
+    cols = torch.empty(V * (Hi // 16) * (Wi // 16), 768, device=DEV, dtype=torch.bfloat16)
+    lib.im2col_patch16(img.to(DEV), cols, V, Hi, Wi)
+    out = torch.empty(cols.shape[0], C, device=DEV)
+    lib.gemm(cols, p["patch_embed.proj.weight"].reshape(C, 768).to(DEV).bfloat16(), lib.EPI_LINEAR,
+             bias=p["patch_embed.proj.bias"].to(DEV), out=out, out_f32=True)
+    assert (out.cpu() - ref).abs().max().item() < 1e-3
+
+
+def test_bad_arguments_fail_loudly(lib):
+    A = torch.zeros(8, 60, device=DEV, dtype=torch.bfloat16)
+    B = torch.zeros(8, 60, device=DEV, dtype=torch.bfloat16)
+    out = torch.zeros(8, 8, device=DEV)
+    with pytest.raises(RuntimeError, match="multiples of 8"):
+        lib.gemm(A, B, lib.EPI_LINEAR, out=out, out_f32=True)
+    with pytest.raises(RuntimeError, match="multiple of the 16x16 patch"):
+        lib.im2col_patch16(torch.zeros(1, 3, 30, 32, device=DEV), torch.zeros(4, 768, device=DEV, dtype=torch.bfloat16), 1, 30, 32)

@@ -1,0 +1,653 @@
+"""Drop-in `img_backbone` plugins: ToC3DEVAViT and EVA_ViT on hand-written sm_100a kernels.
+
+Host-side mirror of the reference plugin interface (same registry names, constructor
+kwargs, keyword `forward` signature, return type and state-dict keys):
+  projects/mmdet3d_plugin/models/backbones/toc3d_eva_vit.py:25-310  (ToC3DEVAViT)
+  projects/mmdet3d_plugin/models/backbones/eva_vit.py:270-428       (EVA_ViT)
+  caller: projects/mmdet3d_plugin/models/detectors/petr3d.py:145-179
+
+nn.Module is used as the parameter container (so reference checkpoints load with
+`load_state_dict`); all arithmetic on the path runs in libtoc3d_b200.so through
+toc3d_b200.lib (ctypes, raw device pointers).  Inference only.  There is no CPU or
+PyTorch fallback: CPU inputs or a missing library raise.
+"""
+import math
+from functools import partial
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import lib as L
+
+LN_EPS = 1e-6
+
+try:  # register with mmdet when it is importable (reference: toc3d_eva_vit.py:25, eva_vit.py:270)
+    from mmdet.models.builder import BACKBONES as _BACKBONES
+
+    def _register(cls):
+        return _BACKBONES.register_module(force=True)(cls)
+except Exception:  # mmdet absent: plain nn.Module
+    def _register(cls):
+        return cls
+
+try:  # inside the reference tree Petr3D isinstance-checks this exact class (petr3d.py:17,159)
+    from projects.mmdet3d_plugin.models.backbones.toc3d_utils import ToC3DViTReturnType
+except Exception:
+    class ToC3DViTReturnType:
+        """toc3d_utils.py:10-25."""
+
+        def __init__(self, img_feats=None, token_masks=None, attn_scores=None, keep_idx=None, drop_idx=None,
+                     aux_outputs=None):
+            self.img_feats = img_feats
+            self.token_masks = token_masks
+            self.attn_scores = attn_scores
+            self.keep_idx = keep_idx
+            self.drop_idx = drop_idx
+            self.aux_outputs = aux_outputs
+
+try:
+    from projects.mmdet3d_plugin.models.utils.gpu_timer import GLOBAL_TIMER
+except Exception:
+    class _NoTimer:
+        def event_start(self, name):
+            pass
+
+        def event_end(self, name):
+            pass
+    GLOBAL_TIMER = _NoTimer()
+
+
+# ------------------------------------------------------------------------------- weight repacking
+def hidden_pad(hd):
+    """SwiGLU hidden width padded to the GEMM K block (2730 -> 2752): TMA needs 16-byte row strides."""
+    return (hd + 63) // 64 * 64
+
+
+def interleave_w12(w1, b1, w2, b2, hp):
+    """[w1; w2] -> rows interleaved in blocks of 32 so one accumulator tile holds both SwiGLU factors.
+    Row 64*b + j = w1[32*b + j], row 64*b + 32 + j = w2[32*b + j] (zero beyond the true width)."""
+    hd, k = w1.shape
+    W = w1.new_zeros(hp // 32, 2, 32, k)
+    B = b1.new_zeros(hp // 32, 2, 32)
+    w1p = F.pad(w1, (0, 0, 0, hp - hd)); w2p = F.pad(w2, (0, 0, 0, hp - hd))
+    W[:, 0] = w1p.reshape(hp // 32, 32, k); W[:, 1] = w2p.reshape(hp // 32, 32, k)
+    B[:, 0] = F.pad(b1, (0, hp - hd)).reshape(-1, 32); B[:, 1] = F.pad(b2, (0, hp - hd)).reshape(-1, 32)
+    return W.reshape(2 * hp, k).contiguous(), B.reshape(2 * hp).contiguous()
+
+
+# ------------------------------------------------------------------------------- parameter containers
+class _Rope(nn.Module):
+    """eva_utils.py:325-371 buffers (freqs_cos/freqs_sin of shape (ft*ft, 2*dim))."""
+
+    def __init__(self, dim, pt_seq_len, ft_seq_len, theta=10000.0):
+        super().__init__()
+        ft = ft_seq_len if ft_seq_len is not None else pt_seq_len
+        freqs = 1.0 / (theta ** (torch.arange(0, dim, 2)[: dim // 2].float() / dim))
+        t = torch.arange(ft) / ft * pt_seq_len
+        ang = (t[:, None] * freqs[None, :]).repeat_interleave(2, dim=-1)
+        full = torch.cat([ang[:, None, :].expand(ft, ft, dim), ang[None, :, :].expand(ft, ft, dim)], -1)
+        full = full.reshape(ft * ft, 2 * dim)
+        self.ft = ft
+        self.register_buffer("freqs_cos", full.cos())
+        self.register_buffer("freqs_sin", full.sin())
+
+
+class _Attention(nn.Module):
+    def __init__(self, dim, heads, qkv_bias, rope):
+        super().__init__()
+        self.num_heads = heads
+        self.q_proj = nn.Linear(dim, dim, bias=False)
+        self.k_proj = nn.Linear(dim, dim, bias=False)
+        self.v_proj = nn.Linear(dim, dim, bias=False)
+        if qkv_bias:
+            self.q_bias = nn.Parameter(torch.zeros(dim))
+            self.v_bias = nn.Parameter(torch.zeros(dim))
+        else:
+            self.q_bias = self.v_bias = None
+        self.rope = rope
+        self.proj = nn.Linear(dim, dim)
+
+
+class _SwiGLU(nn.Module):
+    def __init__(self, dim, hidden):
+        super().__init__()
+        self.w1 = nn.Linear(dim, hidden)
+        self.w2 = nn.Linear(dim, hidden)
+        self.ffn_ln = nn.LayerNorm(hidden, eps=LN_EPS)
+        self.w3 = nn.Linear(hidden, dim)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, heads, mlp_ratio, qkv_bias, window_size, rope, accelerate):
+        super().__init__()
+        self.norm1 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.attn = _Attention(dim, heads, qkv_bias, rope)
+        self.norm2 = nn.LayerNorm(dim, eps=LN_EPS)
+        self.mlp = _SwiGLU(dim, int(dim * mlp_ratio))
+        self.window_size = window_size
+        self.accelerate = accelerate
+
+
+class _PatchEmbed(nn.Module):
+    def __init__(self, patch, in_chans, dim):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, dim, kernel_size=patch, stride=patch)
+
+
+class _MLN(nn.Module):
+    """misc.py:154-188."""
+
+    def __init__(self, c_dim, f_dim=256):
+        super().__init__()
+        self.reduce = nn.Sequential(nn.Linear(c_dim, f_dim), nn.ReLU())
+        self.gamma = nn.Linear(f_dim, f_dim)
+        self.beta = nn.Linear(f_dim, f_dim)
+        nn.init.zeros_(self.gamma.weight); nn.init.zeros_(self.beta.weight)
+        nn.init.ones_(self.gamma.bias); nn.init.zeros_(self.beta.bias)
+
+    def forward(self, x, c):
+        x = F.layer_norm(x, (x.shape[-1],))
+        c = self.reduce(c)
+        return self.gamma(c) * x + self.beta(c)
+
+
+def _posemb(pos, feats, temperature=10000):
+    pos = pos * (2 * math.pi)
+    dim_t = torch.arange(feats, dtype=torch.float32, device=pos.device)
+    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / feats)
+    out = []
+    for c in range(pos.shape[-1]):
+        a = pos[..., c, None] / dim_t
+        out.append(torch.stack((a[..., 0::2].sin(), a[..., 1::2].cos()), dim=-1).flatten(-2))
+    return out
+
+
+class _Selector(nn.Module):
+    """Parameter container of MotionAwareQueryGuidedTokenSelector (toc3d_utils.py:92-112,196-230,294-332)
+    plus the tiny per-frame query encoder (toc3d_utils.py:334-360; 64 queries x 256 channels)."""
+
+    def __init__(self, embed_dim, num_queries, ratio, pc_range, query_dim=256):
+        super().__init__()
+        self.ratio = ratio
+        self.num_queries = num_queries
+        self.scale = query_dim ** -0.5
+        self.in_conv = nn.Sequential(nn.LayerNorm(embed_dim), nn.Linear(embed_dim, embed_dim), nn.GELU())
+        self.out_conv = nn.Sequential(nn.Linear(embed_dim, embed_dim // 2), nn.GELU(),
+                                      nn.Linear(embed_dim // 2, embed_dim // 4), nn.GELU(),
+                                      nn.Linear(embed_dim // 4, 2), nn.LogSoftmax(dim=-1))
+        self.input_proj = nn.Sequential(nn.Linear(embed_dim, query_dim))
+        self.aggregate = nn.Sequential(nn.Linear(num_queries, 2), nn.LogSoftmax(dim=-1))
+        self.pc_range = nn.Parameter(torch.tensor(pc_range, dtype=torch.float32), requires_grad=False)
+        self.query_embedding = nn.Sequential(nn.Linear(query_dim * 3 // 2, query_dim), nn.ReLU(),
+                                             nn.Linear(query_dim, query_dim))
+        self.ego_pose_pe = _MLN(180)
+        self.ego_pose_queries = _MLN(180)
+        self.time_embedding = nn.Sequential(nn.Linear(query_dim, query_dim), nn.LayerNorm(query_dim))
+
+    @torch.no_grad()
+    def motion_aware_queries(self, temp_queries, temp_ref_points, temp_vel, temp_timestamp, temp_ego_pose,
+                             ego_pose_inv):
+        assert ego_pose_inv is not None                                          # toc3d_utils.py:345
+        ref = torch.cat([temp_ref_points, torch.ones_like(temp_ref_points[..., :1])], dim=-1)
+        ref = (ego_pose_inv.unsqueeze(1) @ ref.unsqueeze(-1)).squeeze(-1)[..., :3]
+        ref = (ref - self.pc_range[:3]) / (self.pc_range[3:6] - self.pc_range[0:3])
+        ex, ey, ez = _posemb(ref, 128)
+        pos = self.query_embedding(torch.cat((ey, ex, ez), dim=-1))
+        motion = torch.cat([temp_vel, temp_timestamp, temp_ego_pose[..., :3, :].flatten(-2)], dim=-1).float()
+        bands = 2.0 ** torch.linspace(0.0, 5.0, 6, dtype=motion.dtype, device=motion.device)
+        motion = torch.cat([fn(motion * f) for f in bands for fn in (torch.sin, torch.cos)], dim=-1)
+        pos = self.ego_pose_pe(pos, motion)
+        pos = pos + self.time_embedding(_posemb(temp_timestamp[..., :1], 256)[0].float())
+        return (self.ego_pose_queries(temp_queries, motion) + pos).contiguous()
+
+
+# ------------------------------------------------------------------------------- device engine
+class _Workspace:
+    """Per-(V, H, W) device buffers and static window maps, sized for the largest block."""
+
+    def __init__(self, eng, V, H, W):
+        dev, C = eng.device, eng.C
+        self.V, self.H, self.W, self.N = V, H, W, H * W
+        rows = 0
+        self.win = {}
+        for ws in sorted(set(eng.block_ws)):
+            nWh, nWw = -(-H // ws), -(-W // ws)
+            nW, n = V * nWh * nWw, ws * ws
+            idx = torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W)
+            idx = F.pad(idx, (0, nWw * ws - W, 0, nWh * ws - H), value=-1.0)
+            idx = idx.reshape(V, nWh, ws, nWw, ws).permute(0, 1, 3, 2, 4).reshape(-1)
+            self.win[ws] = dict(nW=nW, n=n, map=idx.to(torch.int32).to(dev))
+            rows = max(rows, nW * n)
+        self.rows = rows
+        bf = dict(device=dev, dtype=torch.bfloat16)
+        self.cols = torch.empty(V * self.N, 768, **bf) if eng.patch == 16 else None
+        self.a = torch.empty(rows, C, **bf)            # LN outputs / attention outputs (GEMM A operands)
+        self.qkv = torch.empty(rows, 3 * C, **bf)
+        self.ao = torch.empty(rows, C, **bf)
+        self.hid = torch.empty(rows, eng.Hp, **bf)
+        self.T = torch.empty(rows, C, device=dev, dtype=torch.float32)   # packed slow+rep residual stream
+        self.stage = {}                                # (stage, ws) -> selection tables
+
+
+class _Engine:
+    """Device-resident, repacked (bf16, padded, interleaved) weights + the launch sequence."""
+
+    def __init__(self, model, device):
+        self.device = device
+        m = model
+        self.C, self.heads, self.patch = m.embed_dim, m.num_heads, m.patch_size
+        self.block_ws = [b.window_size for b in m.blocks]
+        self.block_acc = [b.accelerate for b in m.blocks]
+        f32 = lambda t: t.detach().to(device=device, dtype=torch.float32).contiguous()
+        b16 = lambda t: t.detach().to(device=device, dtype=torch.float32).to(torch.bfloat16).contiguous()
+        C = self.C
+        self.Hd = m.blocks[0].mlp.w1.out_features
+        self.Hp = hidden_pad(self.Hd)
+        self.w_pe = b16(m.patch_embed.proj.weight.reshape(C, -1))
+        self.b_pe = f32(m.patch_embed.proj.bias)
+        self.pos_embed = f32(m.pos_embed) if m.pos_embed is not None else None
+        self.pos_cache = {}
+        self.blocks = []
+        for b in m.blocks:
+            a = b.attn
+            zeros = torch.zeros(C, device=device)
+            qb = f32(a.q_bias) if a.q_bias is not None else zeros
+            vb = f32(a.v_bias) if a.v_bias is not None else zeros
+            w12, b12 = interleave_w12(f32(b.mlp.w1.weight), f32(b.mlp.w1.bias), f32(b.mlp.w2.weight),
+                                      f32(b.mlp.w2.bias), self.Hp)
+            ft = a.rope.ft
+            self.blocks.append(dict(
+                n1w=f32(b.norm1.weight), n1b=f32(b.norm1.bias), n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias),
+                wqkv=b16(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
+                bqkv=torch.cat([qb, zeros, vb]).contiguous(),
+                wproj=b16(a.proj.weight), bproj=f32(a.proj.bias),
+                w12=w12.to(torch.bfloat16).contiguous(), b12=b12,
+                lnw=F.pad(f32(b.mlp.ffn_ln.weight), (0, self.Hp - self.Hd)).contiguous(),
+                lnb=F.pad(f32(b.mlp.ffn_ln.bias), (0, self.Hp - self.Hd)).contiguous(),
+                w3=F.pad(f32(b.mlp.w3.weight), (0, self.Hp - self.Hd)).to(torch.bfloat16).contiguous(),
+                b3=f32(b.mlp.w3.bias), ft=ft,
+                cos=f32(a.rope.freqs_cos).reshape(ft, ft, -1)[:, 0, 0:32:2].contiguous(),
+                sin=f32(a.rope.freqs_sin).reshape(ft, ft, -1)[:, 0, 0:32:2].contiguous(),
+            ))
+        self.sel = []
+        for s in getattr(m, "score_predictor", []):
+            self.sel.append(dict(
+                w_in=f32(s.input_proj[0].weight), b_in=f32(s.input_proj[0].bias),
+                w_agg=f32(s.aggregate[0].weight), b_agg=f32(s.aggregate[0].bias),
+                ln_w=f32(s.in_conv[0].weight), ln_b=f32(s.in_conv[0].bias),
+                w_ic=b16(s.in_conv[1].weight), b_ic=f32(s.in_conv[1].bias),
+                w_o0=b16(s.out_conv[0].weight), b_o0=f32(s.out_conv[0].bias),
+                w_o2=b16(s.out_conv[2].weight), b_o2=f32(s.out_conv[2].bias),
+                # 256 -> 2 head padded to 8 output rows (GEMM N granularity)
+                w_o4=F.pad(b16(s.out_conv[4].weight), (0, 0, 0, 6)).contiguous(),
+                b_o4=F.pad(f32(s.out_conv[4].bias), (0, 6)).contiguous(),
+            ))
+        self.ws_cache = {}
+
+    # -- helpers ---------------------------------------------------------------------------
+    def workspace(self, V, H, W):
+        key = (V, H, W)
+        if key not in self.ws_cache:
+            self.ws_cache[key] = _Workspace(self, V, H, W)
+        return self.ws_cache[key]
+
+    def abs_pos(self, H, W):
+        """eva_utils.py:229-258, cached per token grid (the reference re-interpolates every call)."""
+        if self.pos_embed is None:
+            return None
+        if (H, W) not in self.pos_cache:
+            a = self.pos_embed[:, 1:] if self.has_cls else self.pos_embed
+            size = int(math.sqrt(a.shape[1]))
+            assert size * size == a.shape[1]
+            if size != H or size != W:
+                a = F.interpolate(a.reshape(1, size, size, -1).permute(0, 3, 1, 2), size=(H, W), mode="bicubic",
+                                  align_corners=False).permute(0, 2, 3, 1)
+            self.pos_cache[(H, W)] = a.reshape(H * W, self.C).contiguous()
+        return self.pos_cache[(H, W)]
+
+    # -- stem ------------------------------------------------------------------------------
+    def stem(self, img, wsp):
+        V, _, Hi, Wi = img.shape
+        L.im2col_patch16(img, wsp.cols, V, Hi, Wi)
+        X = torch.empty(V * wsp.N, self.C, device=self.device, dtype=torch.float32)
+        pos = self.abs_pos(wsp.H, wsp.W)
+        if pos is not None:
+            L.gemm(wsp.cols, self.w_pe, L.EPI_RESID, bias=self.b_pe, out=X, resid=pos, resid_mod=wsp.N)
+        else:
+            L.gemm(wsp.cols, self.w_pe, L.EPI_LINEAR, bias=self.b_pe, out=X, out_f32=True)
+        return X
+
+    # -- MLP shared by both block kinds ----------------------------------------------------------
+    def _mlp(self, bp, wsp, M, **resid_kw):
+        L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid)
+        L.subln(wsp.hid, wsp.hid, bp["lnw"], bp["lnb"], M, self.Hd, self.Hp, LN_EPS)
+        L.gemm(wsp.hid, bp["w3"], L.EPI_RESID, M=M, bias=bp["b3"], ldo=self.C, **resid_kw)
+
+    def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots):
+        C = self.C
+        L.gemm(wsp.a, bp["wqkv"], L.EPI_QKV_ROPE, M=M, bias=bp["bqkv"], out=wsp.qkv, rope_rows=rope_rows,
+               rope_slots=rope_slots, rope_ft=bp["ft"], rope_cols=2 * C, q_scale=64 ** -0.5,
+               cos_axis=bp["cos"], sin_axis=bp["sin"])
+        L.window_attention(wsp.qkv, wsp.ao, nW, seq, self.heads)
+
+    def dense_block(self, i, X, wsp):
+        """eva_vit.py:247-268."""
+        bp, C = self.blocks[i], self.C
+        w = wsp.win[self.block_ws[i]]
+        Mw, VN = w["nW"] * w["n"], wsp.V * wsp.N
+        L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, Mw, C, LN_EPS, row_map=w["map"], pad_mode=0)
+        self._qkv_attn(bp, wsp, Mw, w["nW"], w["n"], None, w["n"])
+        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mw, bias=bp["bproj"], out=X, ldo=C, resid=X,
+               resid_map=w["map"], out_map=w["map"])
+        L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS)
+        self._mlp(bp, wsp, VN, out=X, resid=X)
+
+    def select_windows(self, stage, score, ratio, wsp):
+        """Per-window stable top-k tables for every window size used after this stage.  The reference
+        re-sorts inside each of the 6 blocks of a stage (toc3d_eva_vit.py:419); the indices only depend
+        on (stage scores, window size), so they are computed once per (stage, ws)."""
+        dev = self.device
+        for ws, w in wsp.win.items():
+            n, nW = w["n"], w["nW"]
+            k = int(n * ratio)                      # toc3d_utils.py:136
+            if k >= n:
+                raise NotImplementedError("token_ratio=1.0 hits a latent bug in the reference "
+                                          "(toc3d_eva_vit.py:462-463) and is not supported")
+            t = wsp.stage.get((stage, ws))
+            if t is None or t["k"] != k:
+                i32 = dict(device=dev, dtype=torch.int32)
+                t = dict(k=k, nf=n - k, tok_map=torch.empty(nW * (k + 1), **i32),
+                         rope_rows=torch.empty(nW * (k + 1), **i32), fast_map=torch.empty(nW, n - k, **i32),
+                         fast_score=torch.empty(nW, n - k, device=dev), rep=torch.empty(nW, self.C, device=dev))
+                wsp.stage[(stage, ws)] = t
+            L.window_topk(score, wsp.V, wsp.H, wsp.W, ws, k, fast_score=t["fast_score"], tok_map=t["tok_map"],
+                          rope_rows=t["rope_rows"], fast_map=t["fast_map"])
+
+    def toc3d_block(self, i, X, wsp, stage):
+        """toc3d_eva_vit.py:395-473 (accelerated branch)."""
+        bp, C = self.blocks[i], self.C
+        ws = self.block_ws[i]
+        w, t = wsp.win[ws], wsp.stage[(stage, ws)]
+        nW, k, nf = w["nW"], t["k"], t["nf"]
+        Mp = nW * (k + 1)
+        L.merge_fast_tokens(X, t["fast_map"], t["fast_score"], nW, nf, k, C, t["rep"], wsp.T)
+        L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, Mp, C, LN_EPS, row_map=t["tok_map"], alt=wsp.T, pad_mode=1)
+        self._qkv_attn(bp, wsp, Mp, nW, k + 1, t["rope_rows"], 0)
+        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mp, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
+               resid_map=t["tok_map"], out_alt=wsp.T)                                  # t1 = t + attn
+        L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mp, C, LN_EPS)
+        self._mlp(bp, wsp, Mp, out=X, resid=wsp.T, out_map=t["tok_map"], out_alt=wsp.T)   # t2 -> image rows
+        L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C)
+
+    # -- scorers ----------------------------------------------------------------------------
+    def score_stage(self, j, sel_mod, X, mask_prev, wsp, q_kw, prev_exists, gumbel, seed):
+        dev, V, N, C = self.device, wsp.V, wsp.N, self.C
+        sp = self.sel[j]
+        pred = torch.empty(V, N, 2, device=dev)
+        score = torch.empty(V, N, device=dev)
+        mask = torch.empty(V, N, device=dev)
+        if prev_exists:
+            q = sel_mod.motion_aware_queries(**q_kw)
+            Bf = q.shape[0]
+            assert V % Bf == 0, "views*batch must be a multiple of the query batch (toc3d_utils.py:240)"
+            A = torch.empty(Bf, 2, C, device=dev); c = torch.empty(Bf, 2, device=dev)
+            L.score_fold_queries(q.float(), sp["w_in"], sp["b_in"], sp["w_agg"], sp["b_agg"], sel_mod.scale, A, c)
+            L.score_tokens(X, mask_prev, A, c, V, N, C, V // Bf, gumbel, seed, pred, score, mask)
+        else:
+            VN = V * N
+            src = X
+            if mask_prev is not None:
+                src = torch.empty_like(X)
+                L.mask_rows(X, mask_prev, src, VN, C)
+            L.layernorm_rows(src, sp["ln_w"], sp["ln_b"], wsp.a, VN, C, 1e-5)
+            y = wsp.ao[:VN]
+            L.gemm(wsp.a, sp["w_ic"], L.EPI_LINEAR, M=VN, bias=sp["b_ic"], out=y, act=L.ACT_GELU)
+            L.global_half_mean(y, V, N, C)
+            y1 = wsp.qkv.view(-1)[: VN * (C // 2)].view(VN, C // 2)
+            L.gemm(y, sp["w_o0"], L.EPI_LINEAR, M=VN, bias=sp["b_o0"], out=y1, act=L.ACT_GELU)
+            y2 = wsp.hid.view(-1)[: VN * (C // 4)].view(VN, C // 4)
+            L.gemm(y1, sp["w_o2"], L.EPI_LINEAR, M=VN, bias=sp["b_o2"], out=y2, act=L.ACT_GELU)
+            logits8 = torch.empty(VN, 8, device=dev)
+            L.gemm(y2, sp["w_o4"], L.EPI_LINEAR, M=VN, bias=sp["b_o4"], out=logits8, out_f32=True)
+            logits = logits8[:, :2].contiguous()
+            L.score_finish(logits, VN, gumbel, seed, pred, score, mask)
+        return pred, score, mask
+
+
+class _EvaBase(nn.Module):
+    """Shared construction / engine plumbing of the two backbones."""
+
+    def _build_common(self, img_size, patch_size, in_chans, embed_dim, num_heads, use_abs_pos, pretrain_img_size,
+                      pretrain_use_cls_token, pt_hw_seq_len, intp_freq, window_size):
+        if patch_size != 16 or in_chans != 3:
+            raise NotImplementedError("the sm_100a stem kernel is specialised for 16x16 RGB patches")
+        if embed_dim // num_heads != 64:
+            raise NotImplementedError("attention / RoPE kernels are specialised for head_dim 64")
+        self.embed_dim, self.num_heads, self.patch_size = embed_dim, num_heads, patch_size
+        self.pretrain_use_cls_token = pretrain_use_cls_token
+        self.patch_embed = _PatchEmbed(patch_size, in_chans, embed_dim)
+        if use_abs_pos:
+            npos = (pretrain_img_size // patch_size) ** 2 + (1 if pretrain_use_cls_token else 0)
+            self.pos_embed = nn.Parameter(torch.zeros(1, npos, embed_dim))
+        else:
+            self.pos_embed = None
+        hh = embed_dim // num_heads // 2
+        self.rope_win = _Rope(hh, pt_hw_seq_len, window_size if intp_freq else None)
+        self.rope_glb = _Rope(hh, pt_hw_seq_len, img_size // patch_size if intp_freq else None)
+        self._engine = None
+
+    def _init_weights(self):
+        """toc3d_eva_vit.py:214-228 / eva_vit.py:396-407."""
+        if self.pos_embed is not None:
+            nn.init.trunc_normal_(self.pos_embed, std=0.02)
+        for m in self.modules():
+            if isinstance(m, nn.Linear):
+                nn.init.trunc_normal_(m.weight, std=0.02)
+                if m.bias is not None:
+                    nn.init.constant_(m.bias, 0)
+            elif isinstance(m, nn.LayerNorm):
+                nn.init.constant_(m.bias, 0)
+                nn.init.constant_(m.weight, 1.0)
+
+    # any change of the parameters invalidates the repacked device copies
+    def _apply(self, fn, *a, **k):
+        self._engine = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._engine = None
+        return super().load_state_dict(*a, **k)
+
+    def refresh_weights(self):
+        """Call after mutating parameters in place (the engine holds repacked bf16 copies)."""
+        self._engine = None
+
+    def _get_engine(self, x):
+        if not x.is_cuda:
+            raise RuntimeError("toc3d_b200 backbones run on CUDA (sm_100a) only; got a %s tensor. "
+                               "There is no CPU fallback." % x.device)
+        if self.training:
+            raise RuntimeError("toc3d_b200 backbones are inference-only; call .eval()")
+        if self._engine is None or self._engine.device != x.device:
+            L.load()
+            self._engine = _Engine(self, x.device)
+            self._engine.has_cls = self.pretrain_use_cls_token
+        return self._engine
+
+    @staticmethod
+    def _prep_img(x):
+        if x.dim() != 4:
+            raise ValueError("expected images of shape (B*views, 3, H, W)")
+        return x.float().contiguous()
+
+
+@_register
+class EVA_ViT(_EvaBase):
+    """Dense EVA-02 ViT backbone (eva_vit.py:270-428); returns {'last_feat': (V,C,H/16,W/16)}."""
+
+    def __init__(self, img_size=1024, patch_size=16, in_chans=3, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4 * 2 / 3, qkv_bias=True, drop_path_rate=0.0, norm_layer=None, act_layer=None,
+                 use_abs_pos=True, use_rel_pos=False, rope=True, pt_hw_seq_len=16, intp_freq=True, window_size=0,
+                 global_window_size=20, use_checkpoint=True, global_attn_indexes=(), residual_block_indexes=(),
+                 use_act_checkpoint=False, pretrain_img_size=224, pretrain_use_cls_token=True,
+                 return_intermediate=False, out_feature="last_feat", xattn=True):
+        super().__init__()
+        if len(residual_block_indexes) or return_intermediate or window_size <= 0:
+            raise NotImplementedError("residual blocks / return_intermediate / window_size=0 are not used by any "
+                                      "shipped config and are not implemented")
+        self._build_common(img_size, patch_size, in_chans, embed_dim, num_heads, use_abs_pos, pretrain_img_size,
+                           pretrain_use_cls_token, pt_hw_seq_len, intp_freq, window_size)
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            g = i in global_attn_indexes
+            self.blocks.append(_Block(embed_dim, num_heads, mlp_ratio, qkv_bias,
+                                      global_window_size if g else window_size,
+                                      self.rope_glb if g else self.rope_win, accelerate=False))
+        self._out_features = [out_feature]
+        self._out_feature_channels = {out_feature: embed_dim}
+        self._out_feature_strides = {out_feature: patch_size}
+        self._init_weights()
+
+    @torch.no_grad()
+    def forward(self, x, *args, **kwargs):
+        x = self._prep_img(x)
+        eng = self._get_engine(x)
+        V, _, Hi, Wi = x.shape
+        wsp = eng.workspace(V, Hi // 16, Wi // 16)
+        X = eng.stem(x, wsp)
+        GLOBAL_TIMER.event_start("StreamPETR-EVA-ViT/backbone")
+        for i in range(len(self.blocks)):
+            eng.dense_block(i, X, wsp)
+        GLOBAL_TIMER.event_end("StreamPETR-EVA-ViT/backbone")
+        return {self._out_features[0]: X.view(V, wsp.H, wsp.W, -1).permute(0, 3, 1, 2)}
+
+
+@_register
+class ToC3DEVAViT(_EvaBase):
+    """EVA-02 ViT with ToC3D motion-aware token compression (toc3d_eva_vit.py:25-326)."""
+
+    def __init__(self, img_size=1024, patch_size=16, in_chans=3, embed_dim=768, depth=12, num_heads=12,
+                 mlp_ratio=4 * 2 / 3, qkv_bias=True, drop_path_rate=0.0, norm_layer=None, act_layer=None,
+                 use_abs_pos=True, use_rel_pos=False, rope=True, rope_acc=False, pt_hw_seq_len=16, intp_freq=True,
+                 window_size=0, global_window_size=20, use_checkpoint=True, global_attn_indexes=(),
+                 residual_block_indexes=(), use_act_checkpoint=False, pretrain_img_size=224,
+                 pretrain_use_cls_token=True, out_feature="last_feat", return_intermediate=False, xattn=True,
+                 pruning_loc=None, pruning_score_type="attention", score_mask=True, pruning_attn_scale=True,
+                 pruning_num_queries=256, accelerate_global=True, token_ratio=None, use_represent_tokens=True,
+                 pc_range=None, token_selection_loss=None):
+        super().__init__()
+        if pruning_score_type != "attention":
+            raise NotImplementedError("Not supported score type: %s, only support: ['attention']" % pruning_score_type)
+        unsupported = dict(residual_block_indexes=len(residual_block_indexes) > 0, return_intermediate=return_intermediate,
+                           rope=not rope, rope_acc=not rope_acc, accelerate_global=not accelerate_global,
+                           use_represent_tokens=not use_represent_tokens, score_mask=not score_mask,
+                           pruning_attn_scale=not pruning_attn_scale, window_size=window_size <= 0)
+        bad = [k for k, v in unsupported.items() if v]
+        if bad:
+            raise NotImplementedError("options %s take code paths no shipped ToC3D config reaches "
+                                      "(SURVEY.md §8a) and are not implemented" % bad)
+        assert pruning_loc is not None and token_ratio is not None and pc_range is not None
+        assert len(set(pruning_loc) & set(global_attn_indexes)) == 0, \
+            "The pruning score calculation layer cannot be the global attention layer"      # toc3d_eva_vit.py:141
+        assert list(pruning_loc) == sorted(pruning_loc) and len(token_ratio) >= len(pruning_loc)
+        self._build_common(img_size, patch_size, in_chans, embed_dim, num_heads, use_abs_pos, pretrain_img_size,
+                           pretrain_use_cls_token, pt_hw_seq_len, intp_freq, window_size)
+        self.pruning_loc = pruning_loc
+        self.pruning_num_queries = pruning_num_queries
+        self.token_ratio = token_ratio
+        self.use_represent_tokens = use_represent_tokens
+        self.accelerate_global = accelerate_global
+        self.token_selection_loss = None
+        if token_selection_loss is not None:
+            try:
+                from mmdet3d.models.builder import build_loss
+                self.token_selection_loss = build_loss(token_selection_loss)
+            except ImportError:
+                raise RuntimeError("token_selection_loss needs mmdet3d (training only); pass None for inference")
+        self.score_predictor = nn.ModuleList([
+            _Selector(embed_dim, pruning_num_queries, token_ratio[i], pc_range) for i in range(len(pruning_loc))])
+        hh = embed_dim // num_heads // 2
+        self.rope_win_acc = _Rope(hh, pt_hw_seq_len, window_size if intp_freq else None)
+        self.rope_glb_acc = _Rope(hh, pt_hw_seq_len, img_size // patch_size if intp_freq else None)
+        self.blocks = nn.ModuleList()
+        for i in range(depth):
+            g = i in global_attn_indexes
+            acc = len(pruning_loc) > 0 and i >= pruning_loc[0]                               # toc3d_eva_vit.py:178-180
+            rope_m = (self.rope_glb_acc if g else self.rope_win_acc) if acc else (self.rope_glb if g else self.rope_win)
+            self.blocks.append(_Block(embed_dim, num_heads, mlp_ratio, qkv_bias,
+                                      global_window_size if g else window_size, rope_m, accelerate=acc))
+        self._out_features = [out_feature]
+        self._out_feature_channels = {out_feature: embed_dim}
+        self._out_feature_strides = {out_feature: patch_size}
+        self.gumbel_seed = 0
+        self._init_weights()
+
+    @torch.no_grad()
+    def forward(self, x, temp_queries=None, prev_exists=None, temp_ref_points=None, temp_vel=None,
+                temp_timestamp=None, temp_ego_pose=None, ego_pose_inv=None, *args, gumbel_noise=None,
+                teacher_scores=None, tap=None, **kwargs):
+        """Same keyword contract as the reference (extra kwargs such as gt_bboxes are ignored).
+
+        gumbel_noise: optional list of per-stage (V,N,2) tensors (parity pin 2); default draws
+        -log(-log(u)) on device.  teacher_scores / tap are test hooks (teacher forcing, intermediates).
+        """
+        x = self._prep_img(x)
+        eng = self._get_engine(x)
+        V, _, Hi, Wi = x.shape
+        wsp = eng.workspace(V, Hi // 16, Wi // 16)
+        H, W = wsp.H, wsp.W
+        X = eng.stem(x, wsp)
+        prev = bool(prev_exists) if prev_exists is not None else False
+        q_kw = dict(temp_queries=temp_queries, temp_ref_points=temp_ref_points, temp_vel=temp_vel,
+                    temp_timestamp=temp_timestamp, temp_ego_pose=temp_ego_pose, ego_pose_inv=ego_pose_inv)
+        masks, keep_idxes, drop_idxes, scores_l = [], [], [], []
+        mask_prev, stage = None, -1
+        if tap is not None:
+            tap["stem"] = X.clone()
+            tap["block_out"] = []
+        GLOBAL_TIMER.event_start("ToC3D-StreamPETR-EVAViT/backbone")
+        for i, blk in enumerate(self.blocks):
+            if i in self.pruning_loc:
+                stage += 1
+                g = None
+                if gumbel_noise is not None:
+                    g = gumbel_noise[stage].to(device=x.device, dtype=torch.float32).contiguous()
+                self.gumbel_seed += 1
+                pred, score, mask = eng.score_stage(stage, self.score_predictor[stage], X, mask_prev, wsp, q_kw, prev,
+                                                    g, self.gumbel_seed)
+                if tap is not None:
+                    tap.setdefault("scores_raw", []).append(score.view(V, H, W).clone())
+                if teacher_scores is not None:
+                    score = teacher_scores[stage].to(x.device).reshape(V, H * W).contiguous()
+                N = H * W
+                k = int(N * self.token_ratio[stage])
+                keep = torch.empty(V, k, device=x.device, dtype=torch.int64)
+                drop = torch.empty(V, N - k, device=x.device, dtype=torch.int64)
+                L.topk_split(score, V, N, k, keep, drop)
+                eng.select_windows(stage, score, self.token_ratio[stage], wsp)
+                mask_prev = mask
+                masks.append(mask.view(V, H, W, 1))
+                keep_idxes.append(keep)
+                drop_idxes.append(drop)
+                scores_l.append(score.view(V, H, W))
+            if blk.accelerate:
+                eng.toc3d_block(i, X, wsp, stage)
+            else:
+                eng.dense_block(i, X, wsp)
+            if tap is not None:
+                tap["block_out"].append(X.clone())
+        GLOBAL_TIMER.event_end("ToC3D-StreamPETR-EVAViT/backbone")
+        if tap is not None:
+            tap["scores"] = scores_l
+        outputs = {self._out_features[0]: X.view(V, H, W, -1).permute(0, 3, 1, 2)}
+        none_if_empty = lambda l: l if len(l) else None
+        return ToC3DViTReturnType(outputs, none_if_empty(masks), None, keep_idx=none_if_empty(keep_idxes),
+                                  drop_idx=none_if_empty(drop_idxes), aux_outputs=None)
+
+    def loss(self, pred_masks, gt_bboxes, *args, **kwargs):
+        """toc3d_eva_vit.py:312-326 (training only; delegates to the mmdet3d-built loss when present)."""
+        losses = dict()
+        if self.token_selection_loss is not None:
+            losses.update(self.token_selection_loss(pred_mask=pred_masks, gt_bboxes=gt_bboxes))
+        return losses

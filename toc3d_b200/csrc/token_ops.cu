@@ -1,0 +1,582 @@
+// HBM-bound token kernels of the ToC3D path: LayerNorm over gathered rows, SwiGLU sub-LN, per-window
+// stable top-k, representative-token merge, fast-token update, the folded history-query scorer,
+// im2col for the patch stem.  Warp-per-row, 16-byte vector accesses, fp32 math.
+// Reference call sites per function: include/toc3d_b200.h.
+#include "common.cuh"
+#include "../../include/toc3d_b200.h"
+
+#include <stdarg.h>
+#include <string.h>
+
+namespace toc3d {
+
+static thread_local char g_err[512] = "";
+void set_last_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+constexpr float PAD_SCORE = -1e6f;  // toc3d_eva_vit.py:415
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm over gathered fp32 rows -> bf16.  One warp per row, C/128 float4 per lane.
+template <int VPL>  // float4 per lane: C = VPL * 128
+__global__ void __launch_bounds__(256)
+layernorm_rows_kernel(const float* __restrict__ x, const int* __restrict__ row_map, const float* __restrict__ alt,
+                      const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
+                      int M, float eps, int pad_mode) {
+  const int C = VPL * 128;
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  int src = row_map ? row_map[m] : m;
+  const float* p = nullptr;
+  if (src >= 0) p = x + (size_t)src * C;
+  else if (src == -2) p = alt + (size_t)m * C;
+  uint2* o = reinterpret_cast<uint2*>(out + (size_t)m * C);
+  if (p == nullptr && pad_mode == 0) {
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) o[lane + 32 * i] = make_uint2(0u, 0u);
+    return;
+  }
+  float4 v[VPL];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = p ? reinterpret_cast<const float4*>(p)[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+  }
+  const float mean = warp_sum(s) / (float)C;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+    q += (a * a + b * b) + (c * c + d * d);
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    const float4 g = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
+    const float4 b = reinterpret_cast<const float4*>(beta)[lane + 32 * i];
+    uint2 u;
+    u.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+    u.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+    o[lane + 32 * i] = u;
+  }
+}
+
+// SwiGLU sub-LN over bf16 hidden rows [M, ld], true width Hd (<= ld, ld % 8 == 0).
+__global__ void __launch_bounds__(256)
+subln_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
+             const float* __restrict__ beta, int M, int Hd, int ld, float eps) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const int lane = threadIdx.x & 31;
+  const uint4* p = reinterpret_cast<const uint4*>(h + (size_t)m * ld);
+  uint4* o = reinterpret_cast<uint4*>(out + (size_t)m * ld);
+  const int nvec = ld >> 3;
+  constexpr int MAXV = 12;  // supports ld <= 3072
+  uint4 v[MAXV];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      v[i] = p[j];
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        const int col = j * 8 + e * 2;
+        s += (col < Hd ? f.x : 0.f) + (col + 1 < Hd ? f.y : 0.f);
+      }
+    }
+  }
+  const float mean = warp_sum(s) / (float)Hd;
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        const int col = j * 8 + e * 2;
+        const float a = f.x - mean, b = f.y - mean;
+        q += (col < Hd ? a * a : 0.f) + (col + 1 < Hd ? b * b : 0.f);
+      }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / (float)Hd + eps);
+#pragma unroll
+  for (int i = 0; i < MAXV; ++i) {
+    const int j = lane + 32 * i;
+    if (j < nvec) {
+      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+      uint32_t r[4];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = unpack_bf16(w[e]);
+        const int col = j * 8 + e * 2;
+        const float y0 = col < Hd ? (f.x - mean) * rstd * gamma[col] + beta[col] : 0.f;
+        const float y1 = col + 1 < Hd ? (f.y - mean) * rstd * gamma[col + 1] + beta[col + 1] : 0.f;
+        r[e] = pack_bf16(y0, y1);
+      }
+      o[j] = make_uint4(r[0], r[1], r[2], r[3]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Total order of torch.sort(descending=True, stable=True): NaN first, then larger values, ties by
+// lower index.  a_before_b == "a ranks strictly ahead of b".
+__device__ __forceinline__ bool ranks_before(float a, int ia, float b, int ib) {
+  const bool an = a != a, bn = b != b;
+  if (an || bn) return an && (!bn || ia < ib);
+  return a > b || (a == b && ia < ib);
+}
+
+// One CTA per window, one thread per slot (n = ws*ws <= 1024).
+__global__ void window_topk_kernel(const float* __restrict__ scores, int V, int H, int W, int ws, int k,
+                                   int* __restrict__ slow_idx, int* __restrict__ fast_idx,
+                                   float* __restrict__ fast_score, int* __restrict__ tok_map,
+                                   int* __restrict__ rope_rows, int* __restrict__ fast_map) {
+  extern __shared__ float s_sc[];
+  const int n = ws * ws;
+  const int nWw = (W + ws - 1) / ws, nWh = (H + ws - 1) / ws;
+  const int w = blockIdx.x;
+  const int v = w / (nWh * nWw);
+  const int wr = (w / nWw) % nWh, wc = w % nWw;
+  const int i = threadIdx.x;
+  int img_row = -1;
+  float sc = PAD_SCORE;
+  if (i < n) {
+    const int r = wr * ws + i / ws, c = wc * ws + i % ws;
+    if (r < H && c < W) {
+      img_row = (v * H + r) * W + c;
+      sc = scores[img_row];
+    }
+    s_sc[i] = sc;
+  }
+  __syncthreads();
+  if (i >= n) return;
+  int rank = 0;
+  for (int j = 0; j < n; ++j) rank += ranks_before(s_sc[j], j, sc, i) ? 1 : 0;
+  const int nf = n - k;
+  if (rank < k) {
+    if (slow_idx) slow_idx[(size_t)w * k + rank] = i;
+    const size_t m = (size_t)w * (k + 1) + rank;
+    if (tok_map) tok_map[m] = img_row;
+    if (rope_rows) rope_rows[m] = i;
+  } else {
+    const size_t f = (size_t)w * nf + (rank - k);
+    if (fast_idx) fast_idx[f] = i;
+    if (fast_score) fast_score[f] = sc;
+    if (fast_map) fast_map[f] = img_row;
+  }
+  if (i == 0) {
+    const size_t m = (size_t)w * (k + 1) + k;
+    if (tok_map) tok_map[m] = -2;
+    if (rope_rows) rope_rows[m] = k;
+  }
+}
+
+// Image-level stable sort split by rank counting; grid (ceil(N/256), B), scores of one row in smem.
+__global__ void __launch_bounds__(256)
+topk_split_kernel(const float* __restrict__ scores, int N, int k, long long* __restrict__ keep_idx,
+                  long long* __restrict__ drop_idx) {
+  extern __shared__ float s_sc[];
+  const int b = blockIdx.y;
+  const float* row = scores + (size_t)b * N;
+  for (int j = threadIdx.x; j < N; j += blockDim.x) s_sc[j] = row[j];
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const float sc = s_sc[i];
+  int rank = 0;
+  for (int j = 0; j < N; ++j) rank += ranks_before(s_sc[j], j, sc, i) ? 1 : 0;
+  if (rank < k) keep_idx[(size_t)b * k + rank] = i;
+  else drop_idx[(size_t)b * (N - k) + (rank - k)] = i;
+}
+
+// ------------------------------------------------------------------------------------------------
+// rep[w] = sum_j (s_j / sum s) * x[fast_map[w,j]];  grid (nW, C/128), 128 threads, 1 channel each.
+__global__ void __launch_bounds__(128)
+merge_fast_kernel(const float* __restrict__ x, const int* __restrict__ fast_map, const float* __restrict__ fast_score,
+                  int n_fast, int k, int C, float* __restrict__ rep_out, float* __restrict__ packed) {
+  __shared__ float s_part[4];
+  __shared__ float s_wgt[1024];
+  __shared__ int s_row[1024];
+  const int w = blockIdx.x;
+  const int ch = blockIdx.y * 128 + threadIdx.x;
+  const float* fs = fast_score + (size_t)w * n_fast;
+  const int* fm = fast_map + (size_t)w * n_fast;
+  float part = 0.f;
+  for (int j = threadIdx.x; j < n_fast; j += 128) {
+    const float s = fs[j];
+    s_wgt[j] = s;
+    s_row[j] = fm[j];
+    part += s;
+  }
+  part = warp_sum(part);
+  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  __syncthreads();
+  const float total = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
+  for (int j = threadIdx.x; j < n_fast; j += 128) s_wgt[j] = s_wgt[j] / total;   // weight = score / sum(score)
+  __syncthreads();
+  float acc = 0.f;
+  int j = 0;
+  for (; j + 4 <= n_fast; j += 4) {
+    float xv[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int r = s_row[j + u];
+      xv[u] = r >= 0 ? x[(size_t)r * C + ch] : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) acc += s_wgt[j + u] * xv[u];
+  }
+  for (; j < n_fast; ++j) {
+    const int r = s_row[j];
+    acc += s_wgt[j] * (r >= 0 ? x[(size_t)r * C + ch] : 0.f);
+  }
+  rep_out[(size_t)w * C + ch] = acc;
+  if (packed) packed[((size_t)w * (k + 1) + k) * C + ch] = acc;
+}
+
+// x[fast_map[w,j]] += packed[rep row of w] - rep[w];  one warp per fast token, float4 lanes.
+__global__ void __launch_bounds__(256)
+fast_update_kernel(float* __restrict__ x, const int* __restrict__ fast_map, const float* __restrict__ packed,
+                   const float* __restrict__ rep, int total_fast, int n_fast, int k, int C) {
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= total_fast) return;
+  const int row = fast_map[f];
+  if (row < 0) return;
+  const int w = f / n_fast;
+  const int lane = threadIdx.x & 31;
+  const float4* t2 = reinterpret_cast<const float4*>(packed + ((size_t)w * (k + 1) + k) * C);
+  const float4* t0 = reinterpret_cast<const float4*>(rep + (size_t)w * C);
+  float4* xr = reinterpret_cast<float4*>(x + (size_t)row * C);
+  for (int i = lane; i < (C >> 2); i += 32) {
+    const float4 a = t2[i], b = t0[i];
+    float4 v = xr[i];
+    v.x += a.x - b.x; v.y += a.y - b.y; v.z += a.z - b.z; v.w += a.w - b.w;
+    xr[i] = v;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Scorer folding: P = w_agg (2xQ) * queries[f] (QxCq); A[f] = scale * P * w_in (CqxC);
+// c[f] = scale * P . b_in + b_agg.   grid (Bf, C/128), 128 threads.
+__global__ void __launch_bounds__(128)
+score_fold_kernel(const float* __restrict__ queries, const float* __restrict__ w_in, const float* __restrict__ b_in,
+                  const float* __restrict__ w_agg, const float* __restrict__ b_agg, float scale, int Q, int Cq, int C,
+                  float* __restrict__ A_out, float* __restrict__ c_out) {
+  extern __shared__ float s_p[];  // [2][Cq]
+  const int f = blockIdx.x;
+  const float* q = queries + (size_t)f * Q * Cq;
+  for (int c = threadIdx.x; c < Cq; c += blockDim.x) {
+    float p0 = 0.f, p1 = 0.f;
+    for (int j = 0; j < Q; ++j) {
+      const float qv = q[(size_t)j * Cq + c];
+      p0 += w_agg[j] * qv;
+      p1 += w_agg[Q + j] * qv;
+    }
+    s_p[c] = p0;
+    s_p[Cq + c] = p1;
+  }
+  __syncthreads();
+  const int ch = blockIdx.y * 128 + threadIdx.x;
+  if (ch < C) {
+    float a0 = 0.f, a1 = 0.f;
+    for (int c = 0; c < Cq; ++c) {
+      const float wv = w_in[(size_t)c * C + ch];
+      a0 += s_p[c] * wv;
+      a1 += s_p[Cq + c] * wv;
+    }
+    A_out[((size_t)f * 2 + 0) * C + ch] = a0 * scale;
+    A_out[((size_t)f * 2 + 1) * C + ch] = a1 * scale;
+  }
+  if (blockIdx.y == 0 && threadIdx.x < 2) {
+    float acc = 0.f;
+    for (int c = 0; c < Cq; ++c) acc += s_p[threadIdx.x * Cq + c] * b_in[c];
+    c_out[f * 2 + threadIdx.x] = acc * scale + b_agg[threadIdx.x];
+  }
+}
+
+__device__ __forceinline__ float gumbel_from_hash(uint64_t seed, uint64_t idx) {
+  uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;   // splitmix64
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  z ^= z >> 31;
+  const float u = ((float)(z >> 40) + 0.5f) * (1.0f / 16777216.0f);   // (0,1)
+  return -logf(-logf(u));
+}
+
+__device__ __forceinline__ void score_tail(float l0, float l1, size_t tok, const float* gumbel, uint64_t seed,
+                                           float* pred, float* score, float* mask_out) {
+  const float mx = fmaxf(l0, l1);
+  const float lse = mx + logf(expf(l0 - mx) + expf(l1 - mx));
+  const float p0 = l0 - lse, p1 = l1 - lse;
+  if (pred) { pred[tok * 2] = p0; pred[tok * 2 + 1] = p1; }
+  if (score) score[tok] = p0;
+  if (mask_out) {
+    const float g0 = gumbel ? gumbel[tok * 2] : gumbel_from_hash(seed, tok * 2);
+    const float g1 = gumbel ? gumbel[tok * 2 + 1] : gumbel_from_hash(seed, tok * 2 + 1);
+    const float a = p0 + g0, b = p1 + g1;
+    const float m2 = fmaxf(a, b);
+    const float ea = expf(a - m2), eb = expf(b - m2);
+    mask_out[tok] = ea / (ea + eb);
+  }
+}
+
+// one warp per token: logit_o = mask * (x . A[f][o]) + c[f][o]
+__global__ void __launch_bounds__(256)
+score_tokens_kernel(const float* __restrict__ x, const float* __restrict__ mask_in, const float* __restrict__ A,
+                    const float* __restrict__ cvec, int V, int N, int C, int vpf, const float* __restrict__ gumbel,
+                    uint64_t seed, float* __restrict__ pred, float* __restrict__ score, float* __restrict__ mask_out) {
+  const size_t tok = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (tok >= (size_t)V * N) return;
+  const int lane = threadIdx.x & 31;
+  const int f = (int)(tok / N) / vpf;
+  const float4* xr = reinterpret_cast<const float4*>(x + tok * C);
+  const float4* a0 = reinterpret_cast<const float4*>(A + ((size_t)f * 2) * C);
+  const float4* a1 = reinterpret_cast<const float4*>(A + ((size_t)f * 2 + 1) * C);
+  float d0 = 0.f, d1 = 0.f;
+  for (int i = lane; i < (C >> 2); i += 32) {
+    const float4 xv = xr[i], u = __ldg(a0 + i), w = __ldg(a1 + i);
+    d0 += (xv.x * u.x + xv.y * u.y) + (xv.z * u.z + xv.w * u.w);
+    d1 += (xv.x * w.x + xv.y * w.y) + (xv.z * w.z + xv.w * w.w);
+  }
+  d0 = warp_sum(d0);
+  d1 = warp_sum(d1);
+  if (lane == 0) {
+    const float mk = mask_in ? mask_in[tok] : 1.0f;
+    score_tail(mk * d0 + cvec[f * 2], mk * d1 + cvec[f * 2 + 1], tok, gumbel, seed, pred, score, mask_out);
+  }
+}
+
+__global__ void score_finish_kernel(const float* __restrict__ logits, int M, const float* __restrict__ gumbel,
+                                    uint64_t seed, float* pred, float* score, float* mask_out) {
+  const int tok = blockIdx.x * blockDim.x + threadIdx.x;
+  if (tok >= M) return;
+  score_tail(logits[tok * 2], logits[tok * 2 + 1], (size_t)tok, gumbel, seed, pred, score, mask_out);
+}
+
+// ------------------------------------------------------------------------------------------------
+// im2col for the 16x16 stride-16 stem: thread = 8 consecutive kx of one (v, c, y, patch-col).
+__global__ void __launch_bounds__(256)
+im2col_patch16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int V, int Hi, int Wi) {
+  const int Wp = Wi >> 4, Hp = Hi >> 4;
+  const int halves = Wp * 2;                       // 8-pixel chunks per image row
+  const size_t total = (size_t)V * 3 * Hi * halves;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int hx = (int)(idx % halves);
+  size_t r = idx / halves;
+  const int y = (int)(r % Hi); r /= Hi;
+  const int c = (int)(r % 3);
+  const int v = (int)(r / 3);
+  const float4* src = reinterpret_cast<const float4*>(img + (((size_t)v * 3 + c) * Hi + y) * Wi + hx * 8);
+  const float4 a = src[0], b = src[1];
+  const int pw = hx >> 1, kx0 = (hx & 1) * 8, ph = y >> 4, ky = y & 15;
+  const size_t row = ((size_t)v * Hp + ph) * Wp + pw;
+  uint4 u;
+  u.x = pack_bf16(a.x, a.y); u.y = pack_bf16(a.z, a.w);
+  u.z = pack_bf16(b.x, b.y); u.w = pack_bf16(b.z, b.w);
+  *reinterpret_cast<uint4*>(out + row * 768 + c * 256 + ky * 16 + kx0) = u;
+}
+
+__global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(in + i);
+    uint2 u;
+    u.x = pack_bf16(v.x, v.y); u.y = pack_bf16(v.z, v.w);
+    *reinterpret_cast<uint2*>(out + i) = u;
+  } else {
+    for (long long j = i; j < n; ++j) out[j] = __float2bfloat16_rn(in[j]);
+  }
+}
+
+__global__ void __launch_bounds__(256)
+mask_rows_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int M, int C) {
+  const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (m >= M) return;
+  const float mk = mask[m];
+  const float4* p = reinterpret_cast<const float4*>(x + (size_t)m * C);
+  float4* o = reinterpret_cast<float4*>(out + (size_t)m * C);
+  for (int i = threadIdx.x & 31; i < (C >> 2); i += 32) {
+    float4 v = p[i];
+    v.x *= mk; v.y *= mk; v.z *= mk; v.w *= mk;
+    o[i] = v;
+  }
+}
+
+// y[v, :, C/2:] <- mean over tokens; grid (V, C/2/128) x 128 threads; two passes over N.
+__global__ void __launch_bounds__(128)
+global_half_mean_kernel(__nv_bfloat16* __restrict__ y, int N, int C) {
+  const int v = blockIdx.x;
+  const int ch = C / 2 + blockIdx.y * 128 + threadIdx.x;
+  __nv_bfloat16* base = y + (size_t)v * N * C + ch;
+  float acc = 0.f;
+  for (int n = 0; n < N; ++n) acc += __bfloat162float(base[(size_t)n * C]);
+  const __nv_bfloat16 m = __float2bfloat16_rn(acc / (float)N);
+  for (int n = 0; n < N; ++n) base[(size_t)n * C] = m;
+}
+
+}  // namespace toc3d
+
+// =================================================================================================
+using namespace toc3d;
+#define ST(s) reinterpret_cast<cudaStream_t>(s)
+
+extern "C" int toc3d_abi_version(void) { return TOC3D_B200_ABI_VERSION; }
+extern "C" const char* toc3d_last_error(void) { return toc3d::g_err; }
+
+extern "C" int toc3d_layernorm_rows(const float* x, const int32_t* row_map, const float* alt, const float* gamma,
+                                    const float* beta, void* out, int32_t M, int32_t C, float eps, int32_t pad_mode,
+                                    void* stream) {
+  TOC3D_REQUIRE(x && gamma && beta && out, kErrBadArg, "toc3d_layernorm_rows: null pointer");
+  TOC3D_REQUIRE(M > 0 && C % 128 == 0 && C >= 128 && C <= 4096, kErrBadArg, "toc3d_layernorm_rows: bad shape M=%d C=%d", M, C);
+  const int rows_per_block = 8;
+  dim3 grid((M + rows_per_block - 1) / rows_per_block), block(256);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+#define LN_CASE(V)                                                                                                  \
+  case V: layernorm_rows_kernel<V><<<grid, block, 0, ST(stream)>>>(x, row_map, alt, gamma, beta, o, M, eps, pad_mode); break;
+  switch (C / 128) {
+    LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12) LN_CASE(16) LN_CASE(32)
+    default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_layernorm_rows: unsupported C=%d", C);
+  }
+#undef LN_CASE
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_subln_bf16(const void* h, void* out, const float* gamma, const float* beta, int32_t M, int32_t Hd,
+                                int32_t ld, float eps, void* stream) {
+  TOC3D_REQUIRE(h && out && gamma && beta, kErrBadArg, "toc3d_subln_bf16: null pointer");
+  TOC3D_REQUIRE(M > 0 && Hd > 0 && Hd <= ld && ld % 8 == 0 && ld <= 3072, kErrBadArg,
+                "toc3d_subln_bf16: bad shape M=%d Hd=%d ld=%d", M, Hd, ld);
+  subln_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(h),
+                                                    reinterpret_cast<__nv_bfloat16*>(out), gamma, beta, M, Hd, ld, eps);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int32_t W, int32_t ws, int32_t k,
+                                 int32_t* slow_idx, int32_t* fast_idx, float* fast_score, int32_t* tok_map,
+                                 int32_t* rope_rows, int32_t* fast_map, void* stream) {
+  TOC3D_REQUIRE(scores, kErrBadArg, "toc3d_window_topk: null scores");
+  const int n = ws * ws;
+  TOC3D_REQUIRE(V > 0 && H > 0 && W > 0 && ws > 0 && n <= 1024 && k >= 0 && k <= n, kErrBadArg,
+                "toc3d_window_topk: bad shape V=%d H=%d W=%d ws=%d k=%d", V, H, W, ws, k);
+  const int nW = V * ((H + ws - 1) / ws) * ((W + ws - 1) / ws);
+  const int threads = ((n + 31) / 32) * 32;
+  window_topk_kernel<<<nW, threads, n * sizeof(float), ST(stream)>>>(scores, V, H, W, ws, k, slow_idx, fast_idx,
+                                                                      fast_score, tok_map, rope_rows, fast_map);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_topk_split(const float* scores, int32_t B, int32_t N, int32_t k, int64_t* keep_idx,
+                                int64_t* drop_idx, void* stream) {
+  TOC3D_REQUIRE(scores && keep_idx && drop_idx, kErrBadArg, "toc3d_topk_split: null pointer");
+  TOC3D_REQUIRE(B > 0 && N > 0 && N <= 12288 && k >= 0 && k <= N, kErrBadArg, "toc3d_topk_split: bad shape B=%d N=%d k=%d", B, N, k);
+  dim3 grid((N + 255) / 256, B);
+  topk_split_kernel<<<grid, 256, N * sizeof(float), ST(stream)>>>(scores, N, k, reinterpret_cast<long long*>(keep_idx),
+                                                                   reinterpret_cast<long long*>(drop_idx));
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, const float* fast_score, int32_t nW,
+                                       int32_t n_fast, int32_t k, int32_t C, float* rep_out, float* packed, void* stream) {
+  TOC3D_REQUIRE(x && fast_map && fast_score && rep_out, kErrBadArg, "toc3d_merge_fast_tokens: null pointer");
+  TOC3D_REQUIRE(nW > 0 && n_fast > 0 && n_fast <= 1024 && C % 128 == 0, kErrBadArg,
+                "toc3d_merge_fast_tokens: bad shape nW=%d n_fast=%d C=%d", nW, n_fast, C);
+  dim3 grid(nW, C / 128);
+  merge_fast_kernel<<<grid, 128, 0, ST(stream)>>>(x, fast_map, fast_score, n_fast, k, C, rep_out, packed);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* packed, const float* rep,
+                                       int32_t nW, int32_t n_fast, int32_t k, int32_t C, void* stream) {
+  TOC3D_REQUIRE(x && fast_map && packed && rep, kErrBadArg, "toc3d_fast_token_update: null pointer");
+  TOC3D_REQUIRE(nW > 0 && n_fast > 0 && C % 4 == 0, kErrBadArg, "toc3d_fast_token_update: bad shape");
+  const int total = nW * n_fast;
+  fast_update_kernel<<<(total + 7) / 8, 256, 0, ST(stream)>>>(x, fast_map, packed, rep, total, n_fast, k, C);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_score_fold_queries(const float* queries, const float* w_in, const float* b_in, const float* w_agg,
+                                        const float* b_agg, float scale, int32_t Bf, int32_t Q, int32_t Cq, int32_t C,
+                                        float* A_out, float* c_out, void* stream) {
+  TOC3D_REQUIRE(queries && w_in && b_in && w_agg && b_agg && A_out && c_out, kErrBadArg, "toc3d_score_fold_queries: null pointer");
+  TOC3D_REQUIRE(Bf > 0 && Q > 0 && Cq > 0 && Cq <= 4096 && C > 0, kErrBadArg, "toc3d_score_fold_queries: bad shape");
+  dim3 grid(Bf, (C + 127) / 128);
+  score_fold_kernel<<<grid, 128, 2 * Cq * sizeof(float), ST(stream)>>>(queries, w_in, b_in, w_agg, b_agg, scale, Q, Cq, C,
+                                                                        A_out, c_out);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_score_tokens(const float* x, const float* mask_in, const float* A, const float* c, int32_t V,
+                                  int32_t N, int32_t C, int32_t views_per_frame, const float* gumbel, uint64_t seed,
+                                  float* pred, float* score, float* mask_out, void* stream) {
+  TOC3D_REQUIRE(x && A && c, kErrBadArg, "toc3d_score_tokens: null pointer");
+  TOC3D_REQUIRE(V > 0 && N > 0 && C % 4 == 0 && views_per_frame > 0 && V % views_per_frame == 0, kErrBadArg,
+                "toc3d_score_tokens: bad shape V=%d N=%d C=%d vpf=%d", V, N, C, views_per_frame);
+  const long long toks = (long long)V * N;
+  score_tokens_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, ST(stream)>>>(x, mask_in, A, c, V, N, C, views_per_frame, gumbel,
+                                                                          seed, pred, score, mask_out);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed, float* pred,
+                                  float* score, float* mask_out, void* stream) {
+  TOC3D_REQUIRE(logits && M > 0, kErrBadArg, "toc3d_score_finish: bad args");
+  score_finish_kernel<<<(M + 255) / 256, 256, 0, ST(stream)>>>(logits, M, gumbel, seed, pred, score, mask_out);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_im2col_patch16(const float* img, void* out, int32_t V, int32_t Hi, int32_t Wi, void* stream) {
+  TOC3D_REQUIRE(img && out, kErrBadArg, "toc3d_im2col_patch16: null pointer");
+  TOC3D_REQUIRE(V > 0 && Hi > 0 && Wi > 0 && Hi % 16 == 0 && Wi % 16 == 0, kErrBadArg,
+                "toc3d_im2col_patch16: image %dx%d must be a multiple of the 16x16 patch", Hi, Wi);
+  const size_t total = (size_t)V * 3 * Hi * (Wi / 8);
+  im2col_patch16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(img, reinterpret_cast<__nv_bfloat16*>(out), V, Hi, Wi);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_cast_f32_to_bf16(const float* in, void* out, int64_t n, void* stream) {
+  TOC3D_REQUIRE(in && out && n > 0, kErrBadArg, "toc3d_cast_f32_to_bf16: bad args");
+  TOC3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0, kErrBadArg, "toc3d_cast_f32_to_bf16: unaligned");
+  const long long threads = (n + 3) / 4;
+  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_mask_rows(const float* x, const float* mask, float* out, int32_t M, int32_t C, void* stream) {
+  TOC3D_REQUIRE(x && mask && out && M > 0 && C % 4 == 0, kErrBadArg, "toc3d_mask_rows: bad args");
+  mask_rows_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(x, mask, out, M, C);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_global_half_mean(void* y, int32_t V, int32_t N, int32_t C, void* stream) {
+  TOC3D_REQUIRE(y && V > 0 && N > 0 && C % 256 == 0, kErrBadArg, "toc3d_global_half_mean: bad args");
+  dim3 grid(V, C / 2 / 128);
+  global_half_mean_kernel<<<grid, 128, 0, ST(stream)>>>(reinterpret_cast<__nv_bfloat16*>(y), N, C);
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}

@@ -1,0 +1,204 @@
+"""ctypes binding of libtoc3d_b200.so (include/toc3d_b200.h).
+
+torch is used only for device memory and streams: every wrapper passes raw
+device pointers + sizes + the current CUDA stream.  There is NO fallback: if the
+shared library is missing or a call fails, a RuntimeError is raised.
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libtoc3d_b200.so")
+
+EPI_LINEAR, EPI_QKV_ROPE, EPI_RESID, EPI_SWIGLU = 0, 1, 2, 3
+ACT_NONE, ACT_GELU, ACT_RELU = 0, 1, 2
+
+_c_void_p, _c_int, _c_i64, _c_float, _c_u64 = (ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64, ctypes.c_float,
+                                               ctypes.c_uint64)
+
+
+class Epilogue(ctypes.Structure):
+    _fields_ = [
+        ("bias", _c_void_p), ("out", _c_void_p), ("ldo", _c_int), ("out_f32", _c_int), ("act", _c_int),
+        ("resid", _c_void_p), ("resid_map", _c_void_p), ("resid_mod", _c_int), ("out_map", _c_void_p),
+        ("out_alt", _c_void_p), ("rope_rows", _c_void_p), ("rope_slots", _c_int), ("rope_ft", _c_int),
+        ("rope_cols", _c_int), ("q_scale", _c_float), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p),
+    ]
+
+
+_SIGS = {
+    "toc3d_abi_version": ([], _c_int),
+    "toc3d_last_error": ([], ctypes.c_char_p),
+    "toc3d_gemm_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int,
+                         ctypes.POINTER(Epilogue), _c_void_p], _c_int),
+    "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
+    "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                              _c_float, _c_int, _c_void_p], _c_int),
+    "toc3d_subln_bf16": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
+                         _c_int),
+    "toc3d_window_topk": ([_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
+                           _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_topk_split": ([_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_merge_fast_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                                 _c_void_p, _c_void_p], _c_int),
+    "toc3d_fast_token_update": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
+                                 _c_void_p], _c_int),
+    "toc3d_score_fold_queries": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int,
+                                  _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_score_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
+                            _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_score_finish": ([_c_void_p, _c_int, _c_void_p, _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
+                           _c_int),
+    "toc3d_im2col_patch16": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
+    "toc3d_cast_f32_to_bf16": ([_c_void_p, _c_void_p, _c_i64, _c_void_p], _c_int),
+    "toc3d_mask_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p], _c_int),
+    "toc3d_global_half_mean": ([_c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
+}
+
+EXPORTS = tuple(_SIGS.keys())
+_lib = None
+launch_count = 0   # number of kernel-launching C-ABI calls issued (bench.py's gpu_launches)
+
+
+def load():
+    """Load the shared library once; raise loudly if it is not built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                "toc3d_b200: %s is missing - build it with `python -m toc3d_b200.build` "
+                "(there is no CPU or PyTorch fallback)" % LIB_PATH)
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (args, res) in _SIGS.items():
+            fn = getattr(lib, name)
+            fn.argtypes = args
+            fn.restype = res
+        if lib.toc3d_abi_version() != 1:
+            raise RuntimeError("toc3d_b200: ABI version mismatch")
+        _lib = lib
+    return _lib
+
+
+def _p(t):
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), "toc3d_b200 kernels need contiguous CUDA tensors"
+    return t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(rc, name):
+    global launch_count
+    if rc != 0:
+        msg = load().toc3d_last_error().decode()
+        raise RuntimeError("%s failed (rc=%d): %s" % (name, rc, msg))
+    launch_count += 1
+
+
+def _want(t, dtype, name):
+    assert t.dtype == dtype, "%s must be %s, got %s" % (name, dtype, t.dtype)
+
+
+# ------------------------------------------------------------------------------- wrappers
+def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, resid=None,
+         resid_map=None, resid_mod=0, out_map=None, out_alt=None, rope_rows=None, rope_slots=0, rope_ft=0,
+         rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None):
+    """C = A[M,K] @ B[N,K]^T with fused epilogue `kind` (see include/toc3d_b200.h)."""
+    _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
+    M = A.shape[0] if M is None else M
+    N, K = B.shape
+    assert A.shape[1] == K and A.stride(1) == 1 and B.stride(1) == 1
+    e = Epilogue()
+    e.bias = _p(bias); e.out = _p(out); e.ldo = out.shape[-1] if ldo is None else ldo
+    e.out_f32 = int(out_f32); e.act = act
+    e.resid = _p(resid); e.resid_map = _p(resid_map); e.resid_mod = resid_mod
+    e.out_map = _p(out_map); e.out_alt = _p(out_alt)
+    e.rope_rows = _p(rope_rows); e.rope_slots = rope_slots; e.rope_ft = rope_ft; e.rope_cols = rope_cols
+    e.q_scale = q_scale; e.cos_axis = _p(cos_axis); e.sin_axis = _p(sin_axis)
+    rc = load().toc3d_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, kind,
+                                ctypes.byref(e), _stream())
+    _check(rc, "toc3d_gemm_bf16")
+    return out
+
+
+def window_attention(qkv, out, n_windows, seq_len, heads):
+    _want(qkv, torch.bfloat16, "qkv"); _want(out, torch.bfloat16, "out")
+    _check(load().toc3d_window_attention(_p(qkv), _p(out), n_windows, seq_len, heads, _stream()),
+           "toc3d_window_attention")
+    return out
+
+
+def layernorm_rows(x, gamma, beta, out, M, C, eps, row_map=None, alt=None, pad_mode=0):
+    _want(x, torch.float32, "x"); _want(out, torch.bfloat16, "out")
+    _check(load().toc3d_layernorm_rows(_p(x), _p(row_map), _p(alt), _p(gamma), _p(beta), _p(out), M, C, eps,
+                                       pad_mode, _stream()), "toc3d_layernorm_rows")
+    return out
+
+
+def subln(h, out, gamma, beta, M, Hd, ld, eps):
+    _check(load().toc3d_subln_bf16(_p(h), _p(out), _p(gamma), _p(beta), M, Hd, ld, eps, _stream()),
+           "toc3d_subln_bf16")
+    return out
+
+
+def window_topk(scores, V, H, W, ws, k, slow_idx=None, fast_idx=None, fast_score=None, tok_map=None,
+                rope_rows=None, fast_map=None):
+    _want(scores, torch.float32, "scores")
+    _check(load().toc3d_window_topk(_p(scores), V, H, W, ws, k, _p(slow_idx), _p(fast_idx), _p(fast_score),
+                                    _p(tok_map), _p(rope_rows), _p(fast_map), _stream()), "toc3d_window_topk")
+
+
+def topk_split(scores, B, N, k, keep_idx, drop_idx):
+    _want(scores, torch.float32, "scores"); _want(keep_idx, torch.int64, "keep_idx")
+    _check(load().toc3d_topk_split(_p(scores), B, N, k, _p(keep_idx), _p(drop_idx), _stream()), "toc3d_topk_split")
+
+
+def merge_fast_tokens(x, fast_map, fast_score, nW, n_fast, k, C, rep_out, packed=None):
+    _check(load().toc3d_merge_fast_tokens(_p(x), _p(fast_map), _p(fast_score), nW, n_fast, k, C, _p(rep_out),
+                                          _p(packed), _stream()), "toc3d_merge_fast_tokens")
+
+
+def fast_token_update(x, fast_map, packed, rep, nW, n_fast, k, C):
+    _check(load().toc3d_fast_token_update(_p(x), _p(fast_map), _p(packed), _p(rep), nW, n_fast, k, C, _stream()),
+           "toc3d_fast_token_update")
+
+
+def score_fold_queries(queries, w_in, b_in, w_agg, b_agg, scale, A_out, c_out):
+    Bf, Q, Cq = queries.shape
+    C = w_in.shape[1]
+    _check(load().toc3d_score_fold_queries(_p(queries), _p(w_in), _p(b_in), _p(w_agg), _p(b_agg), scale, Bf, Q, Cq,
+                                           C, _p(A_out), _p(c_out), _stream()), "toc3d_score_fold_queries")
+
+
+def score_tokens(x, mask_in, A, c, V, N, C, views_per_frame, gumbel, seed, pred, score, mask_out):
+    _check(load().toc3d_score_tokens(_p(x), _p(mask_in), _p(A), _p(c), V, N, C, views_per_frame, _p(gumbel), seed,
+                                     _p(pred), _p(score), _p(mask_out), _stream()), "toc3d_score_tokens")
+
+
+def score_finish(logits, M, gumbel, seed, pred, score, mask_out):
+    _check(load().toc3d_score_finish(_p(logits), M, _p(gumbel), seed, _p(pred), _p(score), _p(mask_out), _stream()),
+           "toc3d_score_finish")
+
+
+def im2col_patch16(img, out, V, Hi, Wi):
+    _want(img, torch.float32, "img")
+    _check(load().toc3d_im2col_patch16(_p(img), _p(out), V, Hi, Wi, _stream()), "toc3d_im2col_patch16")
+
+
+def cast_bf16(src, dst):
+    _want(src, torch.float32, "src"); _want(dst, torch.bfloat16, "dst")
+    _check(load().toc3d_cast_f32_to_bf16(_p(src), _p(dst), src.numel(), _stream()), "toc3d_cast_f32_to_bf16")
+    return dst
+
+
+def mask_rows(x, mask, out, M, C):
+    _check(load().toc3d_mask_rows(_p(x), _p(mask), _p(out), M, C, _stream()), "toc3d_mask_rows")
+
+
+def global_half_mean(y, V, N, C):
+    _check(load().toc3d_global_half_mean(_p(y), V, N, C, _stream()), "toc3d_global_half_mean")
