@@ -1,0 +1,329 @@
+#!/usr/bin/env python
+"""Benchmark of the ToC3D image-backbone hot path: 6-cam samples/s on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--config toc3d_fast] [--batch B]
+    python bench.py --impl reference ...      # the oracle port of the reference on the host cores
+
+One step = one backbone forward over `batch` synthetic 6-view samples per GPU (weights: seeded
+random init of the EVA-ViT-L + ToC3D architecture; there are no checkpoints offline).  N>1 is weak
+scaling: every rank runs its own samples and the ranks all-gather `last_feat` over NCCL (the one
+collective north_star names).  Prints ONE JSON line (rank 0).
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from toc3d_b200.configs import CONFIGS  # noqa: E402
+from toc3d_b200.synthetic import make_gumbel, make_inputs, randomize_state_dict  # noqa: E402
+
+METRIC = "6-cam samples/sec, EVA-ViT-L+ToC3D backbone fwd"
+UNIT = "samples/s"
+VIEWS = 6
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+# ------------------------------------------------------------------------------- algorithmic work
+def algorithmic_work(cfg, kind, hw, views):
+    """FLOPs of the reference semantics incl. padded window slots, MAC = 2 FLOP, and
+    the prune/gather bytes (bf16-activation convention of the survey)."""
+    C, Hd = cfg["embed_dim"], int(cfg["embed_dim"] * cfg["mlp_ratio"])
+    H, W = hw[0] // 16, hw[1] // 16
+    V, N = views, H * W
+    lin = attn = gather_b = 0.0
+    lin += V * N * 2 * 768 * C
+    stage = -1
+    for i in range(cfg["depth"]):
+        g = i in cfg["global_attn_indexes"]
+        ws = cfg["global_window_size"] if g else cfg["window_size"]
+        n = ws * ws
+        nW = V * -(-H // ws) * -(-W // ws)
+        if kind == "ToC3DEVAViT" and i in cfg["pruning_loc"]:
+            stage += 1
+            lin += V * N * (2 * C * 256 + 2 * 256 * 64 + 2 * 64 * 2)
+        if kind == "ToC3DEVAViT" and i >= cfg["pruning_loc"][0]:
+            k = int(n * cfg["token_ratio"][stage])
+            rows = nW * (k + 1)
+            lin += rows * (8 * C * C + 6 * C * Hd)
+            attn += nW * 4 * (k + 1) ** 2 * C
+            gather_b += 2 * (nW * n + rows) * C * 2
+        else:
+            lin += nW * n * 8 * C * C + V * N * 6 * C * Hd
+            attn += nW * 4 * n * n * C
+    return dict(flops=lin + attn, linear=lin, attention=attn, gather_bytes=gather_b)
+
+
+# ------------------------------------------------------------------------------- clocks
+class ClockSampler:
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.t.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1])); mx.append(float(r[2]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        busy = [s for s in sm if s > 0]
+        return dict(sm_mhz=statistics.median(busy or sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+
+
+# ------------------------------------------------------------------------------- reference arm (CPU)
+def oracle_step_fn(name, views_sample):
+    """The oracle port of the reference forward on the host cores, on `views_sample` views of the
+    workload (bounded sample).  bench.py is one of the two places allowed to execute oracle/."""
+    from oracle import toc3d_oracle as O
+    from toc3d_b200 import EVA_ViT, ToC3DEVAViT
+    kind, cfg, hw = CONFIGS[name]
+    torch.manual_seed(0)
+    model = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
+    sd = randomize_state_dict(model.state_dict(), seed=0, bias_std=0.02)
+    del model
+    inp = make_inputs(1, views_sample, hw, seed=0)
+    gn = make_gumbel(views_sample, (hw[0] // 16) * (hw[1] // 16))
+
+    def step():
+        with torch.no_grad():
+            if kind == "EVA_ViT":
+                return O.forward_dense(sd, cfg, inp["x"])
+            return O.forward_toc3d(sd, cfg, inp["x"], inp["temp_queries"], inp["temp_ref_points"], inp["temp_vel"],
+                                   inp["temp_timestamp"], inp["temp_ego_pose"], inp["ego_pose_inv"], True, gn)
+    return step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    views_sample = 1
+    step = oracle_step_fn(args.config, views_sample)
+    for _ in range(max(1, min(args.warmup, 2))):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = (time.perf_counter() - t0) / args.steps
+    value = 1.0 / (dt * VIEWS / views_sample)
+    sample = "%d of %d views per step (fp32 oracle port of the reference forward, %d torch threads); scaled x%d" % (
+        views_sample, VIEWS, cores, VIEWS // views_sample)
+    kind, cfg, hw = CONFIGS[args.config]
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * VIEWS / views_sample, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": args.config, "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": 1},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------- native arm (B200)
+def run_native(args):
+    import torch.distributed as dist
+    from toc3d_b200 import EVA_ViT, ToC3DEVAViT
+    from toc3d_b200 import lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py (native arm) needs a CUDA device; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    kind, cfg, hw = CONFIGS[args.config]
+    torch.manual_seed(0)
+    model = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
+    model.load_state_dict(randomize_state_dict(model.state_dict(), seed=0, bias_std=0.02))
+    model = model.eval().to(dev)
+    B = args.batch
+    V = B * VIEWS
+    H, W = hw[0] // 16, hw[1] // 16
+    inp = make_inputs(B, VIEWS, hw, seed=rank)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    res = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    out_host = torch.empty(V, cfg["embed_dim"], H, W, dtype=torch.float32).pin_memory()
+    gathered = torch.empty(world * V, H, W, cfg["embed_dim"], device=dev) if world > 1 else None
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
+
+    def forward(d):
+        out = model(**d)
+        lf = out["last_feat"] if isinstance(out, dict) else out.img_feats["last_feat"]
+        if world > 1:   # all-gather the feature list for the detection head (NHWC storage of last_feat)
+            dist.all_gather_into_tensor(gathered, lf.permute(0, 2, 3, 1))
+        return lf
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        """K steps, each bracketed by CUDA events on the launch stream; L2 flushed between steps."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        for s, e in ev:
+            flush.zero_()
+            s.record()
+            fn()
+            e.record()
+        barrier()
+        ms = [s.elapsed_time(e) for s, e in ev]
+        tot = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+        return tot.item(), ms
+
+    def e2e_step():
+        d = {k: (v.to(dev, non_blocking=True) if torch.is_tensor(v) else v) for k, v in host.items()}
+        lf = forward(d)
+        out_host.copy_(lf, non_blocking=True)
+
+    for _ in range(max(args.warmup, 3)):
+        forward(res)
+    for _ in range(2):
+        e2e_step()
+    torch.cuda.synchronize()
+
+    with ClockSampler(local) as clk:
+        l0 = L.launch_count
+        total_ms, ms = timed(lambda: forward(res), args.steps)
+        launches = (L.launch_count - l0) // args.steps
+        e2e_ms, _ = timed(e2e_step, args.steps)
+    clocks = clk.summary()
+
+    # --- roofline of the dominant kernel (the tcgen05 GEMM): one extra instrumented step, events around
+    #     every GEMM launch on the launch stream (kept out of the timed steps so it does not perturb them)
+    work = algorithmic_work(cfg, kind, hw, V)
+    recs = []
+    orig = L.gemm
+
+    def traced(A, Bw, kind_, M=None, **kw):
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        r = orig(A, Bw, kind_, M, **kw)
+        e.record()
+        m = A.shape[0] if M is None else M
+        recs.append((s, e, 2.0 * m * Bw.shape[0] * Bw.shape[1]))
+        return r
+    L.gemm = traced
+    forward(res)
+    torch.cuda.synchronize()
+    L.gemm = orig
+    g_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
+    g_fl = sum(f for _, _, f in recs)
+    peaks = load_peaks()
+    step_ms = total_ms / args.steps
+    ach = g_fl / (g_ms * 1e-3) / 1e12
+    roofline = {"bound": "tensor", "kernel": "toc3d::gemm::gemm_kernel (tcgen05, all epilogues)",
+                "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
+                "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained",
+                "launches_per_step": len(recs), "avg_launch_us": g_ms * 1e3 / max(1, len(recs)),
+                "gemm_share_of_step": g_ms / step_ms, "measured": "one instrumented step after the timed region",
+                "whole_step_tflops": work["flops"] / (step_ms * 1e-3) / 1e12}
+
+    value = world * B * args.steps / (total_ms * 1e-3)
+    e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values() if torch.is_tensor(v))
+    d2h = out_host.numel() * out_host.element_size()
+
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+        "data": "synthetic",
+        "config": {"workload": args.config, "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": B,
+                   "prev_exists": True, "weights": "random-init EVA-ViT-L + ToC3D selectors (seed 0)",
+                   "parallelism": "dp%d (views x batch sharded, all-gather of last_feat)" % world,
+                   "l2": "256 MiB buffer zeroed between timed steps (L2 flush)",
+                   "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate"},
+        "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "ms_per_step": e2e_ms / args.steps},
+        "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
+        "clocks": clocks, "roofline": roofline,
+    }
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        step = oracle_step_fn(args.config, 1)
+        step()
+        t0 = time.perf_counter(); n = 0
+        while n < 3 or (time.perf_counter() - t0 < 10 and n < 10):
+            step(); n += 1
+        dt = (time.perf_counter() - t0) / n
+        line["cpu_baseline"] = {"value": 1.0 / (dt * VIEWS), "unit": UNIT, "cores": cores, "kind": "port",
+                                "sample": "1 of 6 views x %d runs, fp32 oracle port of the reference, scaled x6" % n}
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--config", default="toc3d_fast", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=1, help="6-view samples per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

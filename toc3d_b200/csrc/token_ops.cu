@@ -421,6 +421,7 @@ __global__ void __launch_bounds__(128)
 global_half_mean_kernel(__nv_bfloat16* __restrict__ y, int N, int C) {
   const int v = blockIdx.x;
   const int ch = C / 2 + blockIdx.y * 128 + threadIdx.x;
+  if (ch >= C) return;
   __nv_bfloat16* base = y + (size_t)v * N * C + ch;
   float acc = 0.f;
   for (int n = 0; n < N; ++n) acc += __bfloat162float(base[(size_t)n * C]);
@@ -574,8 +575,8 @@ extern "C" int toc3d_mask_rows(const float* x, const float* mask, float* out, in
 }
 
 extern "C" int toc3d_global_half_mean(void* y, int32_t V, int32_t N, int32_t C, void* stream) {
-  TOC3D_REQUIRE(y && V > 0 && N > 0 && C % 256 == 0, kErrBadArg, "toc3d_global_half_mean: bad args");
-  dim3 grid(V, C / 2 / 128);
+  TOC3D_REQUIRE(y && V > 0 && N > 0 && C % 2 == 0, kErrBadArg, "toc3d_global_half_mean: bad args");
+  dim3 grid(V, (C / 2 + 127) / 128);
   global_half_mean_kernel<<<grid, 128, 0, ST(stream)>>>(reinterpret_cast<__nv_bfloat16*>(y), N, C);
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
