@@ -1,0 +1,36 @@
+"""Run a few forwards of one config for profiling under ncu (never a source of bench numbers).
+
+    ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file gpurun_out/launches.csv \
+        python tools/profile_step.py --config toc3d_fast --iters 3
+The LAST forward is bracketed by cudaProfilerStart/Stop-free NVTX-less markers: a tiny marker kernel
+(torch fill of a 1-element tensor named by size 7777) is launched before it so the launch list can be cut.
+"""
+import argparse
+import os
+import sys
+
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from toc3d_b200 import CONFIGS, EVA_ViT, ToC3DEVAViT  # noqa: E402
+from toc3d_b200.synthetic import make_inputs, randomize_state_dict  # noqa: E402
+
+ap = argparse.ArgumentParser()
+ap.add_argument("--config", default="toc3d_fast")
+ap.add_argument("--iters", type=int, default=3)
+ap.add_argument("--batch", type=int, default=1)
+args = ap.parse_args()
+kind, cfg, hw = CONFIGS[args.config]
+torch.manual_seed(0)
+m = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
+m.load_state_dict(randomize_state_dict(m.state_dict(), seed=0, bias_std=0.02))
+m = m.eval().cuda()
+inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in make_inputs(args.batch, 6, hw, seed=0).items()}
+marker = torch.zeros(7777, device="cuda")
+for i in range(args.iters):
+    if i == args.iters - 1:
+        marker.fill_(1.0)     # marker launch: vectorized fill of 7777 elements
+    with torch.no_grad():
+        m(**inp)
+torch.cuda.synchronize()
+print("done")
