@@ -100,7 +100,8 @@ int toc3d_layernorm_rows(const float* x, const int32_t* row_map, const float* al
                          void* stream);
 
 /* SwiGLU sub-LayerNorm (eva_vit.py:48, ffn_ln over the true hidden width `Hd`) on the padded bf16
- * hidden buffer [M, ld]; columns >= Hd are written as zero.  In place allowed (out == h). */
+ * hidden buffer [M, ld].  Contract: columns >= Hd of h are exactly zero on input and gamma/beta are
+ * zero-padded to ld; they are written as zero.  In place allowed (out == h). */
 int toc3d_subln_bf16(const void* h, void* out, const float* gamma, const float* beta, int32_t M, int32_t Hd,
                      int32_t ld, float eps, void* stream);
 

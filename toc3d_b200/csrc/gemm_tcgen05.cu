@@ -3,7 +3,7 @@
 //
 //   warp 0 : TMA producer (one elected lane)
 //   warp 1 : TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2-5 : epilogue, one TMEM lane quarter each (lane quarter = warp_id % 4)
+//   warps 2-9 : epilogue; warp w reads TMEM lane quarter (w % 4), column half ((w - 2) / 4)
 //
 // Call sites replaced: see include/toc3d_b200.h (toc3d_gemm_bf16).
 #include "common.cuh"
@@ -19,11 +19,11 @@ constexpr int STAGES = 4;
 constexpr int A_BYTES = BM * BK * 2;
 constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-constexpr int NUM_THREADS = 192;
+constexpr int NUM_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;                    // 2 accumulator buffers x 256 fp32 columns
 constexpr int ROPE_MAX_FT = 32;
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;  // 196608
-constexpr int SMEM_AUX = 256 + 2 * ROPE_MAX_FT * 16 * 4;
+constexpr int SMEM_AUX = 256 + 2 * ROPE_MAX_FT * 16 * 4 + 8 * 32 * 20 * 4;   // barriers, RoPE tables, epilogue staging
 constexpr int SMEM_BYTES = SMEM_TILES + SMEM_AUX + 1024;  // + alignment slack
 
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10),
@@ -53,54 +53,196 @@ struct EpiParams {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
 
-__device__ __forceinline__ void store_bf16x32(__nv_bfloat16* dst, const float (&f)[32], int ncols) {
-  if (ncols >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+// ---------------------------------------------------------------------------------------------
+// Epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) and column half ((w - 2) / 4) of the
+// 128 x 256 accumulator.  Each 32-row x 16-column sub-chunk goes TMEM -> registers (thread = row)
+// -> padded smem staging -> "coalesced domain" (4 lanes x float4 per row, 8 rows per instruction),
+// where bias / RoPE / residual / activation are applied and global memory is touched with
+// contiguous 64-byte row segments instead of one 16-byte piece per row.
+constexpr int SUB = 16;            // columns per staged sub-chunk
+constexpr int STG_LD = SUB + 4;    // padded staging row (floats): conflict-free for the mappings below
+constexpr int EPI_WARPS = 8;
+
+__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+
+__device__ __forceinline__ void stage_rows16(float* stage, int lane, const float (&f)[16]) {
+  float4* d = reinterpret_cast<float4*>(stage + lane * STG_LD);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      uint4 u;
-      u.x = pack_bf16(f[8 * i + 0], f[8 * i + 1]);
-      u.y = pack_bf16(f[8 * i + 2], f[8 * i + 3]);
-      u.z = pack_bf16(f[8 * i + 4], f[8 * i + 5]);
-      u.w = pack_bf16(f[8 * i + 6], f[8 * i + 7]);
-      d4[i] = u;
+  for (int j = 0; j < 4; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+}
+
+template <int EPI>
+__device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int n0, int M, int N,
+                                                   float* stage, const float* s_cos, const float* s_sin, int lane) {
+  // coalesced-domain coordinates: rows {rin, rin+8, rin+16, rin+24}, columns 4*cseg..4*cseg+3 of the sub-chunk
+  const int rin = ((lane >> 2) & 1) * 4 + (lane >> 3);
+  const int cseg = lane & 3;
+  const bool my_row_ok = (m0 + lane) < M;
+
+  int rr_t = -1, or_t = -1, pos_t = 0;
+  if constexpr (EPI == TOC3D_EPI_RESID) {
+    if (my_row_ok) {
+      const int row = m0 + lane;
+      rr_t = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
+      or_t = ep.out_map ? ep.out_map[row] : row;
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) dst[i] = __float2bfloat16_rn(f[i]);
   }
-}
-__device__ __forceinline__ void store_f32x32(float* dst, const float (&f)[32], int ncols) {
-  if (ncols >= 32 && ((reinterpret_cast<uintptr_t>(dst) & 15) == 0)) {
-    float4* d4 = reinterpret_cast<float4*>(dst);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) d4[i] = make_float4(f[4 * i], f[4 * i + 1], f[4 * i + 2], f[4 * i + 3]);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i)
-      if (i < ncols) dst[i] = f[i];
-  }
-}
-__device__ __forceinline__ void load_f32x32(const float* src, float (&f)[32], int ncols) {
-  if (ncols >= 32 && ((reinterpret_cast<uintptr_t>(src) & 15) == 0)) {
-    const float4* s4 = reinterpret_cast<const float4*>(src);
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      float4 v = s4[i];
-      f[4 * i] = v.x; f[4 * i + 1] = v.y; f[4 * i + 2] = v.z; f[4 * i + 3] = v.w;
+  if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
+    if (my_row_ok) {
+      const int row = m0 + lane;
+      const int t = ep.rope_rows ? ep.rope_rows[row] : (row % ep.rope_slots);
+      const int r = t / ep.rope_ft;
+      pos_t = (r << 16) | (t - r * ep.rope_ft);
     }
-  } else {
-#pragma unroll
-    for (int i = 0; i < 32; ++i) f[i] = (i < ncols) ? src[i] : 0.0f;
   }
-}
-// bias is warp-uniform per column chunk -> broadcast loads
-__device__ __forceinline__ void add_bias32(float (&f)[32], const float* bias, int col0, int ncols) {
-  if (bias == nullptr) return;
+
+  if constexpr (EPI == TOC3D_EPI_SWIGLU) {
+    // this warp's 128 GEMM columns = 2 blocks of [32 x w1 | 32 x w2]; 16 hidden columns per step
+    __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+#pragma unroll 1
+    for (int st = 0; st < 4; ++st) {
+      const int blk = st >> 1, sub = st & 1;
+      const int col1 = n0 + blk * 64 + sub * SUB;        // GEMM column of the w1 part
+      if (col1 >= N) break;                               // warp-uniform
+      uint32_t v1[16], v2[16];
+      tmem_ld_32x16(taddr + blk * 64 + sub * SUB, v1);
+      tmem_ld_32x16(taddr + blk * 64 + 32 + sub * SUB, v2);
+      tmem_ld_wait();
+      float h[16];
 #pragma unroll
-  for (int i = 0; i < 32; ++i)
-    if (i < ncols) f[i] += __ldg(bias + col0 + i);
+      for (int j = 0; j < 4; ++j) {
+        float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
+        if (ep.bias != nullptr) {
+          b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1) + j);
+          b2 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1 + 32) + j);
+        }
+        h[4 * j + 0] = silu(__uint_as_float(v1[4 * j + 0]) + b1.x) * (__uint_as_float(v2[4 * j + 0]) + b2.x);
+        h[4 * j + 1] = silu(__uint_as_float(v1[4 * j + 1]) + b1.y) * (__uint_as_float(v2[4 * j + 1]) + b2.y);
+        h[4 * j + 2] = silu(__uint_as_float(v1[4 * j + 2]) + b1.z) * (__uint_as_float(v2[4 * j + 2]) + b2.z);
+        h[4 * j + 3] = silu(__uint_as_float(v1[4 * j + 3]) + b1.w) * (__uint_as_float(v2[4 * j + 3]) + b2.w);
+      }
+      stage_rows16(stage, lane, h);
+      __syncwarp();
+      const int hcol = ((n0 + blk * 64) >> 1) + sub * SUB + 4 * cseg;   // hidden column of this lane
+      if (hcol < ep.ldo) {
+#pragma unroll
+        for (int it = 0; it < 4; ++it) {
+          const int row = it * 8 + rin;
+          const float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+          if (m0 + row < M) {
+            uint2 u;
+            u.x = pack_bf16(a.x, a.y);
+            u.y = pack_bf16(a.z, a.w);
+            *reinterpret_cast<uint2*>(out + (size_t)(m0 + row) * ep.ldo + hcol) = u;
+          }
+        }
+      }
+      __syncwarp();
+    }
+    return;
+  }
+
+#pragma unroll 1
+  for (int sc = 0; sc < 128 / SUB; ++sc) {
+    const int col0 = n0 + sc * SUB;
+    if (col0 >= N) break;                                 // warp-uniform
+    uint32_t v[16];
+    tmem_ld_32x16(taddr + sc * SUB, v);
+    tmem_ld_wait();
+    float f[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
+    stage_rows16(stage, lane, f);
+    __syncwarp();
+
+    const int col = col0 + 4 * cseg;
+    const bool col_ok = col < N;                          // N % 4 == 0
+    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr && col_ok) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+
+    if constexpr (EPI == TOC3D_EPI_RESID) {
+      float4 r[4];
+      int orow[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 8 + rin;
+        orow[it] = __shfl_sync(0xffffffffu, or_t, row);
+        const int rrow = __shfl_sync(0xffffffffu, rr_t, row);
+        r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col_ok && orow[it] != -1) {
+          if (rrow >= 0) r[it] = *reinterpret_cast<const float4*>(ep.resid + (size_t)rrow * ep.ldo + col);
+          else if (rrow == -2) r[it] = *reinterpret_cast<const float4*>(ep.out_alt + (size_t)(m0 + row) * ep.ldo + col);
+        }
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 8 + rin;
+        const float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+        if (col_ok && orow[it] != -1) {
+          float4 o;
+          o.x = r[it].x + (a.x + b.x); o.y = r[it].y + (a.y + b.y);
+          o.z = r[it].z + (a.z + b.z); o.w = r[it].w + (a.w + b.w);
+          float* dst = (orow[it] >= 0) ? reinterpret_cast<float*>(ep.out) + (size_t)orow[it] * ep.ldo
+                                       : ep.out_alt + (size_t)(m0 + row) * ep.ldo;
+          *reinterpret_cast<float4*>(dst + col) = o;
+        }
+      }
+    } else if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
+      const bool rot = col < ep.rope_cols;
+      const bool col_axis = (col >> 5) & 1;               // second 32 channels of a head use the column coordinate
+      const int j0 = (col & 31) >> 1;
+      const float sc_q = (col < (ep.rope_cols >> 1)) ? ep.q_scale : 1.0f;
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 8 + rin;
+        const int pos_pk = __shfl_sync(0xffffffffu, pos_t, row);
+        float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (rot) {
+          const int pos = col_axis ? (pos_pk & 0xffff) : (pos_pk >> 16);
+          const float c0 = s_cos[pos * 16 + j0], s0 = s_sin[pos * 16 + j0];
+          const float c1 = s_cos[pos * 16 + j0 + 1], s1 = s_sin[pos * 16 + j0 + 1];
+          const float x0 = a.x, x1 = a.y, x2 = a.z, x3 = a.w;
+          a.x = (x0 * c0 - x1 * s0) * sc_q; a.y = (x1 * c0 + x0 * s0) * sc_q;
+          a.z = (x2 * c1 - x3 * s1) * sc_q; a.w = (x3 * c1 + x2 * s1) * sc_q;
+        }
+        if (col_ok && m0 + row < M) {
+          uint2 u;
+          u.x = pack_bf16(a.x, a.y);
+          u.y = pack_bf16(a.z, a.w);
+          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)(m0 + row) * ep.ldo + col) = u;
+        }
+      }
+    } else {  // TOC3D_EPI_LINEAR
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const int row = it * 8 + rin;
+        float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+        if (ep.act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
+        else if (ep.act == 2) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
+        if (col_ok && m0 + row < M) {
+          if (ep.out_f32) {
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)(m0 + row) * ep.ldo + col) = a;
+          } else {
+            uint2 u;
+            u.x = pack_bf16(a.x, a.y);
+            u.y = pack_bf16(a.z, a.w);
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)(m0 + row) * ep.ldo + col) = u;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  }
 }
 
 template <int EPI>
@@ -116,6 +258,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
   float* s_cos = reinterpret_cast<float*>(smem + SMEM_TILES + 256);
   float* s_sin = s_cos + ROPE_MAX_FT * 16;
+  float* s_stage = s_sin + ROPE_MAX_FT * 16;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -133,13 +276,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 4);
+      mbar_init(&tmem_empty[a], EPI_WARPS);
     }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
   if (EPI == TOC3D_EPI_QKV_ROPE && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < ep.rope_ft * 16; i += 128) {
+    for (int i = threadIdx.x - 64; i < ep.rope_ft * 16; i += EPI_WARPS * 32) {
       s_cos[i] = ep.cos_axis[i];
       s_sin[i] = ep.sin_axis[i];
     }
@@ -198,8 +341,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (4 warps)
-    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    // ------------------------------------------------------------------ epilogue (8 warps)
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may read (warp_id % 4)
+    const int half = (warp - 2) >> 2;      // which 128 accumulator columns
+    float* stage_buf = s_stage + (warp - 2) * 32 * STG_LD;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -207,109 +352,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int n_idx = (tile / num_m) * BN;
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
-      const int row = m_idx + quarter * 32 + lane;
-      const bool row_ok = row < M;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
-
-      if constexpr (EPI == TOC3D_EPI_SWIGLU) {
-        // B rows are interleaved [32 x w1 | 32 x w2]; each chunk pair yields 32 hidden columns.
-        __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
-#pragma unroll 1
-        for (int c = 0; c < BN / 64; ++c) {
-          uint32_t v1[32], v2[32];
-          tmem_ld_32x32(taddr + c * 64, v1);
-          tmem_ld_32x32(taddr + c * 64 + 32, v2);
-          tmem_ld_wait();
-          const int col1 = n_idx + c * 64;             // GEMM column of the w1 part
-          const int hcol = (n_idx >> 1) + c * 32;      // hidden column
-          if (col1 < N) {
-            float h[32];
-#pragma unroll
-            for (int i = 0; i < 32; ++i) {
-              float a = __uint_as_float(v1[i]), g = __uint_as_float(v2[i]);
-              if (ep.bias != nullptr) {
-                a += __ldg(ep.bias + col1 + i);
-                g += __ldg(ep.bias + col1 + 32 + i);
-              }
-              h[i] = silu(a) * g;
-            }
-            if (row_ok) store_bf16x32(out + (size_t)row * ep.ldo + hcol, h, min(32, ep.ldo - hcol));
-          }
-        }
-      } else {
-        int rope_r = 0, rope_c = 0;
-        if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
-          int t = 0;
-          if (row_ok) t = ep.rope_rows ? ep.rope_rows[row] : (row % ep.rope_slots);
-          rope_r = t / ep.rope_ft;
-          rope_c = t - rope_r * ep.rope_ft;
-        }
-        int rrow = -1, orow = -1;
-        if constexpr (EPI == TOC3D_EPI_RESID) {
-          if (row_ok) {
-            rrow = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
-            orow = ep.out_map ? ep.out_map[row] : row;
-          }
-        }
-#pragma unroll 1
-        for (int c = 0; c < BN / 32; ++c) {
-          uint32_t v[32];
-          tmem_ld_32x32(taddr + c * 32, v);
-          tmem_ld_wait();
-          const int col0 = n_idx + c * 32;
-          if (col0 >= N) continue;   // warp-uniform
-          const int ncols = min(32, N - col0);
-          float f[32];
-#pragma unroll
-          for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
-          add_bias32(f, ep.bias, col0, ncols);
-
-          if constexpr (EPI == TOC3D_EPI_LINEAR) {
-            if (ep.act == 1) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = gelu_erf(f[i]);
-            } else if (ep.act == 2) {
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = fmaxf(f[i], 0.0f);
-            }
-            if (row_ok) {
-              if (ep.out_f32) store_f32x32(reinterpret_cast<float*>(ep.out) + (size_t)row * ep.ldo + col0, f, ncols);
-              else store_bf16x32(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0, f, ncols);
-            }
-          } else if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
-            if (col0 < ep.rope_cols) {
-              // head-dim 64: chunk parity selects the row-axis (first 32) or column-axis (last 32) angles
-              const int pos = ((col0 >> 5) & 1) ? rope_c : rope_r;
-              const float* cs = s_cos + pos * 16;
-              const float* sn = s_sin + pos * 16;
-              const float sc = (col0 < (ep.rope_cols >> 1)) ? ep.q_scale : 1.0f;
-#pragma unroll
-              for (int j = 0; j < 16; ++j) {
-                const float x0 = f[2 * j], x1 = f[2 * j + 1];
-                const float cj = cs[j], sj = sn[j];
-                f[2 * j] = (x0 * cj - x1 * sj) * sc;
-                f[2 * j + 1] = (x1 * cj + x0 * sj) * sc;
-              }
-            }
-            if (row_ok) store_bf16x32(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)row * ep.ldo + col0, f, ncols);
-          } else if constexpr (EPI == TOC3D_EPI_RESID) {
-            if (row_ok && orow != -1) {
-              float r[32];
-              if (rrow >= 0) load_f32x32(ep.resid + (size_t)rrow * ep.ldo + col0, r, ncols);
-              else if (rrow == -2) load_f32x32(ep.out_alt + (size_t)row * ep.ldo + col0, r, ncols);
-              else {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = 0.0f;
-              }
-#pragma unroll
-              for (int i = 0; i < 32; ++i) f[i] = r[i] + f[i];
-              float* dst = (orow >= 0) ? reinterpret_cast<float*>(ep.out) + (size_t)orow * ep.ldo
-                                       : ep.out_alt + (size_t)row * ep.ldo;
-              store_f32x32(dst + col0, f, ncols);
-            }
-          }
-        }
-      }
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
+      epilogue_warp_tile<EPI>(ep, taddr, m_idx + quarter * 32, n_idx + half * 128, M, N, stage_buf, s_cos, s_sin, lane);
       // release this accumulator buffer to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -403,7 +447,10 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   ep.resid = e->resid; ep.resid_map = e->resid_map; ep.resid_mod = e->resid_mod; ep.out_map = e->out_map;
   ep.out_alt = e->out_alt; ep.rope_rows = e->rope_rows; ep.rope_slots = e->rope_slots; ep.rope_ft = e->rope_ft;
   ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
-  TOC3D_REQUIRE(ep.ldo > 0, kErrBadArg, "toc3d_gemm_bf16: ldo must be positive");
+  TOC3D_REQUIRE(ep.ldo > 0 && ep.ldo % 4 == 0 && N % 4 == 0, kErrBadArg,
+                "toc3d_gemm_bf16: N and ldo must be positive multiples of 4 (vector epilogue), got N=%d ldo=%d", N, ep.ldo);
+  TOC3D_REQUIRE(((uintptr_t)ep.out & 15) == 0 && ((uintptr_t)ep.bias & 15) == 0 && ((uintptr_t)ep.resid & 15) == 0 &&
+                ((uintptr_t)ep.out_alt & 15) == 0, kErrBadArg, "toc3d_gemm_bf16: epilogue pointers must be 16-byte aligned");
   if (kind == TOC3D_EPI_QKV_ROPE) {
     TOC3D_REQUIRE(ep.cos_axis && ep.sin_axis && ep.rope_ft > 0 && ep.rope_ft <= ROPE_MAX_FT, kErrBadArg,
                   "toc3d_gemm_bf16: bad RoPE tables (ft=%d)", ep.rope_ft);

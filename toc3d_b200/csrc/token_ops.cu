@@ -67,7 +67,9 @@ layernorm_rows_kernel(const float* __restrict__ x, const int* __restrict__ row_m
   }
 }
 
-// SwiGLU sub-LN over bf16 hidden rows [M, ld], true width Hd (<= ld, ld % 8 == 0).
+// SwiGLU sub-LN over bf16 hidden rows [M, ld], true width Hd (<= ld, ld % 8 == 0).  Contract: the pad
+// columns [Hd, ld) of h are exactly zero (they are: zero weight rows and biases in the SwiGLU GEMM) and
+// gamma/beta are zero there, so sums run unmasked over ld and the variance is corrected analytically.
 __global__ void __launch_bounds__(256)
 subln_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
              const float* __restrict__ beta, int M, int Hd, int ld, float eps) {
@@ -78,54 +80,47 @@ subln_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ ou
   uint4* o = reinterpret_cast<uint4*>(out + (size_t)m * ld);
   const int nvec = ld >> 3;
   constexpr int MAXV = 12;  // supports ld <= 3072
-  uint4 v[MAXV];
+  float x[MAXV][8];
   float s = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int j = lane + 32 * i;
     if (j < nvec) {
-      v[i] = p[j];
-      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16(w[e]);
-        const int col = j * 8 + e * 2;
-        s += (col < Hd ? f.x : 0.f) + (col + 1 < Hd ? f.y : 0.f);
-      }
+      const uint4 v = p[j];
+      const float2 a = unpack_bf16(v.x), b = unpack_bf16(v.y), c = unpack_bf16(v.z), d = unpack_bf16(v.w);
+      x[i][0] = a.x; x[i][1] = a.y; x[i][2] = b.x; x[i][3] = b.y;
+      x[i][4] = c.x; x[i][5] = c.y; x[i][6] = d.x; x[i][7] = d.y;
+      s += ((a.x + a.y) + (b.x + b.y)) + ((c.x + c.y) + (d.x + d.y));
     }
   }
   const float mean = warp_sum(s) / (float)Hd;
   float q = 0.f;
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
-    const int j = lane + 32 * i;
-    if (j < nvec) {
-      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
+    if (lane + 32 * i < nvec) {
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16(w[e]);
-        const int col = j * 8 + e * 2;
-        const float a = f.x - mean, b = f.y - mean;
-        q += (col < Hd ? a * a : 0.f) + (col + 1 < Hd ? b * b : 0.f);
+      for (int e = 0; e < 8; ++e) {
+        const float t = x[i][e] - mean;
+        q += t * t;
       }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / (float)Hd + eps);
+  q = warp_sum(q) - (float)(ld - Hd) * mean * mean;      // pad columns each contributed mean^2
+  const float rstd = rsqrtf(fmaxf(q, 0.f) / (float)Hd + eps);
 #pragma unroll
   for (int i = 0; i < MAXV; ++i) {
     const int j = lane + 32 * i;
     if (j < nvec) {
-      const uint32_t w[4] = {v[i].x, v[i].y, v[i].z, v[i].w};
-      uint32_t r[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float2 f = unpack_bf16(w[e]);
-        const int col = j * 8 + e * 2;
-        const float y0 = col < Hd ? (f.x - mean) * rstd * gamma[col] + beta[col] : 0.f;
-        const float y1 = col + 1 < Hd ? (f.y - mean) * rstd * gamma[col + 1] + beta[col + 1] : 0.f;
-        r[e] = pack_bf16(y0, y1);
-      }
-      o[j] = make_uint4(r[0], r[1], r[2], r[3]);
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * j);
+      const float4 g1 = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * j + 1);
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * j);
+      const float4 b1 = __ldg(reinterpret_cast<const float4*>(beta) + 2 * j + 1);
+      uint4 r;
+      r.x = pack_bf16((x[i][0] - mean) * rstd * g0.x + b0.x, (x[i][1] - mean) * rstd * g0.y + b0.y);
+      r.y = pack_bf16((x[i][2] - mean) * rstd * g0.z + b0.z, (x[i][3] - mean) * rstd * g0.w + b0.w);
+      r.z = pack_bf16((x[i][4] - mean) * rstd * g1.x + b1.x, (x[i][5] - mean) * rstd * g1.y + b1.y);
+      r.w = pack_bf16((x[i][6] - mean) * rstd * g1.z + b1.z, (x[i][7] - mean) * rstd * g1.w + b1.w);
+      o[j] = r;
     }
   }
 }
