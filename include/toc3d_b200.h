@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 1
+#define TOC3D_B200_ABI_VERSION 2
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -74,6 +74,19 @@ typedef struct toc3d_epilogue {
   float q_scale;
   const float* cos_axis;
   const float* sin_axis;
+  /* Folded LayerNorm of the A rows (SwiGLU sub-LN, eva_vit.py:48, without a separate pass):
+   *   SWIGLU: row_stats != NULL -> atomically accumulates [sum * 2^30, sum of squares * 2^26] of the
+   *           bf16-rounded hidden row as int64 fixed point (order-independent, hence deterministic)
+   *           into row_stats[m*2 .. m*2+1] (int64 [M,2], 16-byte aligned, zeroed by the caller);
+   *   RESID:  row_stats != NULL -> the GEMM's A rows are the UN-normalised hidden rows, B is
+   *           W * gamma (column-scaled), and the epilogue applies
+   *             y = rstd_m * acc - rstd_m * mean_m * ln_u[n] + bias[n]
+   *           with mean/rstd from row_stats over ln_n true columns (eps = ln_eps),
+   *           ln_u = W * gamma (fp32 [N]), bias = W * beta + b. */
+  int64_t* row_stats;
+  const float* ln_u;
+  int32_t ln_n;
+  float ln_eps;
 } toc3d_epilogue;
 
 int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
@@ -93,11 +106,13 @@ int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_
  *   -1: pad slot -> pad_mode 0: output zeros (dense Block pads AFTER norm1, eva_vit.py:249-254)
  *                   pad_mode 1: LN of a zero vector = beta (ToC3D block pads BEFORE norm1,
  *                               toc3d_eva_vit.py:412-415 then :369)
+ * zero_stats (optional, int64 [M,2]): rows are zeroed as a side effect -- the accumulator the SwiGLU
+ * GEMM epilogue adds its folded sub-LN statistics to (toc3d_epilogue.row_stats).
  * Replaces nn.LayerNorm at eva_vit.py:249,263; toc3d_eva_vit.py:371,379; toc3d_utils.py:99.
  */
 int toc3d_layernorm_rows(const float* x, const int32_t* row_map, const float* alt, const float* gamma,
                          const float* beta, void* out_bf16, int32_t M, int32_t C, float eps, int32_t pad_mode,
-                         void* stream);
+                         int64_t* zero_stats, void* stream);
 
 /* SwiGLU sub-LayerNorm (eva_vit.py:48, ffn_ln over the true hidden width `Hd`) on the padded bf16
  * hidden buffer [M, ld].  Contract: columns >= Hd of h are exactly zero on input and gamma/beta are
@@ -151,16 +166,18 @@ int toc3d_score_fold_queries(const float* queries, const float* w_in, const floa
 
 /* Per token: logit = mask_in * (x . A[f]) + c[f]; pred = log_softmax(logit) (fp32 [V*N,2]);
  * mask_out = softmax(pred + g)[0] (toc3d_utils.py:147, pin 2) with g = gumbel [V*N,2] or, when
- * gumbel == NULL, -log(-log(u)) drawn on device from (seed, token index).
+ * gumbel == NULL, -log(-log(u)) drawn on device from (seed, token index); when seed_dev != NULL the
+ * effective seed is seed + 1000003 * *seed_dev (a device-resident call counter, so that a captured
+ * CUDA graph draws fresh noise on every replay).
  * mask_in NULL = all ones.  views_per_frame = V / Bf (repeat_interleave, toc3d_utils.py:240). */
 int toc3d_score_tokens(const float* x, const float* mask_in, const float* A, const float* c, int32_t V, int32_t N,
-                       int32_t C, int32_t views_per_frame, const float* gumbel, uint64_t seed, float* pred,
-                       float* score, float* mask_out, void* stream);
+                       int32_t C, int32_t views_per_frame, const float* gumbel, uint64_t seed,
+                       const uint64_t* seed_dev, float* pred, float* score, float* mask_out, void* stream);
 
 /* Same tail for the first-frame scorer (toc3d_utils.py:114-129) whose logits come from the MLP
  * GEMM chain: logits fp32 [M,2] -> pred, score, mask_out. */
-int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed, float* pred,
-                       float* score, float* mask_out, void* stream);
+int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed,
+                       const uint64_t* seed_dev, float* pred, float* score, float* mask_out, void* stream);
 
 /* ------------------------------------------------------------------ stem
  * im2col for the 16x16/stride-16 patch conv (eva_utils.py:283-287): img fp32 NCHW [V,3,Hi,Wi] ->

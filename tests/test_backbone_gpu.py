@@ -141,3 +141,48 @@ def test_dense_vitl_contract():
     with torch.no_grad():
         out = model(x, some_ignored_kw=1)
     assert out["last_feat"].shape == (2, 1024, 20, 50) and torch.isfinite(out["last_feat"]).all()
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The whole forward replayed as one CUDA graph (default) is bit-identical to the eager launch
+    sequence, draws fresh Gumbel noise per call, and does not alias outputs across calls."""
+    kind, cfg, hw = CONFIGS["toc3d_fast"]
+    model = build_model("toc3d", dict(cfg, depth=8, global_attn_indexes=(1, 3, 5, 7), pruning_loc=[2, 4, 6]))
+    model.load_state_dict(randomize_state_dict(model.state_dict(), seed=5, bias_std=0.05))
+    model = model.cuda()
+    inp = to_cuda(make_inputs(1, 2, hw, seed=5, pose="random"))
+    with torch.no_grad():
+        model(**inp)                                   # captures
+        eng = model._engine
+        eng.seed_t.fill_(41)
+        a = model(**inp)                               # replay, seed 42
+        eng.seed_t.fill_(41)
+        model.use_cuda_graph = False
+        b = model(**inp)                               # eager, seed 42
+        model.use_cuda_graph = True
+        c = model(**inp)                               # replay, seed 43
+    assert torch.equal(a.img_feats["last_feat"], b.img_feats["last_feat"])
+    for x, y in zip(a.keep_idx + a.drop_idx + a.token_masks, b.keep_idx + b.drop_idx + b.token_masks):
+        assert torch.equal(x, y)
+    assert not torch.equal(a.token_masks[0], c.token_masks[0])              # fresh noise
+    assert a.img_feats["last_feat"].data_ptr() != c.img_feats["last_feat"].data_ptr()
+    assert torch.equal(a.img_feats["last_feat"], b.img_feats["last_feat"])  # a survived the later replay
+    # first frame of a scene (prev_exists=False) takes its own graph
+    with torch.no_grad():
+        d = model(**dict(inp, prev_exists=False))
+        model.use_cuda_graph = False
+        eng.seed_t.sub_(1)
+        e = model(**dict(inp, prev_exists=False))
+    assert torch.equal(d.img_feats["last_feat"], e.img_feats["last_feat"])
+
+
+def test_dense_cuda_graph_matches_eager():
+    kind, cfg, hw = CONFIGS["eva_vit_l"]
+    model = build_model("dense", dict(cfg, depth=3, global_attn_indexes=(2,))).cuda()
+    x = torch.randn(2, 3, 160, 352, device="cuda")
+    with torch.no_grad():
+        a = model(x)["last_feat"]
+        a2 = model(x)["last_feat"]
+        model.use_cuda_graph = False
+        b = model(x)["last_feat"]
+    assert torch.equal(a, b) and torch.equal(a2, b)

@@ -130,6 +130,45 @@ def test_gemm_swiglu(lib, M, Hd):
     assert (got[:, Hd:] == 0).all()
 
 
+@pytest.mark.parametrize("M,Hd,C", [(300, 2730, 256), (1000, 341, 128)])
+def test_gemm_swiglu_folded_subln(lib, M, Hd, C):
+    """SwiGLU.forward (eva_vit.py:44-51) with the sub-LN folded into the two GEMM epilogues:
+    w3(LN(h)) == rstd * (h @ (W3*gamma)^T) - rstd * mean * (W3 gamma) + (W3 beta + b3)."""
+    from toc3d_b200.backbone import interleave_w12, hidden_pad
+    F = torch.nn.functional
+    g = torch.Generator().manual_seed(Hd + 1)
+    K, Hp, eps = 128, hidden_pad(Hd), 1e-6
+    A = bf16_round(torch.randn(M, K, generator=g))
+    w1 = bf16_round(torch.randn(Hd, K, generator=g) * 0.1); w2 = bf16_round(torch.randn(Hd, K, generator=g) * 0.1)
+    b1 = torch.randn(Hd, generator=g) * 0.5; b2 = torch.randn(Hd, generator=g) * 0.5 + 0.3
+    gamma = 1 + 0.2 * torch.randn(Hd, generator=g); beta = 0.2 * torch.randn(Hd, generator=g)
+    w3 = torch.randn(C, Hd, generator=g) * 0.05; b3 = torch.randn(C, generator=g)
+    resid = torch.randn(M, C, generator=g)
+    h = F.silu(A @ w1.t() + b1) * (A @ w2.t() + b2)
+    ref = resid + F.layer_norm(h, (Hd,), gamma, beta, eps) @ w3.t() + b3
+    W12, b12 = interleave_w12(w1, b1, w2, b2, Hp)
+    hid = torch.empty(M, Hp, device=DEV, dtype=torch.bfloat16)
+    stats = torch.full((M, 2), 7, device=DEV, dtype=torch.int64)
+    # the LN launch that precedes the MLP zeroes the statistics rows
+    lib.layernorm_rows(torch.randn(M, 128, device=DEV), torch.ones(128, device=DEV), torch.zeros(128, device=DEV),
+                       torch.empty(M, 128, device=DEV, dtype=torch.bfloat16), M, 128, 1e-6, zero_stats=stats)
+    assert (stats == 0).all()
+    lib.gemm(A.to(DEV).bfloat16(), W12.to(DEV).bfloat16(), lib.EPI_SWIGLU, bias=b12.to(DEV), out=hid, row_stats=stats)
+    hb = hid.float().cpu()[:, :Hd]
+    st = stats.cpu().double()
+    assert rel_err(st[:, 0] / 2 ** 30, hb.double().sum(1)) < 1e-5 and rel_err(st[:, 1] / 2 ** 26, hb.double().pow(2).sum(1)) < 1e-5
+    stats2 = torch.zeros_like(stats)                                  # integer accumulation is order-independent
+    lib.gemm(A.to(DEV).bfloat16(), W12.to(DEV).bfloat16(), lib.EPI_SWIGLU, bias=b12.to(DEV), out=hid, row_stats=stats2)
+    assert torch.equal(stats, stats2)
+    w3g = torch.nn.functional.pad(w3 * gamma[None, :], (0, Hp - Hd)).to(DEV).bfloat16().contiguous()
+    u3 = (w3 @ gamma).to(DEV); c3 = (w3 @ beta + b3).to(DEV)
+    out = torch.empty(M, C, device=DEV)
+    lib.gemm(hid, w3g, lib.EPI_RESID, bias=c3, out=out, resid=resid.to(DEV), row_stats=stats, ln_u=u3, ln_n=Hd, ln_eps=eps)
+    err = (out.cpu() - ref).abs().max().item()
+    print("folded sub-LN MLP max-abs %.4g (|ref| max %.3g)" % (err, ref.abs().max()))
+    assert err < 8e-2 and ((out.cpu() - ref).pow(2).sum().sqrt() / ref.pow(2).sum().sqrt()).item() < 4e-3
+
+
 # ------------------------------------------------------------------------------------ attention
 @pytest.mark.parametrize("seq", [1, 64, 77, 129, 180, 256, 281, 400, 401])
 def test_window_attention(lib, seq):

@@ -227,6 +227,7 @@ class _Workspace:
         self.ao = torch.empty(rows, C, **bf)
         self.hid = torch.empty(rows, eng.Hp, **bf)
         self.T = torch.empty(rows, C, device=dev, dtype=torch.float32)   # packed slow+rep residual stream
+        self.stats = torch.zeros(rows, 2, device=dev, dtype=torch.int64)   # sub-LN fixed-point [sum, sum sq] per MLP row
         self.stage = {}                                # (stage, ws) -> selection tables
 
 
@@ -263,10 +264,12 @@ class _Engine:
                 bqkv=torch.cat([qb, zeros, vb]).contiguous(),
                 wproj=b16(a.proj.weight), bproj=f32(a.proj.bias),
                 w12=w12.to(torch.bfloat16).contiguous(), b12=b12,
-                lnw=F.pad(f32(b.mlp.ffn_ln.weight), (0, self.Hp - self.Hd)).contiguous(),
-                lnb=F.pad(f32(b.mlp.ffn_ln.bias), (0, self.Hp - self.Hd)).contiguous(),
-                w3=F.pad(f32(b.mlp.w3.weight), (0, self.Hp - self.Hd)).to(torch.bfloat16).contiguous(),
-                b3=f32(b.mlp.w3.bias), ft=ft,
+                # SwiGLU sub-LN (eva_vit.py:48) folded into the w3 GEMM: w3g = W3 * gamma (columns),
+                # u3 = W3 gamma, c3 = W3 beta + b3; the epilogue applies rstd * acc - rstd * mean * u3 + c3
+                w3=F.pad(f32(b.mlp.w3.weight) * f32(b.mlp.ffn_ln.weight)[None, :],
+                         (0, self.Hp - self.Hd)).to(torch.bfloat16).contiguous(),
+                u3=(f32(b.mlp.w3.weight) @ f32(b.mlp.ffn_ln.weight)).contiguous(),
+                b3=(f32(b.mlp.w3.weight) @ f32(b.mlp.ffn_ln.bias) + f32(b.mlp.w3.bias)).contiguous(), ft=ft,
                 cos=f32(a.rope.freqs_cos).reshape(ft, ft, -1)[:, 0, 0:32:2].contiguous(),
                 sin=f32(a.rope.freqs_sin).reshape(ft, ft, -1)[:, 0, 0:32:2].contiguous(),
             ))
@@ -284,6 +287,8 @@ class _Engine:
                 b_o4=F.pad(f32(s.out_conv[4].bias), (0, 6)).contiguous(),
             ))
         self.ws_cache = {}
+        self.side = torch.cuda.Stream(device=device)      # query folding / image-level top-k overlap the blocks
+        self.seed_t = torch.zeros(1, device=device, dtype=torch.int64)   # forward counter (Gumbel seed, graph-safe)
 
     # -- helpers ---------------------------------------------------------------------------
     def workspace(self, V, H, W):
@@ -320,9 +325,10 @@ class _Engine:
 
     # -- MLP shared by both block kinds ----------------------------------------------------------
     def _mlp(self, bp, wsp, M, **resid_kw):
-        L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid)
-        L.subln(wsp.hid, wsp.hid, bp["lnw"], bp["lnb"], M, self.Hd, self.Hp, LN_EPS)
-        L.gemm(wsp.hid, bp["w3"], L.EPI_RESID, M=M, bias=bp["b3"], ldo=self.C, **resid_kw)
+        """eva_vit.py:44-51.  wsp.stats rows [0, M) must be zero on entry (the norm2 launch zeroes them)."""
+        L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats)
+        L.gemm(wsp.hid, bp["w3"], L.EPI_RESID, M=M, bias=bp["b3"], ldo=self.C, row_stats=wsp.stats, ln_u=bp["u3"],
+               ln_n=self.Hd, ln_eps=LN_EPS, **resid_kw)
 
     def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots):
         C = self.C
@@ -340,7 +346,7 @@ class _Engine:
         self._qkv_attn(bp, wsp, Mw, w["nW"], w["n"], None, w["n"])
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mw, bias=bp["bproj"], out=X, ldo=C, resid=X,
                resid_map=w["map"], out_map=w["map"])
-        L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS)
+        L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
         self._mlp(bp, wsp, VN, out=X, resid=X)
 
     def select_windows(self, stage, score, ratio, wsp):
@@ -376,24 +382,34 @@ class _Engine:
         self._qkv_attn(bp, wsp, Mp, nW, k + 1, t["rope_rows"], 0)
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mp, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
                resid_map=t["tok_map"], out_alt=wsp.T)                                  # t1 = t + attn
-        L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mp, C, LN_EPS)
+        L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mp, C, LN_EPS, zero_stats=wsp.stats)
         self._mlp(bp, wsp, Mp, out=X, resid=wsp.T, out_map=t["tok_map"], out_alt=wsp.T)   # t2 -> image rows
         L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C)
 
     # -- scorers ----------------------------------------------------------------------------
-    def score_stage(self, j, sel_mod, X, mask_prev, wsp, q_kw, prev_exists, gumbel, seed):
+    def fold_queries(self, j, sel_mod, q_kw, V):
+        """Motion-aware query encoding + folding of the query bank into (A, c) for stage j.  Depends only
+        on the history queries, not on the image, so the caller runs it on the side stream."""
+        sp = self.sel[j]
+        q = sel_mod.motion_aware_queries(**q_kw)
+        Bf = q.shape[0]
+        assert V % Bf == 0, "views*batch must be a multiple of the query batch (toc3d_utils.py:240)"
+        A = torch.empty(Bf, 2, self.C, device=self.device); c = torch.empty(Bf, 2, device=self.device)
+        L.score_fold_queries(q.float(), sp["w_in"], sp["b_in"], sp["w_agg"], sp["b_agg"], sel_mod.scale, A, c)
+        return A, c
+
+    def score_stage(self, j, X, mask_prev, wsp, folded, gumbel):
+        """folded = (A, c) from fold_queries when the previous frame exists, else None (first-frame scorer)."""
         dev, V, N, C = self.device, wsp.V, wsp.N, self.C
         sp = self.sel[j]
         pred = torch.empty(V, N, 2, device=dev)
         score = torch.empty(V, N, device=dev)
         mask = torch.empty(V, N, device=dev)
-        if prev_exists:
-            q = sel_mod.motion_aware_queries(**q_kw)
-            Bf = q.shape[0]
-            assert V % Bf == 0, "views*batch must be a multiple of the query batch (toc3d_utils.py:240)"
-            A = torch.empty(Bf, 2, C, device=dev); c = torch.empty(Bf, 2, device=dev)
-            L.score_fold_queries(q.float(), sp["w_in"], sp["b_in"], sp["w_agg"], sp["b_agg"], sel_mod.scale, A, c)
-            L.score_tokens(X, mask_prev, A, c, V, N, C, V // Bf, gumbel, seed, pred, score, mask)
+        seed = j
+        if folded is not None:
+            A, c = folded
+            L.score_tokens(X, mask_prev, A, c, V, N, C, V // A.shape[0], gumbel, seed, pred, score, mask,
+                           seed_dev=self.seed_t)
         else:
             VN = V * N
             src = X
@@ -411,7 +427,7 @@ class _Engine:
             logits8 = torch.empty(VN, 8, device=dev)
             L.gemm(y2, sp["w_o4"], L.EPI_LINEAR, M=VN, bias=sp["b_o4"], out=logits8, out_f32=True)
             logits = logits8[:, :2].contiguous()
-            L.score_finish(logits, VN, gumbel, seed, pred, score, mask)
+            L.score_finish(logits, VN, gumbel, seed, pred, score, mask, seed_dev=self.seed_t)
         return pred, score, mask
 
 
@@ -436,6 +452,9 @@ class _EvaBase(nn.Module):
         self.rope_win = _Rope(hh, pt_hw_seq_len, window_size if intp_freq else None)
         self.rope_glb = _Rope(hh, pt_hw_seq_len, img_size // patch_size if intp_freq else None)
         self._engine = None
+        self._graphs = {}
+        self.use_cuda_graph = True     # replay the whole forward as one CUDA graph per (shape, prev_exists)
+        self.graph_outputs = "clone"   # "static": return the graph's own buffers (overwritten by the next call)
 
     def _init_weights(self):
         """toc3d_eva_vit.py:214-228 / eva_vit.py:396-407."""
@@ -452,16 +471,40 @@ class _EvaBase(nn.Module):
 
     # any change of the parameters invalidates the repacked device copies
     def _apply(self, fn, *a, **k):
-        self._engine = None
+        self.refresh_weights()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._engine = None
+        self.refresh_weights()
         return super().load_state_dict(*a, **k)
 
     def refresh_weights(self):
-        """Call after mutating parameters in place (the engine holds repacked bf16 copies)."""
+        """Call after mutating parameters in place (the engine holds repacked bf16 copies, the captured
+        graphs hold pointers into it)."""
         self._engine = None
+        self._graphs = {}
+
+    def _graphed(self, key, inputs, core):
+        """Run core(static_inputs) -> tuple of tensors through a CUDA graph captured once per `key`.
+        inputs: dict name -> CUDA tensor (copied into the graph's static input buffers before replay)."""
+        entry = self._graphs.get(key)
+        if entry is None:
+            static_in = {k: v.clone() for k, v in inputs.items()}
+            core(static_in)                         # eager warm-up: lazy inits, workspaces, selection tables
+            g = torch.cuda.CUDAGraph()
+            l0 = L.launch_count
+            with torch.cuda.graph(g):
+                out = core(static_in)
+            entry = (g, static_in, out, L.launch_count - l0)
+            self._graphs[key] = entry
+        g, static_in, out, n_launch = entry
+        for k, v in inputs.items():
+            static_in[k].copy_(v, non_blocking=True)
+        g.replay()
+        L.launch_count += n_launch
+        if self.graph_outputs == "static":
+            return out
+        return tuple(t.clone() for t in out)
 
     def _get_engine(self, x):
         if not x.is_cuda:
@@ -514,13 +557,21 @@ class EVA_ViT(_EvaBase):
         x = self._prep_img(x)
         eng = self._get_engine(x)
         V, _, Hi, Wi = x.shape
-        wsp = eng.workspace(V, Hi // 16, Wi // 16)
-        X = eng.stem(x, wsp)
+
+        def core(t):
+            wsp = eng.workspace(V, Hi // 16, Wi // 16)
+            X = eng.stem(t["x"], wsp)
+            for i in range(len(self.blocks)):
+                eng.dense_block(i, X, wsp)
+            return (X,)
+
         GLOBAL_TIMER.event_start("StreamPETR-EVA-ViT/backbone")
-        for i in range(len(self.blocks)):
-            eng.dense_block(i, X, wsp)
+        if self.use_cuda_graph:
+            (X,) = self._graphed(("dense", V, Hi, Wi), {"x": x}, core)
+        else:
+            (X,) = core({"x": x})
         GLOBAL_TIMER.event_end("StreamPETR-EVA-ViT/backbone")
-        return {self._out_features[0]: X.view(V, wsp.H, wsp.W, -1).permute(0, 3, 1, 2)}
+        return {self._out_features[0]: X.view(V, Hi // 16, Wi // 16, -1).permute(0, 3, 1, 2)}
 
 
 @_register
@@ -595,39 +646,81 @@ class ToC3DEVAViT(_EvaBase):
         x = self._prep_img(x)
         eng = self._get_engine(x)
         V, _, Hi, Wi = x.shape
+        H, W = Hi // 16, Wi // 16
+        prev = bool(prev_exists) if prev_exists is not None else False
+        q_names = ("temp_queries", "temp_ref_points", "temp_vel", "temp_timestamp", "temp_ego_pose", "ego_pose_inv")
+        q_vals = (temp_queries, temp_ref_points, temp_vel, temp_timestamp, temp_ego_pose, ego_pose_inv)
+        tensors = {"x": x}
+        if prev:
+            assert ego_pose_inv is not None                                              # toc3d_utils.py:345
+            tensors.update({k: v.contiguous() for k, v in zip(q_names, q_vals)})
+        nst = len(self.pruning_loc)
+
+        def core(t):
+            q_kw = {k: t[k] for k in q_names} if prev else None
+            return self._forward_core(eng, t["x"], q_kw, gumbel_noise, teacher_scores, tap)
+
+        GLOBAL_TIMER.event_start("ToC3D-StreamPETR-EVAViT/backbone")
+        if self.use_cuda_graph and gumbel_noise is None and teacher_scores is None and tap is None:
+            key = ("toc3d", prev) + tuple((k, tuple(v.shape), v.dtype) for k, v in tensors.items())
+            flat = self._graphed(key, tensors, core)
+        else:
+            flat = core(tensors)
+        GLOBAL_TIMER.event_end("ToC3D-StreamPETR-EVAViT/backbone")
+        X, masks, keeps, drops = flat[0], list(flat[1:1 + nst]), list(flat[1 + nst:1 + 2 * nst]), list(flat[1 + 2 * nst:])
+        outputs = {self._out_features[0]: X.view(V, H, W, -1).permute(0, 3, 1, 2)}
+        none_if_empty = lambda l: l if len(l) else None
+        return ToC3DViTReturnType(outputs, none_if_empty([m.view(V, H, W, 1) for m in masks]), None,
+                                  keep_idx=none_if_empty(keeps), drop_idx=none_if_empty(drops), aux_outputs=None)
+
+    def _forward_core(self, eng, x, q_kw, gumbel_noise, teacher_scores, tap):
+        """The launch sequence of one forward (toc3d_eva_vit.py:243-310); capturable in a CUDA graph.
+        Returns (X, *masks, *keep_idx, *drop_idx)."""
+        V, _, Hi, Wi = x.shape
         wsp = eng.workspace(V, Hi // 16, Wi // 16)
         H, W = wsp.H, wsp.W
+        N = H * W
+        cur, side = torch.cuda.current_stream(), eng.side
+        nst = len(self.pruning_loc)
+        # side stream: the history queries do not depend on the image -> encode + fold all stages up front
+        side.wait_stream(cur)
+        folded = [None] * nst
+        with torch.cuda.stream(side):
+            eng.seed_t.add_(1)
+            if q_kw is not None:
+                for j in range(nst):
+                    folded[j] = eng.fold_queries(j, self.score_predictor[j], q_kw, V)
+            ev_q = torch.cuda.Event()
+            ev_q.record(side)
         X = eng.stem(x, wsp)
-        prev = bool(prev_exists) if prev_exists is not None else False
-        q_kw = dict(temp_queries=temp_queries, temp_ref_points=temp_ref_points, temp_vel=temp_vel,
-                    temp_timestamp=temp_timestamp, temp_ego_pose=temp_ego_pose, ego_pose_inv=ego_pose_inv)
         masks, keep_idxes, drop_idxes, scores_l = [], [], [], []
         mask_prev, stage = None, -1
         if tap is not None:
             tap["stem"] = X.clone()
             tap["block_out"] = []
-        GLOBAL_TIMER.event_start("ToC3D-StreamPETR-EVAViT/backbone")
         for i, blk in enumerate(self.blocks):
             if i in self.pruning_loc:
                 stage += 1
                 g = None
                 if gumbel_noise is not None:
                     g = gumbel_noise[stage].to(device=x.device, dtype=torch.float32).contiguous()
-                self.gumbel_seed += 1
-                pred, score, mask = eng.score_stage(stage, self.score_predictor[stage], X, mask_prev, wsp, q_kw, prev,
-                                                    g, self.gumbel_seed)
+                if stage == 0:
+                    cur.wait_event(ev_q)
+                pred, score, mask = eng.score_stage(stage, X, mask_prev, wsp, folded[stage], g)
                 if tap is not None:
                     tap.setdefault("scores_raw", []).append(score.view(V, H, W).clone())
                 if teacher_scores is not None:
-                    score = teacher_scores[stage].to(x.device).reshape(V, H * W).contiguous()
-                N = H * W
+                    score = teacher_scores[stage].to(x.device).reshape(V, N).contiguous()
                 k = int(N * self.token_ratio[stage])
                 keep = torch.empty(V, k, device=x.device, dtype=torch.int64)
                 drop = torch.empty(V, N - k, device=x.device, dtype=torch.int64)
-                L.topk_split(score, V, N, k, keep, drop)
+                # the image-level sort only feeds the returned keep/drop lists -> off the critical path
+                side.wait_stream(cur)
+                with torch.cuda.stream(side):
+                    L.topk_split(score, V, N, k, keep, drop)
                 eng.select_windows(stage, score, self.token_ratio[stage], wsp)
                 mask_prev = mask
-                masks.append(mask.view(V, H, W, 1))
+                masks.append(mask)
                 keep_idxes.append(keep)
                 drop_idxes.append(drop)
                 scores_l.append(score.view(V, H, W))
@@ -637,13 +730,10 @@ class ToC3DEVAViT(_EvaBase):
                 eng.dense_block(i, X, wsp)
             if tap is not None:
                 tap["block_out"].append(X.clone())
-        GLOBAL_TIMER.event_end("ToC3D-StreamPETR-EVAViT/backbone")
+        cur.wait_stream(side)
         if tap is not None:
             tap["scores"] = scores_l
-        outputs = {self._out_features[0]: X.view(V, H, W, -1).permute(0, 3, 1, 2)}
-        none_if_empty = lambda l: l if len(l) else None
-        return ToC3DViTReturnType(outputs, none_if_empty(masks), None, keep_idx=none_if_empty(keep_idxes),
-                                  drop_idx=none_if_empty(drop_idxes), aux_outputs=None)
+        return (X, *masks, *keep_idxes, *drop_idxes)
 
     def loss(self, pred_masks, gt_bboxes, *args, **kwargs):
         """toc3d_eva_vit.py:312-326 (training only; delegates to the mmdet3d-built loss when present)."""

@@ -48,7 +48,16 @@ struct EpiParams {
   float q_scale;
   const float* cos_axis;
   const float* sin_axis;
+  long long* row_stats;
+  const float* ln_u;
+  int ln_n;
+  float ln_eps;
 };
+
+// Folded-LayerNorm row statistics are accumulated as int64 fixed point: sum * 2^30 (|sum| < 8.6e9,
+// step 9e-10) and sum of squares * 2^26 (< 1.4e11, step 1.5e-8; the LN eps is 1e-6 * n).
+constexpr double STAT_SUM_SCALE = 1073741824.0;
+constexpr double STAT_SQ_SCALE = 67108864.0;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
@@ -88,11 +97,20 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
   const bool my_row_ok = (m0 + lane) < M;
 
   int rr_t = -1, or_t = -1, pos_t = 0;
+  float lnA_t = 1.0f, lnB_t = 0.0f;    // folded LayerNorm of the A rows: y = lnA * acc + lnB * u[col] + bias[col]
   if constexpr (EPI == TOC3D_EPI_RESID) {
     if (my_row_ok) {
       const int row = m0 + lane;
       rr_t = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
       or_t = ep.out_map ? ep.out_map[row] : row;
+      if (ep.row_stats != nullptr) {
+        const longlong2 st = *reinterpret_cast<const longlong2*>(ep.row_stats + 2 * (size_t)row);
+        const double inv_n = 1.0 / (double)ep.ln_n;
+        const double mean = (double)st.x * (1.0 / STAT_SUM_SCALE) * inv_n;
+        const double var = fmax((double)st.y * (1.0 / STAT_SQ_SCALE) * inv_n - mean * mean, 0.0);
+        lnA_t = rsqrtf((float)var + ep.ln_eps);
+        lnB_t = -lnA_t * (float)mean;
+      }
     }
   }
   if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
@@ -107,6 +125,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
   if constexpr (EPI == TOC3D_EPI_SWIGLU) {
     // this warp's 128 GEMM columns = 2 blocks of [32 x w1 | 32 x w2]; 16 hidden columns per step
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+    float st_sum = 0.f, st_sq = 0.f;     // this row's sum / sum of squares of the bf16-rounded hidden values
 #pragma unroll 1
     for (int st = 0; st < 4; ++st) {
       const int blk = st >> 1, sub = st & 1;
@@ -129,6 +148,14 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         h[4 * j + 2] = silu(__uint_as_float(v1[4 * j + 2]) + b1.z) * (__uint_as_float(v2[4 * j + 2]) + b2.z);
         h[4 * j + 3] = silu(__uint_as_float(v1[4 * j + 3]) + b1.w) * (__uint_as_float(v2[4 * j + 3]) + b2.w);
       }
+      if (ep.row_stats != nullptr) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          h[i] = __bfloat162float(__float2bfloat16_rn(h[i]));   // statistics of exactly what the next GEMM reads
+          st_sum += h[i];
+          st_sq += h[i] * h[i];
+        }
+      }
       stage_rows16(stage, lane, h);
       __syncwarp();
       const int hcol = ((n0 + blk * 64) >> 1) + sub * SUB + 4 * cseg;   // hidden column of this lane
@@ -146,6 +173,12 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         }
       }
       __syncwarp();
+    }
+    if (ep.row_stats != nullptr && my_row_ok) {
+      // fixed-point (integer) atomics: the accumulated statistics do not depend on arrival order
+      unsigned long long* dst = reinterpret_cast<unsigned long long*>(ep.row_stats + 2 * (size_t)(m0 + lane));
+      atomicAdd(dst, (unsigned long long)__float2ll_rn(st_sum * (float)STAT_SUM_SCALE));
+      atomicAdd(dst + 1, (unsigned long long)__float2ll_rn(st_sq * (float)STAT_SQ_SCALE));
     }
     return;
   }
@@ -171,6 +204,8 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
     if constexpr (EPI == TOC3D_EPI_RESID) {
       float4 r[4];
       int orow[4];
+      float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ep.ln_u != nullptr && col_ok) u4 = __ldg(reinterpret_cast<const float4*>(ep.ln_u + col));
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         const int row = it * 8 + rin;
@@ -186,10 +221,12 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       for (int it = 0; it < 4; ++it) {
         const int row = it * 8 + rin;
         const float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+        const float la = __shfl_sync(0xffffffffu, lnA_t, row);
+        const float lb = __shfl_sync(0xffffffffu, lnB_t, row);
         if (col_ok && orow[it] != -1) {
           float4 o;
-          o.x = r[it].x + (a.x + b.x); o.y = r[it].y + (a.y + b.y);
-          o.z = r[it].z + (a.z + b.z); o.w = r[it].w + (a.w + b.w);
+          o.x = r[it].x + (fmaf(la, a.x, lb * u4.x) + b.x); o.y = r[it].y + (fmaf(la, a.y, lb * u4.y) + b.y);
+          o.z = r[it].z + (fmaf(la, a.z, lb * u4.z) + b.z); o.w = r[it].w + (fmaf(la, a.w, lb * u4.w) + b.w);
           float* dst = (orow[it] >= 0) ? reinterpret_cast<float*>(ep.out) + (size_t)orow[it] * ep.ldo
                                        : ep.out_alt + (size_t)(m0 + row) * ep.ldo;
           *reinterpret_cast<float4*>(dst + col) = o;
@@ -447,6 +484,10 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   ep.resid = e->resid; ep.resid_map = e->resid_map; ep.resid_mod = e->resid_mod; ep.out_map = e->out_map;
   ep.out_alt = e->out_alt; ep.rope_rows = e->rope_rows; ep.rope_slots = e->rope_slots; ep.rope_ft = e->rope_ft;
   ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
+  ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
+  if (kind == TOC3D_EPI_RESID && ep.row_stats != nullptr)
+    TOC3D_REQUIRE(ep.ln_u != nullptr && ep.ln_n > 0 && ((uintptr_t)ep.ln_u & 15) == 0 && ((uintptr_t)ep.row_stats & 15) == 0,
+                  kErrBadArg, "toc3d_gemm_bf16: folded LayerNorm needs ln_u (16-byte aligned), ln_n > 0");
   TOC3D_REQUIRE(ep.ldo > 0 && ep.ldo % 4 == 0 && N % 4 == 0, kErrBadArg,
                 "toc3d_gemm_bf16: N and ldo must be positive multiples of 4 (vector epilogue), got N=%d ldo=%d", N, ep.ldo);
   TOC3D_REQUIRE(((uintptr_t)ep.out & 15) == 0 && ((uintptr_t)ep.bias & 15) == 0 && ((uintptr_t)ep.resid & 15) == 0 &&

@@ -26,11 +26,12 @@ template <int VPL>  // float4 per lane: C = VPL * 128
 __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const int* __restrict__ row_map, const float* __restrict__ alt,
                       const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
-                      int M, float eps, int pad_mode) {
+                      int M, float eps, int pad_mode, long long* __restrict__ zero_stats) {
   const int C = VPL * 128;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
   const int lane = threadIdx.x & 31;
+  if (zero_stats != nullptr && lane == 0) *reinterpret_cast<longlong2*>(zero_stats + 2 * (size_t)m) = make_longlong2(0, 0);
   int src = row_map ? row_map[m] : m;
   const float* p = nullptr;
   if (src >= 0) p = x + (size_t)src * C;
@@ -126,12 +127,32 @@ subln_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ ou
 }
 
 // ------------------------------------------------------------------------------------------------
-// Total order of torch.sort(descending=True, stable=True): NaN first, then larger values, ties by
-// lower index.  a_before_b == "a ranks strictly ahead of b".
-__device__ __forceinline__ bool ranks_before(float a, int ia, float b, int ib) {
-  const bool an = a != a, bn = b != b;
-  if (an || bn) return an && (!bn || ia < ib);
-  return a > b || (a == b && ia < ib);
+// Total order of torch.sort(descending=True, stable=True): NaN first, then larger values, ties
+// (incl. -0.0 == +0.0) by lower index.  order_key maps a float to a uint32 that is larger for
+// elements that rank earlier, so "a ranks before b" == key_a > key_b || (key_a == key_b && ia < ib).
+__device__ __forceinline__ uint32_t order_key(float a) {
+  if (a != a) return 0xFFFFFFFFu;
+  if (a == 0.0f) a = 0.0f;                       // -0.0 ties with +0.0
+  const uint32_t b = __float_as_uint(a);
+  return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+
+// rank of element i (key ki) among keys[0, n): number of elements ranking strictly before it.
+// n4 = ceil(n / 4) uint4 groups; slots in [n, 4*n4) hold key 0, which never ranks before a real element
+// (order_key >= 0x007FFFFF for every float, -inf included).
+__device__ __forceinline__ int rank_of(const uint32_t* __restrict__ keys, int n4, uint32_t ki, int i) {
+  int rank = 0;
+  const uint4* k4 = reinterpret_cast<const uint4*>(keys);
+#pragma unroll 4
+  for (int g = 0; g < n4; ++g) {
+    const uint4 kj = k4[g];
+    const int j = 4 * g;
+    rank += (kj.x > ki) || (kj.x == ki && j + 0 < i);
+    rank += (kj.y > ki) || (kj.y == ki && j + 1 < i);
+    rank += (kj.z > ki) || (kj.z == ki && j + 2 < i);
+    rank += (kj.w > ki) || (kj.w == ki && j + 3 < i);
+  }
+  return rank;
 }
 
 // One CTA per window, one thread per slot (n = ws*ws <= 1024).
@@ -139,7 +160,7 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
                                    int* __restrict__ slow_idx, int* __restrict__ fast_idx,
                                    float* __restrict__ fast_score, int* __restrict__ tok_map,
                                    int* __restrict__ rope_rows, int* __restrict__ fast_map) {
-  extern __shared__ float s_sc[];
+  __shared__ __align__(16) uint32_t s_key[1024];
   const int n = ws * ws;
   const int nWw = (W + ws - 1) / ws, nWh = (H + ws - 1) / ws;
   const int w = blockIdx.x;
@@ -154,12 +175,12 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
       img_row = (v * H + r) * W + c;
       sc = scores[img_row];
     }
-    s_sc[i] = sc;
   }
+  const uint32_t ki = order_key(sc);
+  s_key[i] = i < n ? ki : 0u;                    // blockDim.x = n rounded up to 32 (a multiple of 4)
   __syncthreads();
   if (i >= n) return;
-  int rank = 0;
-  for (int j = 0; j < n; ++j) rank += ranks_before(s_sc[j], j, sc, i) ? 1 : 0;
+  const int rank = rank_of(s_key, (n + 3) >> 2, ki, i);
   const int nf = n - k;
   if (rank < k) {
     if (slow_idx) slow_idx[(size_t)w * k + rank] = i;
@@ -179,67 +200,86 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
   }
 }
 
-// Image-level stable sort split by rank counting; grid (ceil(N/256), B), scores of one row in smem.
-__global__ void __launch_bounds__(256)
+// Image-level stable sort split by rank counting; grid (ceil(N/128), B), keys of one row in smem.
+__global__ void __launch_bounds__(128)
 topk_split_kernel(const float* __restrict__ scores, int N, int k, long long* __restrict__ keep_idx,
                   long long* __restrict__ drop_idx) {
-  extern __shared__ float s_sc[];
+  extern __shared__ __align__(16) uint32_t s_keys[];
   const int b = blockIdx.y;
   const float* row = scores + (size_t)b * N;
-  for (int j = threadIdx.x; j < N; j += blockDim.x) s_sc[j] = row[j];
+  const int n4 = (N + 3) >> 2;
+  for (int j = threadIdx.x; j < 4 * n4; j += blockDim.x) s_keys[j] = j < N ? order_key(row[j]) : 0u;
   __syncthreads();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const float sc = s_sc[i];
-  int rank = 0;
-  for (int j = 0; j < N; ++j) rank += ranks_before(s_sc[j], j, sc, i) ? 1 : 0;
+  const int rank = rank_of(s_keys, n4, s_keys[i], i);
   if (rank < k) keep_idx[(size_t)b * k + rank] = i;
   else drop_idx[(size_t)b * (N - k) + (rank - k)] = i;
 }
 
 // ------------------------------------------------------------------------------------------------
-// rep[w] = sum_j (s_j / sum s) * x[fast_map[w,j]];  grid (nW, C/128), 128 threads, 1 channel each.
-__global__ void __launch_bounds__(128)
+// rep[w] = sum_j (s_j / sum s) * x[fast_map[w,j]];  grid (nW, C/(128*LV)), 256 threads: warp q owns
+// rows j = q (mod 8) with LV float4 per lane (128*LV channels per CTA), 4 rows in flight; partials meet in smem.
+template <int LV>
+__global__ void __launch_bounds__(256)
 merge_fast_kernel(const float* __restrict__ x, const int* __restrict__ fast_map, const float* __restrict__ fast_score,
                   int n_fast, int k, int C, float* __restrict__ rep_out, float* __restrict__ packed) {
-  __shared__ float s_part[4];
+  __shared__ float s_part[8];
   __shared__ float s_wgt[1024];
   __shared__ int s_row[1024];
+  __shared__ float4 s_acc[8][32 * LV];
+  constexpr int CH = 128 * LV;
   const int w = blockIdx.x;
-  const int ch = blockIdx.y * 128 + threadIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const float* fs = fast_score + (size_t)w * n_fast;
   const int* fm = fast_map + (size_t)w * n_fast;
   float part = 0.f;
-  for (int j = threadIdx.x; j < n_fast; j += 128) {
+  for (int j = threadIdx.x; j < n_fast; j += 256) {
     const float s = fs[j];
     s_wgt[j] = s;
     s_row[j] = fm[j];
     part += s;
   }
   part = warp_sum(part);
-  if ((threadIdx.x & 31) == 0) s_part[threadIdx.x >> 5] = part;
+  if (lane == 0) s_part[warp] = part;
   __syncthreads();
-  const float total = (s_part[0] + s_part[1]) + (s_part[2] + s_part[3]);
-  for (int j = threadIdx.x; j < n_fast; j += 128) s_wgt[j] = s_wgt[j] / total;   // weight = score / sum(score)
-  __syncthreads();
-  float acc = 0.f;
-  int j = 0;
-  for (; j + 4 <= n_fast; j += 4) {
-    float xv[4];
+  const float total = ((s_part[0] + s_part[1]) + (s_part[2] + s_part[3])) + ((s_part[4] + s_part[5]) + (s_part[6] + s_part[7]));
+  const float4* xb = reinterpret_cast<const float4*>(x + blockIdx.y * CH) + lane;
+  const size_t ld4 = (size_t)C >> 2;
+  float4 a[LV];
+#pragma unroll
+  for (int i = 0; i < LV; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j0 = warp; j0 < n_fast; j0 += 32) {
+    float4 v[4][LV];
+    float wg[4];
 #pragma unroll
     for (int u = 0; u < 4; ++u) {
-      const int r = s_row[j + u];
-      xv[u] = r >= 0 ? x[(size_t)r * C + ch] : 0.f;
+      const int j = j0 + 8 * u;
+      const int r = j < n_fast ? s_row[j] : -1;
+      wg[u] = j < n_fast ? s_wgt[j] / total : 0.f;             // weight = score / sum(score)
+#pragma unroll
+      for (int i = 0; i < LV; ++i) v[u][i] = r >= 0 ? xb[(size_t)r * ld4 + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 4; ++u) acc += s_wgt[j + u] * xv[u];
+    for (int u = 0; u < 4; ++u)
+#pragma unroll
+      for (int i = 0; i < LV; ++i) {
+        a[i].x += wg[u] * v[u][i].x; a[i].y += wg[u] * v[u][i].y;
+        a[i].z += wg[u] * v[u][i].z; a[i].w += wg[u] * v[u][i].w;
+      }
   }
-  for (; j < n_fast; ++j) {
-    const int r = s_row[j];
-    acc += s_wgt[j] * (r >= 0 ? x[(size_t)r * C + ch] : 0.f);
+#pragma unroll
+  for (int i = 0; i < LV; ++i) s_acc[warp][lane + 32 * i] = a[i];
+  __syncthreads();
+  if (threadIdx.x < CH) {
+    const float* sa = reinterpret_cast<const float*>(s_acc);
+    float acc = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) acc += sa[q * CH + threadIdx.x];
+    const int ch = blockIdx.y * CH + threadIdx.x;
+    rep_out[(size_t)w * C + ch] = acc;
+    if (packed) packed[((size_t)w * (k + 1) + k) * C + ch] = acc;
   }
-  rep_out[(size_t)w * C + ch] = acc;
-  if (packed) packed[((size_t)w * (k + 1) + k) * C + ch] = acc;
 }
 
 // x[fast_map[w,j]] += packed[rep row of w] - rep[w];  one warp per fast token, float4 lanes.
@@ -311,6 +351,12 @@ __device__ __forceinline__ float gumbel_from_hash(uint64_t seed, uint64_t idx) {
   return -logf(-logf(u));
 }
 
+// effective noise seed = seed + 1000003 * *seed_dev (device-resident call counter, so a captured CUDA
+// graph draws fresh noise on every replay)
+__device__ __forceinline__ uint64_t mix_seed(uint64_t seed, const uint64_t* seed_dev) {
+  return seed_dev ? seed + 1000003ull * (*seed_dev) : seed;
+}
+
 __device__ __forceinline__ void score_tail(float l0, float l1, size_t tok, const float* gumbel, uint64_t seed,
                                            float* pred, float* score, float* mask_out) {
   const float mx = fmaxf(l0, l1);
@@ -332,7 +378,7 @@ __device__ __forceinline__ void score_tail(float l0, float l1, size_t tok, const
 __global__ void __launch_bounds__(256)
 score_tokens_kernel(const float* __restrict__ x, const float* __restrict__ mask_in, const float* __restrict__ A,
                     const float* __restrict__ cvec, int V, int N, int C, int vpf, const float* __restrict__ gumbel,
-                    uint64_t seed, float* __restrict__ pred, float* __restrict__ score, float* __restrict__ mask_out) {
+                    uint64_t seed, const uint64_t* __restrict__ seed_dev, float* __restrict__ pred, float* __restrict__ score, float* __restrict__ mask_out) {
   const size_t tok = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= (size_t)V * N) return;
   const int lane = threadIdx.x & 31;
@@ -350,15 +396,17 @@ score_tokens_kernel(const float* __restrict__ x, const float* __restrict__ mask_
   d1 = warp_sum(d1);
   if (lane == 0) {
     const float mk = mask_in ? mask_in[tok] : 1.0f;
-    score_tail(mk * d0 + cvec[f * 2], mk * d1 + cvec[f * 2 + 1], tok, gumbel, seed, pred, score, mask_out);
+    score_tail(mk * d0 + cvec[f * 2], mk * d1 + cvec[f * 2 + 1], tok, gumbel, mix_seed(seed, seed_dev), pred, score,
+               mask_out);
   }
 }
 
 __global__ void score_finish_kernel(const float* __restrict__ logits, int M, const float* __restrict__ gumbel,
-                                    uint64_t seed, float* pred, float* score, float* mask_out) {
+                                    uint64_t seed, const uint64_t* __restrict__ seed_dev, float* pred, float* score,
+                                    float* mask_out) {
   const int tok = blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= M) return;
-  score_tail(logits[tok * 2], logits[tok * 2 + 1], (size_t)tok, gumbel, seed, pred, score, mask_out);
+  score_tail(logits[tok * 2], logits[tok * 2 + 1], (size_t)tok, gumbel, mix_seed(seed, seed_dev), pred, score, mask_out);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -435,14 +483,14 @@ extern "C" const char* toc3d_last_error(void) { return toc3d::g_err; }
 
 extern "C" int toc3d_layernorm_rows(const float* x, const int32_t* row_map, const float* alt, const float* gamma,
                                     const float* beta, void* out, int32_t M, int32_t C, float eps, int32_t pad_mode,
-                                    void* stream) {
+                                    int64_t* zero_stats, void* stream) {
   TOC3D_REQUIRE(x && gamma && beta && out, kErrBadArg, "toc3d_layernorm_rows: null pointer");
   TOC3D_REQUIRE(M > 0 && C % 128 == 0 && C >= 128 && C <= 4096, kErrBadArg, "toc3d_layernorm_rows: bad shape M=%d C=%d", M, C);
   const int rows_per_block = 8;
   dim3 grid((M + rows_per_block - 1) / rows_per_block), block(256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #define LN_CASE(V)                                                                                                  \
-  case V: layernorm_rows_kernel<V><<<grid, block, 0, ST(stream)>>>(x, row_map, alt, gamma, beta, o, M, eps, pad_mode); break;
+  case V: layernorm_rows_kernel<V><<<grid, block, 0, ST(stream)>>>(x, row_map, alt, gamma, beta, o, M, eps, pad_mode, reinterpret_cast<long long*>(zero_stats)); break;
   switch (C / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12) LN_CASE(16) LN_CASE(32)
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_layernorm_rows: unsupported C=%d", C);
@@ -472,7 +520,7 @@ extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int3
                 "toc3d_window_topk: bad shape V=%d H=%d W=%d ws=%d k=%d", V, H, W, ws, k);
   const int nW = V * ((H + ws - 1) / ws) * ((W + ws - 1) / ws);
   const int threads = ((n + 31) / 32) * 32;
-  window_topk_kernel<<<nW, threads, n * sizeof(float), ST(stream)>>>(scores, V, H, W, ws, k, slow_idx, fast_idx,
+  window_topk_kernel<<<nW, threads, 0, ST(stream)>>>(scores, V, H, W, ws, k, slow_idx, fast_idx,
                                                                       fast_score, tok_map, rope_rows, fast_map);
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -482,8 +530,8 @@ extern "C" int toc3d_topk_split(const float* scores, int32_t B, int32_t N, int32
                                 int64_t* drop_idx, void* stream) {
   TOC3D_REQUIRE(scores && keep_idx && drop_idx, kErrBadArg, "toc3d_topk_split: null pointer");
   TOC3D_REQUIRE(B > 0 && N > 0 && N <= 12288 && k >= 0 && k <= N, kErrBadArg, "toc3d_topk_split: bad shape B=%d N=%d k=%d", B, N, k);
-  dim3 grid((N + 255) / 256, B);
-  topk_split_kernel<<<grid, 256, N * sizeof(float), ST(stream)>>>(scores, N, k, reinterpret_cast<long long*>(keep_idx),
+  dim3 grid((N + 127) / 128, B);
+  topk_split_kernel<<<grid, 128, ((N + 3) / 4) * 16, ST(stream)>>>(scores, N, k, reinterpret_cast<long long*>(keep_idx),
                                                                    reinterpret_cast<long long*>(drop_idx));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -494,8 +542,10 @@ extern "C" int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, 
   TOC3D_REQUIRE(x && fast_map && fast_score && rep_out, kErrBadArg, "toc3d_merge_fast_tokens: null pointer");
   TOC3D_REQUIRE(nW > 0 && n_fast > 0 && n_fast <= 1024 && C % 128 == 0, kErrBadArg,
                 "toc3d_merge_fast_tokens: bad shape nW=%d n_fast=%d C=%d", nW, n_fast, C);
-  dim3 grid(nW, C / 128);
-  merge_fast_kernel<<<grid, 128, 0, ST(stream)>>>(x, fast_map, fast_score, n_fast, k, C, rep_out, packed);
+  if (C % 256 == 0)
+    merge_fast_kernel<2><<<dim3(nW, C / 256), 256, 0, ST(stream)>>>(x, fast_map, fast_score, n_fast, k, C, rep_out, packed);
+  else
+    merge_fast_kernel<1><<<dim3(nW, C / 128), 256, 0, ST(stream)>>>(x, fast_map, fast_score, n_fast, k, C, rep_out, packed);
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -524,21 +574,21 @@ extern "C" int toc3d_score_fold_queries(const float* queries, const float* w_in,
 
 extern "C" int toc3d_score_tokens(const float* x, const float* mask_in, const float* A, const float* c, int32_t V,
                                   int32_t N, int32_t C, int32_t views_per_frame, const float* gumbel, uint64_t seed,
-                                  float* pred, float* score, float* mask_out, void* stream) {
+                                  const uint64_t* seed_dev, float* pred, float* score, float* mask_out, void* stream) {
   TOC3D_REQUIRE(x && A && c, kErrBadArg, "toc3d_score_tokens: null pointer");
   TOC3D_REQUIRE(V > 0 && N > 0 && C % 4 == 0 && views_per_frame > 0 && V % views_per_frame == 0, kErrBadArg,
                 "toc3d_score_tokens: bad shape V=%d N=%d C=%d vpf=%d", V, N, C, views_per_frame);
   const long long toks = (long long)V * N;
   score_tokens_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, ST(stream)>>>(x, mask_in, A, c, V, N, C, views_per_frame, gumbel,
-                                                                          seed, pred, score, mask_out);
+                                                                          seed, seed_dev, pred, score, mask_out);
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
-extern "C" int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed, float* pred,
-                                  float* score, float* mask_out, void* stream) {
+extern "C" int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed,
+                                  const uint64_t* seed_dev, float* pred, float* score, float* mask_out, void* stream) {
   TOC3D_REQUIRE(logits && M > 0, kErrBadArg, "toc3d_score_finish: bad args");
-  score_finish_kernel<<<(M + 255) / 256, 256, 0, ST(stream)>>>(logits, M, gumbel, seed, pred, score, mask_out);
+  score_finish_kernel<<<(M + 255) / 256, 256, 0, ST(stream)>>>(logits, M, gumbel, seed, seed_dev, pred, score, mask_out);
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

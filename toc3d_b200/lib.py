@@ -25,6 +25,7 @@ class Epilogue(ctypes.Structure):
         ("resid", _c_void_p), ("resid_map", _c_void_p), ("resid_mod", _c_int), ("out_map", _c_void_p),
         ("out_alt", _c_void_p), ("rope_rows", _c_void_p), ("rope_slots", _c_int), ("rope_ft", _c_int),
         ("rope_cols", _c_int), ("q_scale", _c_float), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p),
+        ("row_stats", _c_void_p), ("ln_u", _c_void_p), ("ln_n", _c_int), ("ln_eps", _c_float),
     ]
 
 
@@ -35,7 +36,7 @@ _SIGS = {
                          ctypes.POINTER(Epilogue), _c_void_p], _c_int),
     "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
-                              _c_float, _c_int, _c_void_p], _c_int),
+                              _c_float, _c_int, _c_void_p, _c_void_p], _c_int),
     "toc3d_subln_bf16": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
                          _c_int),
     "toc3d_window_topk": ([_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
@@ -48,9 +49,9 @@ _SIGS = {
     "toc3d_score_fold_queries": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int,
                                   _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
-                            _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
-    "toc3d_score_finish": ([_c_void_p, _c_int, _c_void_p, _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p],
-                           _c_int),
+                            _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_score_finish": ([_c_void_p, _c_int, _c_void_p, _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                            _c_void_p], _c_int),
     "toc3d_im2col_patch16": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_cast_f32_to_bf16": ([_c_void_p, _c_void_p, _c_i64, _c_void_p], _c_int),
     "toc3d_mask_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p], _c_int),
@@ -75,7 +76,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 1:
+        if lib.toc3d_abi_version() != 2:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -107,7 +108,7 @@ def _want(t, dtype, name):
 # ------------------------------------------------------------------------------- wrappers
 def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, resid=None,
          resid_map=None, resid_mod=0, out_map=None, out_alt=None, rope_rows=None, rope_slots=0, rope_ft=0,
-         rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None):
+         rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None, row_stats=None, ln_u=None, ln_n=0, ln_eps=0.0):
     """C = A[M,K] @ B[N,K]^T with fused epilogue `kind` (see include/toc3d_b200.h)."""
     _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
     M = A.shape[0] if M is None else M
@@ -120,6 +121,7 @@ def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, ac
     e.out_map = _p(out_map); e.out_alt = _p(out_alt)
     e.rope_rows = _p(rope_rows); e.rope_slots = rope_slots; e.rope_ft = rope_ft; e.rope_cols = rope_cols
     e.q_scale = q_scale; e.cos_axis = _p(cos_axis); e.sin_axis = _p(sin_axis)
+    e.row_stats = _p(row_stats); e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps
     rc = load().toc3d_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, kind,
                                 ctypes.byref(e), _stream())
     _check(rc, "toc3d_gemm_bf16")
@@ -133,10 +135,10 @@ def window_attention(qkv, out, n_windows, seq_len, heads):
     return out
 
 
-def layernorm_rows(x, gamma, beta, out, M, C, eps, row_map=None, alt=None, pad_mode=0):
+def layernorm_rows(x, gamma, beta, out, M, C, eps, row_map=None, alt=None, pad_mode=0, zero_stats=None):
     _want(x, torch.float32, "x"); _want(out, torch.bfloat16, "out")
     _check(load().toc3d_layernorm_rows(_p(x), _p(row_map), _p(alt), _p(gamma), _p(beta), _p(out), M, C, eps,
-                                       pad_mode, _stream()), "toc3d_layernorm_rows")
+                                       pad_mode, _p(zero_stats), _stream()), "toc3d_layernorm_rows")
     return out
 
 
@@ -175,14 +177,15 @@ def score_fold_queries(queries, w_in, b_in, w_agg, b_agg, scale, A_out, c_out):
                                            C, _p(A_out), _p(c_out), _stream()), "toc3d_score_fold_queries")
 
 
-def score_tokens(x, mask_in, A, c, V, N, C, views_per_frame, gumbel, seed, pred, score, mask_out):
+def score_tokens(x, mask_in, A, c, V, N, C, views_per_frame, gumbel, seed, pred, score, mask_out, seed_dev=None):
     _check(load().toc3d_score_tokens(_p(x), _p(mask_in), _p(A), _p(c), V, N, C, views_per_frame, _p(gumbel), seed,
-                                     _p(pred), _p(score), _p(mask_out), _stream()), "toc3d_score_tokens")
+                                     _p(seed_dev), _p(pred), _p(score), _p(mask_out), _stream()),
+           "toc3d_score_tokens")
 
 
-def score_finish(logits, M, gumbel, seed, pred, score, mask_out):
-    _check(load().toc3d_score_finish(_p(logits), M, _p(gumbel), seed, _p(pred), _p(score), _p(mask_out), _stream()),
-           "toc3d_score_finish")
+def score_finish(logits, M, gumbel, seed, pred, score, mask_out, seed_dev=None):
+    _check(load().toc3d_score_finish(_p(logits), M, _p(gumbel), seed, _p(seed_dev), _p(pred), _p(score),
+                                     _p(mask_out), _stream()), "toc3d_score_finish")
 
 
 def im2col_patch16(img, out, V, Hi, Wi):
