@@ -243,37 +243,63 @@ def run_native(args):
         e2e_ms, _ = timed(e2e_step, args.steps)
     clocks = clk.summary()
 
-    # --- roofline of the dominant kernel (the tcgen05 GEMM): one extra instrumented step, events around
-    #     every GEMM launch on the launch stream (kept out of the timed steps so it does not perturb them)
+    # --- roofline of the dominant kernel (the tcgen05 GEMM) + per-kernel breakdown: one extra instrumented
+    #     eager step after the timed region, CUDA events around every C-ABI launch on the launch stream.  A
+    #     device-side sleep is queued first so the host runs ahead and the events bracket kernels, not launch gaps.
     work = algorithmic_work(cfg, kind, hw, V)
     recs = []
-    orig = L.gemm
+    names = ["gemm", "window_attention", "layernorm_rows", "subln", "window_topk", "topk_split", "merge_fast_tokens",
+             "fast_token_update", "score_fold_queries", "score_tokens", "score_finish", "im2col_patch16", "mask_rows",
+             "global_half_mean"]
+    saved = {n: getattr(L, n) for n in names}
+    kind_names = {L.EPI_LINEAR: "linear", L.EPI_QKV_ROPE: "qkv_rope", L.EPI_RESID: "resid", L.EPI_SWIGLU: "swiglu"}
 
-    def traced(A, Bw, kind_, M=None, **kw):
-        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        s.record()
-        r = orig(A, Bw, kind_, M, **kw)
-        e.record()
-        m = A.shape[0] if M is None else M
-        recs.append((s, e, 2.0 * m * Bw.shape[0] * Bw.shape[1]))
-        return r
-    L.gemm = traced
+    def wrap(name, fn):
+        def traced(*a, **kw):
+            s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            s.record()
+            r = fn(*a, **kw)
+            e.record()
+            label, fl = name, 0.0
+            if name == "gemm":
+                A_, Bw = a[0], a[1]
+                m = kw.get("M") if kw.get("M") is not None else (a[3] if len(a) > 3 and a[3] is not None else A_.shape[0])
+                fl = 2.0 * m * Bw.shape[0] * Bw.shape[1]
+                label = "gemm_" + kind_names[a[2]] + ("_lnfold" if kw.get("ln_u") is not None else "")
+            recs.append((label, s, e, fl))
+            return r
+        return traced
+    for n in names:
+        setattr(L, n, wrap(n, saved[n]))
     model.use_cuda_graph = False          # the timed steps replay a CUDA graph; this one launches eagerly
+    torch.cuda.synchronize()
+    torch.cuda._sleep(int(40e6))
     forward(res)
     torch.cuda.synchronize()
     model.use_cuda_graph = True
-    L.gemm = orig
-    g_ms = sum(s.elapsed_time(e) for s, e, _ in recs)
-    g_fl = sum(f for _, _, f in recs)
+    for n in names:
+        setattr(L, n, saved[n])
+    breakdown = {}
+    for label, s, e, fl in recs:
+        b = breakdown.setdefault(label, {"n": 0, "ms": 0.0, "flops": 0.0})
+        b["n"] += 1; b["ms"] += s.elapsed_time(e); b["flops"] += fl
+    for b in breakdown.values():
+        b["ms"] = round(b["ms"], 4)
+        fl = b.pop("flops")
+        if fl:
+            b["tflops"] = round(fl / (b["ms"] * 1e-3) / 1e12, 1)
+    g = [(s, e, fl) for label, s, e, fl in recs if label.startswith("gemm")]
+    g_ms = sum(s.elapsed_time(e) for s, e, _ in g)
+    g_fl = sum(f for _, _, f in g)
     peaks = load_peaks()
     step_ms = total_ms / args.steps
     ach = g_fl / (g_ms * 1e-3) / 1e12
     roofline = {"bound": "tensor", "kernel": "toc3d::gemm::gemm_kernel (tcgen05, all epilogues)",
                 "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
                 "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained",
-                "launches_per_step": len(recs), "avg_launch_us": g_ms * 1e3 / max(1, len(recs)),
-                "gemm_share_of_step": g_ms / step_ms, "measured": "one instrumented step after the timed region",
-                "whole_step_tflops": work["flops"] / (step_ms * 1e-3) / 1e12}
+                "launches_per_step": len(g), "avg_launch_us": g_ms * 1e3 / max(1, len(g)),
+                "gemm_share_of_step": g_ms / step_ms, "measured": "one instrumented eager step after the timed region",
+                "whole_step_tflops": work["flops"] / (step_ms * 1e-3) / 1e12, "breakdown": breakdown}
 
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)

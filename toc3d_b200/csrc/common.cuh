@@ -83,15 +83,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug traps (after ~4 s) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  while (!mbar_try_wait(bar, parity)) {
-    uint64_t t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 4000000000ull) {
-      printf("toc3d: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
-      __trap();
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    if (mbar_try_wait(bar, parity)) return;
+    if ((spin & 0x3FFFu) == 0) {          // the (slow) timer is only consulted every 16384 polls
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      else if (t1 - t0 > 4000000000ull) {
+        printf("toc3d: mbarrier wait timed out (block %d thread %d parity %u)\n", blockIdx.x, threadIdx.x, parity);
+        __trap();
+      }
     }
   }
 }

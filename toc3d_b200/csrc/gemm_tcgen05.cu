@@ -21,9 +21,9 @@ constexpr int B_BYTES = BN * BK * 2;
 constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
 constexpr int NUM_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;                    // 2 accumulator buffers x 256 fp32 columns
-constexpr int ROPE_MAX_FT = 32;
+constexpr int ROPE_MAX_FT = 256;
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;  // 196608
-constexpr int SMEM_AUX = 256 + 2 * ROPE_MAX_FT * 16 * 4 + 8 * 32 * 20 * 4;   // barriers, RoPE tables, epilogue staging
+constexpr int SMEM_AUX = 256 + 8 * 32 * 32 * 4;   // barriers + epilogue staging (8 warps x 32 rows x 32 fp32)
 constexpr int SMEM_BYTES = SMEM_TILES + SMEM_AUX + 1024;  // + alignment slack
 
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10),
@@ -60,110 +60,87 @@ constexpr double STAT_SUM_SCALE = 1073741824.0;
 constexpr double STAT_SQ_SCALE = 67108864.0;
 
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float silu(float x) { return x / (1.0f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------
 // Epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) and column half ((w - 2) / 4) of the
-// 128 x 256 accumulator.  Each 32-row x 16-column sub-chunk goes TMEM -> registers (thread = row)
-// -> padded smem staging -> "coalesced domain" (4 lanes x float4 per row, 8 rows per instruction),
-// where bias / RoPE / residual / activation are applied and global memory is touched with
-// contiguous 64-byte row segments instead of one 16-byte piece per row.
-constexpr int SUB = 16;            // columns per staged sub-chunk
-constexpr int STG_LD = SUB + 4;    // padded staging row (floats): conflict-free for the mappings below
+// 128 x 256 accumulator, processed as 4 chunks of 32 columns.  Each chunk goes TMEM -> registers
+// (thread = row) -> XOR-swizzled smem staging (4 KB per warp, conflict-free both ways) -> "coalesced
+// domain": 8 lanes x float4 cover the 32 columns of one row, 4 rows per instruction, 8 independent
+// iterations per chunk.  Bias / RoPE / residual / activation are applied there, so global memory
+// sees contiguous 128-byte (fp32) or 64-byte (bf16) row segments.  The TMEM load of chunk c+1 and
+// the residual loads of chunk c+1 are issued before chunk c is processed.
+constexpr int CHUNK = 32;          // columns per staged chunk
 constexpr int EPI_WARPS = 8;
+constexpr int STAGE_FLOATS = 32 * CHUNK;   // per warp
 
-__device__ __forceinline__ void tmem_ld_32x16(uint32_t taddr, uint32_t (&v)[16]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
-        "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
-      : "r"(taddr)
-      : "memory");
-}
-
-__device__ __forceinline__ void stage_rows16(float* stage, int lane, const float (&f)[16]) {
-  float4* d = reinterpret_cast<float4*>(stage + lane * STG_LD);
+__device__ __forceinline__ void stage_rows32(float* stage, int lane, const float (&f)[32]) {
+  float4* d = reinterpret_cast<float4*>(stage) + lane * 8;
 #pragma unroll
-  for (int j = 0; j < 4; ++j) d[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  for (int j = 0; j < 8; ++j) d[j ^ (lane & 7)] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+}
+__device__ __forceinline__ float4 stage_read(const float* stage, int row, int cseg) {
+  return reinterpret_cast<const float4*>(stage)[row * 8 + (cseg ^ (row & 7))];
+}
+__device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&f)[32]) {
+  uint32_t v[32];
+  tmem_ld_32x32(taddr, v);
+  tmem_ld_wait();
+#pragma unroll
+  for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
 }
 
-template <int EPI>
+template <int EPI, bool LNF>
 __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int n0, int M, int N,
-                                                   float* stage, const float* s_cos, const float* s_sin, int lane) {
-  // coalesced-domain coordinates: rows {rin, rin+8, rin+16, rin+24}, columns 4*cseg..4*cseg+3 of the sub-chunk
-  const int rin = ((lane >> 2) & 1) * 4 + (lane >> 3);
-  const int cseg = lane & 3;
+                                                   float* stage, int lane) {
+  // coalesced-domain coordinates: rows {rin, rin+4, ..., rin+28}, columns 4*cseg..4*cseg+3 of the chunk
+  const int rin = lane >> 3;
+  const int cseg = lane & 7;
   const bool my_row_ok = (m0 + lane) < M;
 
-  int rr_t = -1, or_t = -1, pos_t = 0;
-  float lnA_t = 1.0f, lnB_t = 0.0f;    // folded LayerNorm of the A rows: y = lnA * acc + lnB * u[col] + bias[col]
-  if constexpr (EPI == TOC3D_EPI_RESID) {
-    if (my_row_ok) {
-      const int row = m0 + lane;
-      rr_t = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
-      or_t = ep.out_map ? ep.out_map[row] : row;
-      if (ep.row_stats != nullptr) {
-        const longlong2 st = *reinterpret_cast<const longlong2*>(ep.row_stats + 2 * (size_t)row);
-        const double inv_n = 1.0 / (double)ep.ln_n;
-        const double mean = (double)st.x * (1.0 / STAT_SUM_SCALE) * inv_n;
-        const double var = fmax((double)st.y * (1.0 / STAT_SQ_SCALE) * inv_n - mean * mean, 0.0);
-        lnA_t = rsqrtf((float)var + ep.ln_eps);
-        lnB_t = -lnA_t * (float)mean;
-      }
-    }
-  }
-  if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
-    if (my_row_ok) {
-      const int row = m0 + lane;
-      const int t = ep.rope_rows ? ep.rope_rows[row] : (row % ep.rope_slots);
-      const int r = t / ep.rope_ft;
-      pos_t = (r << 16) | (t - r * ep.rope_ft);
-    }
-  }
-
   if constexpr (EPI == TOC3D_EPI_SWIGLU) {
-    // this warp's 128 GEMM columns = 2 blocks of [32 x w1 | 32 x w2]; 16 hidden columns per step
+    // this warp's 128 GEMM columns = 2 blocks of [32 x w1 | 32 x w2] -> 2 x 32 hidden columns
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
     float st_sum = 0.f, st_sq = 0.f;     // this row's sum / sum of squares of the bf16-rounded hidden values
 #pragma unroll 1
-    for (int st = 0; st < 4; ++st) {
-      const int blk = st >> 1, sub = st & 1;
-      const int col1 = n0 + blk * 64 + sub * SUB;        // GEMM column of the w1 part
-      if (col1 >= N) break;                               // warp-uniform
-      uint32_t v1[16], v2[16];
-      tmem_ld_32x16(taddr + blk * 64 + sub * SUB, v1);
-      tmem_ld_32x16(taddr + blk * 64 + 32 + sub * SUB, v2);
-      tmem_ld_wait();
-      float h[16];
+    for (int blk = 0; blk < 2; ++blk) {
+      const int col1 = n0 + blk * 64;                    // GEMM column of the w1 part
+      if (col1 >= N) break;                              // warp-uniform
+      float h[32];
+      {
+        uint32_t v1[32], v2[32];
+        tmem_ld_32x32(taddr + blk * 64, v1);
+        tmem_ld_32x32(taddr + blk * 64 + 32, v2);
+        tmem_ld_wait();
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
-        if (ep.bias != nullptr) {
-          b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1) + j);
-          b2 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1 + 32) + j);
+        for (int j = 0; j < 8; ++j) {
+          float4 b1 = make_float4(0.f, 0.f, 0.f, 0.f), b2 = b1;
+          if (ep.bias != nullptr) {
+            b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1) + j);
+            b2 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1 + 32) + j);
+          }
+          h[4 * j + 0] = silu(__uint_as_float(v1[4 * j + 0]) + b1.x) * (__uint_as_float(v2[4 * j + 0]) + b2.x);
+          h[4 * j + 1] = silu(__uint_as_float(v1[4 * j + 1]) + b1.y) * (__uint_as_float(v2[4 * j + 1]) + b2.y);
+          h[4 * j + 2] = silu(__uint_as_float(v1[4 * j + 2]) + b1.z) * (__uint_as_float(v2[4 * j + 2]) + b2.z);
+          h[4 * j + 3] = silu(__uint_as_float(v1[4 * j + 3]) + b1.w) * (__uint_as_float(v2[4 * j + 3]) + b2.w);
         }
-        h[4 * j + 0] = silu(__uint_as_float(v1[4 * j + 0]) + b1.x) * (__uint_as_float(v2[4 * j + 0]) + b2.x);
-        h[4 * j + 1] = silu(__uint_as_float(v1[4 * j + 1]) + b1.y) * (__uint_as_float(v2[4 * j + 1]) + b2.y);
-        h[4 * j + 2] = silu(__uint_as_float(v1[4 * j + 2]) + b1.z) * (__uint_as_float(v2[4 * j + 2]) + b2.z);
-        h[4 * j + 3] = silu(__uint_as_float(v1[4 * j + 3]) + b1.w) * (__uint_as_float(v2[4 * j + 3]) + b2.w);
       }
       if (ep.row_stats != nullptr) {
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
+        for (int i = 0; i < 32; ++i) {
           h[i] = __bfloat162float(__float2bfloat16_rn(h[i]));   // statistics of exactly what the next GEMM reads
           st_sum += h[i];
           st_sq += h[i] * h[i];
         }
       }
-      stage_rows16(stage, lane, h);
+      stage_rows32(stage, lane, h);
       __syncwarp();
-      const int hcol = ((n0 + blk * 64) >> 1) + sub * SUB + 4 * cseg;   // hidden column of this lane
+      const int hcol = (col1 >> 1) + 4 * cseg;            // hidden column of this lane
       if (hcol < ep.ldo) {
 #pragma unroll
-        for (int it = 0; it < 4; ++it) {
-          const int row = it * 8 + rin;
-          const float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+        for (int it = 0; it < 8; ++it) {
+          const int row = it * 4 + rin;
+          const float4 a = stage_read(stage, row, cseg);
           if (m0 + row < M) {
             uint2 u;
             u.x = pack_bf16(a.x, a.y);
@@ -183,86 +160,160 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
     return;
   }
 
-#pragma unroll 1
-  for (int sc = 0; sc < 128 / SUB; ++sc) {
-    const int col0 = n0 + sc * SUB;
-    if (col0 >= N) break;                                 // warp-uniform
-    uint32_t v[16];
-    tmem_ld_32x16(taddr + sc * SUB, v);
-    tmem_ld_wait();
-    float f[16];
+  if constexpr (EPI == TOC3D_EPI_RESID) {
+    // per-row maps and folded-LN coefficients, computed by the lane that owns the row, then
+    // redistributed to the coalesced-domain owners (8 rows per lane)
+    int rr_t = -1, or_t = -1;
+    float lnA_t = 1.0f, lnB_t = 0.0f;    // y = lnA * acc + lnB * u[col] + bias[col]
+    if (my_row_ok) {
+      const int row = m0 + lane;
+      rr_t = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
+      or_t = ep.out_map ? ep.out_map[row] : row;
+      if constexpr (LNF) {
+        const longlong2 st = *reinterpret_cast<const longlong2*>(ep.row_stats + 2 * (size_t)row);
+        const double inv_n = 1.0 / (double)ep.ln_n;
+        const double mean = (double)st.x * (1.0 / STAT_SUM_SCALE) * inv_n;
+        const double var = fmax((double)st.y * (1.0 / STAT_SQ_SCALE) * inv_n - mean * mean, 0.0);
+        lnA_t = rsqrtf((float)var + ep.ln_eps);
+        lnB_t = -lnA_t * (float)mean;
+      }
+    }
+    // 32-bit row indices + masks instead of 16 pointers (register pressure)
+    int o_row[8], r_row[8];
+    uint32_t o_ok = 0, o_alt = 0, r_ok = 0, r_alt = 0;
+    float la[8], lb[8];
 #pragma unroll
-    for (int i = 0; i < 16; ++i) f[i] = __uint_as_float(v[i]);
-    stage_rows16(stage, lane, f);
-    __syncwarp();
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + rin;
+      const int orow = __shfl_sync(0xffffffffu, or_t, row);
+      const int rrow = __shfl_sync(0xffffffffu, rr_t, row);
+      if constexpr (LNF) {
+        la[it] = __shfl_sync(0xffffffffu, lnA_t, row);
+        lb[it] = __shfl_sync(0xffffffffu, lnB_t, row);
+      } else {
+        la[it] = 1.0f;
+        lb[it] = 0.0f;
+      }
+      o_row[it] = orow >= 0 ? orow : m0 + row;
+      r_row[it] = rrow >= 0 ? rrow : m0 + row;
+      if (orow != -1) {
+        o_ok |= 1u << it;
+        if (orow == -2) o_alt |= 1u << it;
+        if (rrow != -1) r_ok |= 1u << it;
+        if (rrow == -2) r_alt |= 1u << it;
+      }
+    }
+    auto load_resid = [&](float4 (&r)[8], int col) {
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (col < N && ((r_ok >> it) & 1u)) {
+          const float* base = ((r_alt >> it) & 1u) ? ep.out_alt : ep.resid;
+          r[it] = *reinterpret_cast<const float4*>(base + (size_t)r_row[it] * ep.ldo + col);
+        }
+      }
+    };
+    float4 r_cur[8], r_nxt[8];
+    load_resid(r_cur, n0 + 4 * cseg);
+    float f[32];
+    tmem_ld_f32x32(taddr, f);
+#pragma unroll
+    for (int ch = 0; ch < 4; ++ch) {
+      const int col0 = n0 + ch * CHUNK;
+      if (col0 >= N) break;                               // warp-uniform
+      stage_rows32(stage, lane, f);
+      __syncwarp();
+      const bool more = ch + 1 < 4 && col0 + CHUNK < N;
+      if (more) {
+        load_resid(r_nxt, col0 + CHUNK + 4 * cseg);
+        tmem_ld_f32x32(taddr + (ch + 1) * CHUNK, f);
+      }
+      const int col = col0 + 4 * cseg;
+      const bool col_ok = col < N;                        // N % 4 == 0
+      float4 b = make_float4(0.f, 0.f, 0.f, 0.f), u4 = b;
+      if (col_ok) {
+        if (ep.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+        if constexpr (LNF) u4 = __ldg(reinterpret_cast<const float4*>(ep.ln_u + col));
+      }
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const float4 a = stage_read(stage, it * 4 + rin, cseg);
+        if (col_ok && ((o_ok >> it) & 1u)) {
+          float4 o;
+          o.x = r_cur[it].x + (fmaf(la[it], a.x, lb[it] * u4.x) + b.x);
+          o.y = r_cur[it].y + (fmaf(la[it], a.y, lb[it] * u4.y) + b.y);
+          o.z = r_cur[it].z + (fmaf(la[it], a.z, lb[it] * u4.z) + b.z);
+          o.w = r_cur[it].w + (fmaf(la[it], a.w, lb[it] * u4.w) + b.w);
+          float* base = ((o_alt >> it) & 1u) ? ep.out_alt : reinterpret_cast<float*>(ep.out);
+          *reinterpret_cast<float4*>(base + (size_t)o_row[it] * ep.ldo + col) = o;
+        }
+      }
+      __syncwarp();
+      if (more) {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) r_cur[it] = r_nxt[it];
+      }
+    }
+    return;
+  }
 
+  // ---- QKV_ROPE and LINEAR
+  int pos_t = 0;
+  if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
+    if (my_row_ok) {
+      const int row = m0 + lane;
+      const int t = ep.rope_rows ? ep.rope_rows[row] : (row % ep.rope_slots);
+      const int r = t / ep.rope_ft;
+      pos_t = (r << 16) | (t - r * ep.rope_ft);
+    }
+  }
+  int pos[8];
+#pragma unroll
+  for (int it = 0; it < 8; ++it) pos[it] = __shfl_sync(0xffffffffu, pos_t, it * 4 + rin);
+  float f[32];
+  tmem_ld_f32x32(taddr, f);
+#pragma unroll
+  for (int ch = 0; ch < 4; ++ch) {
+    const int col0 = n0 + ch * CHUNK;
+    if (col0 >= N) break;                                 // warp-uniform
+    stage_rows32(stage, lane, f);
+    __syncwarp();
+    if (ch + 1 < 4 && col0 + CHUNK < N) tmem_ld_f32x32(taddr + (ch + 1) * CHUNK, f);
     const int col = col0 + 4 * cseg;
     const bool col_ok = col < N;                          // N % 4 == 0
     float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ep.bias != nullptr && col_ok) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
-
-    if constexpr (EPI == TOC3D_EPI_RESID) {
-      float4 r[4];
-      int orow[4];
-      float4 u4 = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (ep.ln_u != nullptr && col_ok) u4 = __ldg(reinterpret_cast<const float4*>(ep.ln_u + col));
+    if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
+      const bool rot = col0 < ep.rope_cols;               // warp-uniform (rope_cols % 128 == 0)
+      const bool col_axis = (col0 >> 5) & 1;              // second 32 channels of a head use the column coordinate
+      const int j0 = 2 * cseg;                            // frequency index of this lane's first pair
+      const float sc_q = (col0 < (ep.rope_cols >> 1)) ? ep.q_scale : 1.0f;
+      __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int row = it * 8 + rin;
-        orow[it] = __shfl_sync(0xffffffffu, or_t, row);
-        const int rrow = __shfl_sync(0xffffffffu, rr_t, row);
-        r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (col_ok && orow[it] != -1) {
-          if (rrow >= 0) r[it] = *reinterpret_cast<const float4*>(ep.resid + (size_t)rrow * ep.ldo + col);
-          else if (rrow == -2) r[it] = *reinterpret_cast<const float4*>(ep.out_alt + (size_t)(m0 + row) * ep.ldo + col);
-        }
-      }
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int row = it * 8 + rin;
-        const float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
-        const float la = __shfl_sync(0xffffffffu, lnA_t, row);
-        const float lb = __shfl_sync(0xffffffffu, lnB_t, row);
-        if (col_ok && orow[it] != -1) {
-          float4 o;
-          o.x = r[it].x + (fmaf(la, a.x, lb * u4.x) + b.x); o.y = r[it].y + (fmaf(la, a.y, lb * u4.y) + b.y);
-          o.z = r[it].z + (fmaf(la, a.z, lb * u4.z) + b.z); o.w = r[it].w + (fmaf(la, a.w, lb * u4.w) + b.w);
-          float* dst = (orow[it] >= 0) ? reinterpret_cast<float*>(ep.out) + (size_t)orow[it] * ep.ldo
-                                       : ep.out_alt + (size_t)(m0 + row) * ep.ldo;
-          *reinterpret_cast<float4*>(dst + col) = o;
-        }
-      }
-    } else if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
-      const bool rot = col < ep.rope_cols;
-      const bool col_axis = (col >> 5) & 1;               // second 32 channels of a head use the column coordinate
-      const int j0 = (col & 31) >> 1;
-      const float sc_q = (col < (ep.rope_cols >> 1)) ? ep.q_scale : 1.0f;
-#pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int row = it * 8 + rin;
-        const int pos_pk = __shfl_sync(0xffffffffu, pos_t, row);
-        float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rin;
+        float4 a = stage_read(stage, row, cseg);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         if (rot) {
-          const int pos = col_axis ? (pos_pk & 0xffff) : (pos_pk >> 16);
-          const float c0 = s_cos[pos * 16 + j0], s0 = s_sin[pos * 16 + j0];
-          const float c1 = s_cos[pos * 16 + j0 + 1], s1 = s_sin[pos * 16 + j0 + 1];
+          const int p = col_axis ? (pos[it] & 0xffff) : (pos[it] >> 16);
+          const float2 c = __ldg(reinterpret_cast<const float2*>(ep.cos_axis + p * 16 + j0));
+          const float2 sn = __ldg(reinterpret_cast<const float2*>(ep.sin_axis + p * 16 + j0));
           const float x0 = a.x, x1 = a.y, x2 = a.z, x3 = a.w;
-          a.x = (x0 * c0 - x1 * s0) * sc_q; a.y = (x1 * c0 + x0 * s0) * sc_q;
-          a.z = (x2 * c1 - x3 * s1) * sc_q; a.w = (x3 * c1 + x2 * s1) * sc_q;
+          a.x = (x0 * c.x - x1 * sn.x) * sc_q; a.y = (x1 * c.x + x0 * sn.x) * sc_q;
+          a.z = (x2 * c.y - x3 * sn.y) * sc_q; a.w = (x3 * c.y + x2 * sn.y) * sc_q;
         }
         if (col_ok && m0 + row < M) {
           uint2 u;
           u.x = pack_bf16(a.x, a.y);
           u.y = pack_bf16(a.z, a.w);
-          *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)(m0 + row) * ep.ldo + col) = u;
+          *reinterpret_cast<uint2*>(out + (size_t)(m0 + row) * ep.ldo + col) = u;
         }
       }
     } else {  // TOC3D_EPI_LINEAR
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const int row = it * 8 + rin;
-        float4 a = *reinterpret_cast<const float4*>(stage + row * STG_LD + 4 * cseg);
+      for (int it = 0; it < 8; ++it) {
+        const int row = it * 4 + rin;
+        float4 a = stage_read(stage, row, cseg);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         if (ep.act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
         else if (ep.act == 2) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
@@ -282,20 +333,20 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
   }
 }
 
-template <int EPI>
+template <int EPI, bool LNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
             const EpiParams ep) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // 1024-byte alignment for the 128B swizzle; pointer arithmetic (not an integer round trip) keeps the
+  // shared address space visible to the compiler (LDS/STS instead of generic loads in the epilogue)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_TILES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  float* s_cos = reinterpret_cast<float*>(smem + SMEM_TILES + 256);
-  float* s_sin = s_cos + ROPE_MAX_FT * 16;
-  float* s_stage = s_sin + ROPE_MAX_FT * 16;
+  float* s_stage = reinterpret_cast<float*>(smem + SMEM_TILES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -318,12 +369,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
-  if (EPI == TOC3D_EPI_QKV_ROPE && warp >= 2) {
-    for (int i = threadIdx.x - 64; i < ep.rope_ft * 16; i += EPI_WARPS * 32) {
-      s_cos[i] = ep.cos_axis[i];
-      s_sin[i] = ep.sin_axis[i];
-    }
-  }
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
@@ -381,7 +426,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     // ------------------------------------------------------------------ epilogue (8 warps)
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read (warp_id % 4)
     const int half = (warp - 2) >> 2;      // which 128 accumulator columns
-    float* stage_buf = s_stage + (warp - 2) * 32 * STG_LD;
+    float* stage_buf = s_stage + (warp - 2) * STAGE_FLOATS;
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -390,7 +435,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       mbar_wait(&tmem_full[acc], acc_phase);
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
-      epilogue_warp_tile<EPI>(ep, taddr, m_idx + quarter * 32, n_idx + half * 128, M, N, stage_buf, s_cos, s_sin, lane);
+      epilogue_warp_tile<EPI, LNF>(ep, taddr, m_idx + quarter * 32, n_idx + half * 128, M, N, stage_buf, lane);
       // release this accumulator buffer to the MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -452,17 +497,17 @@ static int sm_count() {
   return n;
 }
 
-template <int EPI>
+template <int EPI, bool LNF = false>
 static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
                   cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
-    TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
   const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
   const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_kernel<EPI><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, M, N, K, ep);
+  gemm_kernel<EPI, LNF><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, M, N, K, ep);
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -512,7 +557,9 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   switch (kind) {
     case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(ta, tb, M, N, K, ep, st);
     case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(ta, tb, M, N, K, ep, st);
-    case TOC3D_EPI_RESID: return launch<TOC3D_EPI_RESID>(ta, tb, M, N, K, ep, st);
+    case TOC3D_EPI_RESID:
+      return ep.row_stats != nullptr ? launch<TOC3D_EPI_RESID, true>(ta, tb, M, N, K, ep, st)
+                                     : launch<TOC3D_EPI_RESID, false>(ta, tb, M, N, K, ep, st);
     case TOC3D_EPI_SWIGLU: return launch<TOC3D_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_gemm_bf16: unknown epilogue kind %d", kind);
   }
