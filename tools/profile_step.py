@@ -19,12 +19,15 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--config", default="toc3d_fast")
 ap.add_argument("--iters", type=int, default=3)
 ap.add_argument("--batch", type=int, default=1)
+ap.add_argument("--eager", action="store_true", help="launch kernels eagerly instead of replaying the CUDA graph")
 args = ap.parse_args()
 kind, cfg, hw = CONFIGS[args.config]
 torch.manual_seed(0)
 m = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
 m.load_state_dict(randomize_state_dict(m.state_dict(), seed=0, bias_std=0.02))
 m = m.eval().cuda()
+if args.eager:
+    m.use_cuda_graph = False
 inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in make_inputs(args.batch, 6, hw, seed=0).items()}
 marker = torch.zeros(7777, device="cuda")
 for i in range(args.iters):
