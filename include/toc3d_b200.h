@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 2
+#define TOC3D_B200_ABI_VERSION 3
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -39,6 +39,8 @@ const char* toc3d_last_error(void);
  * eva_vit.py:45-49 (w1,w2,w3), eva_utils.py:284 (patch conv as im2col GEMM),
  * toc3d_utils.py:122,127 (first-frame scorer MLP).
  * Requirements: K % 8 == 0, lda % 8 == 0, ldb % 8 == 0, A/B 16-byte aligned.
+ * Runs on CTA pairs (tcgen05 cta_group::2, 256 x tile_n pair tiles).  Like every kernel of the library it is
+ * launched with programmatic stream serialization and waits for its stream predecessor on the device.
  */
 enum toc3d_epilogue_kind {
   TOC3D_EPI_LINEAR = 0, /* out = act(acc + bias), bf16 or fp32                                   */
@@ -87,6 +89,9 @@ typedef struct toc3d_epilogue {
   const float* ln_u;
   int32_t ln_n;
   float ln_eps;
+  /* Tile width override (tuning / tests): 0 = chosen per launch to minimise wave quantisation on the
+   * 74 CTA pairs; else a multiple of 32 (64 for SWIGLU) in [64, 256]. */
+  int32_t tile_n;
 } toc3d_epilogue;
 
 int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,

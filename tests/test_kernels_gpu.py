@@ -39,6 +39,44 @@ def test_gemm_linear(lib, M, N, K, f32):
     assert rel_err(got, ref) < tol, rel_err(got, ref)
 
 
+@pytest.mark.parametrize("tile_n", [64, 96, 128, 160, 192, 224, 256])
+@pytest.mark.parametrize("M,N,K", [(700, 1024, 256), (129, 328, 64), (3000, 3072, 128)])
+def test_gemm_tile_width_sweep(lib, tile_n, M, N, K):
+    """Every legal pair-tile width gives the same result (runtime BN, CTA-pair tiles with row / column tails)."""
+    g = torch.Generator().manual_seed(M + tile_n)
+    A = bf16_round(torch.randn(M, K, generator=g))
+    B = bf16_round(torch.randn(N, K, generator=g) * 0.05)
+    bias = torch.randn(N, generator=g)
+    ref = A.double() @ B.double().t() + bias.double()
+    out = torch.full((M, N), float("nan"), device=DEV, dtype=torch.float32)
+    lib.gemm(A.to(DEV).bfloat16(), B.to(DEV).bfloat16(), lib.EPI_LINEAR, bias=bias.to(DEV), out=out, out_f32=True,
+             tile_n=tile_n)
+    got = out.cpu().double()
+    assert torch.isfinite(got).all()
+    assert rel_err(got, ref) < 2e-5
+
+
+def test_gemm_back_to_back_stream_order(lib):
+    """Programmatic dependent launch: a chain of GEMMs where each consumes the previous output in place of A
+    must equal the serial result (the device-side wait orders them)."""
+    g = torch.Generator().manual_seed(11)
+    M, C = 2000, 256
+    x = bf16_round(torch.randn(M, C, generator=g))
+    Ws = [bf16_round(torch.randn(C, C, generator=g) * 0.06) for _ in range(6)]
+    ref = x.clone()
+    for W in Ws:
+        ref = bf16_round(ref @ W.t())
+    a = x.to(DEV).bfloat16()
+    bufs = [torch.empty(M, C, device=DEV, dtype=torch.bfloat16) for _ in range(2)]
+    Wd = [W.to(DEV).bfloat16() for W in Ws]
+    cur = a
+    for i, W in enumerate(Wd):
+        lib.gemm(cur, W, lib.EPI_LINEAR, out=bufs[i % 2])
+        cur = bufs[i % 2]
+    torch.cuda.synchronize()
+    assert rel_err(cur.float().cpu(), ref) < 2e-2
+
+
 @pytest.mark.parametrize("act", [1, 2])
 def test_gemm_linear_act(lib, act):
     g = torch.Generator().manual_seed(7)
@@ -112,8 +150,9 @@ def test_gemm_resid_maps(lib):
     assert (out.cpu() - (acc + pos[torch.arange(M) % 100])).abs().max().item() < 2e-4
 
 
+@pytest.mark.parametrize("tile_n", [0, 64, 128, 192, 256])
 @pytest.mark.parametrize("M,Hd", [(257, 2730), (1000, 341)])
-def test_gemm_swiglu(lib, M, Hd):
+def test_gemm_swiglu(lib, M, Hd, tile_n):
     from toc3d_b200.backbone import interleave_w12, hidden_pad
     g = torch.Generator().manual_seed(Hd)
     K = 128
@@ -124,7 +163,7 @@ def test_gemm_swiglu(lib, M, Hd):
     ref = torch.nn.functional.silu(A @ w1.t() + b1) * (A @ w2.t() + b2)
     W12, b12 = interleave_w12(w1, b1, w2, b2, Hp)
     out = torch.full((M, Hp), float("nan"), device=DEV, dtype=torch.bfloat16)
-    lib.gemm(A.to(DEV).bfloat16(), W12.to(DEV).bfloat16(), lib.EPI_SWIGLU, bias=b12.to(DEV), out=out)
+    lib.gemm(A.to(DEV).bfloat16(), W12.to(DEV).bfloat16(), lib.EPI_SWIGLU, bias=b12.to(DEV), out=out, tile_n=tile_n)
     got = out.float().cpu()
     assert rel_err(got[:, :Hd], ref) < 8e-3
     assert (got[:, Hd:] == 0).all()

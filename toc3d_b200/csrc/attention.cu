@@ -37,6 +37,8 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16 (*dst)[LDS], const __nv_
 __global__ void __launch_bounds__(NTHREADS)
 window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int seq, int heads) {
   __shared__ __align__(16) Smem sm;
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = heads * D;
   const int64_t ld = 3 * (int64_t)C;
   const int qt = blockIdx.x, h = blockIdx.y, w = blockIdx.z;
@@ -186,8 +188,8 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
                 "toc3d_window_attention: bad shape nW=%d seq=%d heads=%d", n_windows, seq_len, heads);
   TOC3D_REQUIRE(n_windows <= 65535, kErrBadArg, "toc3d_window_attention: too many windows (%d)", n_windows);
   dim3 grid((seq_len + attn::BQ - 1) / attn::BQ, heads, n_windows);
-  attn::window_attention_kernel<<<grid, attn::NTHREADS, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads);
-  TOC3D_CHECK_CUDA(cudaGetLastError());
+  TOC3D_CHECK_CUDA(launch_pdl(attn::window_attention_kernel, grid, dim3(attn::NTHREADS), 0,
+                              reinterpret_cast<cudaStream_t>(stream), 1, reinterpret_cast<const __nv_bfloat16*>(qkv),
+                              reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads));
   return 0;
 }

@@ -1,9 +1,16 @@
-// Persistent warp-specialised bf16 GEMM for sm_100a: TMA -> 128B-swizzled smem -> tcgen05.mma
-// (128x256x16, fp32 accumulators double-buffered in TMEM) -> fused epilogues read with tcgen05.ld.
+// Persistent warp-specialised bf16 GEMM for sm_100a on CTA PAIRS: TMA -> 128B-swizzled smem ->
+// tcgen05.mma.cta_group::2 (256 x BN x 16 per pair, fp32 accumulators double-buffered in TMEM) ->
+// fused epilogues read with tcgen05.ld.
 //
-//   warp 0 : TMA producer (one elected lane)
-//   warp 1 : TMEM allocator + tcgen05.mma issuer (one elected lane)
-//   warps 2-9 : epilogue; warp w reads TMEM lane quarter (w % 4), column half ((w - 2) / 4)
+//   cluster = 2 CTAs (one TPC).  CTA r owns rows [128 r, 128 r + 128) of the 256-row pair tile and
+//   stages its own A rows plus HALF of the B tile (BN/2 weight rows): 32 KB per k-block per CTA
+//   instead of 48 KB for a single-CTA 128x256 tile, so the same 192 KB of smem holds 6 stages and the
+//   L2 -> SM traffic per FLOP drops by a third.
+//   warp 0 : TMA producer (one elected lane, both CTAs; completion bytes land on the leader's barrier)
+//   warp 1 : TMEM allocator (both CTAs) + tcgen05.mma issuer (leader CTA only, one elected lane)
+//   warps 2-9 : epilogue; warp w reads TMEM lane quarter (w % 4) and every other 32-column chunk
+//   BN (tile width) is a runtime multiple of 32 in [64, 256], picked per launch to minimise wave
+//   quantisation on the 74 CTA pairs.
 //
 // Call sites replaced: see include/toc3d_b200.h (toc3d_gemm_bf16).
 #include "common.cuh"
@@ -14,21 +21,24 @@
 namespace toc3d {
 namespace gemm {
 
-constexpr int BM = 128, BN = 256, BK = 64, UMMA_K = 16;
-constexpr int STAGES = 4;
-constexpr int A_BYTES = BM * BK * 2;
-constexpr int B_BYTES = BN * BK * 2;
-constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+constexpr int BM = 128;                  // rows per CTA; the pair tile has 2 * BM rows
+constexpr int BN_MAX = 256, BK = 64, UMMA_K = 16;
+constexpr int STAGES = 6;
+constexpr int A_BYTES = BM * BK * 2;                 // 16 KB
+constexpr int B_BYTES_MAX = (BN_MAX / 2) * BK * 2;   // 16 KB: this CTA's half of the B tile
+constexpr int STAGE_BYTES = A_BYTES + B_BYTES_MAX;
 constexpr int NUM_THREADS = 64 + 8 * 32;   // TMA warp, MMA warp, 8 epilogue warps
 constexpr int TMEM_COLS = 512;                    // 2 accumulator buffers x 256 fp32 columns
 constexpr int ROPE_MAX_FT = 256;
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;  // 196608
 constexpr int SMEM_AUX = 256 + 8 * 32 * 32 * 4;   // barriers + epilogue staging (8 warps x 32 rows x 32 fp32)
-constexpr int SMEM_BYTES = SMEM_TILES + SMEM_AUX + 1024;  // + alignment slack
+constexpr int SMEM_BYTES = SMEM_TILES + SMEM_AUX + 1024;  // + alignment slack (230656 <= 232448)
 
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10),
-// B=bf16 [10,13), A/B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).
-constexpr uint32_t IDESC = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+// B=bf16 [10,13), A/B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).  M = 256 over the pair.
+__device__ __forceinline__ uint32_t make_idesc(int bn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)((2 * BM) >> 4) << 24);
+}
 
 struct EpiParams {
   const float* bias;
@@ -63,13 +73,15 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------
-// Epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) and column half ((w - 2) / 4) of the
-// 128 x 256 accumulator, processed as 4 chunks of 32 columns.  Each chunk goes TMEM -> registers
-// (thread = row) -> XOR-swizzled smem staging (4 KB per warp, conflict-free both ways) -> "coalesced
-// domain": 8 lanes x float4 cover the 32 columns of one row, 4 rows per instruction, 8 independent
-// iterations per chunk.  Bias / RoPE / residual / activation are applied there, so global memory
-// sees contiguous 128-byte (fp32) or 64-byte (bf16) row segments.  The TMEM load of chunk c+1 and
-// the residual loads of chunk c+1 are issued before chunk c is processed.
+// Epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) = 32 rows of this CTA's 128 x BN
+// accumulator and the 32-column chunks ch = half, half + 2, ... (half = (w - 2) / 4).  Each chunk
+// goes TMEM -> registers (thread = row) -> XOR-swizzled smem staging (4 KB per warp, conflict-free
+// both ways) -> "coalesced domain": 8 lanes x float4 cover the 32 columns of one row, 4 rows per
+// instruction, 8 independent iterations per chunk.  Bias / RoPE / residual / activation are applied
+// there, so global memory sees contiguous 128-byte (fp32) or 64-byte (bf16) row segments.
+// Everything that does not depend on the accumulator (row maps, folded-LN coefficients, the first
+// chunk's residual) is fetched BEFORE waiting for the MMA warp, and the TMEM / residual loads of
+// the next chunk are issued before the current chunk is processed.
 constexpr int CHUNK = 32;          // columns per staged chunk
 constexpr int EPI_WARPS = 8;
 constexpr int STAGE_FLOATS = 32 * CHUNK;   // per warp
@@ -90,21 +102,29 @@ __device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&f)[32]) {
   for (int i = 0; i < 32; ++i) f[i] = __uint_as_float(v[i]);
 }
 
+// taddr: accumulator base of this warp's lane quarter (column 0 of the tile); m0: first global row
+// of the quarter; nt0: first global column of the tile; bn: tile width.  full_bar/parity: the
+// "accumulator complete" barrier this warp must observe before its first TMEM load.
 template <int EPI, bool LNF>
-__device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int n0, int M, int N,
-                                                   float* stage, int lane) {
+__device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int nt0, int bn, int half,
+                                                   int M, int N, float* stage, int lane, uint64_t* full_bar,
+                                                   uint32_t parity) {
   // coalesced-domain coordinates: rows {rin, rin+4, ..., rin+28}, columns 4*cseg..4*cseg+3 of the chunk
   const int rin = lane >> 3;
   const int cseg = lane & 7;
   const bool my_row_ok = (m0 + lane) < M;
 
   if constexpr (EPI == TOC3D_EPI_SWIGLU) {
-    // this warp's 128 GEMM columns = 2 blocks of [32 x w1 | 32 x w2] -> 2 x 32 hidden columns
+    // 64 GEMM columns = [32 x w1 | 32 x w2] -> 32 hidden columns; this warp takes every other 64-block
     __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
-    float st_sum = 0.f, st_sq = 0.f;     // this row's sum / sum of squares of the bf16-rounded hidden values
+    // this row's sum / sum of squares of the bf16-rounded hidden values, accumulated per 32-column block
+    // in fixed point so that the result does not depend on the tile width or on which warp owns a block
+    long long st_sum = 0, st_sq = 0;
+    mbar_wait(full_bar, parity);
+    tcgen05_fence_after();
 #pragma unroll 1
-    for (int blk = 0; blk < 2; ++blk) {
-      const int col1 = n0 + blk * 64;                    // GEMM column of the w1 part
+    for (int blk = half; blk * 64 < bn; blk += 2) {
+      const int col1 = nt0 + blk * 64;                   // GEMM column of the w1 part
       if (col1 >= N) break;                              // warp-uniform
       float h[32];
       {
@@ -126,12 +146,15 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         }
       }
       if (ep.row_stats != nullptr) {
+        float bs = 0.f, bq = 0.f;
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
           h[i] = __bfloat162float(__float2bfloat16_rn(h[i]));   // statistics of exactly what the next GEMM reads
-          st_sum += h[i];
-          st_sq += h[i] * h[i];
+          bs += h[i];
+          bq += h[i] * h[i];
         }
+        st_sum += __float2ll_rn(bs * (float)STAT_SUM_SCALE);
+        st_sq += __float2ll_rn(bq * (float)STAT_SQ_SCALE);
       }
       stage_rows32(stage, lane, h);
       __syncwarp();
@@ -154,12 +177,13 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
     if (ep.row_stats != nullptr && my_row_ok) {
       // fixed-point (integer) atomics: the accumulated statistics do not depend on arrival order
       unsigned long long* dst = reinterpret_cast<unsigned long long*>(ep.row_stats + 2 * (size_t)(m0 + lane));
-      atomicAdd(dst, (unsigned long long)__float2ll_rn(st_sum * (float)STAT_SUM_SCALE));
-      atomicAdd(dst + 1, (unsigned long long)__float2ll_rn(st_sq * (float)STAT_SQ_SCALE));
+      atomicAdd(dst, (unsigned long long)st_sum);
+      atomicAdd(dst + 1, (unsigned long long)st_sq);
     }
     return;
   }
 
+  const int ch0 = half * CHUNK;       // this warp's first chunk (tile-relative column)
   if constexpr (EPI == TOC3D_EPI_RESID) {
     // per-row maps and folded-LN coefficients, computed by the lane that owns the row, then
     // redistributed to the coalesced-domain owners (8 rows per lane)
@@ -213,28 +237,39 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         }
       }
     };
-    float4 r_cur[8], r_nxt[8];
-    load_resid(r_cur, n0 + 4 * cseg);
-    float f[32];
-    tmem_ld_f32x32(taddr, f);
-#pragma unroll
-    for (int ch = 0; ch < 4; ++ch) {
-      const int col0 = n0 + ch * CHUNK;
-      if (col0 >= N) break;                               // warp-uniform
-      stage_rows32(stage, lane, f);
-      __syncwarp();
-      const bool more = ch + 1 < 4 && col0 + CHUNK < N;
-      if (more) {
-        load_resid(r_nxt, col0 + CHUNK + 4 * cseg);
-        tmem_ld_f32x32(taddr + (ch + 1) * CHUNK, f);
-      }
-      const int col = col0 + 4 * cseg;
-      const bool col_ok = col < N;                        // N % 4 == 0
-      float4 b = make_float4(0.f, 0.f, 0.f, 0.f), u4 = b;
-      if (col_ok) {
+    auto load_cols = [&](float4& b, float4& u4, int col) {      // per-column bias and folded-LN vector
+      b = make_float4(0.f, 0.f, 0.f, 0.f);
+      u4 = b;
+      if (col < N) {
         if (ep.bias != nullptr) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
         if constexpr (LNF) u4 = __ldg(reinterpret_cast<const float4*>(ep.ln_u + col));
       }
+    };
+    float4 r_cur[8], r_nxt[8];
+    float4 b, u4, b_nxt, u_nxt;
+    if (ch0 < bn) {                                               // in flight while the MMAs finish
+      load_resid(r_cur, nt0 + ch0 + 4 * cseg);
+      load_cols(b, u4, nt0 + ch0 + 4 * cseg);
+    }
+    mbar_wait(full_bar, parity);
+    tcgen05_fence_after();
+    if (ch0 >= bn || nt0 + ch0 >= N) return;                      // warp-uniform
+    float f[32];
+    tmem_ld_f32x32(taddr + ch0, f);
+#pragma unroll 1
+    for (int c = ch0; c < bn; c += 2 * CHUNK) {
+      const int col0 = nt0 + c;
+      if (col0 >= N) break;                               // warp-uniform
+      stage_rows32(stage, lane, f);
+      __syncwarp();
+      const bool more = c + 2 * CHUNK < bn && col0 + 2 * CHUNK < N;
+      if (more) {
+        load_resid(r_nxt, col0 + 2 * CHUNK + 4 * cseg);
+        load_cols(b_nxt, u_nxt, col0 + 2 * CHUNK + 4 * cseg);
+        tmem_ld_f32x32(taddr + c + 2 * CHUNK, f);
+      }
+      const int col = col0 + 4 * cseg;
+      const bool col_ok = col < N;                        // N % 4 == 0
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
         const float4 a = stage_read(stage, it * 4 + rin, cseg);
@@ -252,41 +287,61 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       if (more) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) r_cur[it] = r_nxt[it];
+        b = b_nxt;
+        u4 = u_nxt;
       }
     }
     return;
   }
 
   // ---- QKV_ROPE and LINEAR
-  int pos_t = 0;
+  // Everything below the accumulator is fetched before the wait.  A warp's chunks are 64 columns apart
+  // (half = chunk parity), i.e. always the same half of a 64-wide head: the same RoPE axis and the same
+  // 16 frequencies for all of them, so its cos/sin values are loaded once per tile (8 rows x 2 pairs).
+  float2 rc[8], rs[8];
   if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
+    int pos_t = 0;
     if (my_row_ok) {
       const int row = m0 + lane;
       const int t = ep.rope_rows ? ep.rope_rows[row] : (row % ep.rope_slots);
       const int r = t / ep.rope_ft;
       pos_t = (r << 16) | (t - r * ep.rope_ft);
     }
+    const bool col_axis = ((nt0 + ch0) >> 5) & 1;         // second 32 channels of a head use the column coordinate
+    const int j0 = 2 * cseg;                              // frequency index of this lane's first pair
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int pp = __shfl_sync(0xffffffffu, pos_t, it * 4 + rin);
+      const int p = col_axis ? (pp & 0xffff) : (pp >> 16);
+      rc[it] = __ldg(reinterpret_cast<const float2*>(ep.cos_axis + p * 16 + j0));
+      rs[it] = __ldg(reinterpret_cast<const float2*>(ep.sin_axis + p * 16 + j0));
+    }
   }
-  int pos[8];
+  float4 bias4[BN_MAX / (2 * CHUNK)];
 #pragma unroll
-  for (int it = 0; it < 8; ++it) pos[it] = __shfl_sync(0xffffffffu, pos_t, it * 4 + rin);
+  for (int i = 0; i < BN_MAX / (2 * CHUNK); ++i) {
+    const int col = nt0 + ch0 + i * 2 * CHUNK + 4 * cseg;
+    bias4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (ep.bias != nullptr && ch0 + i * 2 * CHUNK < bn && col < N) bias4[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+  }
+  mbar_wait(full_bar, parity);
+  tcgen05_fence_after();
+  if (ch0 >= bn || nt0 + ch0 >= N) return;                        // warp-uniform
   float f[32];
-  tmem_ld_f32x32(taddr, f);
+  tmem_ld_f32x32(taddr + ch0, f);
 #pragma unroll
-  for (int ch = 0; ch < 4; ++ch) {
-    const int col0 = n0 + ch * CHUNK;
-    if (col0 >= N) break;                                 // warp-uniform
+  for (int i = 0; i < BN_MAX / (2 * CHUNK); ++i) {
+    const int c = ch0 + i * 2 * CHUNK;
+    const int col0 = nt0 + c;
+    if (c >= bn || col0 >= N) break;                      // warp-uniform
     stage_rows32(stage, lane, f);
     __syncwarp();
-    if (ch + 1 < 4 && col0 + CHUNK < N) tmem_ld_f32x32(taddr + (ch + 1) * CHUNK, f);
+    if (c + 2 * CHUNK < bn && col0 + 2 * CHUNK < N) tmem_ld_f32x32(taddr + c + 2 * CHUNK, f);
     const int col = col0 + 4 * cseg;
     const bool col_ok = col < N;                          // N % 4 == 0
-    float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (ep.bias != nullptr && col_ok) b = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
+    const float4 b = bias4[i];
     if constexpr (EPI == TOC3D_EPI_QKV_ROPE) {
       const bool rot = col0 < ep.rope_cols;               // warp-uniform (rope_cols % 128 == 0)
-      const bool col_axis = (col0 >> 5) & 1;              // second 32 channels of a head use the column coordinate
-      const int j0 = 2 * cseg;                            // frequency index of this lane's first pair
       const float sc_q = (col0 < (ep.rope_cols >> 1)) ? ep.q_scale : 1.0f;
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
 #pragma unroll
@@ -295,12 +350,10 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         float4 a = stage_read(stage, row, cseg);
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         if (rot) {
-          const int p = col_axis ? (pos[it] & 0xffff) : (pos[it] >> 16);
-          const float2 c = __ldg(reinterpret_cast<const float2*>(ep.cos_axis + p * 16 + j0));
-          const float2 sn = __ldg(reinterpret_cast<const float2*>(ep.sin_axis + p * 16 + j0));
+          const float2 c2 = rc[it], sn = rs[it];
           const float x0 = a.x, x1 = a.y, x2 = a.z, x3 = a.w;
-          a.x = (x0 * c.x - x1 * sn.x) * sc_q; a.y = (x1 * c.x + x0 * sn.x) * sc_q;
-          a.z = (x2 * c.y - x3 * sn.y) * sc_q; a.w = (x3 * c.y + x2 * sn.y) * sc_q;
+          a.x = (x0 * c2.x - x1 * sn.x) * sc_q; a.y = (x1 * c2.x + x0 * sn.x) * sc_q;
+          a.z = (x2 * c2.y - x3 * sn.y) * sc_q; a.w = (x3 * c2.y + x2 * sn.y) * sc_q;
         }
         if (col_ok && m0 + row < M) {
           uint2 u;
@@ -333,13 +386,16 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
   }
 }
 
+// (registers are allocated per 4 warps: 10 warps count as 12, hence the 168-register cap)
 template <int EPI, bool LNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-            const EpiParams ep) {
+            int BN, const EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle; pointer arithmetic (not an integer round trip) keeps the
-  // shared address space visible to the compiler (LDS/STS instead of generic loads in the epilogue)
+  // shared address space visible to the compiler (LDS/STS instead of generic loads in the epilogue).
+  // Both CTAs of the pair compute the same offset (same kernel, same static layout), which the
+  // cta_group::2 MMA and the multicast commits rely on.
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_TILES);
   uint64_t* empty_bar = full_bar + STAGES;
@@ -350,10 +406,14 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int num_m = (M + BM - 1) / BM;
+  const uint32_t rank = cluster_ctarank();          // 0 = leader of the pair
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);    // 256-row pair tiles
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
+  const int b_rows = BN >> 1;                       // weight rows staged by this CTA
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -364,45 +424,65 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], EPI_WARPS);
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);     // the epilogue warps of BOTH CTAs release the leader's MMA
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr, TMEM_COLS);
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();                               // barriers + TMEM of both CTAs are ready
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();            // the next kernel may start its prologue; it waits for this grid itself
 
   if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int m_idx = (tile % num_m) * BM;
-        const int n_idx = (tile / num_m) * BN;
+      const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);    // both CTAs' bytes
+      // The weights (B) do not depend on the previous kernel in the stream: the first ring of B loads
+      // is issued before the programmatic-dependency wait and overlaps that kernel's tail.
+      int pre = 0;
+      if (pair < num_tiles) {
+        const int n_idx = (pair / num_m) * BN + (int)rank * b_rows;
+        pre = num_k < STAGES ? num_k : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
+          tma_load_2d_2sm(&tmB, mapa_u32(smem_u32(&full_bar[kb]), 0), smem + kb * STAGE_BYTES + A_BYTES, kb * BK, n_idx);
+        }
+      }
+      pdl_wait();
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int m_idx = (tile % num_m) * (2 * BM) + (int)rank * BM;
+        const int n_idx = (tile / num_m) * BN + (int)rank * b_rows;
         for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1);
-          mbar_arrive_expect_tx(&full_bar[stage], STAGE_BYTES);
+          const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
           uint8_t* sa = smem + stage * STAGE_BYTES;
-          tma_load_2d(&tmA, &full_bar[stage], sa, kb * BK, m_idx);
-          tma_load_2d(&tmB, &full_bar[stage], sa + A_BYTES, kb * BK, n_idx);
+          if (pre > 0) {                              // B of this slot is already in flight
+            --pre;
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_2d_2sm(&tmB, lead_full, sa + A_BYTES, kb * BK, n_idx);
+          }
+          tma_load_2d_2sm(&tmA, lead_full, sa, kb * BK, m_idx);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
     }
   } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const uint32_t idesc = make_idesc(BN);
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN_MAX);
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
@@ -412,43 +492,43 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 #pragma unroll
           for (int k = 0; k < BK / UMMA_K; ++k) {
             // advance 32 bytes (16 bf16) along K inside the 128B swizzle row: +2 in the >>4 address field
-            umma_bf16_ss(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), IDESC,
-                         (kb | k) != 0 ? 1u : 0u);
+            umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
+                             (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit(&empty_bar[stage]);  // smem slot reusable once these MMAs retire
+          tcgen05_commit_2sm(&empty_bar[stage], 3);   // smem slot reusable in BOTH CTAs once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit(&tmem_full[acc]);      // accumulator complete -> epilogue
+        tcgen05_commit_2sm(&tmem_full[acc], 3);       // accumulator complete -> both epilogues
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (8 warps)
+    // ------------------------------------------------------------------ epilogue (8 warps per CTA)
     const int quarter = warp & 3;          // TMEM lane quarter this warp may read (warp_id % 4)
-    const int half = (warp - 2) >> 2;      // which 128 accumulator columns
+    const int half = (warp - 2) >> 2;      // even / odd 32-column chunks
     float* stage_buf = s_stage + (warp - 2) * STAGE_FLOATS;
     int acc = 0;
     uint32_t acc_phase = 0;
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int m_idx = (tile % num_m) * BM;
+    pdl_wait();                            // residual / maps / statistics come from the previous kernels
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int m_idx = (tile % num_m) * (2 * BM) + (int)rank * BM;
       const int n_idx = (tile / num_m) * BN;
-      mbar_wait(&tmem_full[acc], acc_phase);
-      tcgen05_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + half * 128);
-      epilogue_warp_tile<EPI, LNF>(ep, taddr, m_idx + quarter * 32, n_idx + half * 128, M, N, stage_buf, lane);
-      // release this accumulator buffer to the MMA warp
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX);
+      epilogue_warp_tile<EPI, LNF>(ep, taddr, m_idx + quarter * 32, n_idx, BN, half, M, N, stage_buf, lane,
+                                   &tmem_full[acc], acc_phase);
+      // release this accumulator buffer to the leader's MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  cluster_sync_all();                      // nobody may still signal a barrier / read TMEM of an exited peer
   if (warp == 1) {
     tcgen05_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
 
@@ -497,18 +577,44 @@ static int sm_count() {
   return n;
 }
 
+// Tile width.  The mainloop is L2 -> SM bandwidth bound (measured: 8192^3 runs at 1.49 PFLOP/s with 256-wide
+// tiles and time per tile scales as 256 + BN, i.e. with the A + B bytes staged per k-block), so narrower
+// tiles re-read A more often and only pay off when they remove a mostly empty last wave:
+//   cost(BN) = waves * (k_blocks * (256 + BN) + c_tile) + c_epi * BN      (last epilogue is exposed)
+static int pick_tile_n(int M, int N, int K, int kind, int pairs) {
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);
+  const int step = kind == TOC3D_EPI_SWIGLU ? 64 : 32;
+  const double kb = (double)((K + BK - 1) / BK);
+  double best = 1e30;
+  int best_bn = BN_MAX;
+  for (int bn = BN_MAX; bn >= 128; bn -= step) {
+    const long tiles = (long)num_m * ((N + bn - 1) / bn);
+    const long waves = (tiles + pairs - 1) / pairs;
+    const double cost = (double)waves * (kb * (256.0 + bn) + 1024.0) + 16.0 * bn;
+    if (cost < best * 0.97) { best = cost; best_bn = bn; }     // prefer the widest tile unless clearly better
+  }
+  return best_bn;
+}
+
 template <int EPI, bool LNF = false>
-static int launch(const CUtensorMap& ta, const CUtensorMap& tb, int M, int N, int K, const EpiParams& ep,
-                  cudaStream_t st) {
+static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int tile_n,
+                  const EpiParams& ep, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     configured = true;
   }
-  const int tiles = ((M + BM - 1) / BM) * ((N + BN - 1) / BN);
-  const int grid = tiles < sm_count() ? tiles : sm_count();
-  gemm_kernel<EPI, LNF><<<grid, NUM_THREADS, SMEM_BYTES, st>>>(ta, tb, M, N, K, ep);
-  TOC3D_CHECK_CUDA(cudaGetLastError());
+  const int max_pairs = sm_count() / 2;
+  const int bn = tile_n > 0 ? tile_n : pick_tile_n(M, N, K, EPI, max_pairs);
+  CUtensorMap ta, tb;
+  int rc = make_tmap(&ta, A, M, K, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap(&tb, B, N, K, ldb, bn / 2);
+  if (rc) return rc;
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn);
+  const int pairs = tiles < max_pairs ? tiles : max_pairs;
+  TOC3D_CHECK_CUDA(launch_pdl(gemm_kernel<EPI, LNF>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, st, 2, ta, tb, M, N, K,
+                              bn, ep));
   return 0;
 }
 
@@ -530,6 +636,10 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   ep.out_alt = e->out_alt; ep.rope_rows = e->rope_rows; ep.rope_slots = e->rope_slots; ep.rope_ft = e->rope_ft;
   ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
   ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
+  const int tile_n = e->tile_n;
+  TOC3D_REQUIRE(tile_n == 0 || (tile_n >= 64 && tile_n <= BN_MAX && tile_n % 32 == 0 &&
+                                (kind != TOC3D_EPI_SWIGLU || tile_n % 64 == 0)), kErrBadArg,
+                "toc3d_gemm_bf16: tile_n must be 0 (auto) or a multiple of 32 (64 for SWIGLU) in [64, 256], got %d", tile_n);
   if (kind == TOC3D_EPI_RESID && ep.row_stats != nullptr)
     TOC3D_REQUIRE(ep.ln_u != nullptr && ep.ln_n > 0 && ((uintptr_t)ep.ln_u & 15) == 0 && ((uintptr_t)ep.row_stats & 15) == 0,
                   kErrBadArg, "toc3d_gemm_bf16: folded LayerNorm needs ln_u (16-byte aligned), ln_n > 0");
@@ -548,19 +658,14 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
     TOC3D_REQUIRE(ep.resid != nullptr || ep.resid_map != nullptr, kErrBadArg, "toc3d_gemm_bf16: RESID needs resid");
   }
   if (kind == TOC3D_EPI_SWIGLU) TOC3D_REQUIRE(N % 64 == 0, kErrBadArg, "toc3d_gemm_bf16: SWIGLU needs N %% 64 == 0");
-  CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, A, M, K, lda, BM);
-  if (rc) return rc;
-  rc = make_tmap(&tb, B, N, K, ldb, BN);
-  if (rc) return rc;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (kind) {
-    case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(ta, tb, M, N, K, ep, st);
-    case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(ta, tb, M, N, K, ep, st);
+    case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
+    case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
     case TOC3D_EPI_RESID:
-      return ep.row_stats != nullptr ? launch<TOC3D_EPI_RESID, true>(ta, tb, M, N, K, ep, st)
-                                     : launch<TOC3D_EPI_RESID, false>(ta, tb, M, N, K, ep, st);
-    case TOC3D_EPI_SWIGLU: return launch<TOC3D_EPI_SWIGLU>(ta, tb, M, N, K, ep, st);
+      return ep.row_stats != nullptr ? launch<TOC3D_EPI_RESID, true>(A, lda, B, ldb, M, N, K, tile_n, ep, st)
+                                     : launch<TOC3D_EPI_RESID, false>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
+    case TOC3D_EPI_SWIGLU: return launch<TOC3D_EPI_SWIGLU>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_gemm_bf16: unknown epilogue kind %d", kind);
   }
   return 0;

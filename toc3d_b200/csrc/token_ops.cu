@@ -27,6 +27,8 @@ __global__ void __launch_bounds__(256)
 layernorm_rows_kernel(const float* __restrict__ x, const int* __restrict__ row_map, const float* __restrict__ alt,
                       const float* __restrict__ gamma, const float* __restrict__ beta, __nv_bfloat16* __restrict__ out,
                       int M, float eps, int pad_mode, long long* __restrict__ zero_stats) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int C = VPL * 128;
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
@@ -74,6 +76,8 @@ layernorm_rows_kernel(const float* __restrict__ x, const int* __restrict__ row_m
 __global__ void __launch_bounds__(256)
 subln_kernel(const __nv_bfloat16* __restrict__ h, __nv_bfloat16* __restrict__ out, const float* __restrict__ gamma,
              const float* __restrict__ beta, int M, int Hd, int ld, float eps) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
   const int lane = threadIdx.x & 31;
@@ -160,6 +164,8 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
                                    int* __restrict__ slow_idx, int* __restrict__ fast_idx,
                                    float* __restrict__ fast_score, int* __restrict__ tok_map,
                                    int* __restrict__ rope_rows, int* __restrict__ fast_map) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ __align__(16) uint32_t s_key[1024];
   const int n = ws * ws;
   const int nWw = (W + ws - 1) / ws, nWh = (H + ws - 1) / ws;
@@ -204,6 +210,8 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
 __global__ void __launch_bounds__(128)
 topk_split_kernel(const float* __restrict__ scores, int N, int k, long long* __restrict__ keep_idx,
                   long long* __restrict__ drop_idx) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ __align__(16) uint32_t s_keys[];
   const int b = blockIdx.y;
   const float* row = scores + (size_t)b * N;
@@ -224,6 +232,8 @@ template <int LV>
 __global__ void __launch_bounds__(256)
 merge_fast_kernel(const float* __restrict__ x, const int* __restrict__ fast_map, const float* __restrict__ fast_score,
                   int n_fast, int k, int C, float* __restrict__ rep_out, float* __restrict__ packed) {
+  pdl_wait();
+  pdl_launch_dependents();
   __shared__ float s_part[8];
   __shared__ float s_wgt[1024];
   __shared__ int s_row[1024];
@@ -286,6 +296,8 @@ merge_fast_kernel(const float* __restrict__ x, const int* __restrict__ fast_map,
 __global__ void __launch_bounds__(256)
 fast_update_kernel(float* __restrict__ x, const int* __restrict__ fast_map, const float* __restrict__ packed,
                    const float* __restrict__ rep, int total_fast, int n_fast, int k, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (f >= total_fast) return;
   const int row = fast_map[f];
@@ -310,6 +322,8 @@ __global__ void __launch_bounds__(128)
 score_fold_kernel(const float* __restrict__ queries, const float* __restrict__ w_in, const float* __restrict__ b_in,
                   const float* __restrict__ w_agg, const float* __restrict__ b_agg, float scale, int Q, int Cq, int C,
                   float* __restrict__ A_out, float* __restrict__ c_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   extern __shared__ float s_p[];  // [2][Cq]
   const int f = blockIdx.x;
   const float* q = queries + (size_t)f * Q * Cq;
@@ -379,6 +393,8 @@ __global__ void __launch_bounds__(256)
 score_tokens_kernel(const float* __restrict__ x, const float* __restrict__ mask_in, const float* __restrict__ A,
                     const float* __restrict__ cvec, int V, int N, int C, int vpf, const float* __restrict__ gumbel,
                     uint64_t seed, const uint64_t* __restrict__ seed_dev, float* __restrict__ pred, float* __restrict__ score, float* __restrict__ mask_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const size_t tok = (size_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (tok >= (size_t)V * N) return;
   const int lane = threadIdx.x & 31;
@@ -404,6 +420,8 @@ score_tokens_kernel(const float* __restrict__ x, const float* __restrict__ mask_
 __global__ void score_finish_kernel(const float* __restrict__ logits, int M, const float* __restrict__ gumbel,
                                     uint64_t seed, const uint64_t* __restrict__ seed_dev, float* pred, float* score,
                                     float* mask_out) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int tok = blockIdx.x * blockDim.x + threadIdx.x;
   if (tok >= M) return;
   score_tail(logits[tok * 2], logits[tok * 2 + 1], (size_t)tok, gumbel, mix_seed(seed, seed_dev), pred, score, mask_out);
@@ -413,6 +431,8 @@ __global__ void score_finish_kernel(const float* __restrict__ logits, int M, con
 // im2col for the 16x16 stride-16 stem: thread = 8 consecutive kx of one (v, c, y, patch-col).
 __global__ void __launch_bounds__(256)
 im2col_patch16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__ out, int V, int Hi, int Wi) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int Wp = Wi >> 4, Hp = Hi >> 4;
   const int halves = Wp * 2;                       // 8-pixel chunks per image row
   const size_t total = (size_t)V * 3 * Hi * halves;
@@ -434,6 +454,8 @@ im2col_patch16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__
 }
 
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
+  pdl_wait();
+  pdl_launch_dependents();
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
   if (i + 3 < n) {
     const float4 v = *reinterpret_cast<const float4*>(in + i);
@@ -447,6 +469,8 @@ __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __
 
 __global__ void __launch_bounds__(256)
 mask_rows_kernel(const float* __restrict__ x, const float* __restrict__ mask, float* __restrict__ out, int M, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int m = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (m >= M) return;
   const float mk = mask[m];
@@ -462,6 +486,8 @@ mask_rows_kernel(const float* __restrict__ x, const float* __restrict__ mask, fl
 // y[v, :, C/2:] <- mean over tokens; grid (V, C/2/128) x 128 threads; two passes over N.
 __global__ void __launch_bounds__(128)
 global_half_mean_kernel(__nv_bfloat16* __restrict__ y, int N, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
   const int v = blockIdx.x;
   const int ch = C / 2 + blockIdx.y * 128 + threadIdx.x;
   if (ch >= C) return;
@@ -490,7 +516,7 @@ extern "C" int toc3d_layernorm_rows(const float* x, const int32_t* row_map, cons
   dim3 grid((M + rows_per_block - 1) / rows_per_block), block(256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
 #define LN_CASE(V)                                                                                                  \
-  case V: layernorm_rows_kernel<V><<<grid, block, 0, ST(stream)>>>(x, row_map, alt, gamma, beta, o, M, eps, pad_mode, reinterpret_cast<long long*>(zero_stats)); break;
+  case V: TOC3D_CHECK_CUDA(launch_pdl(layernorm_rows_kernel<V>, dim3(grid), dim3(block), 0, ST(stream), 1, x, row_map, alt, gamma, beta, o, M, eps, pad_mode, reinterpret_cast<long long*>(zero_stats))); break;
   switch (C / 128) {
     LN_CASE(1) LN_CASE(2) LN_CASE(4) LN_CASE(6) LN_CASE(8) LN_CASE(10) LN_CASE(12) LN_CASE(16) LN_CASE(32)
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_layernorm_rows: unsupported C=%d", C);
@@ -505,8 +531,8 @@ extern "C" int toc3d_subln_bf16(const void* h, void* out, const float* gamma, co
   TOC3D_REQUIRE(h && out && gamma && beta, kErrBadArg, "toc3d_subln_bf16: null pointer");
   TOC3D_REQUIRE(M > 0 && Hd > 0 && Hd <= ld && ld % 8 == 0 && ld <= 3072, kErrBadArg,
                 "toc3d_subln_bf16: bad shape M=%d Hd=%d ld=%d", M, Hd, ld);
-  subln_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(reinterpret_cast<const __nv_bfloat16*>(h),
-                                                    reinterpret_cast<__nv_bfloat16*>(out), gamma, beta, M, Hd, ld, eps);
+  TOC3D_CHECK_CUDA(launch_pdl(subln_kernel, dim3((M + 7) / 8), dim3(256), 0, ST(stream), 1, reinterpret_cast<const __nv_bfloat16*>(h),
+                                                    reinterpret_cast<__nv_bfloat16*>(out), gamma, beta, M, Hd, ld, eps));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -520,8 +546,8 @@ extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int3
                 "toc3d_window_topk: bad shape V=%d H=%d W=%d ws=%d k=%d", V, H, W, ws, k);
   const int nW = V * ((H + ws - 1) / ws) * ((W + ws - 1) / ws);
   const int threads = ((n + 31) / 32) * 32;
-  window_topk_kernel<<<nW, threads, 0, ST(stream)>>>(scores, V, H, W, ws, k, slow_idx, fast_idx,
-                                                                      fast_score, tok_map, rope_rows, fast_map);
+  TOC3D_CHECK_CUDA(launch_pdl(window_topk_kernel, dim3(nW), dim3(threads), 0, ST(stream), 1, scores, V, H, W, ws, k, slow_idx, fast_idx,
+                                                                      fast_score, tok_map, rope_rows, fast_map));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -531,8 +557,8 @@ extern "C" int toc3d_topk_split(const float* scores, int32_t B, int32_t N, int32
   TOC3D_REQUIRE(scores && keep_idx && drop_idx, kErrBadArg, "toc3d_topk_split: null pointer");
   TOC3D_REQUIRE(B > 0 && N > 0 && N <= 12288 && k >= 0 && k <= N, kErrBadArg, "toc3d_topk_split: bad shape B=%d N=%d k=%d", B, N, k);
   dim3 grid((N + 127) / 128, B);
-  topk_split_kernel<<<grid, 128, ((N + 3) / 4) * 16, ST(stream)>>>(scores, N, k, reinterpret_cast<long long*>(keep_idx),
-                                                                   reinterpret_cast<long long*>(drop_idx));
+  TOC3D_CHECK_CUDA(launch_pdl(topk_split_kernel, dim3(grid), dim3(128), ((N + 3) / 4) * 16, ST(stream), 1, scores, N, k, reinterpret_cast<long long*>(keep_idx),
+                                                                   reinterpret_cast<long long*>(drop_idx)));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -543,9 +569,9 @@ extern "C" int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, 
   TOC3D_REQUIRE(nW > 0 && n_fast > 0 && n_fast <= 1024 && C % 128 == 0, kErrBadArg,
                 "toc3d_merge_fast_tokens: bad shape nW=%d n_fast=%d C=%d", nW, n_fast, C);
   if (C % 256 == 0)
-    merge_fast_kernel<2><<<dim3(nW, C / 256), 256, 0, ST(stream)>>>(x, fast_map, fast_score, n_fast, k, C, rep_out, packed);
+    TOC3D_CHECK_CUDA(launch_pdl(merge_fast_kernel<2>, dim3(nW, C / 256), dim3(256), 0, ST(stream), 1, x, fast_map, fast_score, n_fast, k, C, rep_out, packed));
   else
-    merge_fast_kernel<1><<<dim3(nW, C / 128), 256, 0, ST(stream)>>>(x, fast_map, fast_score, n_fast, k, C, rep_out, packed);
+    TOC3D_CHECK_CUDA(launch_pdl(merge_fast_kernel<1>, dim3(nW, C / 128), dim3(256), 0, ST(stream), 1, x, fast_map, fast_score, n_fast, k, C, rep_out, packed));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -555,7 +581,7 @@ extern "C" int toc3d_fast_token_update(float* x, const int32_t* fast_map, const 
   TOC3D_REQUIRE(x && fast_map && packed && rep, kErrBadArg, "toc3d_fast_token_update: null pointer");
   TOC3D_REQUIRE(nW > 0 && n_fast > 0 && C % 4 == 0, kErrBadArg, "toc3d_fast_token_update: bad shape");
   const int total = nW * n_fast;
-  fast_update_kernel<<<(total + 7) / 8, 256, 0, ST(stream)>>>(x, fast_map, packed, rep, total, n_fast, k, C);
+  TOC3D_CHECK_CUDA(launch_pdl(fast_update_kernel, dim3((total + 7) / 8), dim3(256), 0, ST(stream), 1, x, fast_map, packed, rep, total, n_fast, k, C));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -566,8 +592,8 @@ extern "C" int toc3d_score_fold_queries(const float* queries, const float* w_in,
   TOC3D_REQUIRE(queries && w_in && b_in && w_agg && b_agg && A_out && c_out, kErrBadArg, "toc3d_score_fold_queries: null pointer");
   TOC3D_REQUIRE(Bf > 0 && Q > 0 && Cq > 0 && Cq <= 4096 && C > 0, kErrBadArg, "toc3d_score_fold_queries: bad shape");
   dim3 grid(Bf, (C + 127) / 128);
-  score_fold_kernel<<<grid, 128, 2 * Cq * sizeof(float), ST(stream)>>>(queries, w_in, b_in, w_agg, b_agg, scale, Q, Cq, C,
-                                                                        A_out, c_out);
+  TOC3D_CHECK_CUDA(launch_pdl(score_fold_kernel, dim3(grid), dim3(128), 2 * Cq * sizeof(float), ST(stream), 1, queries, w_in, b_in, w_agg, b_agg, scale, Q, Cq, C,
+                                                                        A_out, c_out));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -579,8 +605,8 @@ extern "C" int toc3d_score_tokens(const float* x, const float* mask_in, const fl
   TOC3D_REQUIRE(V > 0 && N > 0 && C % 4 == 0 && views_per_frame > 0 && V % views_per_frame == 0, kErrBadArg,
                 "toc3d_score_tokens: bad shape V=%d N=%d C=%d vpf=%d", V, N, C, views_per_frame);
   const long long toks = (long long)V * N;
-  score_tokens_kernel<<<(unsigned)((toks + 7) / 8), 256, 0, ST(stream)>>>(x, mask_in, A, c, V, N, C, views_per_frame, gumbel,
-                                                                          seed, seed_dev, pred, score, mask_out);
+  TOC3D_CHECK_CUDA(launch_pdl(score_tokens_kernel, dim3((unsigned)((toks + 7) / 8)), dim3(256), 0, ST(stream), 1, x, mask_in, A, c, V, N, C, views_per_frame, gumbel,
+                                                                          seed, seed_dev, pred, score, mask_out));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -588,7 +614,7 @@ extern "C" int toc3d_score_tokens(const float* x, const float* mask_in, const fl
 extern "C" int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed,
                                   const uint64_t* seed_dev, float* pred, float* score, float* mask_out, void* stream) {
   TOC3D_REQUIRE(logits && M > 0, kErrBadArg, "toc3d_score_finish: bad args");
-  score_finish_kernel<<<(M + 255) / 256, 256, 0, ST(stream)>>>(logits, M, gumbel, seed, seed_dev, pred, score, mask_out);
+  TOC3D_CHECK_CUDA(launch_pdl(score_finish_kernel, dim3((M + 255) / 256), dim3(256), 0, ST(stream), 1, logits, M, gumbel, seed, seed_dev, pred, score, mask_out));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -598,7 +624,7 @@ extern "C" int toc3d_im2col_patch16(const float* img, void* out, int32_t V, int3
   TOC3D_REQUIRE(V > 0 && Hi > 0 && Wi > 0 && Hi % 16 == 0 && Wi % 16 == 0, kErrBadArg,
                 "toc3d_im2col_patch16: image %dx%d must be a multiple of the 16x16 patch", Hi, Wi);
   const size_t total = (size_t)V * 3 * Hi * (Wi / 8);
-  im2col_patch16_kernel<<<(unsigned)((total + 255) / 256), 256, 0, ST(stream)>>>(img, reinterpret_cast<__nv_bfloat16*>(out), V, Hi, Wi);
+  TOC3D_CHECK_CUDA(launch_pdl(im2col_patch16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), 1, img, reinterpret_cast<__nv_bfloat16*>(out), V, Hi, Wi));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -607,14 +633,14 @@ extern "C" int toc3d_cast_f32_to_bf16(const float* in, void* out, int64_t n, voi
   TOC3D_REQUIRE(in && out && n > 0, kErrBadArg, "toc3d_cast_f32_to_bf16: bad args");
   TOC3D_REQUIRE(((uintptr_t)in & 15) == 0 && ((uintptr_t)out & 7) == 0, kErrBadArg, "toc3d_cast_f32_to_bf16: unaligned");
   const long long threads = (n + 3) / 4;
-  cast_bf16_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, ST(stream)>>>(in, reinterpret_cast<__nv_bfloat16*>(out), n);
+  TOC3D_CHECK_CUDA(launch_pdl(cast_bf16_kernel, dim3((unsigned)((threads + 255) / 256)), dim3(256), 0, ST(stream), 1, in, reinterpret_cast<__nv_bfloat16*>(out), n));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 
 extern "C" int toc3d_mask_rows(const float* x, const float* mask, float* out, int32_t M, int32_t C, void* stream) {
   TOC3D_REQUIRE(x && mask && out && M > 0 && C % 4 == 0, kErrBadArg, "toc3d_mask_rows: bad args");
-  mask_rows_kernel<<<(M + 7) / 8, 256, 0, ST(stream)>>>(x, mask, out, M, C);
+  TOC3D_CHECK_CUDA(launch_pdl(mask_rows_kernel, dim3((M + 7) / 8), dim3(256), 0, ST(stream), 1, x, mask, out, M, C));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -622,7 +648,7 @@ extern "C" int toc3d_mask_rows(const float* x, const float* mask, float* out, in
 extern "C" int toc3d_global_half_mean(void* y, int32_t V, int32_t N, int32_t C, void* stream) {
   TOC3D_REQUIRE(y && V > 0 && N > 0 && C % 2 == 0, kErrBadArg, "toc3d_global_half_mean: bad args");
   dim3 grid(V, (C / 2 + 127) / 128);
-  global_half_mean_kernel<<<grid, 128, 0, ST(stream)>>>(reinterpret_cast<__nv_bfloat16*>(y), N, C);
+  TOC3D_CHECK_CUDA(launch_pdl(global_half_mean_kernel, dim3(grid), dim3(128), 0, ST(stream), 1, reinterpret_cast<__nv_bfloat16*>(y), N, C));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
