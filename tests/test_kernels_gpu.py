@@ -209,8 +209,9 @@ def test_gemm_swiglu_folded_subln(lib, M, Hd, C):
 
 
 # ------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("seq", [1, 64, 77, 129, 180, 256, 281, 400, 401])
+@pytest.mark.parametrize("seq", [1, 16, 64, 77, 103, 121, 129, 161, 180, 192, 193, 201, 256, 257, 281, 400, 401, 448, 449, 600])
 def test_window_attention(lib, seq):
+    """seq <= 448: tcgen05/TMEM kernel (256 or 512 TMEM columns, 1 or 2 S halves); above: mma.sync fallback."""
     g = torch.Generator().manual_seed(seq)
     nW, heads = 5, 3
     C = heads * 64

@@ -1,5 +1,15 @@
 // Windowed multi-head attention, head dim 64, sequence = one window (<= 401 tokens in the shipped
-// configs).  Flash-style: one CTA = 64 query rows of one (window, head); K/V tiles of 64 keys are
+// configs).  Two kernels:
+//   attn_tc  (seq <= 448): tcgen05 / TMEM / TMA.  One CTA per (window, head): Q, K, V of the window are
+//            staged once by TMA (128B swizzle); per 128-row query tile S = Q K^T is one or two
+//            tcgen05.mma into TMEM, four softmax warps (thread = row) read S with tcgen05.ld, take the
+//            exact row max over the whole window (no online rescaling needed at these lengths), write
+//            P = exp2(.) as packed bf16 back over S with tcgen05.st, and O = P V runs as tcgen05.mma with
+//            the A operand in TMEM and V as an MN-major smem operand.  Two CTAs share an SM when the
+//            window is short enough for 256 TMEM columns, so one CTA's softmax overlaps the other's MMAs.
+//   attn     (fallback, seq > 448): flash-style mma.sync kernel.
+//
+// Fallback kernel: one CTA = 64 query rows of one (window, head); K/V tiles of 64 keys are
 // double-buffered with cp.async; S = QK^T and O += PV run on mma.sync m16n8k16 (bf16 in, fp32
 // accumulate); softmax is online in fp32.  q arrives rotated and pre-scaled (QKV epilogue).
 //
@@ -178,6 +188,391 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
 }
 
 }  // namespace attn
+
+namespace attn_tc {
+
+constexpr int D = 64;
+constexpr int BOX_ROWS = 64;                    // TMA box: 64 rows x 64 bf16 (128 B) = 8 KB
+constexpr int BOX_BYTES = BOX_ROWS * D * 2;
+constexpr int NTHREADS = 160;                   // single-tile kernel: warp 0 TMA + MMA issue; warps 1-4 softmax / epilogue
+constexpr int MAX_SEQ = 448;                    // S (<= 448 fp32 columns) + O (64) fill the 512 TMEM columns
+constexpr int PP_MAX_SEQ = 256;                 // ping-pong kernel: two 256-column slots
+constexpr int PP_THREADS = 320;                 // warp 0 TMA, warp 1 MMA issue, warps 2-5 / 6-9 softmax of slot 0 / 1
+constexpr float LOG2E = 1.4426950408889634f;
+
+// kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128; b_mn = 1 selects an MN-major B operand
+__device__ __forceinline__ uint32_t idesc_m128(int n, int b_mn) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)b_mn << 16) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// Softmax of one 128-row query tile whose scores S sit in TMEM (thread = row, `lane_base` = TMEM address of
+// this warp's lane quarter at the first S column), followed by the O epilogue.
+//   pass 1: exact row max over the window (no online rescaling at these lengths);
+//   pass 2: p = exp2(s log2e - max log2e), fp32 row sum, packed bf16 P written over S with tcgen05.st;
+//   then P is handed to the MMA thread (bar_p), O = P V is awaited (bar_o), read, released (bar_ofree),
+//   scaled by 1 / sum and stored as bf16.  The TMEM load of chunk c+1 is in flight while chunk c is
+//   processed (two named register buffers; tcgen05.wait::ld covers every outstanding load).
+// Warps whose 32 rows are all beyond the window (`active` false, warp-uniform) keep the barrier protocol
+// but skip the arithmetic.
+__device__ __forceinline__ void softmax_tile(uint32_t lane_base, uint32_t o_off, int seq, bool active, bool row_ok,
+                                             __nv_bfloat16* out_row, uint64_t* bar_s, uint64_t* bar_p, uint64_t* bar_o,
+                                             uint64_t* bar_ofree, uint32_t parity) {
+  const int nchunks = (seq + 31) >> 5;
+  mbar_wait(bar_s, parity);
+  tcgen05_fence_after();
+  float sum = 0.f;
+  if (active) {
+    float mx = -INFINITY;
+    uint32_t va[32], vb[32];
+    auto max_chunk = [&](const uint32_t (&v)[32], int c) {
+      const int lim = seq - c * 32;                       // valid columns in this chunk (>= 1)
+      if (lim >= 32) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < lim ? __uint_as_float(v[i]) : -INFINITY);
+      }
+    };
+    tmem_ld_32x32(lane_base, va);
+    for (int c = 0; c < nchunks; c += 2) {
+      tmem_ld_wait();
+      if (c + 1 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 1) * 32), vb);
+      max_chunk(va, c);
+      if (c + 1 < nchunks) {
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 2) * 32), va);
+        max_chunk(vb, c + 1);
+      }
+    }
+    const float mneg = -mx * LOG2E;
+    auto exp_chunk = [&](const uint32_t (&v)[32], int c) {
+      uint32_t pk[16];
+      const int lim = seq - c * 32;
+      if (lim >= 32) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg));
+          const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg));
+          sum += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const float p0 = 2 * i < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg)) : 0.f;
+          const float p1 = 2 * i + 1 < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg)) : 0.f;
+          sum += p0 + p1;
+          pk[i] = pack_bf16(p0, p1);
+        }
+      }
+      tmem_st_32x16(lane_base + (uint32_t)(c * 16), pk);
+    };
+    tmem_ld_32x32(lane_base, va);
+    for (int c = 0; c < nchunks; c += 2) {
+      tmem_ld_wait();
+      if (c + 1 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 1) * 32), vb);
+      exp_chunk(va, c);
+      if (c + 1 < nchunks) {
+        tmem_ld_wait();
+        if (c + 2 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 2) * 32), va);
+        exp_chunk(vb, c + 1);
+      }
+    }
+    tmem_st_wait();
+  }
+  tcgen05_fence_before();
+  mbar_arrive(bar_p);
+  // epilogue: O / sum -> bf16 -> global
+  mbar_wait(bar_o, parity);
+  tcgen05_fence_after();
+  uint32_t o0[32], o1[32];
+  if (active) {
+    tmem_ld_32x32(lane_base + o_off, o0);
+    tmem_ld_32x32(lane_base + o_off + 32u, o1);
+    tmem_ld_wait();
+  }
+  tcgen05_fence_before();
+  mbar_arrive(bar_ofree);
+  if (active && row_ok) {
+    const float inv = 1.0f / sum;
+    uint4* dst = reinterpret_cast<uint4*>(out_row);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u;
+      u.x = pack_bf16(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+      u.y = pack_bf16(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+      u.z = pack_bf16(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+      u.w = pack_bf16(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+      dst[j] = u;
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      uint4 u;
+      u.x = pack_bf16(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
+      u.y = pack_bf16(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
+      u.z = pack_bf16(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
+      u.w = pack_bf16(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
+      dst[4 + j] = u;
+    }
+  }
+}
+
+// S(tile) = Q_tile K^T into TMEM columns [s_col, s_col + spad): one MMA chain for the first 256 keys, a second
+// for the rest.
+__device__ __forceinline__ void issue_qk(uint32_t s_addr, const uint8_t* q_tile, const uint8_t* k_base, int spad) {
+  const int n1 = spad < 256 ? spad : 256, n2 = spad - n1;
+  const uint64_t q_desc = umma_desc_k_sw128(smem_u32(q_tile));
+  const uint64_t k_desc = umma_desc_k_sw128(smem_u32(k_base));
+  const uint32_t id1 = idesc_m128(n1, 0);
+#pragma unroll
+  for (int k = 0; k < D / 16; ++k) umma_bf16_ss(s_addr, q_desc + (uint64_t)(2 * k), k_desc + (uint64_t)(2 * k), id1, k);
+  if (n2 > 0) {
+    const uint64_t k_desc2 = umma_desc_k_sw128(smem_u32(k_base + 256 * 128));
+    const uint32_t id2 = idesc_m128(n2, 0);
+#pragma unroll
+    for (int k = 0; k < D / 16; ++k) umma_bf16_ss(s_addr + 256u, q_desc + (uint64_t)(2 * k), k_desc2 + (uint64_t)(2 * k), id2, k);
+  }
+}
+// O = P V: P packed bf16 in TMEM at p_addr (8 columns per 16 keys), V MN-major in smem (8-key groups 1024 B apart)
+__device__ __forceinline__ void issue_pv(uint32_t o_addr, uint32_t p_addr, const uint8_t* v_base, int spad) {
+  const uint64_t v_desc = umma_desc_k_sw128(smem_u32(v_base));
+  const uint32_t id = idesc_m128(D, 1);
+  const int ksteps = spad >> 4;
+  for (int kk = 0; kk < ksteps; ++kk) umma_bf16_ts(o_addr, p_addr + (uint32_t)(8 * kk), v_desc + (uint64_t)(128 * kk), id, kk);
+}
+
+enum { BAR_QK = 0, BAR_V, BAR_S, BAR_P, BAR_O, BAR_OFREE, NUM_BARS };
+
+// ---------------------------------------------------------------------------------------------------
+// Single-slot kernel (256 < seq <= 448, or any seq): one CTA per (window, head), query tiles in sequence.
+__global__ void __launch_bounds__(NTHREADS)
+window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
+                           int tmem_cols) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int T = (seq + 127) >> 7;               // 128-row query tiles
+  const int nb = (seq + BOX_ROWS - 1) / BOX_ROWS;   // 64-row boxes of K / V
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * T * BOX_BYTES;
+  uint8_t* sV = sK + nb * BOX_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + nb * BOX_BYTES);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, w = blockIdx.y;
+  const int C = heads * D;
+  const int row0 = w * seq;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(&bars[BAR_QK], 1);
+    mbar_init(&bars[BAR_V], 1);
+    mbar_init(&bars[BAR_S], 1);
+    mbar_init(&bars[BAR_P], 128);
+    mbar_init(&bars[BAR_O], 1);
+    mbar_init(&bars[BAR_OFREE], 128);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, (uint32_t)tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int spad = (seq + 15) & ~15;            // keys rounded up to the MMA K / N granularity
+  // O (64 fp32 columns) sits in the last 64 allocated columns.  With 256 columns and more than 192 keys it
+  // overlaps the tail of S, which is dead once P (packed, <= 128 columns) has been written; S(t+1) must then
+  // wait until O(t) has been read out.
+  const uint32_t o_col = (uint32_t)tmem_cols - 64u;
+  const bool o_aliases_s = (uint32_t)spad > o_col;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ---------------------------------------------------------------- TMA: K + Q, then V
+      mbar_arrive_expect_tx(&bars[BAR_QK], (uint32_t)((2 * T + nb) * BOX_BYTES));
+      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_QK], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
+      for (int b = 0; b < 2 * T; ++b) tma_load_2d(&tm, &bars[BAR_QK], sQ + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
+      mbar_arrive_expect_tx(&bars[BAR_V], (uint32_t)(nb * BOX_BYTES));
+      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_V], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
+      // ---------------------------------------------------------------- MMA issue
+      mbar_wait(&bars[BAR_QK], 0);
+      tcgen05_fence_after();
+      issue_qk(tmem_base, sQ, sK, spad);
+      tcgen05_commit(&bars[BAR_S]);
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(&bars[BAR_P], t & 1);                     // P(t) is in TMEM (over S(t))
+        if (t == 0) mbar_wait(&bars[BAR_V], 0);
+        else if (!o_aliases_s) mbar_wait(&bars[BAR_OFREE], (t - 1) & 1);      // O(t-1) has been read out
+        tcgen05_fence_after();
+        issue_pv(tmem_base + o_col, tmem_base, sV, spad);
+        tcgen05_commit(&bars[BAR_O]);
+        if (t + 1 < T) {
+          if (o_aliases_s) {
+            mbar_wait(&bars[BAR_OFREE], t & 1);
+            tcgen05_fence_after();
+          }
+          issue_qk(tmem_base, sQ + (t + 1) * 2 * BOX_BYTES, sK, spad);   // executes after PV(t): may overwrite P(t)
+          tcgen05_commit(&bars[BAR_S]);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;                           // TMEM lane quarter this warp may access
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    for (int t = 0; t < T; ++t) {
+      const int q = t * 128 + quarter * 32 + lane;
+      softmax_tile(lane_base, o_col, seq, t * 128 + quarter * 32 < seq, q < seq, out + (size_t)(row0 + q) * C + h * D,
+                   &bars[BAR_S], &bars[BAR_P], &bars[BAR_O], &bars[BAR_OFREE], (uint32_t)(t & 1));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Ping-pong kernel (seq <= 256): persistent CTAs, one per SM, looping over (window, head) items.
+//   * the Q/K/V boxes of the next items are prefetched by TMA into a ring of item buffers while the
+//     current ones are processed;
+//   * TMEM holds two 256-column slots; unit u = (item, query tile) runs on slot u & 1, each slot has its own
+//     four softmax warps, so the MMAs / barrier round trips of one slot overlap the softmax of the other;
+//   * the MMA thread issues S(u) and then P V of unit u-1 (software pipeline of depth 1).
+enum { PB_FULL = 0 /* +nbuf */, PB_EMPTY = 4, PB_S = 8 /* +slot */, PB_P = 10, PB_O = 12, PB_OFREE = 14, PP_NUM_BARS = 16 };
+
+__global__ void __launch_bounds__(PP_THREADS, 1)
+window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
+                           int n_items, int nbuf) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int T = (seq + 127) >> 7;               // 1 or 2 query tiles
+  const int nb = (seq + BOX_ROWS - 1) / BOX_ROWS;
+  const int item_bytes = (2 * T + 2 * nb) * BOX_BYTES;      // [Q tiles | K | V]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nbuf * item_bytes);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + PP_NUM_BARS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = heads * D;
+  const int spad = (seq + 15) & ~15;
+  const uint32_t o_off = 192u;                  // O columns inside a 256-column slot (aliases dead S columns if spad > 192)
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int n_units = my_items * T;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(&bars[PB_FULL + b], 1);
+      mbar_init(&bars[PB_EMPTY + b], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars[PB_S + s], 1);
+      mbar_init(&bars[PB_P + s], 128);
+      mbar_init(&bars[PB_O + s], 1);
+      mbar_init(&bars[PB_OFREE + s], 128);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ TMA producer: ring of item buffers
+      for (int i = 0; i < my_items; ++i) {
+        const int it = (int)blockIdx.x + i * (int)gridDim.x;
+        const int w = it / heads, h = it - w * heads;
+        const int row0 = w * seq;
+        const int buf = i % nbuf;
+        const uint32_t round = (uint32_t)(i / nbuf);
+        mbar_wait(&bars[PB_EMPTY + buf], (round & 1) ^ 1);
+        uint8_t* base = smem + buf * item_bytes;
+        uint8_t* sK = base + 2 * T * BOX_BYTES;
+        uint8_t* sV = sK + nb * BOX_BYTES;
+        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)item_bytes);
+        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
+        for (int b = 0; b < 2 * T; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
+        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      // ------------------------------------------------------------------ MMA issuer
+      auto unit_ptrs = [&](int u, const uint8_t*& q_tile, const uint8_t*& sK, const uint8_t*& sV) {
+        const int i = u / T, t = u - i * T;
+        const uint8_t* base = smem + (i % nbuf) * item_bytes;
+        q_tile = base + t * 2 * BOX_BYTES;
+        sK = base + 2 * T * BOX_BYTES;
+        sV = sK + nb * BOX_BYTES;
+      };
+      auto do_pv = [&](int u) {
+        const int s = u & 1;
+        const uint32_t n = (uint32_t)(u >> 1);              // how many units this slot has seen before
+        const uint8_t *q_tile, *sK, *sV;
+        unit_ptrs(u, q_tile, sK, sV);
+        mbar_wait(&bars[PB_P + s], n & 1);
+        tcgen05_fence_after();
+        issue_pv(tmem_base + (uint32_t)(s * 256) + o_off, tmem_base + (uint32_t)(s * 256), sV, spad);
+        tcgen05_commit(&bars[PB_O + s]);
+        const int i = u / T;
+        if (u - i * T == T - 1) tcgen05_commit(&bars[PB_EMPTY + i % nbuf]);   // all MMAs reading this item are issued
+      };
+      for (int u = 0; u < n_units; ++u) {
+        const int s = u & 1;
+        const uint32_t n = (uint32_t)(u >> 1);
+        const int i = u / T;
+        const uint8_t *q_tile, *sK, *sV;
+        unit_ptrs(u, q_tile, sK, sV);
+        if (u - i * T == 0) mbar_wait(&bars[PB_FULL + i % nbuf], (uint32_t)((i / nbuf) & 1));
+        if (n > 0) mbar_wait(&bars[PB_OFREE + s], (n - 1) & 1);               // slot drained by its softmax warps
+        tcgen05_fence_after();
+        issue_qk(tmem_base + (uint32_t)(s * 256), q_tile, sK, spad);
+        tcgen05_commit(&bars[PB_S + s]);
+        if (u > 0) do_pv(u - 1);
+      }
+      if (n_units > 0) do_pv(n_units - 1);
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax warps: slot = (warp - 2) / 4
+    const int slot = (warp - 2) >> 2;
+    const int quarter = warp & 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 256);
+    for (int u = slot; u < n_units; u += 2) {
+      const int i = u / T, t = u - i * T;
+      const int it = (int)blockIdx.x + i * (int)gridDim.x;
+      const int w = it / heads, h = it - w * heads;
+      const int q = t * 128 + quarter * 32 + lane;
+      softmax_tile(lane_base, o_off, seq, t * 128 + quarter * 32 < seq, q < seq,
+                   out + ((size_t)w * seq + q) * C + h * D, &bars[PB_S + slot], &bars[PB_P + slot], &bars[PB_O + slot],
+                   &bars[PB_OFREE + slot], (uint32_t)((u >> 1) & 1));
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+}  // namespace attn_tc
 }  // namespace toc3d
 
 extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
@@ -187,9 +582,46 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
   TOC3D_REQUIRE(n_windows > 0 && seq_len > 0 && seq_len <= 1024 && heads > 0 && heads <= 65535, kErrBadArg,
                 "toc3d_window_attention: bad shape nW=%d seq=%d heads=%d", n_windows, seq_len, heads);
   TOC3D_REQUIRE(n_windows <= 65535, kErrBadArg, "toc3d_window_attention: too many windows (%d)", n_windows);
+  cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
+  if (seq_len <= attn_tc::MAX_SEQ) {
+    static bool configured = false;
+    static int n_sm = 148;
+    if (!configured) {
+      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            227 * 1024));
+      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            227 * 1024));
+      int dev = 0;
+      cudaGetDevice(&dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      configured = true;
+    }
+    const int C = heads * attn_tc::D;
+    CUtensorMap tm;
+    int rc = make_tmap_bf16_2d(&tm, qkv, (int64_t)n_windows * seq_len, 3 * (int64_t)C, 3 * (int64_t)C, attn_tc::BOX_ROWS);
+    if (rc) return rc;
+    const int T = (seq_len + 127) / 128, nb = (seq_len + 63) / 64;
+    __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+    if (seq_len <= attn_tc::PP_MAX_SEQ) {
+      const int item_bytes = (2 * T + 2 * nb) * attn_tc::BOX_BYTES;
+      int nbuf = (226 * 1024 - 1024 - 256) / item_bytes;
+      nbuf = nbuf > 4 ? 4 : nbuf;                       // >= 2 for seq <= 256 (96 KB per item)
+      const int n_items = n_windows * heads;
+      const int grid = n_items < n_sm ? n_items : n_sm;
+      const size_t smem = (size_t)nbuf * item_bytes + 1024 + 256;
+      TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1, tm, o,
+                                  seq_len, heads, n_items, nbuf));
+      return 0;
+    }
+    const int spad = (seq_len + 15) & ~15;
+    const int tmem_cols = spad <= 256 ? 256 : 512;     // <= 256 keys: two CTAs per SM (O may alias the tail of S)
+    const size_t smem = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128;
+    TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc_kernel, dim3(heads, n_windows), dim3(attn_tc::NTHREADS), smem, st,
+                                1, tm, o, seq_len, heads, tmem_cols));
+    return 0;
+  }
   dim3 grid((seq_len + attn::BQ - 1) / attn::BQ, heads, n_windows);
-  TOC3D_CHECK_CUDA(launch_pdl(attn::window_attention_kernel, grid, dim3(attn::NTHREADS), 0,
-                              reinterpret_cast<cudaStream_t>(stream), 1, reinterpret_cast<const __nv_bfloat16*>(qkv),
-                              reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads));
+  TOC3D_CHECK_CUDA(launch_pdl(attn::window_attention_kernel, grid, dim3(attn::NTHREADS), 0, st, 1,
+                              reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads));
   return 0;
 }

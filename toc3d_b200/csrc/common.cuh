@@ -30,6 +30,10 @@ void set_last_error(const char* fmt, ...);
 constexpr int kErrBadArg = -1;
 constexpr int kErrNoDriver = -2;
 
+// TMA descriptor of a 2-D bf16 row-major [rows, cols] tensor (leading dimension ld elements), box =
+// [box_rows, 64 columns], 128-byte swizzle (defined in gemm_tcgen05.cu).
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows);
+
 // ---------------------------------------------------------------- small device utils
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -153,6 +157,26 @@ __device__ __forceinline__ void tmem_ld_32x32(uint32_t taddr, uint32_t (&v)[32])
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// 32 lanes x 16 consecutive 32-bit columns: thread t of the warp writes row (lane base + t).
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]),
+        "r"(v[8]), "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] * B[smem]: A rows = TMEM lanes, 16-bit K elements packed two per 32-bit column.
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
 
 // ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {

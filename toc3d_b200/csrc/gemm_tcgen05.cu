@@ -550,8 +550,11 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+}  // namespace gemm
+
 // 2-D bf16 row-major [rows, cols] with leading dimension ld (elements); box = [box_rows, 64 cols], 128B swizzle.
-static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  using namespace gemm;
   EncodeTiledFn enc = get_encode_fn();
   TOC3D_REQUIRE(enc != nullptr, kErrNoDriver, "cuTensorMapEncodeTiled entry point not available");
   cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
@@ -565,6 +568,8 @@ static int make_tmap(CUtensorMap* tm, const void* base, int64_t rows, int64_t co
                 (int)r, (long long)rows, (long long)cols, (long long)ld);
   return 0;
 }
+
+namespace gemm {
 
 static int sm_count() {
   static int n = 0;
@@ -607,9 +612,9 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
   const int max_pairs = sm_count() / 2;
   const int bn = tile_n > 0 ? tile_n : pick_tile_n(M, N, K, EPI, max_pairs);
   CUtensorMap ta, tb;
-  int rc = make_tmap(&ta, A, M, K, lda, BM);
+  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap(&tb, B, N, K, ldb, bn / 2);
+  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, bn / 2);
   if (rc) return rc;
   const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn);
   const int pairs = tiles < max_pairs ? tiles : max_pairs;
