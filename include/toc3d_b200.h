@@ -160,6 +160,16 @@ int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, const float
 int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* packed, const float* rep, int32_t nW,
                             int32_t n_fast, int32_t k, int32_t C, void* stream);
 
+/* Fused front end of an accelerated block (toc3d_eva_vit.py:421-427 gather + merge_tokens, then norm1 at
+ * :371): in ONE launch, (1) rep[w] = sum_j (s_j / sum s) x[fast_map[w,j]] -> rep_out[w] and packed row
+ * w*(k+1)+k (fp32), LayerNorm(rep[w]) -> out row w*(k+1)+k; (2) LayerNorm of every gathered slow row
+ * m (tok_map[m] >= 0: x row; -1: pad slot = zero vector -> beta; -2: the representative row, see (1)) ->
+ * bf16 out [nW*(k+1), C].  C in {128, 256, 512, 1024}.  zero_stats as in toc3d_layernorm_rows. */
+int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t* fast_map, const float* fast_score,
+                          const float* gamma, const float* beta, void* out_bf16, float* rep_out, float* packed,
+                          int32_t nW, int32_t k, int32_t n_fast, int32_t C, float eps, int64_t* zero_stats,
+                          void* stream);
+
 /* ------------------------------------------------------------------ history-query scorer
  * toc3d_utils.py:232-252 is linear in the token up to the LogSoftmax, so the query bank is
  * folded once per frame into A[f] (2 x C) and c[f] (2):

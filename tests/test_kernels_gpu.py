@@ -362,6 +362,40 @@ def test_merge_and_fast_update(lib):
     assert (xd.cpu() - ref).abs().max().item() < 1e-5
 
 
+@pytest.mark.parametrize("C,ws,ratio", [(1024, 16, 0.7), (1024, 20, 0.5), (128, 16, 0.3), (256, 20, 0.4)])
+def test_ln_gather_merge_fused(lib, C, ws, ratio):
+    """One launch = batch_index_select (slow + fast), merge_tokens and norm1 of the packed rows
+    (toc3d_eva_vit.py:421-427, :371; pad slots are zero vectors whose LayerNorm is the bias)."""
+    g = torch.Generator().manual_seed(C + ws)
+    V, H, W = 2, 20, 50
+    n, k = ws * ws, int(ws * ws * ratio)
+    x = torch.randn(V, H, W, C, generator=g) * 3 + 0.5
+    s = -torch.rand(V, H, W, generator=g) * 4
+    gamma = 1 + 0.1 * torch.randn(C, generator=g); beta = 0.1 * torch.randn(C, generator=g)
+    xw, _ = O.window_partition(x, ws); xw = xw.reshape(-1, n, C)
+    sw, _ = O.window_partition(s[..., None], ws, pad_value=O.PAD_SCORE); sw = sw.reshape(-1, n)
+    _, fast_s, slow_idx, fast_idx = O.sample(sw, ratio)
+    rep_ref = O.merge_tokens(O.batch_index_select(xw, fast_idx), fast_s)
+    t_ref = torch.cat([O.batch_index_select(xw, slow_idx), rep_ref], dim=1)          # (nW, k+1, C)
+    ln_ref = torch.nn.functional.layer_norm(t_ref, (C,), gamma, beta, 1e-6).reshape(-1, C)
+    nW, nf = sw.shape[0], n - k
+    i32 = dict(dtype=torch.int32, device=DEV)
+    fs = torch.empty(nW, nf, device=DEV); fm = torch.empty(nW, nf, **i32)
+    tok = torch.empty(nW * (k + 1), **i32)
+    lib.window_topk(s.to(DEV), V, H, W, ws, k, fast_score=fs, fast_map=fm, tok_map=tok)
+    xd = x.reshape(-1, C).to(DEV).contiguous()
+    out = torch.full((nW * (k + 1), C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    rep = torch.empty(nW, C, device=DEV); packed = torch.zeros(nW * (k + 1), C, device=DEV)
+    stats = torch.ones(nW * (k + 1), 2, device=DEV, dtype=torch.int64)
+    lib.ln_gather_merge(xd, tok, fm, fs, gamma.to(DEV), beta.to(DEV), out, rep, packed, nW, k, nf, C, 1e-6, zero_stats=stats)
+    assert (rep.cpu() - rep_ref[:, 0]).abs().max().item() < 1e-5 * max(1.0, rep_ref.abs().max().item())
+    assert torch.equal(packed.reshape(nW, k + 1, C)[:, k], rep)
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ln_ref).abs().max().item() < 2e-2 * max(1.0, ln_ref.abs().max().item() / 4)      # bf16 output
+    assert (stats == 0).all()
+
+
 # ------------------------------------------------------------------------------------ scorer
 def test_scorer_fold_and_tokens(lib):
     g = torch.Generator().manual_seed(5)

@@ -377,8 +377,13 @@ class _Engine:
         w, t = wsp.win[ws], wsp.stage[(stage, ws)]
         nW, k, nf = w["nW"], t["k"], t["nf"]
         Mp = nW * (k + 1)
-        L.merge_fast_tokens(X, t["fast_map"], t["fast_score"], nW, nf, k, C, t["rep"], wsp.T)
-        L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, Mp, C, LN_EPS, row_map=t["tok_map"], alt=wsp.T, pad_mode=1)
+        if C in (128, 256, 512, 1024):      # one launch: representative token + norm1 of the packed slow/rep rows
+            L.ln_gather_merge(X, t["tok_map"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
+                              wsp.T, nW, k, nf, C, LN_EPS)
+        else:
+            L.merge_fast_tokens(X, t["fast_map"], t["fast_score"], nW, nf, k, C, t["rep"], wsp.T)
+            L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, Mp, C, LN_EPS, row_map=t["tok_map"], alt=wsp.T,
+                             pad_mode=1)
         self._qkv_attn(bp, wsp, Mp, nW, k + 1, t["rope_rows"], 0)
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mp, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
                resid_map=t["tok_map"], out_alt=wsp.T)                                  # t1 = t + attn

@@ -206,23 +206,43 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
   }
 }
 
-// Image-level stable sort split by rank counting; grid (ceil(N/128), B), keys of one row in smem.
-__global__ void __launch_bounds__(128)
+// Image-level stable sort split by rank counting; grid (ceil(N/32), B) x 256 threads: the keys of one row sit
+// in smem, 8 lanes share one element (lane s counts key groups s, s+8, ...) and combine with shuffles.
+__global__ void __launch_bounds__(256)
 topk_split_kernel(const float* __restrict__ scores, int N, int k, long long* __restrict__ keep_idx,
                   long long* __restrict__ drop_idx) {
+  extern __shared__ __align__(16) uint32_t s_keys[];
   pdl_wait();
   pdl_launch_dependents();
-  extern __shared__ __align__(16) uint32_t s_keys[];
   const int b = blockIdx.y;
   const float* row = scores + (size_t)b * N;
   const int n4 = (N + 3) >> 2;
   for (int j = threadIdx.x; j < 4 * n4; j += blockDim.x) s_keys[j] = j < N ? order_key(row[j]) : 0u;
   __syncthreads();
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= N) return;
-  const int rank = rank_of(s_keys, n4, s_keys[i], i);
-  if (rank < k) keep_idx[(size_t)b * k + rank] = i;
-  else drop_idx[(size_t)b * (N - k) + (rank - k)] = i;
+  const int i = blockIdx.x * 32 + (threadIdx.x >> 3);
+  const int sub = threadIdx.x & 7;
+  const bool ok = i < N;
+  const uint32_t ki = ok ? s_keys[i] : 0u;
+  int rank = 0;
+  if (ok) {
+    const uint4* k4 = reinterpret_cast<const uint4*>(s_keys);
+#pragma unroll 4
+    for (int g = sub; g < n4; g += 8) {
+      const uint4 kj = k4[g];
+      const int j = 4 * g;
+      rank += (kj.x > ki) || (kj.x == ki && j + 0 < i);
+      rank += (kj.y > ki) || (kj.y == ki && j + 1 < i);
+      rank += (kj.z > ki) || (kj.z == ki && j + 2 < i);
+      rank += (kj.w > ki) || (kj.w == ki && j + 3 < i);
+    }
+  }
+  rank += __shfl_xor_sync(0xffffffffu, rank, 1);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 2);
+  rank += __shfl_xor_sync(0xffffffffu, rank, 4);
+  if (ok && sub == 0) {
+    if (rank < k) keep_idx[(size_t)b * k + rank] = i;
+    else drop_idx[(size_t)b * (N - k) + (rank - k)] = i;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -292,10 +312,151 @@ merge_fast_kernel(const float* __restrict__ x, const int* __restrict__ fast_map,
   }
 }
 
-// x[fast_map[w,j]] += packed[rep row of w] - rep[w];  one warp per fast token, float4 lanes.
+// ------------------------------------------------------------------------------------------------
+// Fused norm1 front end of an accelerated block (toc3d_eva_vit.py:421-427 + :371): one launch does
+//   blocks [0, nW)      : representative token of window w = sum_j (s_j / sum s) x[fast_map[w,j]] (fp32, written
+//                         to rep_out[w] and packed[w*(k+1)+k]) followed by its LayerNorm -> out row w*(k+1)+k;
+//   blocks [nW, ...)    : LayerNorm of the gathered slow rows (8 rows per block, warp per row).
+// Merge block: warp q accumulates rows j = q (mod 8) over all C channels (VPL float4 per lane, two rows in
+// flight), the eight partials meet in shared memory in a fixed order (deterministic).
+template <int VPL>
+__global__ void __launch_bounds__(256)
+ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_map, const int* __restrict__ fast_map,
+                       const float* __restrict__ fast_score, const float* __restrict__ gamma,
+                       const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, float* __restrict__ rep_out,
+                       float* __restrict__ packed, int nW, int k, int n_fast, float eps, long long* __restrict__ zero_stats) {
+  constexpr int C = VPL * 128;
+  __shared__ __align__(16) float s_acc[8][C];
+  __shared__ float s_wgt[1024];
+  __shared__ int s_row[1024];
+  __shared__ float s_red[8];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if ((int)blockIdx.x >= nW) {
+    // ---- LayerNorm of gathered slow rows (pad slots are zero vectors -> beta), rep rows belong to the merge blocks
+    const int M = nW * (k + 1);
+    const int m = ((int)blockIdx.x - nW) * 8 + warp;
+    if (m >= M) return;
+    if (zero_stats != nullptr && lane == 0) *reinterpret_cast<longlong2*>(zero_stats + 2 * (size_t)m) = make_longlong2(0, 0);
+    const int src = tok_map[m];
+    if (src == -2) return;
+    const float4* p = src >= 0 ? reinterpret_cast<const float4*>(x + (size_t)src * C) : nullptr;
+    float4 v[VPL];
+    float sm = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      v[i] = p ? p[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+      sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+    const float mean = warp_sum(sm) / (float)C;
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float a = v[i].x - mean, b = v[i].y - mean, c = v[i].z - mean, d = v[i].w - mean;
+      q += (a * a + b * b) + (c * c + d * d);
+    }
+    const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+    uint2* o = reinterpret_cast<uint2*>(out + (size_t)m * C);
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) {
+      const float4 g = reinterpret_cast<const float4*>(gamma)[lane + 32 * i];
+      const float4 b = reinterpret_cast<const float4*>(beta)[lane + 32 * i];
+      uint2 u;
+      u.x = pack_bf16((v[i].x - mean) * rstd * g.x + b.x, (v[i].y - mean) * rstd * g.y + b.y);
+      u.y = pack_bf16((v[i].z - mean) * rstd * g.z + b.z, (v[i].w - mean) * rstd * g.w + b.w);
+      o[lane + 32 * i] = u;
+    }
+    return;
+  }
+  // ---- representative token of window w
+  const int w = blockIdx.x;
+  const float* fs = fast_score + (size_t)w * n_fast;
+  const int* fm = fast_map + (size_t)w * n_fast;
+  float part = 0.f;
+  for (int j = threadIdx.x; j < n_fast; j += 256) {
+    const float sc = fs[j];
+    s_wgt[j] = sc;
+    s_row[j] = fm[j];
+    part += sc;
+  }
+  part = warp_sum(part);
+  if (lane == 0) s_red[warp] = part;
+  __syncthreads();
+  const float total = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
+  float4 a[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* xb = reinterpret_cast<const float4*>(x) + lane;
+  for (int j0 = warp; j0 < n_fast; j0 += 16) {
+    float4 v[2][VPL];
+    float wg[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int j = j0 + 8 * u;
+      const int r = j < n_fast ? s_row[j] : -1;
+      wg[u] = j < n_fast ? s_wgt[j] / total : 0.f;             // weight = score / sum(score)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i)
+        v[u][i] = r >= 0 ? xb[(size_t)r * (C / 4) + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u)
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        a[i].x += wg[u] * v[u][i].x; a[i].y += wg[u] * v[u][i].y;
+        a[i].z += wg[u] * v[u][i].z; a[i].w += wg[u] * v[u][i].w;
+      }
+  }
+  __syncthreads();                        // s_red is reused below
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) reinterpret_cast<float4*>(s_acc[warp])[lane + 32 * i] = a[i];
+  __syncthreads();
+  // thread t owns channels t, t + 256, ... (C / 256 of them; C = 128: threads 0..127 own one)
+  constexpr int PER = (C + 255) / 256;
+  float r[PER];
+  float sm = 0.f;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int ch = threadIdx.x + 256 * e;
+    r[e] = 0.f;
+    if (ch < C) {
+#pragma unroll
+      for (int q = 0; q < 8; ++q) r[e] += s_acc[q][ch];
+      rep_out[(size_t)w * C + ch] = r[e];
+      packed[((size_t)w * (k + 1) + k) * C + ch] = r[e];
+      sm += r[e];
+    }
+  }
+  sm = warp_sum(sm);
+  if (lane == 0) s_red[warp] = sm;
+  __syncthreads();
+  const float mean = (((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]))) / (float)C;
+  float q2 = 0.f;
+#pragma unroll
+  for (int e = 0; e < PER; ++e)
+    if (threadIdx.x + 256 * e < C) q2 += (r[e] - mean) * (r[e] - mean);
+  q2 = warp_sum(q2);
+  __syncthreads();
+  if (lane == 0) s_red[warp] = q2;
+  __syncthreads();
+  const float var = (((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]))) / (float)C;
+  const float rstd = rsqrtf(var + eps);
+  __nv_bfloat16* o = out + ((size_t)w * (k + 1) + k) * C;
+#pragma unroll
+  for (int e = 0; e < PER; ++e) {
+    const int ch = threadIdx.x + 256 * e;
+    if (ch < C) o[ch] = __float2bfloat16_rn((r[e] - mean) * rstd * gamma[ch] + beta[ch]);
+  }
+}
+
+// x[fast_map[w,j]] += packed[rep row of w] - rep[w];  one warp per fast token, VPL float4 per lane, all of the
+// row's loads issued before the first use (the two representative rows are shared by the window: L1/L2 hits).
+template <int VPL>
 __global__ void __launch_bounds__(256)
 fast_update_kernel(float* __restrict__ x, const int* __restrict__ fast_map, const float* __restrict__ packed,
-                   const float* __restrict__ rep, int total_fast, int n_fast, int k, int C) {
+                   const float* __restrict__ rep, int total_fast, int n_fast, int k) {
+  constexpr int C = VPL * 128;
   pdl_wait();
   pdl_launch_dependents();
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -304,14 +465,20 @@ fast_update_kernel(float* __restrict__ x, const int* __restrict__ fast_map, cons
   if (row < 0) return;
   const int w = f / n_fast;
   const int lane = threadIdx.x & 31;
-  const float4* t2 = reinterpret_cast<const float4*>(packed + ((size_t)w * (k + 1) + k) * C);
-  const float4* t0 = reinterpret_cast<const float4*>(rep + (size_t)w * C);
-  float4* xr = reinterpret_cast<float4*>(x + (size_t)row * C);
-  for (int i = lane; i < (C >> 2); i += 32) {
-    const float4 a = t2[i], b = t0[i];
-    float4 v = xr[i];
-    v.x += a.x - b.x; v.y += a.y - b.y; v.z += a.z - b.z; v.w += a.w - b.w;
-    xr[i] = v;
+  const float4* t2 = reinterpret_cast<const float4*>(packed + ((size_t)w * (k + 1) + k) * C) + lane;
+  const float4* t0 = reinterpret_cast<const float4*>(rep + (size_t)w * C) + lane;
+  float4* xr = reinterpret_cast<float4*>(x + (size_t)row * C) + lane;
+  float4 v[VPL], a[VPL], b[VPL];
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i] = xr[32 * i];
+    a[i] = __ldg(t2 + 32 * i);
+    b[i] = __ldg(t0 + 32 * i);
+  }
+#pragma unroll
+  for (int i = 0; i < VPL; ++i) {
+    v[i].x += a[i].x - b[i].x; v[i].y += a[i].y - b[i].y; v[i].z += a[i].z - b[i].z; v[i].w += a[i].w - b[i].w;
+    xr[32 * i] = v[i];
   }
 }
 
@@ -556,8 +723,8 @@ extern "C" int toc3d_topk_split(const float* scores, int32_t B, int32_t N, int32
                                 int64_t* drop_idx, void* stream) {
   TOC3D_REQUIRE(scores && keep_idx && drop_idx, kErrBadArg, "toc3d_topk_split: null pointer");
   TOC3D_REQUIRE(B > 0 && N > 0 && N <= 12288 && k >= 0 && k <= N, kErrBadArg, "toc3d_topk_split: bad shape B=%d N=%d k=%d", B, N, k);
-  dim3 grid((N + 127) / 128, B);
-  TOC3D_CHECK_CUDA(launch_pdl(topk_split_kernel, dim3(grid), dim3(128), ((N + 3) / 4) * 16, ST(stream), 1, scores, N, k, reinterpret_cast<long long*>(keep_idx),
+  dim3 grid((N + 31) / 32, B);
+  TOC3D_CHECK_CUDA(launch_pdl(topk_split_kernel, dim3(grid), dim3(256), ((N + 3) / 4) * 16, ST(stream), 1, scores, N, k, reinterpret_cast<long long*>(keep_idx),
                                                                    reinterpret_cast<long long*>(drop_idx)));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
@@ -579,10 +746,38 @@ extern "C" int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, 
 extern "C" int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* packed, const float* rep,
                                        int32_t nW, int32_t n_fast, int32_t k, int32_t C, void* stream) {
   TOC3D_REQUIRE(x && fast_map && packed && rep, kErrBadArg, "toc3d_fast_token_update: null pointer");
-  TOC3D_REQUIRE(nW > 0 && n_fast > 0 && C % 4 == 0, kErrBadArg, "toc3d_fast_token_update: bad shape");
+  TOC3D_REQUIRE(nW > 0 && n_fast > 0 && C % 128 == 0, kErrBadArg, "toc3d_fast_token_update: bad shape");
   const int total = nW * n_fast;
-  TOC3D_CHECK_CUDA(launch_pdl(fast_update_kernel, dim3((total + 7) / 8), dim3(256), 0, ST(stream), 1, x, fast_map, packed, rep, total, n_fast, k, C));
-  TOC3D_CHECK_CUDA(cudaGetLastError());
+  dim3 grid((total + 7) / 8), block(256);
+#define UPD_CASE(V)                                                                                                  \
+  case V: TOC3D_CHECK_CUDA(launch_pdl(fast_update_kernel<V>, grid, block, 0, ST(stream), 1, x, fast_map, packed, rep, total, n_fast, k)); break;
+  switch (C / 128) {
+    UPD_CASE(1) UPD_CASE(2) UPD_CASE(4) UPD_CASE(6) UPD_CASE(8) UPD_CASE(16)
+    default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_fast_token_update: unsupported C=%d", C);
+  }
+#undef UPD_CASE
+  return 0;
+}
+
+extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t* fast_map,
+                                     const float* fast_score, const float* gamma, const float* beta, void* out,
+                                     float* rep_out, float* packed, int32_t nW, int32_t k, int32_t n_fast, int32_t C,
+                                     float eps, int64_t* zero_stats, void* stream) {
+  TOC3D_REQUIRE(x && tok_map && fast_map && fast_score && gamma && beta && out && rep_out && packed, kErrBadArg,
+                "toc3d_ln_gather_merge: null pointer");
+  TOC3D_REQUIRE(nW > 0 && k >= 0 && n_fast > 0 && n_fast <= 1024, kErrBadArg,
+                "toc3d_ln_gather_merge: bad shape nW=%d k=%d n_fast=%d", nW, k, n_fast);
+  const int M = nW * (k + 1);
+  dim3 grid(nW + (M + 7) / 8), block(256);
+  __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
+  long long* zs = reinterpret_cast<long long*>(zero_stats);
+#define LGM_CASE(V)                                                                                                  \
+  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs)); break;
+  switch (C % 128 == 0 ? C / 128 : 0) {
+    LGM_CASE(1) LGM_CASE(2) LGM_CASE(4) LGM_CASE(8)
+    default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_ln_gather_merge: C must be 128, 256, 512 or 1024 (got %d)", C);
+  }
+#undef LGM_CASE
   return 0;
 }
 

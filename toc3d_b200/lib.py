@@ -46,6 +46,7 @@ _SIGS = {
                                  _c_void_p, _c_void_p], _c_int),
     "toc3d_fast_token_update": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                  _c_void_p], _c_int),
+    "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_fold_queries": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int,
                                   _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
@@ -169,6 +170,14 @@ def merge_fast_tokens(x, fast_map, fast_score, nW, n_fast, k, C, rep_out, packed
 def fast_token_update(x, fast_map, packed, rep, nW, n_fast, k, C):
     _check(load().toc3d_fast_token_update(_p(x), _p(fast_map), _p(packed), _p(rep), nW, n_fast, k, C, _stream()),
            "toc3d_fast_token_update")
+
+
+def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out, packed, nW, k, n_fast, C, eps,
+                    zero_stats=None):
+    _want(x, torch.float32, "x"); _want(out, torch.bfloat16, "out")
+    _check(load().toc3d_ln_gather_merge(_p(x), _p(tok_map), _p(fast_map), _p(fast_score), _p(gamma), _p(beta), _p(out),
+                                        _p(rep_out), _p(packed), nW, k, n_fast, C, eps, _p(zero_stats), _stream()),
+           "toc3d_ln_gather_merge")
 
 
 def score_fold_queries(queries, w_in, b_in, w_agg, b_agg, scale, A_out, c_out):
