@@ -390,7 +390,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
 template <int EPI, bool LNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-            int BN, const EpiParams ep) {
+            int BN, int mc, const EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle; pointer arithmetic (not an integer round trip) keeps the
   // shared address space visible to the compiler (LDS/STS instead of generic loads in the epilogue).
@@ -406,21 +406,31 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();          // 0 = leader of the pair
-  const int pair = blockIdx.x >> 1;
-  const int num_pairs = gridDim.x >> 1;
-  const int num_m = (M + 2 * BM - 1) / (2 * BM);    // 256-row pair tiles
+  // mc = 0: cluster = one CTA pair.  mc = 1: cluster = two pairs working on vertically adjacent 256-row tiles of
+  // the same BN columns; every CTA then loads only HALF of its pair-half of the B tile and multicasts it to the
+  // CTA of the same rank in the other pair (L2 -> SM traffic per k-block 24 KB instead of 32 KB per CTA).
+  const uint32_t crank = cluster_ctarank();         // rank in the cluster (0..1 or 0..3)
+  const uint32_t rank = crank & 1u;                 // rank in the pair, 0 = leader
+  const uint32_t prank = crank >> 1;                // which pair of the cluster
+  const uint32_t lead = crank & ~1u;                // cluster rank of this pair's leader
+  const int csize = mc ? 4 : 2;
+  const int pair = blockIdx.x / csize;              // "scheduling unit" index: cluster (mc) or pair
+  const int num_pairs = gridDim.x / csize;
+  const int mrows = mc ? 4 * BM : 2 * BM;           // rows covered by one scheduling unit
+  const int num_m = (M + mrows - 1) / mrows;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
-  const int b_rows = BN >> 1;                       // weight rows staged by this CTA
+  const int b_rows = BN >> 1;                       // weight rows this CTA feeds to the pair MMA
+  const int b_load = mc ? (b_rows >> 1) : b_rows;   // weight rows this CTA loads itself
+  const uint16_t b_mask = (uint16_t)((1u << rank) | (1u << (2u + rank)));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
+      mbar_init(&empty_bar[s], mc ? 2 : 1);           // mc: both pairs' MMAs must have released the slot
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -440,7 +450,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);    // both CTAs' bytes
+      const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);    // bytes landing in both CTAs of the pair
+      auto load_b = [&](int stage, int kb, int n_idx) {
+        const uint32_t bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;             // pair leader's barrier (peer bit cleared)
+        uint8_t* sb = smem + stage * STAGE_BYTES + A_BYTES;
+        if (mc) tma_load_2d_2sm_mc(&tmB, bar, sb + prank * b_load * BK * 2, kb * BK, n_idx + (int)prank * b_load, b_mask);
+        else tma_load_2d_2sm(&tmB, bar, sb, kb * BK, n_idx);
+      };
       // The weights (B) do not depend on the previous kernel in the stream: the first ring of B loads
       // is issued before the programmatic-dependency wait and overlaps that kernel's tail.
       int pre = 0;
@@ -449,22 +465,22 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         pre = num_k < STAGES ? num_k : STAGES;
         for (int kb = 0; kb < pre; ++kb) {
           if (rank == 0) mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
-          tma_load_2d_2sm(&tmB, mapa_u32(smem_u32(&full_bar[kb]), 0), smem + kb * STAGE_BYTES + A_BYTES, kb * BK, n_idx);
+          load_b(kb, kb, n_idx);
         }
       }
       pdl_wait();
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_idx = (tile % num_m) * (2 * BM) + (int)rank * BM;
+        const int m_idx = (tile % num_m) * mrows + (int)prank * (2 * BM) + (int)rank * BM;
         const int n_idx = (tile / num_m) * BN + (int)rank * b_rows;
         for (int kb = 0; kb < num_k; ++kb) {
-          const uint32_t lead_full = mapa_u32(smem_u32(&full_bar[stage]), 0);
+          const uint32_t lead_full = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
           uint8_t* sa = smem + stage * STAGE_BYTES;
           if (pre > 0) {                              // B of this slot is already in flight
             --pre;
           } else {
             mbar_wait(&empty_bar[stage], phase ^ 1);
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            tma_load_2d_2sm(&tmB, lead_full, sa + A_BYTES, kb * BK, n_idx);
+            load_b(stage, kb, n_idx);
           }
           tma_load_2d_2sm(&tmA, lead_full, sa, kb * BK, m_idx);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -479,6 +495,8 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       int acc = 0;
       uint32_t acc_phase = 0;
       const uint32_t idesc = make_idesc(BN);
+      const uint16_t full_mask = (uint16_t)(3u << lead);
+      const uint16_t empty_mask = mc ? (uint16_t)0xF : full_mask;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -495,10 +513,10 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc,
                              (kb | k) != 0 ? 1u : 0u);
           }
-          tcgen05_commit_2sm(&empty_bar[stage], 3);   // smem slot reusable in BOTH CTAs once these MMAs retire
+          tcgen05_commit_2sm(&empty_bar[stage], empty_mask);   // slot reusable in every CTA that may refill it
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        tcgen05_commit_2sm(&tmem_full[acc], 3);       // accumulator complete -> both epilogues
+        tcgen05_commit_2sm(&tmem_full[acc], full_mask);      // accumulator complete -> both epilogues of the pair
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -511,7 +529,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     pdl_wait();                            // residual / maps / statistics come from the previous kernels
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_idx = (tile % num_m) * (2 * BM) + (int)rank * BM;
+      const int m_idx = (tile % num_m) * mrows + (int)prank * (2 * BM) + (int)rank * BM;
       const int n_idx = (tile / num_m) * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX);
       epilogue_warp_tile<EPI, LNF>(ep, taddr, m_idx + quarter * 32, n_idx, BN, half, M, N, stage_buf, lane,
@@ -519,7 +537,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       // release this accumulator buffer to the leader's MMA warp
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), lead));
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
@@ -583,43 +601,67 @@ static int sm_count() {
 }
 
 // Tile width.  The mainloop is L2 -> SM bandwidth bound (measured: 8192^3 runs at 1.49 PFLOP/s with 256-wide
-// tiles and time per tile scales as 256 + BN, i.e. with the A + B bytes staged per k-block), so narrower
-// tiles re-read A more often and only pay off when they remove a mostly empty last wave:
-//   cost(BN) = waves * (k_blocks * (256 + BN) + c_tile) + c_epi * BN      (last epilogue is exposed)
-static int pick_tile_n(int M, int N, int K, int kind, int pairs) {
-  const int num_m = (M + 2 * BM - 1) / (2 * BM);
+// tiles and time per tile scales with the A + B bytes staged per k-block), so narrower tiles re-read A more
+// often and only pay off when they remove a mostly empty last wave:
+//   cost(BN) = waves * (k_blocks * (A + B bytes per CTA) + c_tile) + c_epi * BN      (last epilogue is exposed)
+static int pick_tile_n(int M, int N, int K, int kind, int units, int mc) {
+  const int mrows = mc ? 4 * BM : 2 * BM;
+  const int num_m = (M + mrows - 1) / mrows;
   const int step = kind == TOC3D_EPI_SWIGLU ? 64 : 32;
   const double kb = (double)((K + BK - 1) / BK);
   double best = 1e30;
   int best_bn = BN_MAX;
   for (int bn = BN_MAX; bn >= 128; bn -= step) {
+    if (mc && bn % 64) continue;                                   // B quarter boxes are whole 8-row swizzle groups
     const long tiles = (long)num_m * ((N + bn - 1) / bn);
-    const long waves = (tiles + pairs - 1) / pairs;
-    const double cost = (double)waves * (kb * (256.0 + bn) + 1024.0) + 16.0 * bn;
+    const long waves = (tiles + units - 1) / units;
+    const double cost = (double)waves * (kb * (256.0 + (mc ? bn / 2.0 : (double)bn)) + 1024.0) + 16.0 * bn;
     if (cost < best * 0.97) { best = cost; best_bn = bn; }     // prefer the widest tile unless clearly better
   }
   return best_bn;
 }
 
 template <int EPI, bool LNF = false>
-static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int tile_n,
+static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int tile_n, int cluster_pairs,
                   const EpiParams& ep, cudaStream_t st) {
   static bool configured = false;
+  static int max_clusters[2] = {0, 0};     // co-resident clusters of 2 / 4 CTAs (GPC boundaries can strand SMs)
   if (!configured) {
     TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    for (int i = 0; i < 2; ++i) {
+      cudaLaunchConfig_t cfg = {};
+      cudaLaunchAttribute at[1];
+      at[0].id = cudaLaunchAttributeClusterDimension;
+      at[0].val.clusterDim.x = 2 << i; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((unsigned)(sm_count() / (2 << i) * (2 << i))); cfg.blockDim = dim3(NUM_THREADS);
+      cfg.dynamicSmemBytes = SMEM_BYTES; cfg.attrs = at; cfg.numAttrs = 1;
+      int n = 0;
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<EPI, LNF>, &cfg) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        n = sm_count() / (2 << i);
+      }
+      max_clusters[i] = n < sm_count() / (2 << i) ? n : sm_count() / (2 << i);
+    }
     configured = true;
   }
-  const int max_pairs = sm_count() / 2;
-  const int bn = tile_n > 0 ? tile_n : pick_tile_n(M, N, K, EPI, max_pairs);
+  // Two pairs per cluster (weight tile multicast) is opt-in: measured on B200 it is 3-10 % SLOWER than one pair on
+  // every shape of this path and on 8192^3 (profiles/r01l_gemm_bench_cluster_pairs.txt) - the mainloop is not
+  // L2 -> SM bandwidth bound, and 4-CTA clusters strand SMs at GPC boundaries.
+  const int mc = cluster_pairs == 2 ? 1 : 0;
+  const int csize = mc ? 4 : 2;
+  const int max_units = max_clusters[mc];
+  const int bn = tile_n > 0 ? tile_n : pick_tile_n(M, N, K, EPI, max_units, mc);
+  TOC3D_REQUIRE(!mc || bn % 64 == 0, kErrBadArg, "toc3d_gemm_bf16: two-pair clusters need tile_n %% 64 == 0 (got %d)", bn);
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, bn / 2);
+  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, mc ? bn / 4 : bn / 2);
   if (rc) return rc;
-  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn);
-  const int pairs = tiles < max_pairs ? tiles : max_pairs;
-  TOC3D_CHECK_CUDA(launch_pdl(gemm_kernel<EPI, LNF>, dim3(2 * pairs), dim3(NUM_THREADS), SMEM_BYTES, st, 2, ta, tb, M, N, K,
-                              bn, ep));
+  const int mrows = mc ? 4 * BM : 2 * BM;
+  const int tiles = ((M + mrows - 1) / mrows) * ((N + bn - 1) / bn);
+  const int units = tiles < max_units ? tiles : max_units;
+  TOC3D_CHECK_CUDA(launch_pdl(gemm_kernel<EPI, LNF>, dim3(csize * units), dim3(NUM_THREADS), SMEM_BYTES, st, csize, ta, tb, M,
+                              N, K, bn, mc, ep));
   return 0;
 }
 
@@ -642,6 +684,8 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
   ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
   const int tile_n = e->tile_n;
+  const int cpairs = e->cluster_pairs;
+  TOC3D_REQUIRE(cpairs >= 0 && cpairs <= 2, kErrBadArg, "toc3d_gemm_bf16: cluster_pairs must be 0 (auto), 1 or 2");
   TOC3D_REQUIRE(tile_n == 0 || (tile_n >= 64 && tile_n <= BN_MAX && tile_n % 32 == 0 &&
                                 (kind != TOC3D_EPI_SWIGLU || tile_n % 64 == 0)), kErrBadArg,
                 "toc3d_gemm_bf16: tile_n must be 0 (auto) or a multiple of 32 (64 for SWIGLU) in [64, 256], got %d", tile_n);
@@ -665,12 +709,12 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   if (kind == TOC3D_EPI_SWIGLU) TOC3D_REQUIRE(N % 64 == 0, kErrBadArg, "toc3d_gemm_bf16: SWIGLU needs N %% 64 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (kind) {
-    case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
-    case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
+    case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
+    case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
     case TOC3D_EPI_RESID:
-      return ep.row_stats != nullptr ? launch<TOC3D_EPI_RESID, true>(A, lda, B, ldb, M, N, K, tile_n, ep, st)
-                                     : launch<TOC3D_EPI_RESID, false>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
-    case TOC3D_EPI_SWIGLU: return launch<TOC3D_EPI_SWIGLU>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
+      return ep.row_stats != nullptr ? launch<TOC3D_EPI_RESID, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st)
+                                     : launch<TOC3D_EPI_RESID, false>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
+    case TOC3D_EPI_SWIGLU: return launch<TOC3D_EPI_SWIGLU>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_gemm_bf16: unknown epilogue kind %d", kind);
   }
   return 0;
