@@ -202,6 +202,12 @@ int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint
  * bf16 [V*(Hi/16)*(Wi/16), 768], column = c*256 + ky*16 + kx (= conv weight flattening). */
 int toc3d_im2col_patch16(const float* img, void* out_bf16, int32_t V, int32_t Hi, int32_t Wi, void* stream);
 
+/* ------------------------------------------------------------------ neck (next row: CPFPN, necks/cp_fpn.py:157-208)
+ * im2col for the 3x3 / stride 1 / pad 1 fpn conv (cp_fpn.py:123-133,182-184) over an NHWC bf16 map
+ * [V,H,W,C] -> bf16 [V*H*W, 9*C], column = (ky*3+kx)*C + c, zeros outside the image.  C % 8 == 0.
+ * The 1x1 lateral conv (cp_fpn.py:114-122) and the 3x3 conv are toc3d_gemm_bf16 calls (LINEAR). */
+int toc3d_im2col_3x3(const void* in_bf16, void* out_bf16, int32_t V, int32_t H, int32_t W, int32_t C, void* stream);
+
 /* Row-wise helpers used by the first-frame scorer and weight repacking. */
 int toc3d_cast_f32_to_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 /* x[m,:] * mask[m] -> LN -> bf16 is toc3d_layernorm_rows on a pre-masked buffer; this masks. */

@@ -27,6 +27,7 @@ Reference files restated (paths under projects/mmdet3d_plugin/models/):
   backbones/eva_vit.py         SwiGLU :27-51, Attention :54-119, Block :200-268, EVA_ViT :409-428
   backbones/eva_utils.py       window_partition/unpartition :89-133, get_abs_pos :229-258,
                                PatchEmbed :261-287, VisionRotaryEmbeddingFast(+WithSelection) :325-402
+  necks/cp_fpn.py              CPFPN.forward :157-208 (shipped config: in_channels=[1024], out 256, num_outs=2)
   utils/misc.py                MLN :154-188, transform_reference_points :191-200
   utils/positional_encoding.py pos2posemb3d :14-26, pos2posemb1d :28-37, nerf_positional_encoding :39-81
 """
@@ -396,3 +397,14 @@ def forward_toc3d(p, cfg, img, temp_queries, temp_ref_points, temp_vel, temp_tim
             tap["block_out"].append(x)
     out["last_feat"] = x.permute(0, 3, 1, 2)
     return out
+
+
+# --------------------------------------------------------------------------- neck
+def neck_cpfpn(p, last_feat, prefix=""):
+    """necks/cp_fpn.py:157-208 with the shipped config (ToC3D_fast.py:70-74: in_channels=[1024],
+    out_channels=256, num_outs=2, no norm / activation / extra convs): lateral 1x1 conv (:114-122, :163-166),
+    3x3 conv pad 1 on level 0 (:123-133, :182-184), then max_pool2d(kernel 1, stride 2) = subsample (:190-191).
+    last_feat (V,C,H,W) -> [(V,256,H,W), (V,256,ceil(H/2),ceil(W/2))]."""
+    lat = F.conv2d(last_feat, p[prefix + "lateral_convs.0.conv.weight"], p[prefix + "lateral_convs.0.conv.bias"])
+    out0 = F.conv2d(lat, p[prefix + "fpn_convs.0.conv.weight"], p[prefix + "fpn_convs.0.conv.bias"], padding=1)
+    return [out0, F.max_pool2d(out0, 1, stride=2)]

@@ -59,7 +59,38 @@ def build_case(name):
     return fx
 
 
+NECK_CASE = dict(views=2, hw=(10, 14), in_ch=1024, out_ch=256, seed=7)
+
+
+def neck_inputs():
+    """Seeded input map and weights of the neck golden (rebuilt identically by the tests)."""
+    c = NECK_CASE
+    g = torch.Generator(); g.manual_seed(c["seed"])
+    x = torch.randn(c["views"], c["in_ch"], c["hw"][0], c["hw"][1], generator=g) * 3.0
+    tmpl = {"lateral_convs.0.conv.weight": torch.empty(c["out_ch"], c["in_ch"], 1, 1),
+            "lateral_convs.0.conv.bias": torch.empty(c["out_ch"]),
+            "fpn_convs.0.conv.weight": torch.empty(c["out_ch"], c["out_ch"], 3, 3),
+            "fpn_convs.0.conv.bias": torch.empty(c["out_ch"])}
+    return x, randomize_state_dict(tmpl, seed=c["seed"], bias_std=0.1)
+
+
+def build_neck_case():
+    """Outputs of the real reference CPFPN (necks/cp_fpn.py) with the shipped config."""
+    ns = load_reference()
+    c = NECK_CASE
+    m = ns.CPFPN(in_channels=[c["in_ch"]], out_channels=c["out_ch"], num_outs=2).eval()
+    x, sd = neck_inputs()
+    m.load_state_dict(sd)
+    with torch.no_grad():
+        outs = m([x])
+    return dict(meta=dict(NECK_CASE, torch=str(torch.__version__), keys=sorted(m.state_dict().keys())),
+                outs=[o.contiguous() for o in outs])
+
+
 def main():
+    fx = build_neck_case()
+    torch.save(fx, os.path.join(HERE, "neck_cpfpn.pt"))
+    print("neck_cpfpn", [tuple(o.shape) for o in fx["outs"]])
     for name in CASES:
         fx = build_case(name)
         path = os.path.join(HERE, name + ".pt")

@@ -130,7 +130,34 @@ def load_reference():
         state["noise"] = list(noise_list)
         state["calls"] = 0
 
+    # neck: cp_fpn.py needs mmcv's ConvModule / BaseModule / auto_fp16 and mmdet's NECKS.
+    # With the shipped config (norm_cfg=None, act_cfg=None) ConvModule is a plain nn.Conv2d with bias,
+    # registered as sub-module `conv` (state-dict keys lateral_convs.0.conv.weight, ...); auto_fp16 is the
+    # identity unless fp16_enabled is set (it is False).
+    _shell("projects.mmdet3d_plugin.models.necks", os.path.join(plug, "models", "necks"))
+    _shell("mmcv", "/nonexistent")
+    mc = _shell("mmcv.cnn")
+
+    class ConvModule(nn.Module):
+        def __init__(self, cin, cout, k, stride=1, padding=0, conv_cfg=None, norm_cfg=None, act_cfg=None, inplace=False):
+            super().__init__()
+            assert conv_cfg is None and norm_cfg is None and act_cfg is None, "only the shipped CPFPN config is stubbed"
+            self.conv = nn.Conv2d(cin, cout, k, stride=stride, padding=padding, bias=True)
+
+        def forward(self, x):
+            return self.conv(x)
+    mc.ConvModule = ConvModule
+    mr = _shell("mmcv.runner")
+
+    class BaseModule(nn.Module):
+        def __init__(self, init_cfg=None):
+            super().__init__()
+    mr.BaseModule = BaseModule
+    mr.auto_fp16 = lambda *a, **k: (lambda fn: fn)
+    sys.modules["mmdet.models"].NECKS = _Registry()
+    nk = importlib.import_module("projects.mmdet3d_plugin.models.necks.cp_fpn")
+
     ns = types.SimpleNamespace(ToC3DEVAViT=tv.ToC3DEVAViT, EVA_ViT=ev.EVA_ViT, toc3d_utils=tu,
-                               toc3d_eva_vit=tv, eva_vit=ev, set_gumbel=set_gumbel)
+                               toc3d_eva_vit=tv, eva_vit=ev, set_gumbel=set_gumbel, CPFPN=nk.CPFPN)
     _loaded["ns"] = ns
     return ns

@@ -1,0 +1,82 @@
+"""CPFPN neck: oracle vs the committed reference output (CPU), CUDA plugin vs oracle (GPU)."""
+import os
+
+import pytest
+import torch
+
+from oracle import toc3d_oracle as O
+from tests.golden.make_golden import NECK_CASE, neck_inputs
+from tests.golden.ref_import import reference_available
+from toc3d_b200 import CPFPN
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "neck_cpfpn.pt")
+
+
+def test_oracle_neck_matches_reference_golden():
+    fx = torch.load(GOLDEN)
+    x, sd = neck_inputs()
+    outs = O.neck_cpfpn(sd, x)
+    assert len(outs) == 2 and outs[1].shape[-2:] == (5, 7)
+    for a, b in zip(outs, fx["outs"]):
+        assert a.shape == b.shape and (a - b).abs().max().item() <= 1e-4 * max(1.0, b.abs().max().item())
+    assert torch.equal(outs[1], outs[0][:, :, ::2, ::2])                  # max_pool2d(k=1, s=2) is a subsample
+
+
+def test_neck_state_dict_keys_and_config_guard():
+    fx = torch.load(GOLDEN)
+    m = CPFPN(in_channels=[NECK_CASE["in_ch"]], out_channels=NECK_CASE["out_ch"], num_outs=2)
+    assert sorted(m.state_dict().keys()) == fx["meta"]["keys"]
+    m.load_state_dict(neck_inputs()[1])                                    # strict
+    with pytest.raises(NotImplementedError):
+        CPFPN(in_channels=[256, 512], out_channels=256, num_outs=2)
+    with pytest.raises(NotImplementedError):
+        CPFPN(in_channels=[1024], out_channels=256, num_outs=2, add_extra_convs="on_output")
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        m.eval()([torch.zeros(1, 1024, 2, 2)])
+
+
+@pytest.mark.skipif(not reference_available(), reason="/root/reference not present (GPU box)")
+def test_oracle_neck_matches_live_reference():
+    from tests.golden.ref_import import load_reference
+    ns = load_reference()
+    m = ns.CPFPN(in_channels=[1024], out_channels=256, num_outs=2).eval()
+    x = torch.randn(1, 1024, 7, 9)
+    with torch.no_grad():
+        r = m([x])
+    o = O.neck_cpfpn(m.state_dict(), x)
+    assert all((a - b).abs().max().item() < 1e-5 for a, b in zip(r, o))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,H,W", [(2, 10, 14), (6, 20, 50), (1, 50, 100)])
+def test_neck_cuda_matches_oracle(V, H, W):
+    g = torch.Generator().manual_seed(V * H)
+    x = torch.randn(V, H, W, 1024, generator=g) * 3.0                      # NHWC storage, like the backbone output
+    _, sd = neck_inputs()
+    ref = O.neck_cpfpn(sd, x.permute(0, 3, 1, 2))
+    m = CPFPN(in_channels=[1024], out_channels=256, num_outs=2).eval()
+    m.load_state_dict(sd)
+    m = m.cuda()
+    outs = m([x.cuda().permute(0, 3, 1, 2)])
+    torch.cuda.synchronize()
+    assert len(outs) == 2
+    for got, want in zip(outs, ref):
+        assert got.shape == want.shape and got.dtype == torch.float32
+        err = (got.cpu() - want).abs().max().item()
+        # two chained bf16-operand GEMMs (K = 1024 and 2304), fp32 accumulate
+        assert err < 1.5e-2 * max(1.0, want.abs().max().item()), err
+
+
+@pytest.mark.gpu
+def test_backbone_then_neck_contract():
+    """ToC3DEVAViT -> CPFPN the way Petr3D chains them (petr3d.py:159-190): list(img_feats.values()) -> neck."""
+    from toc3d_b200 import TINY, ToC3DEVAViT
+    from toc3d_b200.synthetic import make_inputs
+    torch.manual_seed(0)
+    bb = ToC3DEVAViT(**TINY).eval().cuda()
+    neck = CPFPN(in_channels=[TINY["embed_dim"]], out_channels=64, num_outs=2).eval().cuda()
+    inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in make_inputs(1, 2, (160, 352), seed=3).items()}
+    out = bb(**inp)
+    feats = neck(list(out.img_feats.values()))
+    assert feats[0].shape == (2, 64, 10, 22) and feats[1].shape == (2, 64, 5, 11)
+    assert all(torch.isfinite(f).all() for f in feats)

@@ -90,6 +90,34 @@ def test_sharded_forward_equals_full_batch(frames, views):
     assert all((a - b).abs().max().item() < 1e-4 for a, b in zip(masks, full.token_masks))
 
 
+def _gather_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        full = torch.arange(4 * 3 * 4 * 6, dtype=torch.float32).reshape(4, 4, 6, 3)          # NHWC storage
+        loc = full[2 * rank:2 * rank + 2].permute(0, 3, 1, 2)                                  # (2, C, H, W) view
+        feats = S.all_gather_feature_list((loc, loc[:, :, ::2, ::2]), world)
+        if rank == 0:
+            q.put([f.clone() for f in feats])
+    finally:
+        dist.destroy_process_group()
+
+
+def test_feature_list_gather_order_and_strided_levels():
+    ctx = mp.get_context("spawn")
+    q = ctx.SimpleQueue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gather_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    f0, f1 = q.get()
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    full = torch.arange(4 * 3 * 4 * 6, dtype=torch.float32).reshape(4, 4, 6, 3).permute(0, 3, 1, 2)
+    assert torch.equal(f0, full) and torch.equal(f1, full[:, :, ::2, ::2])
+
+
 def test_partition_rules():
     assert S.partition(4, 6, 8) == [(3 * r, 3 * r + 3) for r in range(8)]
     assert S.partition(4, 6, 4) == [(6 * r, 6 * r + 6) for r in range(4)]

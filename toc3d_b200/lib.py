@@ -54,6 +54,7 @@ _SIGS = {
     "toc3d_score_finish": ([_c_void_p, _c_int, _c_void_p, _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                             _c_void_p], _c_int),
     "toc3d_im2col_patch16": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
+    "toc3d_im2col_3x3": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_cast_f32_to_bf16": ([_c_void_p, _c_void_p, _c_i64, _c_void_p], _c_int),
     "toc3d_mask_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_global_half_mean": ([_c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
@@ -201,6 +202,11 @@ def score_finish(logits, M, gumbel, seed, pred, score, mask_out, seed_dev=None):
 def im2col_patch16(img, out, V, Hi, Wi):
     _want(img, torch.float32, "img")
     _check(load().toc3d_im2col_patch16(_p(img), _p(out), V, Hi, Wi, _stream()), "toc3d_im2col_patch16")
+
+
+def im2col_3x3(x, out, V, H, W, C):
+    _want(x, torch.bfloat16, "x"); _want(out, torch.bfloat16, "out")
+    _check(load().toc3d_im2col_3x3(_p(x), _p(out), V, H, W, C, _stream()), "toc3d_im2col_3x3")
 
 
 def cast_bf16(src, dst):

@@ -1,0 +1,103 @@
+"""Drop-in `img_neck` plugin: CPFPN on the sm_100a GEMM (the first "next" row).
+
+Reference: projects/mmdet3d_plugin/models/necks/cp_fpn.py:11-208, shipped config
+`img_neck=dict(type='CPFPN', in_channels=[1024], out_channels=256, num_outs=2)` (ToC3D_fast.py:70-74):
+lateral 1x1 conv 1024 -> 256, 3x3 conv 256 -> 256 (pad 1) on level 0, second level =
+`max_pool2d(kernel=1, stride=2)` of the first (a strided subsample).  Same registry name (`CPFPN` in
+mmdet's NECKS), constructor kwargs, forward(list of NCHW maps) -> tuple of NCHW fp32 maps, and
+state-dict keys (`lateral_convs.0.conv.*`, `fpn_convs.0.conv.*`).  Only the shipped single-level
+configuration is implemented; anything else raises.  Inference only, CUDA only, no fallback.
+"""
+import torch
+import torch.nn as nn
+
+from . import lib as L
+
+try:
+    from mmdet.models import NECKS as _NECKS
+
+    def _register(cls):
+        return _NECKS.register_module(force=True)(cls)
+except Exception:
+    def _register(cls):
+        return cls
+
+
+class _ConvModule(nn.Module):
+    """mmcv ConvModule with norm_cfg=None, act_cfg=None: a Conv2d with bias under the name `conv`."""
+
+    def __init__(self, cin, cout, k, padding=0):
+        super().__init__()
+        self.conv = nn.Conv2d(cin, cout, k, padding=padding, bias=True)
+        nn.init.xavier_uniform_(self.conv.weight)          # init_cfg=dict(type='Xavier', layer='Conv2d', distribution='uniform')
+        nn.init.zeros_(self.conv.bias)
+
+
+@_register
+class CPFPN(nn.Module):
+    def __init__(self, in_channels, out_channels, num_outs, start_level=0, end_level=-1, add_extra_convs=False,
+                 relu_before_extra_convs=False, no_norm_on_lateral=False, conv_cfg=None, norm_cfg=None, act_cfg=None,
+                 upsample_cfg=dict(mode="nearest"), init_cfg=None):
+        super().__init__()
+        assert isinstance(in_channels, list)
+        if (len(in_channels) != 1 or start_level != 0 or end_level not in (-1, 1) or add_extra_convs or conv_cfg or norm_cfg
+                or act_cfg or num_outs < 1):
+            raise NotImplementedError("only the shipped CPFPN configuration (one input level, no norm / activation / "
+                                      "extra convs) is implemented")
+        if in_channels[0] % 64 or out_channels % 8:
+            raise NotImplementedError("channel counts must fit the GEMM tiles (in %% 64 == 0, out %% 8 == 0)")
+        self.in_channels, self.out_channels, self.num_outs = in_channels, out_channels, num_outs
+        self.fp16_enabled = False
+        self.lateral_convs = nn.ModuleList([_ConvModule(in_channels[0], out_channels, 1)])
+        self.fpn_convs = nn.ModuleList([_ConvModule(out_channels, out_channels, 3, padding=1)])
+        self._packed = None
+
+    def _apply(self, fn, *a, **k):
+        self._packed = None
+        return super()._apply(fn, *a, **k)
+
+    def load_state_dict(self, *a, **k):
+        self._packed = None
+        return super().load_state_dict(*a, **k)
+
+    def _weights(self, dev):
+        if self._packed is None or self._packed["dev"] != dev:
+            co = self.out_channels
+            w1 = self.lateral_convs[0].conv.weight.detach().to(dev).float().reshape(co, -1)
+            # [co, ci, ky, kx] -> [co, (ky, kx, ci)]: the column order toc3d_im2col_3x3 produces
+            w3 = self.fpn_convs[0].conv.weight.detach().to(dev).float().permute(0, 2, 3, 1).reshape(co, -1)
+            self._packed = dict(dev=dev, w1=w1.to(torch.bfloat16).contiguous(), w3=w3.to(torch.bfloat16).contiguous(),
+                                b1=self.lateral_convs[0].conv.bias.detach().to(dev).float().contiguous(),
+                                b3=self.fpn_convs[0].conv.bias.detach().to(dev).float().contiguous())
+        return self._packed
+
+    @torch.no_grad()
+    def forward(self, inputs):
+        assert len(inputs) == len(self.in_channels)                                       # cp_fpn.py:160
+        x = inputs[0]
+        if not x.is_cuda:
+            raise RuntimeError("toc3d_b200 CPFPN runs on CUDA (sm_100a) only; there is no CPU fallback")
+        if self.training:
+            raise RuntimeError("toc3d_b200 CPFPN is inference-only; call .eval()")
+        V, C, H, W = x.shape
+        co = self.out_channels
+        p = self._weights(x.device)
+        nhwc = x.permute(0, 2, 3, 1)                        # the backbone hands out a permuted view of NHWC storage
+        nhwc = nhwc if nhwc.is_contiguous() else nhwc.contiguous()
+        M = V * H * W
+        bf = dict(device=x.device, dtype=torch.bfloat16)
+        if nhwc.dtype == torch.bfloat16:
+            a = nhwc.reshape(M, C)
+        else:
+            a = torch.empty(M, C, **bf)
+            L.cast_bf16(nhwc.float().reshape(M, C), a)
+        lat = torch.empty(M, co, **bf)
+        L.gemm(a, p["w1"], L.EPI_LINEAR, bias=p["b1"], out=lat)                            # lateral 1x1 (cp_fpn.py:163-166)
+        cols = torch.empty(M, 9 * co, **bf)
+        L.im2col_3x3(lat, cols, V, H, W, co)
+        out0 = torch.empty(M, co, device=x.device, dtype=torch.float32)
+        L.gemm(cols, p["w3"], L.EPI_LINEAR, bias=p["b3"], out=out0, out_f32=True)          # fpn 3x3 (cp_fpn.py:182-184)
+        outs = [out0.view(V, H, W, co).permute(0, 3, 1, 2)]
+        for _ in range(self.num_outs - 1):
+            outs.append(outs[-1][:, :, ::2, ::2])           # F.max_pool2d(x, 1, stride=2) (cp_fpn.py:190-191)
+        return tuple(outs)

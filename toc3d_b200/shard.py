@@ -72,6 +72,15 @@ def all_gather_last_feat(last_feat, world, group=None, out=None):
     return out.permute(0, 3, 1, 2)
 
 
+def all_gather_feature_list(feats, world, group=None):
+    """Multi-scale feature list of the neck (tuple of (V_local, C, H_l, W_l) maps, possibly strided views):
+    one all-gather per level, images in global order.  At 256 channels this moves 4x fewer bytes than
+    gathering `last_feat`."""
+    if world == 1:
+        return tuple(feats)
+    return tuple(all_gather_last_feat(f, world, group) for f in feats)
+
+
 class ShardedBackbone:
     """Runs `backbone` on this rank's image chunk and returns the result for ALL images.
 
