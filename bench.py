@@ -168,14 +168,14 @@ def run_reference(args):
     sample = "%d of %d views per step (fp32 oracle port of the reference forward, %d torch threads); scaled x%d" % (
         views_sample, VIEWS, cores, VIEWS // views_sample)
     kind, cfg, hw = CONFIGS[args.config]
-    print(json.dumps({
+    emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": dt * 1e3 * VIEWS / views_sample, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": args.config, "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": 1},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------- native arm (B200)
@@ -421,9 +421,29 @@ def run_native(args):
         line["cpu_baseline"] = {"value": 1.0 / (dt * VIEWS), "unit": UNIT, "cores": cores, "kind": "port",
                                 "sample": "1 of 6 views x %d runs, fp32 oracle port of the reference, scaled x6" % n}
     if rank == 0:
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """stdout must carry exactly ONE JSON line: anything a library prints to fd 1 during the run (NCCL prints its
+    version banner there) is diverted to stderr; emit() writes the line to the real stdout."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode()); sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
 
 
 def main():
@@ -436,6 +456,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1, help="6-view samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    _claim_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:
