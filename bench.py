@@ -44,11 +44,40 @@ def load_ncu_traffic(workload):
 
 
 def load_peaks():
+    """Roofline denominators: the driver-written MEASURED_PEAKS.json when present (any reasonable key spelling),
+    else the fallback of /opt/skills/guides/B200_PROFILING.md (6.65 TB/s, 1.59 PF burst / 1.4 PF sustained)."""
+    fb = dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(p):
+    try:
         d = json.load(open(p))
-        return dict(hbm=d["hbm_gbs"], tf_burst=d["bf16_tflops"], tf_sust=d["bf16_tflops_sustained"], src="measured")
-    return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+    except Exception:
+        return fb
+    flat = {}
+
+    def walk(o, pre=""):
+        if isinstance(o, dict):
+            for k, v in o.items():
+                walk(v, pre + str(k).lower() + ".")
+        elif isinstance(o, (int, float)) and not isinstance(o, bool):
+            flat[pre[:-1]] = float(o)
+    walk(d)
+
+    def pick(words, avoid=()):
+        for k, v in flat.items():
+            if all(w in k for w in words) and not any(a in k for a in avoid) and v > 0:
+                return v
+        return None
+    hbm = pick(("hbm",)) or pick(("copy",)) or pick(("gb",))
+    sust = pick(("sustain",))
+    burst = pick(("tflop",), avoid=("sustain",)) or pick(("bf16",), avoid=("sustain",))
+    if hbm and hbm < 100:          # TB/s -> GB/s
+        hbm *= 1000.0
+    out = dict(hbm=hbm or fb["hbm"], tf_burst=burst or fb["tf_burst"], tf_sust=sust or burst or fb["tf_sust"],
+               src="measured" if (hbm and (sust or burst)) else "fallback/partly measured")
+    for k in ("tf_burst", "tf_sust"):
+        if out[k] > 10000:         # GFLOP/s -> TFLOP/s
+            out[k] /= 1000.0
+    return out
 
 
 # ------------------------------------------------------------------------------- algorithmic work

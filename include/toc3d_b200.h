@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 4
+#define TOC3D_B200_ABI_VERSION 5
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -76,19 +76,27 @@ typedef struct toc3d_epilogue {
   float q_scale;
   const float* cos_axis;
   const float* sin_axis;
-  /* Folded LayerNorm of the A rows (SwiGLU sub-LN, eva_vit.py:48, without a separate pass):
-   *   SWIGLU: row_stats != NULL -> atomically accumulates [sum * 2^30, sum of squares * 2^26] of the
-   *           bf16-rounded hidden row as int64 fixed point (order-independent, hence deterministic)
-   *           into row_stats[m*2 .. m*2+1] (int64 [M,2], 16-byte aligned, zeroed by the caller);
-   *   RESID:  row_stats != NULL -> the GEMM's A rows are the UN-normalised hidden rows, B is
-   *           W * gamma (column-scaled), and the epilogue applies
-   *             y = rstd_m * acc - rstd_m * mean_m * ln_u[n] + bias[n]
-   *           with mean/rstd from row_stats over ln_n true columns (eps = ln_eps),
-   *           ln_u = W * gamma (fp32 [N]), bias = W * beta + b. */
+  /* Folded LayerNorms (no separate normalisation pass; statistics are int64 fixed point
+   * [sum * 2^30, sum of squares * 2^26] per row, accumulated with integer atomics = order-independent,
+   * hence deterministic; int64 [rows,2], 16-byte aligned).
+   *   OUTPUT statistics, row_stats != NULL:
+   *     SWIGLU: of the bf16-rounded hidden row m (feeds the sub-LN fold of the w3 GEMM, eva_vit.py:48);
+   *     RESID with a_out != NULL: of the fp32 result row, at the result's destination row (feeds the
+   *            norm2 fold of the SwiGLU GEMM, eva_vit.py:263); a_out receives the bf16 copy of the result
+   *            rows (same destination rows, leading dimension ldo) = the A operand of that GEMM, and
+   *            zero_stats (optional) rows are zeroed (the accumulator the SwiGLU GEMM will add to).
+   *   INPUT statistics, ln_stats != NULL (RESID and SWIGLU): the A rows are UN-normalised, B is
+   *     W * gamma (column-scaled) and the epilogue applies
+   *       y = rstd_m * acc - rstd_m * mean_m * ln_u[n] + bias[n]
+   *     with mean/rstd of row m from ln_stats over ln_n true columns (eps = ln_eps),
+   *     ln_u = W * gamma (fp32 [N]), bias = W * beta + b (SWIGLU: both interleaved like the weights). */
   int64_t* row_stats;
+  const int64_t* ln_stats;
   const float* ln_u;
   int32_t ln_n;
   float ln_eps;
+  void* a_out;
+  int64_t* zero_stats;
   /* Tile width override (tuning / tests): 0 = chosen per launch to minimise wave quantisation on the
    * 74 CTA pairs; else a multiple of 32 (64 for SWIGLU) in [64, 256]. */
   int32_t tile_n;

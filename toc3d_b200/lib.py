@@ -25,7 +25,8 @@ class Epilogue(ctypes.Structure):
         ("resid", _c_void_p), ("resid_map", _c_void_p), ("resid_mod", _c_int), ("out_map", _c_void_p),
         ("out_alt", _c_void_p), ("rope_rows", _c_void_p), ("rope_slots", _c_int), ("rope_ft", _c_int),
         ("rope_cols", _c_int), ("q_scale", _c_float), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p),
-        ("row_stats", _c_void_p), ("ln_u", _c_void_p), ("ln_n", _c_int), ("ln_eps", _c_float), ("tile_n", _c_int), ("cluster_pairs", _c_int),
+        ("row_stats", _c_void_p), ("ln_stats", _c_void_p), ("ln_u", _c_void_p), ("ln_n", _c_int), ("ln_eps", _c_float),
+        ("a_out", _c_void_p), ("zero_stats", _c_void_p), ("tile_n", _c_int), ("cluster_pairs", _c_int),
     ]
 
 
@@ -78,7 +79,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 4:
+        if lib.toc3d_abi_version() != 5:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -111,7 +112,7 @@ def _want(t, dtype, name):
 def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, resid=None,
          resid_map=None, resid_mod=0, out_map=None, out_alt=None, rope_rows=None, rope_slots=0, rope_ft=0,
          rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None, row_stats=None, ln_u=None, ln_n=0, ln_eps=0.0,
-         tile_n=0, cluster_pairs=0):
+         tile_n=0, cluster_pairs=0, ln_stats=None, a_out=None, zero_stats=None):
     """C = A[M,K] @ B[N,K]^T with fused epilogue `kind` (see include/toc3d_b200.h)."""
     _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
     M = A.shape[0] if M is None else M
@@ -124,7 +125,7 @@ def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, ac
     e.out_map = _p(out_map); e.out_alt = _p(out_alt)
     e.rope_rows = _p(rope_rows); e.rope_slots = rope_slots; e.rope_ft = rope_ft; e.rope_cols = rope_cols
     e.q_scale = q_scale; e.cos_axis = _p(cos_axis); e.sin_axis = _p(sin_axis)
-    e.row_stats = _p(row_stats); e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps; e.tile_n = tile_n; e.cluster_pairs = cluster_pairs
+    e.row_stats = _p(row_stats); e.ln_stats = _p(ln_stats); e.a_out = _p(a_out); e.zero_stats = _p(zero_stats); e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps; e.tile_n = tile_n; e.cluster_pairs = cluster_pairs
     rc = load().toc3d_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, kind,
                                 ctypes.byref(e), _stream())
     _check(rc, "toc3d_gemm_bf16")

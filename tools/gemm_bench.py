@@ -82,7 +82,7 @@ for M in [int(m) for m in args.ms.split(",")]:
     stats = torch.zeros(M, 2, device=dev, dtype=torch.int64)
     report("w12 swiglu+stats", M, 2 * Hp, C, lambda t: L.gemm(A, W12, L.EPI_SWIGLU, bias=b12, out=hid, row_stats=stats, tile_n=t, cluster_pairs=args.cp))
     W3 = (rn(C, Hp) * 0.02).bfloat16(); u3 = rn(C)
-    report("w3 ln-fold+resid", M, C, Hp, lambda t: L.gemm(hid, W3, L.EPI_RESID, bias=bp, out=X, resid=T, row_stats=stats,
+    report("w3 ln-fold+resid", M, C, Hp, lambda t: L.gemm(hid, W3, L.EPI_RESID, bias=bp, out=X, resid=T, ln_stats=stats,
                                                          ln_u=u3, ln_n=Hd, ln_eps=1e-6, tile_n=t, cluster_pairs=args.cp))
     ob = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
     report("linear bf16 (N=1024)", M, C, C, lambda t: L.gemm(A, Wp, L.EPI_LINEAR, bias=bp, out=ob, tile_n=t, cluster_pairs=args.cp))

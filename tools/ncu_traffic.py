@@ -43,7 +43,7 @@ for i in sel:
     f[2] += d.get("dram__bytes_read.sum", 0.0) + d.get("dram__bytes_write.sum", 0.0)
 out_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "ncu_traffic.json")
 data = json.load(open(out_path)) if os.path.exists(out_path) else {}
-g = [(k, v) for k, v in fam.items() if k.startswith("gemm_kernel")]
+g = [(k, v) for k, v in fam.items() if "gemm_kernel" in k]
 gn = sum(v[0] for _, v in g)
 data[workload] = {
     "source": "ncu dram__bytes_read.sum + dram__bytes_write.sum, capture %s, last forward of tools/profile_step.py --eager "
