@@ -107,6 +107,30 @@ def test_vitl_one_view_teacher_forced():
         print("score max-abs diff %.4f" % (s_c.cpu() - s_o).abs().max().item())
 
 
+def test_vitl_1600_one_view_teacher_forced():
+    """ToC3D_fast_1600 geometry (BASELINE config 3): 1 view 800x1600 -> 50x100 tokens, ws16 windows padded to
+    64x112 (28 per view), ws20 windows padded to 60x100 (15 per view), 3500/2500/2500 image-level keeps.
+    Full-depth EVA-ViT-L against the CPU oracle with teacher-forced scores: indices bit-exact, features within
+    the bf16 tolerance."""
+    kind, cfg, hw = CONFIGS["toc3d_fast_1600"]
+    model = build_model("toc3d", cfg)
+    sd = randomize_state_dict(model.state_dict(), seed=6, bias_std=0.1)
+    model.load_state_dict(sd)
+    inp = make_inputs(1, 1, hw, seed=6, pose="random")
+    inp["prev_exists"] = True
+    gn = make_gumbel(1, 5000, seed=106)
+    ref = run_oracle("toc3d", cfg, sd, inp, gn)
+    out = _run_cuda(model, inp, gn, teacher_scores=ref["scores"])
+    assert [t.shape[1] for t in out.keep_idx] == [3500, 2500, 2500]
+    for a, b in zip(out.keep_idx + out.drop_idx, ref["keep_idx"] + ref["drop_idx"]):
+        assert torch.equal(a.cpu(), b)
+    for a, b in zip(out.token_masks, ref["token_masks"]):
+        assert (a.cpu().reshape(-1) - b.reshape(-1)).abs().max().item() < 2e-2       # mask = softmax of device scores
+    mx, mean, rel = _stats(out.img_feats["last_feat"].cpu(), ref["last_feat"])
+    print("ViT-L 1600 last_feat max-abs %.4f mean-abs %.5f rel-l2 %.5f |ref|max %.2f" % (mx, mean, rel, ref["last_feat"].abs().max()))
+    assert rel < 2e-2
+
+
 def test_contract_shapes_and_view_independence():
     kind, cfg, hw = CONFIGS["toc3d_fast"]
     model = build_model("toc3d", cfg)
