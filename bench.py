@@ -228,6 +228,8 @@ def run_native(args):
     model = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
     model.load_state_dict(randomize_state_dict(model.state_dict(), seed=0, bias_std=0.02))
     model = model.eval().to(dev)
+    if args.view_groups is not None and hasattr(model, "view_groups"):
+        model.view_groups = args.view_groups
     B = args.batch
     V = B * VIEWS
     H, W = hw[0] // 16, hw[1] // 16
@@ -484,6 +486,7 @@ def main():
     ap.add_argument("--config", default="toc3d_fast", choices=sorted(CONFIGS))
     ap.add_argument("--batch", type=int, default=1, help="6-view samples per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--view-groups", type=int, default=None, help="override the plugin's view_groups (streams of views)")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":

@@ -297,15 +297,21 @@ class _Engine:
                 b_o4=F.pad(f32(s.out_conv[4].bias), (0, 6)).contiguous(),
             ))
         self.ws_cache = {}
+        self._gstreams = []
         self.side = torch.cuda.Stream(device=device)      # query folding / image-level top-k overlap the blocks
         self.seed_t = torch.zeros(1, device=device, dtype=torch.int64)   # forward counter (Gumbel seed, graph-safe)
 
     # -- helpers ---------------------------------------------------------------------------
-    def workspace(self, V, H, W):
-        key = (V, H, W)
+    def workspace(self, V, H, W, group=0):
+        key = (V, H, W, group)
         if key not in self.ws_cache:
             self.ws_cache[key] = _Workspace(self, V, H, W)
         return self.ws_cache[key]
+
+    def group_streams(self, G):
+        while len(self._gstreams) < G:
+            self._gstreams.append(torch.cuda.Stream(device=self.device))
+        return self._gstreams
 
     def abs_pos(self, H, W):
         """eva_utils.py:229-258, cached per token grid (the reference re-interpolates every call)."""
@@ -322,10 +328,11 @@ class _Engine:
         return self.pos_cache[(H, W)]
 
     # -- stem ------------------------------------------------------------------------------
-    def stem(self, img, wsp):
+    def stem(self, img, wsp, X_out=None):
         V, _, Hi, Wi = img.shape
+        img = img if img.is_contiguous() else img.contiguous()
         L.im2col_patch16(img, wsp.cols, V, Hi, Wi)
-        X = torch.empty(V * wsp.N, self.C, device=self.device, dtype=torch.float32)
+        X = X_out if X_out is not None else torch.empty(V * wsp.N, self.C, device=self.device, dtype=torch.float32)
         pos = self.abs_pos(wsp.H, wsp.W)
         if pos is not None:
             L.gemm(wsp.cols, self.w_pe, L.EPI_RESID, bias=self.b_pe, out=X, resid=pos, resid_mod=wsp.N)
@@ -424,14 +431,14 @@ class _Engine:
         L.score_fold_queries(q.float(), sp["w_in"], sp["b_in"], sp["w_agg"], sp["b_agg"], sel_mod.scale, A, c)
         return A, c
 
-    def score_stage(self, j, X, mask_prev, wsp, folded, gumbel):
+    def score_stage(self, j, X, mask_prev, wsp, folded, gumbel, seed=None):
         """folded = (A, c) from fold_queries when the previous frame exists, else None (first-frame scorer)."""
         dev, V, N, C = self.device, wsp.V, wsp.N, self.C
         sp = self.sel[j]
         pred = torch.empty(V, N, 2, device=dev)
         score = torch.empty(V, N, device=dev)
         mask = torch.empty(V, N, device=dev)
-        seed = j
+        seed = j if seed is None else seed
         if folded is not None:
             A, c = folded
             L.score_tokens(X, mask_prev, A, c, V, N, C, V // A.shape[0], gumbel, seed, pred, score, mask,
@@ -484,6 +491,9 @@ class _EvaBase(nn.Module):
         # measured on B200 it saves 0.29 ms of LayerNorm launches but adds 0.28 ms to the (exposed, L2-bound) proj
         # epilogue - 162.9 vs 169 samples/s.  Set before the first forward (or call refresh_weights()) to change.
         self.fold_norm2 = False
+        # views are independent: with G > 1 the forward runs G groups of views on their own streams inside the
+        # one CUDA graph, so the tail / epilogue of one group's kernels overlaps the other group's kernels
+        self.view_groups = 1
         self.graph_outputs = "clone"   # "static": return the graph's own buffers (overwritten by the next call)
 
     def _init_weights(self):
@@ -705,10 +715,13 @@ class ToC3DEVAViT(_EvaBase):
 
     def _forward_core(self, eng, x, q_kw, gumbel_noise, teacher_scores, tap):
         """The launch sequence of one forward (toc3d_eva_vit.py:243-310); capturable in a CUDA graph.
-        Returns (X, *masks, *keep_idx, *drop_idx)."""
+        Returns (X, *masks, *keep_idx, *drop_idx).
+
+        With view_groups = G > 1 the views are cut into G groups that run the whole block sequence on their own
+        streams (every op is independent per image): the ragged tail wave / exposed epilogue of one group's
+        kernel is filled by the other group's next kernel."""
         V, _, Hi, Wi = x.shape
-        wsp = eng.workspace(V, Hi // 16, Wi // 16)
-        H, W = wsp.H, wsp.W
+        H, W = Hi // 16, Wi // 16
         N = H * W
         cur, side = torch.cuda.current_stream(), eng.side
         nst = len(self.pruning_loc)
@@ -722,7 +735,47 @@ class ToC3DEVAViT(_EvaBase):
                     folded[j] = eng.fold_queries(j, self.score_predictor[j], q_kw, V)
             ev_q = torch.cuda.Event()
             ev_q.record(side)
-        X = eng.stem(x, wsp)
+        G = self.view_groups if (tap is None and self.view_groups > 1 and V % self.view_groups == 0) else 1
+        if G > 1 and q_kw is not None:
+            Bf = q_kw["temp_queries"].shape[0]
+            vg = V // G
+            if not (vg % (V // Bf) == 0 or (V // Bf) % vg == 0):     # a group must not straddle frames unevenly
+                G = 1
+        if G == 1:
+            out = self._forward_views(eng, x, eng.workspace(V, H, W), folded, ev_q, gumbel_noise, teacher_scores, tap, 0, 0)
+            cur.wait_stream(side)
+            return out
+        vg = V // G
+        X = torch.empty(V * N, eng.C, device=x.device, dtype=torch.float32)
+        streams = eng.group_streams(G)
+        outs = []
+        for g in range(G):
+            st = streams[g]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                sl = slice(g * vg, (g + 1) * vg)
+                gn = None if gumbel_noise is None else [t[sl] for t in gumbel_noise]
+                ts = None if teacher_scores is None else [t.reshape(V, -1)[sl] for t in teacher_scores]
+                fold_g = folded
+                if q_kw is not None:            # this group's frames only (views are frame-major)
+                    vpf = V // folded[0][0].shape[0]
+                    f0, f1 = (g * vg) // vpf, ((g + 1) * vg - 1) // vpf + 1
+                    fold_g = [(A[f0:f1].contiguous(), c[f0:f1].contiguous()) for A, c in folded]
+                outs.append(self._forward_views(eng, x[sl], eng.workspace(vg, H, W, g), fold_g, ev_q, gn, ts, None, g,
+                                                g * vg, X_out=X[g * vg * N:(g + 1) * vg * N]))
+        for st in streams[:G]:
+            cur.wait_stream(st)
+        cur.wait_stream(side)
+        cat = [torch.cat([o[1 + j] for o in outs], dim=0) for j in range(3 * nst)]
+        return (X, *cat)
+
+    def _forward_views(self, eng, x, wsp, folded, ev_q, gumbel_noise, teacher_scores, tap, group, view0, X_out=None):
+        """Stem + all blocks for a contiguous group of views on the current stream."""
+        V = x.shape[0]
+        H, W = wsp.H, wsp.W
+        N = H * W
+        cur, side = torch.cuda.current_stream(), eng.side
+        X = eng.stem(x, wsp, X_out)
         masks, keep_idxes, drop_idxes, scores_l = [], [], [], []
         mask_prev, stage = None, -1
         if tap is not None:
@@ -736,7 +789,7 @@ class ToC3DEVAViT(_EvaBase):
                     g = gumbel_noise[stage].to(device=x.device, dtype=torch.float32).contiguous()
                 if stage == 0:
                     cur.wait_event(ev_q)
-                pred, score, mask = eng.score_stage(stage, X, mask_prev, wsp, folded[stage], g)
+                pred, score, mask = eng.score_stage(stage, X, mask_prev, wsp, folded[stage], g, seed=stage + 16 * group)
                 if tap is not None:
                     tap.setdefault("scores_raw", []).append(score.view(V, H, W).clone())
                 if teacher_scores is not None:
@@ -760,7 +813,6 @@ class ToC3DEVAViT(_EvaBase):
                 eng.dense_block(i, X, wsp)
             if tap is not None:
                 tap["block_out"].append(X.clone())
-        cur.wait_stream(side)
         if tap is not None:
             tap["scores"] = scores_l
         return (X, *masks, *keep_idxes, *drop_idxes)

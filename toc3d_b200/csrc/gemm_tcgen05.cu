@@ -259,7 +259,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         r[it] = make_float4(0.f, 0.f, 0.f, 0.f);
         if (col < N && ((r_ok >> it) & 1u)) {
           const float* base = ((r_alt >> it) & 1u) ? ep.out_alt : ep.resid;
-          r[it] = *reinterpret_cast<const float4*>(base + (size_t)r_row[it] * ep.ldo + col);
+          r[it] = __ldcg(reinterpret_cast<const float4*>(base + (size_t)r_row[it] * ep.ldo + col));   // one-shot: skip L1
         }
       }
     };
@@ -306,7 +306,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
           o.z = r_cur[it].z + (fmaf(la[it], a.z, lb[it] * u4.z) + b.z);
           o.w = r_cur[it].w + (fmaf(la[it], a.w, lb[it] * u4.w) + b.w);
           float* base = ((o_alt >> it) & 1u) ? ep.out_alt : reinterpret_cast<float*>(ep.out);
-          *reinterpret_cast<float4*>(base + (size_t)o_row[it] * ep.ldo + col) = o;
+          __stcg(reinterpret_cast<float4*>(base + (size_t)o_row[it] * ep.ldo + col), o);
           if constexpr (AOUT) {
             uint2 u;
             u.x = pack_bf16(o.x, o.y);
