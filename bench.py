@@ -116,13 +116,15 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
-        self.rows, self.proc, self.index = [], None, index
+    def __init__(self, index, enabled=True):
+        self.rows, self.proc, self.index, self.enabled = [], None, index, enabled
 
     def __enter__(self):
+        if not self.enabled:      # only rank 0 polls NVML: eight pollers contend on the driver lock and slow every copy
+            return self
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -313,7 +315,7 @@ def run_native(args):
     e2e_run(3, False)
     torch.cuda.synchronize()
 
-    with ClockSampler(local) as clk:
+    with ClockSampler(local, enabled=(rank == 0)) as clk:
         l0 = L.launch_count
         total_ms, ms = timed(lambda: forward(res), args.steps)
         launches = (L.launch_count - l0) // args.steps
