@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 5
+#define TOC3D_B200_ABI_VERSION 6
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -112,9 +112,12 @@ int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int3
  * softmax(q k^T) v per (window, head); q already rotated and scaled by the QKV epilogue.
  * qkv bf16 [n_windows*seq_len, 3*C] (q | k | v), out bf16 [n_windows*seq_len, C]; head dim 64.
  * Replaces eva_vit.py:109-111 and toc3d_eva_vit.py:509-511 (bmm, softmax, bmm). seq_len <= 1024.
+ * out_map (optional, int32 [n_windows*seq_len]): destination row of each query row in `out`, -1 = row not
+ * stored.  Rows that are window PADDING matter only as keys / values; with out_map the attention writes the rows
+ * that are used afterwards in compact order, so that the row-wise GEMMs after it skip the padding.
  */
 int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
-                           void* stream);
+                           const int32_t* out_map, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm over gathered rows
  * out_bf16[m] = LN(row(m)) * gamma + beta over C channels (C % 128 == 0, C <= 4096), m in [0,M).
@@ -154,6 +157,21 @@ int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int32_t W, int3
                       int32_t* slow_idx, int32_t* fast_idx, float* fast_score, int32_t* tok_map,
                       int32_t* rope_rows, int32_t* fast_map, void* stream);
 
+/* Compact row space of an accelerated block (toc3d_eva_vit.py:421-461): of the packed rows [k slow | rep] of a
+ * window, the slow rows that are pad slots (tok_map = -1) are needed as attention keys / values only - proj,
+ * norm2 and the SwiGLU MLP are row-wise and window_unpartition crops their results - so those run on the compact
+ * rows.  coff / rcap int32 [nW] are host-static (rcap = min(k, #real tokens of the window), coff = exclusive
+ * prefix sum of rcap + 1).  Outputs: cmap int32 [nW*(k+1)] packed -> compact row | -1; ctok int32 [sum(rcap+1)]
+ * compact -> image row | -2 (representative) | -1 (unused); rep_row int32 [nW] compact row of the representative. */
+int toc3d_compact_rows(const int32_t* tok_map, const int32_t* coff, const int32_t* rcap, int32_t nW, int32_t k,
+                       int32_t* cmap, int32_t* ctok, int32_t* rep_row, void* stream);
+
+/* Dense blocks (eva_vit.py:247-268) pad AFTER norm1, so pad slots are exact zeros: k = 0 (k_proj has no bias, RoPE
+ * keeps zero), v = v_bias.  Writes those constants into the listed slot rows of the bf16 qkv buffer [.., 3C]
+ * (pad_rows int32 [n_pad]); the QKV GEMM then only runs over real tokens. */
+int toc3d_fill_pad_kv(void* qkv_bf16, const int32_t* pad_rows, int32_t n_pad, const float* v_bias, int32_t C,
+                      void* stream);
+
 /* Image-level stable descending sort split (toc3d_utils.py:137-144): scores fp32 [B,N] ->
  * keep_idx int64 [B,k], drop_idx int64 [B,N-k].  N <= 12288. */
 int toc3d_topk_split(const float* scores, int32_t B, int32_t N, int32_t k, int64_t* keep_idx, int64_t* drop_idx,
@@ -169,7 +187,8 @@ int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, const float
 /* Fast-token update (toc3d_eva_vit.py:452-456): x[fast_map[w,j]] += packed[(w*(k+1)+k)] - rep[w],
  * i.e. the representative token's attention + MLP residual deltas. */
 int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* packed, const float* rep, int32_t nW,
-                            int32_t n_fast, int32_t k, int32_t C, void* stream);
+                            int32_t n_fast, int32_t k, int32_t C, const int32_t* rep_row /* NULL: w*(k+1)+k */,
+                            void* stream);
 
 /* Fused front end of an accelerated block (toc3d_eva_vit.py:421-427 gather + merge_tokens, then norm1 at
  * :371): in ONE launch, (1) rep[w] = sum_j (s_j / sum s) x[fast_map[w,j]] -> rep_out[w] and packed row
@@ -179,6 +198,7 @@ int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* pack
 int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t* fast_map, const float* fast_score,
                           const float* gamma, const float* beta, void* out_bf16, float* rep_out, float* packed,
                           int32_t nW, int32_t k, int32_t n_fast, int32_t C, float eps, int64_t* zero_stats,
+                          const int32_t* rep_row /* row of `packed` for the representative; NULL: w*(k+1)+k */,
                           void* stream);
 
 /* ------------------------------------------------------------------ history-query scorer

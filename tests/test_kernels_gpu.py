@@ -478,6 +478,69 @@ def test_ln_gather_merge_fused(lib, C, ws, ratio):
     assert (stats == 0).all()
 
 
+def test_compact_rows_and_pad_fill(lib):
+    """Compact row space of an accelerated block + constant k / v of dense pad slots."""
+    g = torch.Generator().manual_seed(5)
+    V, H, W, ws, ratio = 2, 20, 50, 16, 0.7
+    n, k = ws * ws, int(ws * ws * ratio)
+    s = -torch.rand(V, H, W, generator=g) * 4
+    nW = V * 2 * 4
+    i32 = dict(dtype=torch.int32, device=DEV)
+    tok = torch.empty(nW * (k + 1), **i32)
+    lib.window_topk(s.to(DEV), V, H, W, ws, k, tok_map=tok)
+    real = torch.tensor([256, 256, 256, 32, 64, 64, 64, 8] * V, dtype=torch.int32)
+    rcap = torch.minimum(real, torch.tensor(k, dtype=torch.int32))
+    coff = torch.cumsum(rcap + 1, 0, dtype=torch.int32) - (rcap + 1)
+    Mc = int((rcap + 1).sum())
+    cmap = torch.full((nW * (k + 1),), -7, **i32); ctok = torch.full((Mc,), -7, **i32); rep_row = torch.full((nW,), -7, **i32)
+    lib.compact_rows(tok, coff.to(DEV), rcap.to(DEV), nW, k, cmap, ctok, rep_row)
+    tok_c, cmap_c, ctok_c = tok.cpu().view(nW, k + 1), cmap.cpu().view(nW, k + 1), ctok.cpu()
+    for w in range(nW):
+        r = int(rcap[w]); c0 = int(coff[w])
+        assert (tok_c[w, :r] >= 0).all() and (tok_c[w, r:k] == -1).all()          # real rows outrank pads
+        assert cmap_c[w, :r].tolist() == list(range(c0, c0 + r)) and (cmap_c[w, r:k] == -1).all()
+        assert cmap_c[w, k] == c0 + r and rep_row[w].item() == c0 + r and ctok_c[c0 + r] == -2
+        assert torch.equal(ctok_c[c0:c0 + r], tok_c[w, :r])
+    # dense pad slots
+    C = 128
+    qkv = torch.full((40, 3 * C), 7.0, device=DEV, dtype=torch.bfloat16)
+    pads = torch.tensor([3, 17, 39], **i32)
+    vb = torch.randn(C, generator=g).to(DEV)
+    lib.fill_pad_kv(qkv, pads, vb, C)
+    q = qkv.float().cpu()
+    assert (q[[3, 17, 39], C:2 * C] == 0).all() and torch.equal(q[[3, 17, 39], 2 * C:], bf16_round(vb.cpu()).expand(3, C))
+    assert (q[[3, 17, 39], :C] == 7).all() and (q[[0, 1, 2, 4]] == 7).all()
+
+
+def test_attention_and_qkv_row_maps(lib):
+    """out_map of the attention (rows stored in compact order, -1 skipped) and of the QKV epilogue (rows scattered)."""
+    g = torch.Generator().manual_seed(9)
+    nW, seq, heads = 4, 77, 2
+    C = heads * 64
+    qkv = bf16_round(torch.randn(nW * seq, 3 * C, generator=g))
+    q, k, v = qkv.reshape(nW, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(nW * seq, C)
+    keep = torch.rand(nW * seq, generator=g) > 0.4
+    omap = torch.full((nW * seq,), -1, dtype=torch.int32)
+    omap[keep] = torch.randperm(int(keep.sum()), generator=g).int()
+    out = torch.full((int(keep.sum()), C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib.window_attention(qkv.to(DEV).bfloat16(), out, nW, seq, heads, out_map=omap.to(DEV))
+    got = out.float().cpu()
+    assert torch.isfinite(got).all()
+    assert (got[omap[keep].long()] - ref[keep]).abs().max().item() < 2e-2
+    # GEMM bf16 rows through out_map
+    M, N, K = 300, 256, 128
+    A = bf16_round(torch.randn(M, K, generator=g)); Wt = bf16_round(torch.randn(N, K, generator=g) * 0.1)
+    perm = torch.randperm(400, generator=g)[:M].int(); perm[::9] = -1
+    o = torch.zeros(400, N, device=DEV, dtype=torch.bfloat16)
+    lib.gemm(A.to(DEV).bfloat16(), Wt.to(DEV).bfloat16(), lib.EPI_LINEAR, out=o, out_map=perm.to(DEV))
+    oc = o.float().cpu(); full = bf16_round(A @ Wt.t())
+    ok = perm >= 0
+    assert (oc[perm[ok].long()] - full[ok]).abs().max().item() < 2e-2
+    untouched = torch.ones(400, dtype=torch.bool); untouched[perm[ok].long()] = False
+    assert (oc[untouched] == 0).all()
+
+
 # ------------------------------------------------------------------------------------ scorer
 def test_scorer_fold_and_tokens(lib):
     g = torch.Generator().manual_seed(5)

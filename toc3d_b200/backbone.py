@@ -217,13 +217,21 @@ class _Workspace:
             idx = torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W)
             idx = F.pad(idx, (0, nWw * ws - W, 0, nWh * ws - H), value=-1.0)
             idx = idx.reshape(V, nWh, ws, nWw, ws).permute(0, 1, 3, 2, 4).reshape(-1)
-            self.win[ws] = dict(nW=nW, n=n, map=idx.to(torch.int32).to(dev))
+            m = idx.to(torch.int32)
+            slots = torch.arange(nW * n, dtype=torch.int32)
+            real = m >= 0
+            inv = torch.empty(V * H * W, dtype=torch.int32)
+            inv[m[real].long()] = slots[real]                  # image row -> window slot (global slot index)
+            self.win[ws] = dict(nW=nW, n=n, map=m.to(dev),
+                                # dense blocks run q/k/v only over real tokens and scatter them to their window slots
+                                slot_of_row=inv.to(dev), rope_slot=(inv % n).to(dev), pad_rows=slots[~real].to(dev),
+                                real_per_window=real.view(nW, n).sum(1).to(torch.int32))
             rows = max(rows, nW * n)
         self.rows = rows
         bf = dict(device=dev, dtype=torch.bfloat16)
         self.cols = torch.empty(V * self.N, 768, **bf) if eng.patch == 16 else None
         self.a = torch.empty(rows, C, **bf)            # LN outputs / attention outputs (GEMM A operands)
-        self.qkv = torch.empty(rows, 3 * C, **bf)
+        self.qkv = torch.zeros(rows, 3 * C, **bf)      # zeroed once: q of pad slots is never written, must stay finite
         self.ao = torch.empty(rows, C, **bf)
         self.hid = torch.empty(rows, eng.Hp, **bf)
         self.T = torch.empty(rows, C, device=dev, dtype=torch.float32)   # packed slow+rep residual stream
@@ -271,7 +279,7 @@ class _Engine:
             self.blocks.append(dict(
                 n1w=f32(b.norm1.weight), n1b=f32(b.norm1.bias), n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias),
                 wqkv=b16(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
-                bqkv=torch.cat([qb, zeros, vb]).contiguous(),
+                bqkv=torch.cat([qb, zeros, vb]).contiguous(), vb=vb.contiguous(),
                 wproj=b16(a.proj.weight), bproj=f32(a.proj.bias),
                 w12=w12.to(torch.bfloat16).contiguous(), b12=b12, u12=u12,
                 # SwiGLU sub-LN (eva_vit.py:48) folded into the w3 GEMM: w3g = W3 * gamma (columns),
@@ -355,23 +363,27 @@ class _Engine:
         the SwiGLU GEMM), their row statistics, and the zeroing of the sub-LN accumulator."""
         return dict(a_out=wsp.a, row_stats=wsp.stats2, zero_stats=wsp.stats) if self.fold_norm2 else {}
 
-    def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots):
+    def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots, qkv_out_map=None, attn_out_map=None):
+        """q/k/v for the M rows of wsp.a (scattered to window slots through qkv_out_map when given), then attention
+        over nW windows of seq slots; attn_out_map sends the rows that are used afterwards to compact positions."""
         C = self.C
         L.gemm(wsp.a, bp["wqkv"], L.EPI_QKV_ROPE, M=M, bias=bp["bqkv"], out=wsp.qkv, rope_rows=rope_rows,
                rope_slots=rope_slots, rope_ft=bp["ft"], rope_cols=2 * C, q_scale=64 ** -0.5,
-               cos_axis=bp["cos"], sin_axis=bp["sin"])
-        L.window_attention(wsp.qkv, wsp.ao, nW, seq, self.heads)
+               cos_axis=bp["cos"], sin_axis=bp["sin"], out_map=qkv_out_map)
+        L.window_attention(wsp.qkv, wsp.ao, nW, seq, self.heads, out_map=attn_out_map)
 
     def dense_block(self, i, X, wsp):
-        """eva_vit.py:247-268."""
+        """eva_vit.py:247-268.  The reference pads the normalised map to whole windows and runs q/k/v, attention and
+        proj on every slot; the pad slots are exact zeros after norm1, so their k is 0 and their v is v_bias, and
+        their own outputs are cropped by window_unpartition.  Here q/k/v and proj run over the real tokens only
+        (image-row order); the pad slots of the window layout get their constant k / v from fill_pad_kv."""
         bp, C = self.blocks[i], self.C
         w = wsp.win[self.block_ws[i]]
-        Mw, VN = w["nW"] * w["n"], wsp.V * wsp.N
-        L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, Mw, C, LN_EPS, row_map=w["map"], pad_mode=0,
-                         zero_stats=wsp.stats2 if self.fold_norm2 else None)
-        self._qkv_attn(bp, wsp, Mw, w["nW"], w["n"], None, w["n"])
-        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mw, bias=bp["bproj"], out=X, ldo=C, resid=X,
-               resid_map=w["map"], out_map=w["map"], **self._proj_kw(wsp))
+        VN = wsp.V * wsp.N
+        L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None)
+        L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
+        self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"])
+        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X, **self._proj_kw(wsp))
         if not self.fold_norm2:
             L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
         self._mlp(bp, wsp, VN, out=X, resid=X)
@@ -390,34 +402,42 @@ class _Engine:
             t = wsp.stage.get((stage, ws))
             if t is None or t["k"] != k:
                 i32 = dict(device=dev, dtype=torch.int32)
+                # compact row space (real slow rows + representative per window); its layout is static: a window
+                # keeps min(k, #real tokens) real rows, because real scores (log-probabilities) outrank the -1e6 pads
+                rcap = torch.minimum(w["real_per_window"], torch.tensor(k, dtype=torch.int32))
+                coff = torch.cumsum(rcap + 1, 0, dtype=torch.int32) - (rcap + 1)
+                Mc = int((rcap + 1).sum())
                 t = dict(k=k, nf=n - k, tok_map=torch.empty(nW * (k + 1), **i32),
                          rope_rows=torch.empty(nW * (k + 1), **i32), fast_map=torch.empty(nW, n - k, **i32),
-                         fast_score=torch.empty(nW, n - k, device=dev), rep=torch.empty(nW, self.C, device=dev))
+                         fast_score=torch.empty(nW, n - k, device=dev), rep=torch.empty(nW, self.C, device=dev),
+                         Mc=Mc, rcap=rcap.to(dev), coff=coff.to(dev), cmap=torch.empty(nW * (k + 1), **i32),
+                         ctok=torch.empty(Mc, **i32), rep_row=torch.empty(nW, **i32))
                 wsp.stage[(stage, ws)] = t
             L.window_topk(score, wsp.V, wsp.H, wsp.W, ws, k, fast_score=t["fast_score"], tok_map=t["tok_map"],
                           rope_rows=t["rope_rows"], fast_map=t["fast_map"])
+            L.compact_rows(t["tok_map"], t["coff"], t["rcap"], nW, k, t["cmap"], t["ctok"], t["rep_row"])
 
     def toc3d_block(self, i, X, wsp, stage):
-        """toc3d_eva_vit.py:395-473 (accelerated branch)."""
+        """toc3d_eva_vit.py:395-473 (accelerated branch).  Packed rows (k slow + rep per window, pad slots included)
+        feed norm1 / q,k,v / attention, where pads act as keys and values; proj, norm2 and the MLP are row-wise and
+        the pads' results are cropped (toc3d_eva_vit.py:459-461), so from the attention output on only the compact
+        rows (real slow rows + rep) are computed."""
         bp, C = self.blocks[i], self.C
         ws = self.block_ws[i]
         w, t = wsp.win[ws], wsp.stage[(stage, ws)]
-        nW, k, nf = w["nW"], t["k"], t["nf"]
+        nW, k, nf, Mc = w["nW"], t["k"], t["nf"], t["Mc"]
         Mp = nW * (k + 1)
-        if C in (128, 256, 512, 1024):      # one launch: representative token + norm1 of the packed slow/rep rows
-            L.ln_gather_merge(X, t["tok_map"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
-                              wsp.T, nW, k, nf, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None)
-        else:
-            L.merge_fast_tokens(X, t["fast_map"], t["fast_score"], nW, nf, k, C, t["rep"], wsp.T)
-            L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, Mp, C, LN_EPS, row_map=t["tok_map"], alt=wsp.T,
-                             pad_mode=1, zero_stats=wsp.stats2 if self.fold_norm2 else None)
-        self._qkv_attn(bp, wsp, Mp, nW, k + 1, t["rope_rows"], 0)
-        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mp, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
-               resid_map=t["tok_map"], out_alt=wsp.T, **self._proj_kw(wsp))            # t1 = t + attn
+        # one launch: representative token (-> T[rep_row]) + norm1 of the packed slow / rep rows
+        L.ln_gather_merge(X, t["tok_map"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
+                          wsp.T, nW, k, nf, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None,
+                          rep_row=t["rep_row"])
+        self._qkv_attn(bp, wsp, Mp, nW, k + 1, t["rope_rows"], 0, attn_out_map=t["cmap"])
+        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
+               resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
         if not self.fold_norm2:
-            L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mp, C, LN_EPS, zero_stats=wsp.stats)
-        self._mlp(bp, wsp, Mp, out=X, resid=wsp.T, out_map=t["tok_map"], out_alt=wsp.T)   # t2 -> image rows
-        L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C)
+            L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
+        self._mlp(bp, wsp, Mc, out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T)     # t2 -> image rows
+        L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C, rep_row=t["rep_row"])
 
     # -- scorers ----------------------------------------------------------------------------
     def fold_queries(self, j, sel_mod, q_kw, V):
@@ -473,6 +493,8 @@ class _EvaBase(nn.Module):
             raise NotImplementedError("the sm_100a stem kernel is specialised for 16x16 RGB patches")
         if embed_dim // num_heads != 64:
             raise NotImplementedError("attention / RoPE kernels are specialised for head_dim 64")
+        if embed_dim not in (128, 256, 512, 768, 1024):
+            raise NotImplementedError("the fused norm1 / merge kernel supports embed_dim 128, 256, 512, 768, 1024")
         self.embed_dim, self.num_heads, self.patch_size = embed_dim, num_heads, patch_size
         self.pretrain_use_cls_token = pretrain_use_cls_token
         self.patch_embed = _PatchEmbed(patch_size, in_chans, embed_dim)

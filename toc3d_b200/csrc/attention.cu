@@ -45,7 +45,8 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16 (*dst)[LDS], const __nv_
 }
 
 __global__ void __launch_bounds__(NTHREADS)
-window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int seq, int heads) {
+window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int seq, int heads,
+                        const int* __restrict__ out_map) {
   __shared__ __align__(16) Smem sm;
   pdl_wait();
   pdl_launch_dependents();
@@ -178,12 +179,15 @@ window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __
   }
   const float inv0 = 1.0f / l_run[0], inv1 = 1.0f / l_run[1];
   const int r0 = qt * BQ + warp * 16 + g, r1 = r0 + 8;
-  __nv_bfloat16* obase = out + row0 * C + h * D;
+  // destination rows: packed order, or through out_map (-1 = row not needed)
+  int64_t d0 = r0 < seq ? (out_map ? out_map[row0 + r0] : row0 + r0) : -1;
+  int64_t d1 = r1 < seq ? (out_map ? out_map[row0 + r1] : row0 + r1) : -1;
+  __nv_bfloat16* obase = out + h * D;
 #pragma unroll
   for (int dt = 0; dt < 8; ++dt) {
     const int col = dt * 8 + 2 * t;
-    if (r0 < seq) *reinterpret_cast<uint32_t*>(obase + (int64_t)r0 * C + col) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
-    if (r1 < seq) *reinterpret_cast<uint32_t*>(obase + (int64_t)r1 * C + col) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
+    if (d0 >= 0) *reinterpret_cast<uint32_t*>(obase + d0 * C + col) = pack_bf16(o[dt][0] * inv0, o[dt][1] * inv0);
+    if (d1 >= 0) *reinterpret_cast<uint32_t*>(obase + d1 * C + col) = pack_bf16(o[dt][2] * inv1, o[dt][3] * inv1);
   }
 }
 
@@ -354,7 +358,7 @@ enum { BAR_QK = 0, BAR_V, BAR_S, BAR_P, BAR_O, BAR_OFREE, NUM_BARS };
 // Single-slot kernel (256 < seq <= 448, or any seq): one CTA per (window, head), query tiles in sequence.
 __global__ void __launch_bounds__(NTHREADS)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                           int tmem_cols) {
+                           int tmem_cols, const int* __restrict__ out_map) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int T = (seq + 127) >> 7;               // 128-row query tiles
@@ -430,7 +434,9 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
     for (int t = 0; t < T; ++t) {
       const int q = t * 128 + quarter * 32 + lane;
-      softmax_tile(lane_base, o_col, seq, t * 128 + quarter * 32 < seq, q < seq, out + (size_t)(row0 + q) * C + h * D,
+      int dst = q < seq ? row0 + q : -1;
+      if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
+      softmax_tile(lane_base, o_col, seq, t * 128 + quarter * 32 < seq, dst >= 0, out + (size_t)(dst < 0 ? 0 : dst) * C + h * D,
                    &bars[BAR_S], &bars[BAR_P], &bars[BAR_O], &bars[BAR_OFREE], (uint32_t)(t & 1));
     }
   }
@@ -454,7 +460,7 @@ enum { PB_FULL = 0 /* +nbuf */, PB_EMPTY = 4, PB_S = 8 /* +slot */, PB_P = 10, P
 
 __global__ void __launch_bounds__(PP_THREADS, 1)
 window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                           int n_items, int nbuf) {
+                           int n_items, int nbuf, const int* __restrict__ out_map) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int T = (seq + 127) >> 7;               // 1 or 2 query tiles
@@ -558,8 +564,10 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       const int it = (int)blockIdx.x + i * (int)gridDim.x;
       const int w = it / heads, h = it - w * heads;
       const int q = t * 128 + quarter * 32 + lane;
-      softmax_tile(lane_base, o_off, seq, t * 128 + quarter * 32 < seq, q < seq,
-                   out + ((size_t)w * seq + q) * C + h * D, &bars[PB_S + slot], &bars[PB_P + slot], &bars[PB_O + slot],
+      int dst = q < seq ? w * seq + q : -1;
+      if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
+      softmax_tile(lane_base, o_off, seq, t * 128 + quarter * 32 < seq, dst >= 0,
+                   out + (size_t)(dst < 0 ? 0 : dst) * C + h * D, &bars[PB_S + slot], &bars[PB_P + slot], &bars[PB_O + slot],
                    &bars[PB_OFREE + slot], (uint32_t)((u >> 1) & 1));
     }
   }
@@ -576,7 +584,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
 }  // namespace toc3d
 
 extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
-                                      void* stream) {
+                                      const int32_t* out_map, void* stream) {
   using namespace toc3d;
   TOC3D_REQUIRE(qkv && out, kErrBadArg, "toc3d_window_attention: null pointer");
   TOC3D_REQUIRE(n_windows > 0 && seq_len > 0 && seq_len <= 1024 && heads > 0 && heads <= 65535, kErrBadArg,
@@ -610,18 +618,18 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
       const int grid = n_items < n_sm ? n_items : n_sm;
       const size_t smem = (size_t)nbuf * item_bytes + 1024 + 256;
       TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1, tm, o,
-                                  seq_len, heads, n_items, nbuf));
+                                  seq_len, heads, n_items, nbuf, out_map));
       return 0;
     }
     const int spad = (seq_len + 15) & ~15;
     const int tmem_cols = spad <= 256 ? 256 : 512;     // <= 256 keys: two CTAs per SM (O may alias the tail of S)
     const size_t smem = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128;
     TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc_kernel, dim3(heads, n_windows), dim3(attn_tc::NTHREADS), smem, st,
-                                1, tm, o, seq_len, heads, tmem_cols));
+                                1, tm, o, seq_len, heads, tmem_cols, out_map));
     return 0;
   }
   dim3 grid((seq_len + attn::BQ - 1) / attn::BQ, heads, n_windows);
   TOC3D_CHECK_CUDA(launch_pdl(attn::window_attention_kernel, grid, dim3(attn::NTHREADS), 0, st, 1,
-                              reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads));
+                              reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads, out_map));
   return 0;
 }

@@ -373,6 +373,14 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       rs[it] = __ldg(reinterpret_cast<const float2*>(ep.sin_axis + p * 16 + j0));
     }
   }
+  // destination rows (QKV_ROPE / LINEAR): identity or out_map (-1 = row dropped), per coalesced-domain row
+  int d_row[8];
+  {
+    int dr_t = my_row_ok ? m0 + lane : -1;
+    if (dr_t >= 0 && ep.out_map != nullptr) dr_t = ep.out_map[dr_t];
+#pragma unroll
+    for (int it = 0; it < 8; ++it) d_row[it] = __shfl_sync(0xffffffffu, dr_t, it * 4 + rin);
+  }
   float4 bias4[BN_MAX / (2 * CHUNK)];
 #pragma unroll
   for (int i = 0; i < BN_MAX / (2 * CHUNK); ++i) {
@@ -411,11 +419,11 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
           a.x = (x0 * c2.x - x1 * sn.x) * sc_q; a.y = (x1 * c2.x + x0 * sn.x) * sc_q;
           a.z = (x2 * c2.y - x3 * sn.y) * sc_q; a.w = (x3 * c2.y + x2 * sn.y) * sc_q;
         }
-        if (col_ok && m0 + row < M) {
+        if (col_ok && d_row[it] >= 0) {
           uint2 u;
           u.x = pack_bf16(a.x, a.y);
           u.y = pack_bf16(a.z, a.w);
-          *reinterpret_cast<uint2*>(out + (size_t)(m0 + row) * ep.ldo + col) = u;
+          *reinterpret_cast<uint2*>(out + (size_t)d_row[it] * ep.ldo + col) = u;
         }
       }
     } else {  // TOC3D_EPI_LINEAR
@@ -426,14 +434,14 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         if (ep.act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
         else if (ep.act == 2) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-        if (col_ok && m0 + row < M) {
+        if (col_ok && d_row[it] >= 0) {
           if (ep.out_f32) {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)(m0 + row) * ep.ldo + col) = a;
+            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)d_row[it] * ep.ldo + col) = a;
           } else {
             uint2 u;
             u.x = pack_bf16(a.x, a.y);
             u.y = pack_bf16(a.z, a.w);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)(m0 + row) * ep.ldo + col) = u;
+            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)d_row[it] * ep.ldo + col) = u;
           }
         }
       }

@@ -206,6 +206,69 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
   }
 }
 
+// Compact row space of an accelerated block.  The packed set of a window is [k slow rows in rank order | rep];
+// slow rows that are PAD slots (tok_map = -1) matter only as attention keys / values: everything after the
+// attention (proj, norm2, SwiGLU) is row-wise and their results are cropped by window_unpartition
+// (toc3d_eva_vit.py:459-461), so those GEMMs run on the compact rows = real slow rows + rep only.
+// coff[w] / rcap[w] (host-static: rcap = min(k, #real tokens of the window)) give the window's compact range.
+//   cmap[w*(k+1)+r] = compact row of packed row r (or -1 for a pad), ctok[c] = image row | -2 (rep) | -1 (unused),
+//   rep_row[w] = compact row of the representative token.  One CTA per window.
+__global__ void __launch_bounds__(1024)
+compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ coff, const int* __restrict__ rcap, int k,
+                    int* __restrict__ cmap, int* __restrict__ ctok, int* __restrict__ rep_row) {
+  __shared__ int s_warp[32];
+  pdl_wait();
+  pdl_launch_dependents();
+  const int w = blockIdx.x, t = threadIdx.x;
+  const int lane = t & 31, wid = t >> 5;
+  const size_t base = (size_t)w * (k + 1);
+  const int src = t < k ? tok_map[base + t] : -1;
+  const bool real = t < k && src >= 0;
+  const unsigned bal = __ballot_sync(0xffffffffu, real);
+  if (lane == 0) s_warp[wid] = __popc(bal);
+  __syncthreads();
+  int before = __popc(bal & ((1u << lane) - 1u));
+  int total = 0;
+  for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
+    const int c = s_warp[i];
+    if (i < wid) before += c;
+    total += c;
+  }
+  const int c0 = coff[w], cap = rcap[w];
+  if (t < k) {
+    const bool ok = real && before < cap;
+    cmap[base + t] = ok ? c0 + before : -1;
+    if (ok) ctok[c0 + before] = src;
+  }
+  if (t >= total && t < cap) ctok[c0 + t] = -1;            // degenerate: fewer real slow rows than the static capacity
+  if (t == 0) {
+    cmap[base + k] = c0 + cap;
+    ctok[c0 + cap] = -2;
+    rep_row[w] = c0 + cap;
+  }
+}
+
+// Dense blocks compute q/k/v only for real tokens; the window slots that are padding hold constants:
+// k = 0 (k_proj has no bias and the padded norm1 output is zero, eva_vit.py:249-254,97-99; RoPE keeps zero) and
+// v = v_bias.  rows: slot rows of the qkv buffer [.., 3C]; thread = 8 channels.
+__global__ void __launch_bounds__(256)
+fill_pad_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ pad_rows, int n_pad, const float* __restrict__ v_bias, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  const int cv = C >> 3;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_pad * 2 * cv) return;
+  const int c8 = (int)(idx % cv);
+  const int part = (int)((idx / cv) & 1);                  // 0: k, 1: v
+  const int row = pad_rows[idx / (2 * cv)];
+  uint4 val = make_uint4(0u, 0u, 0u, 0u);
+  if (part == 1 && v_bias != nullptr) {
+    const float4 a = *reinterpret_cast<const float4*>(v_bias + c8 * 8), b = *reinterpret_cast<const float4*>(v_bias + c8 * 8 + 4);
+    val.x = pack_bf16(a.x, a.y); val.y = pack_bf16(a.z, a.w); val.z = pack_bf16(b.x, b.y); val.w = pack_bf16(b.z, b.w);
+  }
+  *reinterpret_cast<uint4*>(qkv + (size_t)row * 3 * C + (size_t)(1 + part) * C + c8 * 8) = val;
+}
+
 // Image-level stable sort split by rank counting; grid (ceil(N/32), B) x 256 threads: the keys of one row sit
 // in smem, 8 lanes share one element (lane s counts key groups s, s+8, ...) and combine with shuffles.
 __global__ void __launch_bounds__(256)
@@ -324,7 +387,8 @@ __global__ void __launch_bounds__(256)
 ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_map, const int* __restrict__ fast_map,
                        const float* __restrict__ fast_score, const float* __restrict__ gamma,
                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, float* __restrict__ rep_out,
-                       float* __restrict__ packed, int nW, int k, int n_fast, float eps, long long* __restrict__ zero_stats) {
+                       float* __restrict__ packed, int nW, int k, int n_fast, float eps, long long* __restrict__ zero_stats,
+                       const int* __restrict__ rep_row) {
   constexpr int C = VPL * 128;
   __shared__ __align__(16) float s_acc[8][C];
   __shared__ float s_wgt[1024];
@@ -424,7 +488,7 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
 #pragma unroll
       for (int q = 0; q < 8; ++q) r[e] += s_acc[q][ch];
       rep_out[(size_t)w * C + ch] = r[e];
-      packed[((size_t)w * (k + 1) + k) * C + ch] = r[e];
+      packed[(size_t)(rep_row != nullptr ? rep_row[w] : w * (k + 1) + k) * C + ch] = r[e];
       sm += r[e];
     }
   }
@@ -455,7 +519,7 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
 template <int VPL>
 __global__ void __launch_bounds__(256)
 fast_update_kernel(float* __restrict__ x, const int* __restrict__ fast_map, const float* __restrict__ packed,
-                   const float* __restrict__ rep, int total_fast, int n_fast, int k) {
+                   const float* __restrict__ rep, int total_fast, int n_fast, int k, const int* __restrict__ rep_row) {
   constexpr int C = VPL * 128;
   pdl_wait();
   pdl_launch_dependents();
@@ -465,7 +529,7 @@ fast_update_kernel(float* __restrict__ x, const int* __restrict__ fast_map, cons
   if (row < 0) return;
   const int w = f / n_fast;
   const int lane = threadIdx.x & 31;
-  const float4* t2 = reinterpret_cast<const float4*>(packed + ((size_t)w * (k + 1) + k) * C) + lane;
+  const float4* t2 = reinterpret_cast<const float4*>(packed + (size_t)(rep_row != nullptr ? rep_row[w] : w * (k + 1) + k) * C) + lane;
   const float4* t0 = reinterpret_cast<const float4*>(rep + (size_t)w * C) + lane;
   float4* xr = reinterpret_cast<float4*>(x + (size_t)row * C) + lane;
   float4 v[VPL], a[VPL], b[VPL];
@@ -742,6 +806,25 @@ extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int3
   return 0;
 }
 
+extern "C" int toc3d_compact_rows(const int32_t* tok_map, const int32_t* coff, const int32_t* rcap, int32_t nW, int32_t k,
+                                  int32_t* cmap, int32_t* ctok, int32_t* rep_row, void* stream) {
+  TOC3D_REQUIRE(tok_map && coff && rcap && cmap && ctok && rep_row, kErrBadArg, "toc3d_compact_rows: null pointer");
+  TOC3D_REQUIRE(nW > 0 && k >= 1 && k <= 1023, kErrBadArg, "toc3d_compact_rows: bad shape nW=%d k=%d", nW, k);
+  const int threads = ((k + 1 + 31) / 32) * 32;
+  TOC3D_CHECK_CUDA(launch_pdl(compact_rows_kernel, dim3(nW), dim3(threads), 0, ST(stream), 1, tok_map, coff, rcap, k, cmap, ctok, rep_row));
+  return 0;
+}
+
+extern "C" int toc3d_fill_pad_kv(void* qkv, const int32_t* pad_rows, int32_t n_pad, const float* v_bias, int32_t C, void* stream) {
+  TOC3D_REQUIRE(qkv && (pad_rows || n_pad == 0), kErrBadArg, "toc3d_fill_pad_kv: null pointer");
+  TOC3D_REQUIRE(n_pad >= 0 && C > 0 && C % 8 == 0, kErrBadArg, "toc3d_fill_pad_kv: bad shape n_pad=%d C=%d", n_pad, C);
+  if (n_pad == 0) return 0;
+  const size_t total = (size_t)n_pad * 2 * (C / 8);
+  TOC3D_CHECK_CUDA(launch_pdl(fill_pad_kv_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), 1,
+                              reinterpret_cast<__nv_bfloat16*>(qkv), pad_rows, n_pad, v_bias, C));
+  return 0;
+}
+
 extern "C" int toc3d_topk_split(const float* scores, int32_t B, int32_t N, int32_t k, int64_t* keep_idx,
                                 int64_t* drop_idx, void* stream) {
   TOC3D_REQUIRE(scores && keep_idx && drop_idx, kErrBadArg, "toc3d_topk_split: null pointer");
@@ -767,13 +850,13 @@ extern "C" int toc3d_merge_fast_tokens(const float* x, const int32_t* fast_map, 
 }
 
 extern "C" int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* packed, const float* rep,
-                                       int32_t nW, int32_t n_fast, int32_t k, int32_t C, void* stream) {
+                                       int32_t nW, int32_t n_fast, int32_t k, int32_t C, const int32_t* rep_row, void* stream) {
   TOC3D_REQUIRE(x && fast_map && packed && rep, kErrBadArg, "toc3d_fast_token_update: null pointer");
   TOC3D_REQUIRE(nW > 0 && n_fast > 0 && C % 128 == 0, kErrBadArg, "toc3d_fast_token_update: bad shape");
   const int total = nW * n_fast;
   dim3 grid((total + 7) / 8), block(256);
 #define UPD_CASE(V)                                                                                                  \
-  case V: TOC3D_CHECK_CUDA(launch_pdl(fast_update_kernel<V>, grid, block, 0, ST(stream), 1, x, fast_map, packed, rep, total, n_fast, k)); break;
+  case V: TOC3D_CHECK_CUDA(launch_pdl(fast_update_kernel<V>, grid, block, 0, ST(stream), 1, x, fast_map, packed, rep, total, n_fast, k, rep_row)); break;
   switch (C / 128) {
     UPD_CASE(1) UPD_CASE(2) UPD_CASE(4) UPD_CASE(6) UPD_CASE(8) UPD_CASE(16)
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_fast_token_update: unsupported C=%d", C);
@@ -785,7 +868,7 @@ extern "C" int toc3d_fast_token_update(float* x, const int32_t* fast_map, const 
 extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t* fast_map,
                                      const float* fast_score, const float* gamma, const float* beta, void* out,
                                      float* rep_out, float* packed, int32_t nW, int32_t k, int32_t n_fast, int32_t C,
-                                     float eps, int64_t* zero_stats, void* stream) {
+                                     float eps, int64_t* zero_stats, const int32_t* rep_row, void* stream) {
   TOC3D_REQUIRE(x && tok_map && fast_map && fast_score && gamma && beta && out && rep_out && packed, kErrBadArg,
                 "toc3d_ln_gather_merge: null pointer");
   TOC3D_REQUIRE(nW > 0 && k >= 0 && n_fast > 0 && n_fast <= 1024, kErrBadArg,
@@ -795,10 +878,10 @@ extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, con
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   long long* zs = reinterpret_cast<long long*>(zero_stats);
 #define LGM_CASE(V)                                                                                                  \
-  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs)); break;
+  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs, rep_row)); break;
   switch (C % 128 == 0 ? C / 128 : 0) {
-    LGM_CASE(1) LGM_CASE(2) LGM_CASE(4) LGM_CASE(8)
-    default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_ln_gather_merge: C must be 128, 256, 512 or 1024 (got %d)", C);
+    LGM_CASE(1) LGM_CASE(2) LGM_CASE(4) LGM_CASE(6) LGM_CASE(8)
+    default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_ln_gather_merge: C must be 128, 256, 512, 768 or 1024 (got %d)", C);
   }
 #undef LGM_CASE
   return 0;

@@ -35,19 +35,21 @@ _SIGS = {
     "toc3d_last_error": ([], ctypes.c_char_p),
     "toc3d_gemm_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int,
                          ctypes.POINTER(Epilogue), _c_void_p], _c_int),
-    "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
+    "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
     "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                               _c_float, _c_int, _c_void_p, _c_void_p], _c_int),
     "toc3d_subln_bf16": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
                          _c_int),
     "toc3d_window_topk": ([_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_compact_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_fill_pad_kv": ([_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p], _c_int),
     "toc3d_topk_split": ([_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_merge_fast_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                  _c_void_p, _c_void_p], _c_int),
     "toc3d_fast_token_update": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
-                                 _c_void_p], _c_int),
-    "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p], _c_int),
+                                 _c_void_p, _c_void_p], _c_int),
+    "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_fold_queries": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int,
                                   _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
@@ -79,7 +81,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 5:
+        if lib.toc3d_abi_version() != 6:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -132,9 +134,9 @@ def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, ac
     return out
 
 
-def window_attention(qkv, out, n_windows, seq_len, heads):
+def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None):
     _want(qkv, torch.bfloat16, "qkv"); _want(out, torch.bfloat16, "out")
-    _check(load().toc3d_window_attention(_p(qkv), _p(out), n_windows, seq_len, heads, _stream()),
+    _check(load().toc3d_window_attention(_p(qkv), _p(out), n_windows, seq_len, heads, _p(out_map), _stream()),
            "toc3d_window_attention")
     return out
 
@@ -169,16 +171,25 @@ def merge_fast_tokens(x, fast_map, fast_score, nW, n_fast, k, C, rep_out, packed
                                           _p(packed), _stream()), "toc3d_merge_fast_tokens")
 
 
-def fast_token_update(x, fast_map, packed, rep, nW, n_fast, k, C):
-    _check(load().toc3d_fast_token_update(_p(x), _p(fast_map), _p(packed), _p(rep), nW, n_fast, k, C, _stream()),
+def compact_rows(tok_map, coff, rcap, nW, k, cmap, ctok, rep_row):
+    _check(load().toc3d_compact_rows(_p(tok_map), _p(coff), _p(rcap), nW, k, _p(cmap), _p(ctok), _p(rep_row), _stream()),
+           "toc3d_compact_rows")
+
+
+def fill_pad_kv(qkv, pad_rows, v_bias, C):
+    _check(load().toc3d_fill_pad_kv(_p(qkv), _p(pad_rows), pad_rows.numel(), _p(v_bias), C, _stream()), "toc3d_fill_pad_kv")
+
+
+def fast_token_update(x, fast_map, packed, rep, nW, n_fast, k, C, rep_row=None):
+    _check(load().toc3d_fast_token_update(_p(x), _p(fast_map), _p(packed), _p(rep), nW, n_fast, k, C, _p(rep_row), _stream()),
            "toc3d_fast_token_update")
 
 
 def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out, packed, nW, k, n_fast, C, eps,
-                    zero_stats=None):
+                    zero_stats=None, rep_row=None):
     _want(x, torch.float32, "x"); _want(out, torch.bfloat16, "out")
     _check(load().toc3d_ln_gather_merge(_p(x), _p(tok_map), _p(fast_map), _p(fast_score), _p(gamma), _p(beta), _p(out),
-                                        _p(rep_out), _p(packed), nW, k, n_fast, C, eps, _p(zero_stats), _stream()),
+                                        _p(rep_out), _p(packed), nW, k, n_fast, C, eps, _p(zero_stats), _p(rep_row), _stream()),
            "toc3d_ln_gather_merge")
 
 
