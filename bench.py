@@ -336,7 +336,7 @@ def run_native(args):
     #     device-side sleep is queued first so the host runs ahead and the events bracket kernels, not launch gaps.
     work = algorithmic_work(cfg, kind, hw, V)
     recs = []
-    names = ["gemm", "window_attention", "layernorm_rows", "ln_gather_merge", "subln", "window_topk", "topk_split", "merge_fast_tokens",
+    names = ["gemm", "window_attention", "layernorm_rows", "ln_gather_merge", "fill_pad_kv", "fill_pad_kv_rope", "compact_rows", "subln", "window_topk", "topk_split", "merge_fast_tokens",
              "fast_token_update", "score_fold_queries", "score_tokens", "score_finish", "im2col_patch16", "mask_rows",
              "global_half_mean"]
     saved = {n: getattr(L, n) for n in names}

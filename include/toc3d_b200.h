@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 6
+#define TOC3D_B200_ABI_VERSION 8
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -162,9 +162,21 @@ int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int32_t W, int3
  * norm2 and the SwiGLU MLP are row-wise and window_unpartition crops their results - so those run on the compact
  * rows.  coff / rcap int32 [nW] are host-static (rcap = min(k, #real tokens of the window), coff = exclusive
  * prefix sum of rcap + 1).  Outputs: cmap int32 [nW*(k+1)] packed -> compact row | -1; ctok int32 [sum(rcap+1)]
- * compact -> image row | -2 (representative) | -1 (unused); rep_row int32 [nW] compact row of the representative. */
-int toc3d_compact_rows(const int32_t* tok_map, const int32_t* coff, const int32_t* rcap, int32_t nW, int32_t k,
-                       int32_t* cmap, int32_t* ctok, int32_t* rep_row, void* stream);
+ * compact -> image row | -2 (representative) | -1 (unused); rep_row int32 [nW] compact row of the representative.
+ * Optional (NULL to skip): cinv int32 [sum(rcap+1)] compact -> packed row (-1 unused), crope int32 compact ->
+ * RoPE table row (from rope_rows int32 [nW*(k+1)]), for running q/k/v over the compact rows too. */
+int toc3d_compact_rows(const int32_t* tok_map, const int32_t* rope_rows, const int32_t* coff, const int32_t* rcap,
+                       int32_t nW, int32_t k, int32_t* cmap, int32_t* ctok, int32_t* rep_row, int32_t* cinv,
+                       int32_t* crope, void* stream);
+
+/* Accelerated blocks pad BEFORE norm1 (toc3d_eva_vit.py:412-415 then :369), so a pad slot selected as a slow token
+ * is the vector norm1(0) = beta: key = RoPE(W_k beta, slot), value = W_v beta + v_bias.  kpad / vpad fp32 [C] are
+ * those block constants before the rotation; every packed qkv row m with cmap[m] == -1 gets them (slot =
+ * rope_rows[m], per-axis tables as in toc3d_epilogue).  q/k/v of the real rows then come from a GEMM over the
+ * compact rows only. */
+int toc3d_fill_pad_kv_rope(void* qkv_bf16, const int32_t* cmap, const int32_t* rope_rows, int32_t Mp, const float* kpad,
+                           const float* vpad, const float* cos_axis, const float* sin_axis, int32_t ft, int32_t C,
+                           void* stream);
 
 /* Dense blocks (eva_vit.py:247-268) pad AFTER norm1, so pad slots are exact zeros: k = 0 (k_proj has no bias, RoPE
  * keeps zero), v = v_bias.  Writes those constants into the listed slot rows of the bf16 qkv buffer [.., 3C]
@@ -190,6 +202,20 @@ int toc3d_fast_token_update(float* x, const int32_t* fast_map, const float* pack
                             int32_t n_fast, int32_t k, int32_t C, const int32_t* rep_row /* NULL: w*(k+1)+k */,
                             void* stream);
 
+/* Arguments of toc3d_fill_pad_kv_rope as a struct, so that toc3d_ln_gather_merge can do the same work in extra thread
+ * blocks of its own launch (pad_fill != NULL). */
+typedef struct toc3d_pad_fill {
+  void* qkv;                 /* bf16 [Mp, 3C] packed qkv buffer */
+  const int32_t* cmap;       /* [Mp] packed row -> compact row | -1 (pad: gets filled) */
+  const int32_t* rope_rows;  /* [Mp] RoPE table row of each packed row */
+  int32_t Mp;
+  const float* kpad;         /* fp32 [C] W_k beta (before rotation) */
+  const float* vpad;         /* fp32 [C] W_v beta + v_bias */
+  const float* cos_axis;     /* fp32 [ft,16] */
+  const float* sin_axis;
+  int32_t ft;
+} toc3d_pad_fill;
+
 /* Fused front end of an accelerated block (toc3d_eva_vit.py:421-427 gather + merge_tokens, then norm1 at
  * :371): in ONE launch, (1) rep[w] = sum_j (s_j / sum s) x[fast_map[w,j]] -> rep_out[w] and packed row
  * w*(k+1)+k (fp32), LayerNorm(rep[w]) -> out row w*(k+1)+k; (2) LayerNorm of every gathered slow row
@@ -199,7 +225,9 @@ int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t*
                           const float* gamma, const float* beta, void* out_bf16, float* rep_out, float* packed,
                           int32_t nW, int32_t k, int32_t n_fast, int32_t C, float eps, int64_t* zero_stats,
                           const int32_t* rep_row /* row of `packed` for the representative; NULL: w*(k+1)+k */,
-                          void* stream);
+                          int32_t compact_rows /* > 0: tok_map lists that many COMPACT rows (ctok; -1 skipped) and the
+                                                  LayerNorm output uses compact rows (rep at rep_row[w]); 0: packed */,
+                          const toc3d_pad_fill* pad_fill /* host pointer or NULL */, void* stream);
 
 /* ------------------------------------------------------------------ history-query scorer
  * toc3d_utils.py:232-252 is linear in the token up to the LogSoftmax, so the query bank is

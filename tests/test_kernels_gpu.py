@@ -512,6 +512,34 @@ def test_compact_rows_and_pad_fill(lib):
     assert (q[[3, 17, 39], :C] == 7).all() and (q[[0, 1, 2, 4]] == 7).all()
 
 
+@pytest.mark.parametrize("ft", [16, 20])
+def test_fill_pad_kv_rope_matches_qkv_gemm(lib, ft):
+    """Pad rows of an accelerated block (norm1(0) = beta): k / v from the block constants + per-slot rotation equal
+    what the QKV GEMM epilogue produces for an A row holding bf16(beta) (up to one bf16 rounding of k)."""
+    g = torch.Generator().manual_seed(ft)
+    heads, C = 2, 128
+    n = ft * ft
+    Mp = 200
+    beta = bf16_round(torch.randn(C, generator=g) * 0.3)
+    Wt = bf16_round(torch.randn(3 * C, C, generator=g) * 0.1)
+    bias = torch.randn(3 * C, generator=g); bias[C:2 * C] = 0
+    rows = torch.randint(0, n, (Mp,), generator=g).int()
+    cos, sin = O.rope_table(ft, 32, 16)
+    ca = cos.reshape(ft, ft, 64)[:, 0, 0:32:2].contiguous().to(DEV); sa = sin.reshape(ft, ft, 64)[:, 0, 0:32:2].contiguous().to(DEV)
+    A = beta.expand(Mp, C).contiguous().to(DEV).bfloat16()
+    ref = torch.empty(Mp, 3 * C, device=DEV, dtype=torch.bfloat16)
+    lib.gemm(A, Wt.to(DEV).bfloat16(), lib.EPI_QKV_ROPE, bias=bias.to(DEV), out=ref, rope_rows=rows.to(DEV), rope_ft=ft,
+             rope_cols=2 * C, q_scale=0.125, cos_axis=ca, sin_axis=sa)
+    kpad = (Wt[C:2 * C] @ beta).to(DEV); vpad = (Wt[2 * C:] @ beta + bias[2 * C:]).to(DEV)
+    cmap = torch.full((Mp,), -1, dtype=torch.int32); cmap[::3] = 5          # every third row is "real": left alone
+    out = torch.full((Mp, 3 * C), 9.0, device=DEV, dtype=torch.bfloat16)
+    lib.fill_pad_kv_rope(out, cmap.to(DEV), rows.to(DEV), Mp, kpad, vpad, ca, sa, ft, C)
+    got, want = out.float().cpu(), ref.float().cpu()
+    pad = cmap == -1
+    assert (got[~pad] == 9).all() and (got[pad][:, :C] == 9).all()
+    assert (got[pad][:, C:] - want[pad][:, C:]).abs().max().item() <= 2 ** -7 * want[pad][:, C:].abs().max().item()
+
+
 def test_attention_and_qkv_row_maps(lib):
     """out_map of the attention (rows stored in compact order, -1 skipped) and of the QKV epilogue (rows scattered)."""
     g = torch.Generator().manual_seed(9)

@@ -280,6 +280,10 @@ class _Engine:
                 n1w=f32(b.norm1.weight), n1b=f32(b.norm1.bias), n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias),
                 wqkv=b16(torch.cat([a.q_proj.weight, a.k_proj.weight, a.v_proj.weight], 0)),
                 bqkv=torch.cat([qb, zeros, vb]).contiguous(), vb=vb.contiguous(),
+                # k / v of a pad slot selected as slow token in an accelerated block: norm1(0) = beta through
+                # k_proj / v_proj (bf16 operands like the GEMM), before the per-slot rotation
+                kpad=(b16(a.k_proj.weight).float() @ b16(b.norm1.bias).float()).contiguous(),
+                vpad=(b16(a.v_proj.weight).float() @ b16(b.norm1.bias).float() + vb).contiguous(),
                 wproj=b16(a.proj.weight), bproj=f32(a.proj.bias),
                 w12=w12.to(torch.bfloat16).contiguous(), b12=b12, u12=u12,
                 # SwiGLU sub-LN (eva_vit.py:48) folded into the w3 GEMM: w3g = W3 * gamma (columns),
@@ -411,27 +415,32 @@ class _Engine:
                          rope_rows=torch.empty(nW * (k + 1), **i32), fast_map=torch.empty(nW, n - k, **i32),
                          fast_score=torch.empty(nW, n - k, device=dev), rep=torch.empty(nW, self.C, device=dev),
                          Mc=Mc, rcap=rcap.to(dev), coff=coff.to(dev), cmap=torch.empty(nW * (k + 1), **i32),
-                         ctok=torch.empty(Mc, **i32), rep_row=torch.empty(nW, **i32))
+                         ctok=torch.empty(Mc, **i32), rep_row=torch.empty(nW, **i32), cinv=torch.empty(Mc, **i32),
+                         crope=torch.empty(Mc, **i32))
                 wsp.stage[(stage, ws)] = t
             L.window_topk(score, wsp.V, wsp.H, wsp.W, ws, k, fast_score=t["fast_score"], tok_map=t["tok_map"],
                           rope_rows=t["rope_rows"], fast_map=t["fast_map"])
-            L.compact_rows(t["tok_map"], t["coff"], t["rcap"], nW, k, t["cmap"], t["ctok"], t["rep_row"])
+            L.compact_rows(t["tok_map"], t["coff"], t["rcap"], nW, k, t["cmap"], t["ctok"], t["rep_row"],
+                           rope_rows=t["rope_rows"], cinv=t["cinv"], crope=t["crope"])
 
     def toc3d_block(self, i, X, wsp, stage):
-        """toc3d_eva_vit.py:395-473 (accelerated branch).  Packed rows (k slow + rep per window, pad slots included)
-        feed norm1 / q,k,v / attention, where pads act as keys and values; proj, norm2 and the MLP are row-wise and
-        the pads' results are cropped (toc3d_eva_vit.py:459-461), so from the attention output on only the compact
-        rows (real slow rows + rep) are computed."""
+        """toc3d_eva_vit.py:395-473 (accelerated branch).  The packed set of a window (k slow rows + rep) contains pad
+        slots whenever the window holds fewer than k real tokens.  A pad row is norm1(0) = beta: it matters only as an
+        attention key / value (block constants up to the RoPE rotation, written by fill_pad_kv_rope); its own
+        attention / proj / norm2 / MLP results are cropped by window_unpartition (toc3d_eva_vit.py:459-461).  So
+        norm1, q/k/v, proj, norm2 and the MLP run on the COMPACT rows (real slow rows + rep) only; the attention
+        reads the window-packed qkv buffer and writes compact rows."""
         bp, C = self.blocks[i], self.C
         ws = self.block_ws[i]
         w, t = wsp.win[ws], wsp.stage[(stage, ws)]
         nW, k, nf, Mc = w["nW"], t["k"], t["nf"], t["Mc"]
         Mp = nW * (k + 1)
-        # one launch: representative token (-> T[rep_row]) + norm1 of the packed slow / rep rows
-        L.ln_gather_merge(X, t["tok_map"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
+        # one launch: representative token (-> T[rep_row]) + norm1 of the compact rows + k / v of the pad rows
+        L.ln_gather_merge(X, t["ctok"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
                           wsp.T, nW, k, nf, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None,
-                          rep_row=t["rep_row"])
-        self._qkv_attn(bp, wsp, Mp, nW, k + 1, t["rope_rows"], 0, attn_out_map=t["cmap"])
+                          rep_row=t["rep_row"], compact_rows=Mc,
+                          pad_fill=(wsp.qkv, t["cmap"], t["rope_rows"], Mp, bp["kpad"], bp["vpad"], bp["cos"], bp["sin"], bp["ft"]))
+        self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"])
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
                resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
         if not self.fold_norm2:

@@ -214,8 +214,9 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
 //   cmap[w*(k+1)+r] = compact row of packed row r (or -1 for a pad), ctok[c] = image row | -2 (rep) | -1 (unused),
 //   rep_row[w] = compact row of the representative token.  One CTA per window.
 __global__ void __launch_bounds__(1024)
-compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ coff, const int* __restrict__ rcap, int k,
-                    int* __restrict__ cmap, int* __restrict__ ctok, int* __restrict__ rep_row) {
+compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ rope_rows, const int* __restrict__ coff,
+                    const int* __restrict__ rcap, int k, int* __restrict__ cmap, int* __restrict__ ctok,
+                    int* __restrict__ rep_row, int* __restrict__ cinv, int* __restrict__ crope) {
   __shared__ int s_warp[32];
   pdl_wait();
   pdl_launch_dependents();
@@ -238,19 +239,84 @@ compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ cof
   if (t < k) {
     const bool ok = real && before < cap;
     cmap[base + t] = ok ? c0 + before : -1;
-    if (ok) ctok[c0 + before] = src;
+    if (ok) {
+      ctok[c0 + before] = src;
+      if (cinv) cinv[c0 + before] = (int)(base + t);
+      if (crope) crope[c0 + before] = rope_rows ? rope_rows[base + t] : 0;
+    }
   }
-  if (t >= total && t < cap) ctok[c0 + t] = -1;            // degenerate: fewer real slow rows than the static capacity
+  if (t >= total && t < cap) {                             // degenerate: fewer real slow rows than the static capacity
+    ctok[c0 + t] = -1;
+    if (cinv) cinv[c0 + t] = -1;
+    if (crope) crope[c0 + t] = 0;
+  }
   if (t == 0) {
     cmap[base + k] = c0 + cap;
     ctok[c0 + cap] = -2;
     rep_row[w] = c0 + cap;
+    if (cinv) cinv[c0 + cap] = (int)(base + k);
+    if (crope) crope[c0 + cap] = rope_rows ? rope_rows[base + k] : k;
   }
 }
 
 // Dense blocks compute q/k/v only for real tokens; the window slots that are padding hold constants:
 // k = 0 (k_proj has no bias and the padded norm1 output is zero, eva_vit.py:249-254,97-99; RoPE keeps zero) and
 // v = v_bias.  rows: slot rows of the qkv buffer [.., 3C]; thread = 8 channels.
+// Accelerated blocks pad BEFORE norm1 (toc3d_eva_vit.py:412-415), so a pad slot that was selected as a slow token
+// is the vector norm1(0) = beta: its key is RoPE(W_k beta, slot), its value W_v beta + v_bias - block constants
+// (kpad / vpad, fp32 [C]) up to the rotation.  Fills the packed qkv rows m with cmap[m] == -1; thread = 8 channels.
+// Pad rows of an accelerated block as attention keys / values (see toc3d_fill_pad_kv_rope).
+struct PadFill {
+  __nv_bfloat16* qkv;          // packed qkv buffer [Mp, 3C]; nullptr = no fill work
+  const int* cmap;             // packed row -> compact row | -1 (pad)
+  const int* rope_rows;        // packed row -> RoPE table row (window slot)
+  int Mp;
+  const float* kpad;           // fp32 [C] W_k beta
+  const float* vpad;           // fp32 [C] W_v beta + v_bias
+  const float* cos_axis;
+  const float* sin_axis;
+  int ft;
+};
+
+// one warp per packed row: real rows leave at once, a pad row writes its 2 * C bf16 (k then v), 8 channels per lane-step
+__device__ __forceinline__ void fill_pad_row(const PadFill& f, int m, int lane, int C) {
+  if (m >= f.Mp || f.cmap[m] != -1) return;
+  const int slot = f.rope_rows[m];
+  const int r = slot / f.ft, c = slot - r * f.ft;
+  const int cv = C >> 3;
+  __nv_bfloat16* dst = f.qkv + (size_t)m * 3 * C + C;
+  for (int i = lane; i < 2 * cv; i += 32) {
+    const int part = i >= cv;                              // 0: k, 1: v
+    const int ch = (part ? i - cv : i) * 8;
+    float x[8];
+    const float* src = (part == 0 ? f.kpad : f.vpad) + ch;
+    *reinterpret_cast<float4*>(x) = __ldg(reinterpret_cast<const float4*>(src));
+    *reinterpret_cast<float4*>(x + 4) = __ldg(reinterpret_cast<const float4*>(src + 4));
+    if (part == 0) {
+      const int d = ch & 63;                               // channel inside the 64-wide head
+      const int p = d >= 32 ? c : r;                       // second 32 channels use the column coordinate
+      const int j0 = (d & 31) >> 1;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const float cs = __ldg(f.cos_axis + p * 16 + j0 + j), sn = __ldg(f.sin_axis + p * 16 + j0 + j);
+        const float x0 = x[2 * j], x1 = x[2 * j + 1];
+        x[2 * j] = x0 * cs - x1 * sn;
+        x[2 * j + 1] = x1 * cs + x0 * sn;
+      }
+    }
+    uint4 val;
+    val.x = pack_bf16(x[0], x[1]); val.y = pack_bf16(x[2], x[3]); val.z = pack_bf16(x[4], x[5]); val.w = pack_bf16(x[6], x[7]);
+    *reinterpret_cast<uint4*>(dst + (size_t)part * C + ch) = val;
+  }
+}
+
+__global__ void __launch_bounds__(256)
+fill_pad_kv_rope_kernel(const PadFill f, int C) {
+  pdl_wait();
+  pdl_launch_dependents();
+  fill_pad_row(f, blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), threadIdx.x & 31, C);
+}
+
 __global__ void __launch_bounds__(256)
 fill_pad_kv_kernel(__nv_bfloat16* __restrict__ qkv, const int* __restrict__ pad_rows, int n_pad, const float* __restrict__ v_bias, int C) {
   pdl_wait();
@@ -388,7 +454,7 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
                        const float* __restrict__ fast_score, const float* __restrict__ gamma,
                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, float* __restrict__ rep_out,
                        float* __restrict__ packed, int nW, int k, int n_fast, float eps, long long* __restrict__ zero_stats,
-                       const int* __restrict__ rep_row) {
+                       const int* __restrict__ rep_row, int ln_rows, int compact, const PadFill fill) {
   constexpr int C = VPL * 128;
   __shared__ __align__(16) float s_acc[8][C];
   __shared__ float s_wgt[1024];
@@ -397,14 +463,21 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
   pdl_wait();
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int ln_blocks = (ln_rows + 7) >> 3;
+  if ((int)blockIdx.x >= nW + ln_blocks) {
+    // ---- blocks after the LayerNorm ones: constant k / v of the pad rows of the packed qkv buffer
+    fill_pad_row(fill, ((int)blockIdx.x - nW - ln_blocks) * 8 + warp, lane, C);
+    return;
+  }
   if ((int)blockIdx.x >= nW) {
     // ---- LayerNorm of gathered slow rows (pad slots are zero vectors -> beta), rep rows belong to the merge blocks
-    const int M = nW * (k + 1);
+    // compact = 0: tok_map lists the packed rows (-1 = pad slot -> LN(0) = beta, -2 = rep, handled by a merge block);
+    // compact = 1: tok_map lists the compact rows (ctok; -1 = unused row, skipped), out / packed use compact rows
     const int m = ((int)blockIdx.x - nW) * 8 + warp;
-    if (m >= M) return;
+    if (m >= ln_rows) return;
     if (zero_stats != nullptr && lane == 0) *reinterpret_cast<longlong2*>(zero_stats + 2 * (size_t)m) = make_longlong2(0, 0);
     const int src = tok_map[m];
-    if (src == -2) return;
+    if (src == -2 || (compact && src < 0)) return;
     const float4* p = src >= 0 ? reinterpret_cast<const float4*>(x + (size_t)src * C) : nullptr;
     float4 v[VPL];
     float sm = 0.f;
@@ -506,7 +579,7 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
   __syncthreads();
   const float var = (((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]))) / (float)C;
   const float rstd = rsqrtf(var + eps);
-  __nv_bfloat16* o = out + ((size_t)w * (k + 1) + k) * C;
+  __nv_bfloat16* o = out + (size_t)(compact && rep_row != nullptr ? rep_row[w] : w * (k + 1) + k) * C;
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
     const int ch = threadIdx.x + 256 * e;
@@ -806,12 +879,14 @@ extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int3
   return 0;
 }
 
-extern "C" int toc3d_compact_rows(const int32_t* tok_map, const int32_t* coff, const int32_t* rcap, int32_t nW, int32_t k,
-                                  int32_t* cmap, int32_t* ctok, int32_t* rep_row, void* stream) {
+extern "C" int toc3d_compact_rows(const int32_t* tok_map, const int32_t* rope_rows, const int32_t* coff, const int32_t* rcap,
+                                  int32_t nW, int32_t k, int32_t* cmap, int32_t* ctok, int32_t* rep_row, int32_t* cinv,
+                                  int32_t* crope, void* stream) {
   TOC3D_REQUIRE(tok_map && coff && rcap && cmap && ctok && rep_row, kErrBadArg, "toc3d_compact_rows: null pointer");
   TOC3D_REQUIRE(nW > 0 && k >= 1 && k <= 1023, kErrBadArg, "toc3d_compact_rows: bad shape nW=%d k=%d", nW, k);
   const int threads = ((k + 1 + 31) / 32) * 32;
-  TOC3D_CHECK_CUDA(launch_pdl(compact_rows_kernel, dim3(nW), dim3(threads), 0, ST(stream), 1, tok_map, coff, rcap, k, cmap, ctok, rep_row));
+  TOC3D_CHECK_CUDA(launch_pdl(compact_rows_kernel, dim3(nW), dim3(threads), 0, ST(stream), 1, tok_map, rope_rows, coff, rcap, k, cmap, ctok, rep_row,
+                              cinv, crope));
   return 0;
 }
 
@@ -822,6 +897,16 @@ extern "C" int toc3d_fill_pad_kv(void* qkv, const int32_t* pad_rows, int32_t n_p
   const size_t total = (size_t)n_pad * 2 * (C / 8);
   TOC3D_CHECK_CUDA(launch_pdl(fill_pad_kv_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), 1,
                               reinterpret_cast<__nv_bfloat16*>(qkv), pad_rows, n_pad, v_bias, C));
+  return 0;
+}
+
+extern "C" int toc3d_fill_pad_kv_rope(void* qkv, const int32_t* cmap, const int32_t* rope_rows, int32_t Mp, const float* kpad,
+                                      const float* vpad, const float* cos_axis, const float* sin_axis, int32_t ft, int32_t C,
+                                      void* stream) {
+  TOC3D_REQUIRE(qkv && cmap && rope_rows && kpad && vpad && cos_axis && sin_axis, kErrBadArg, "toc3d_fill_pad_kv_rope: null pointer");
+  TOC3D_REQUIRE(Mp > 0 && ft > 0 && C > 0 && C % 64 == 0, kErrBadArg, "toc3d_fill_pad_kv_rope: bad shape Mp=%d ft=%d C=%d", Mp, ft, C);
+  PadFill f{reinterpret_cast<__nv_bfloat16*>(qkv), cmap, rope_rows, Mp, kpad, vpad, cos_axis, sin_axis, ft};
+  TOC3D_CHECK_CUDA(launch_pdl(fill_pad_kv_rope_kernel, dim3((unsigned)((Mp + 7) / 8)), dim3(256), 0, ST(stream), 1, f, C));
   return 0;
 }
 
@@ -868,17 +953,30 @@ extern "C" int toc3d_fast_token_update(float* x, const int32_t* fast_map, const 
 extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t* fast_map,
                                      const float* fast_score, const float* gamma, const float* beta, void* out,
                                      float* rep_out, float* packed, int32_t nW, int32_t k, int32_t n_fast, int32_t C,
-                                     float eps, int64_t* zero_stats, const int32_t* rep_row, void* stream) {
+                                     float eps, int64_t* zero_stats, const int32_t* rep_row, int32_t compact_rows,
+                                     const toc3d_pad_fill* pf, void* stream) {
   TOC3D_REQUIRE(x && tok_map && fast_map && fast_score && gamma && beta && out && rep_out && packed, kErrBadArg,
                 "toc3d_ln_gather_merge: null pointer");
   TOC3D_REQUIRE(nW > 0 && k >= 0 && n_fast > 0 && n_fast <= 1024, kErrBadArg,
                 "toc3d_ln_gather_merge: bad shape nW=%d k=%d n_fast=%d", nW, k, n_fast);
-  const int M = nW * (k + 1);
-  dim3 grid(nW + (M + 7) / 8), block(256);
+  TOC3D_REQUIRE(compact_rows >= 0 && (compact_rows == 0 || rep_row != nullptr), kErrBadArg,
+                "toc3d_ln_gather_merge: compact_rows needs rep_row");
+  const int M = compact_rows > 0 ? compact_rows : nW * (k + 1);
+  const int compact = compact_rows > 0 ? 1 : 0;
+  PadFill fill{};
+  int fill_blocks = 0;
+  if (pf != nullptr && pf->qkv != nullptr) {
+    TOC3D_REQUIRE(pf->cmap && pf->rope_rows && pf->kpad && pf->vpad && pf->cos_axis && pf->sin_axis && pf->Mp > 0 && pf->ft > 0 &&
+                  C % 64 == 0, kErrBadArg, "toc3d_ln_gather_merge: incomplete pad-fill description");
+    fill = PadFill{reinterpret_cast<__nv_bfloat16*>(pf->qkv), pf->cmap, pf->rope_rows, pf->Mp, pf->kpad, pf->vpad, pf->cos_axis,
+                   pf->sin_axis, pf->ft};
+    fill_blocks = (pf->Mp + 7) / 8;
+  }
+  dim3 grid(nW + (M + 7) / 8 + fill_blocks), block(256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   long long* zs = reinterpret_cast<long long*>(zero_stats);
 #define LGM_CASE(V)                                                                                                  \
-  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs, rep_row)); break;
+  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs, rep_row, M, compact, fill)); break;
   switch (C % 128 == 0 ? C / 128 : 0) {
     LGM_CASE(1) LGM_CASE(2) LGM_CASE(4) LGM_CASE(6) LGM_CASE(8)
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_ln_gather_merge: C must be 128, 256, 512, 768 or 1024 (got %d)", C);

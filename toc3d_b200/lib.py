@@ -30,6 +30,11 @@ class Epilogue(ctypes.Structure):
     ]
 
 
+class PadFill(ctypes.Structure):
+    _fields_ = [("qkv", _c_void_p), ("cmap", _c_void_p), ("rope_rows", _c_void_p), ("Mp", _c_int), ("kpad", _c_void_p),
+                ("vpad", _c_void_p), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p), ("ft", _c_int)]
+
+
 _SIGS = {
     "toc3d_abi_version": ([], _c_int),
     "toc3d_last_error": ([], ctypes.c_char_p),
@@ -42,14 +47,18 @@ _SIGS = {
                          _c_int),
     "toc3d_window_topk": ([_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
-    "toc3d_compact_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_compact_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                            _c_void_p, _c_void_p], _c_int),
+    "toc3d_fill_pad_kv_rope": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
+                                _c_void_p], _c_int),
     "toc3d_fill_pad_kv": ([_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p], _c_int),
     "toc3d_topk_split": ([_c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_merge_fast_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                                  _c_void_p, _c_void_p], _c_int),
     "toc3d_fast_token_update": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                  _c_void_p, _c_void_p], _c_int),
-    "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_int,
+                               ctypes.POINTER(PadFill), _c_void_p], _c_int),
     "toc3d_score_fold_queries": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int,
                                   _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
@@ -81,7 +90,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 6:
+        if lib.toc3d_abi_version() != 8:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -171,9 +180,14 @@ def merge_fast_tokens(x, fast_map, fast_score, nW, n_fast, k, C, rep_out, packed
                                           _p(packed), _stream()), "toc3d_merge_fast_tokens")
 
 
-def compact_rows(tok_map, coff, rcap, nW, k, cmap, ctok, rep_row):
-    _check(load().toc3d_compact_rows(_p(tok_map), _p(coff), _p(rcap), nW, k, _p(cmap), _p(ctok), _p(rep_row), _stream()),
-           "toc3d_compact_rows")
+def compact_rows(tok_map, coff, rcap, nW, k, cmap, ctok, rep_row, rope_rows=None, cinv=None, crope=None):
+    _check(load().toc3d_compact_rows(_p(tok_map), _p(rope_rows), _p(coff), _p(rcap), nW, k, _p(cmap), _p(ctok), _p(rep_row),
+                                     _p(cinv), _p(crope), _stream()), "toc3d_compact_rows")
+
+
+def fill_pad_kv_rope(qkv, cmap, rope_rows, Mp, kpad, vpad, cos_axis, sin_axis, ft, C):
+    _check(load().toc3d_fill_pad_kv_rope(_p(qkv), _p(cmap), _p(rope_rows), Mp, _p(kpad), _p(vpad), _p(cos_axis), _p(sin_axis),
+                                         ft, C, _stream()), "toc3d_fill_pad_kv_rope")
 
 
 def fill_pad_kv(qkv, pad_rows, v_bias, C):
@@ -186,10 +200,16 @@ def fast_token_update(x, fast_map, packed, rep, nW, n_fast, k, C, rep_row=None):
 
 
 def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out, packed, nW, k, n_fast, C, eps,
-                    zero_stats=None, rep_row=None):
+                    zero_stats=None, rep_row=None, compact_rows=0, pad_fill=None):
+    """pad_fill = (qkv, cmap, rope_rows, Mp, kpad, vpad, cos_axis, sin_axis, ft): also write the pad rows' k / v."""
+    pf = None
+    if pad_fill is not None:
+        q, cm, rr, Mp, kp, vp, ca, sa, ft = pad_fill
+        pf = PadFill(_p(q), _p(cm), _p(rr), Mp, _p(kp), _p(vp), _p(ca), _p(sa), ft)
     _want(x, torch.float32, "x"); _want(out, torch.bfloat16, "out")
     _check(load().toc3d_ln_gather_merge(_p(x), _p(tok_map), _p(fast_map), _p(fast_score), _p(gamma), _p(beta), _p(out),
-                                        _p(rep_out), _p(packed), nW, k, n_fast, C, eps, _p(zero_stats), _p(rep_row), _stream()),
+                                        _p(rep_out), _p(packed), nW, k, n_fast, C, eps, _p(zero_stats), _p(rep_row), compact_rows,
+                                        ctypes.byref(pf) if pf is not None else None, _stream()),
            "toc3d_ln_gather_merge")
 
 
