@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 8
+#define TOC3D_B200_ABI_VERSION 10
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -115,9 +115,13 @@ int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int3
  * out_map (optional, int32 [n_windows*seq_len]): destination row of each query row in `out`, -1 = row not
  * stored.  Rows that are window PADDING matter only as keys / values; with out_map the attention writes the rows
  * that are used afterwards in compact order, so that the row-wise GEMMs after it skip the padding.
+ * q_rows (optional, int32 [n_windows]): only the first q_rows[w] query rows of window w are needed (the callers
+ * put the needed rows first); query tiles beyond them are not computed.  All seq_len rows still act as keys.
+ * item_order (optional, int32 [n_windows*heads], a permutation of the (window*heads + head) items): processing
+ * order of the persistent kernel, e.g. sorted by query-tile count so that its round-robin deal is balanced.
  */
 int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
-                           const int32_t* out_map, void* stream);
+                           const int32_t* out_map, const int32_t* q_rows, const int32_t* item_order, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm over gathered rows
  * out_bf16[m] = LN(row(m)) * gamma + beta over C channels (C % 128 == 0, C <= 4096), m in [0,M).
@@ -157,17 +161,20 @@ int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int32_t W, int3
                       int32_t* slow_idx, int32_t* fast_idx, float* fast_score, int32_t* tok_map,
                       int32_t* rope_rows, int32_t* fast_map, void* stream);
 
-/* Compact row space of an accelerated block (toc3d_eva_vit.py:421-461): of the packed rows [k slow | rep] of a
- * window, the slow rows that are pad slots (tok_map = -1) are needed as attention keys / values only - proj,
- * norm2 and the SwiGLU MLP are row-wise and window_unpartition crops their results - so those run on the compact
- * rows.  coff / rcap int32 [nW] are host-static (rcap = min(k, #real tokens of the window), coff = exclusive
- * prefix sum of rcap + 1).  Outputs: cmap int32 [nW*(k+1)] packed -> compact row | -1; ctok int32 [sum(rcap+1)]
- * compact -> image row | -2 (representative) | -1 (unused); rep_row int32 [nW] compact row of the representative.
- * Optional (NULL to skip): cinv int32 [sum(rcap+1)] compact -> packed row (-1 unused), crope int32 compact ->
- * RoPE table row (from rope_rows int32 [nW*(k+1)]), for running q/k/v over the compact rows too. */
+/* Compact row space of an accelerated block (toc3d_eva_vit.py:421-461): of the selected rows [k slow | rep] of a
+ * window, the slow rows that are pad slots (tok_map = -1) are needed as attention keys / values only - norm1, q/k/v,
+ * proj, norm2 and the SwiGLU MLP are row-wise and window_unpartition crops the pads' results - so those run on the
+ * compact rows (real slow rows + rep).  coff / rcap int32 [nW] are host-static (rcap = min(k, #real tokens of the
+ * window), coff = exclusive prefix sum of rcap + 1).  The window-packed qkv buffer the attention reads is laid out
+ * [real slow rows | rep | pad rows] per window ("packed position"), so the needed query rows are a prefix.
+ * Inputs tok_map / rope_rows int32 [nW*(k+1)] in rank order (toc3d_window_topk).  Outputs:
+ *   cmap  int32 [nW*(k+1)]  packed position -> compact row | -1 (pad)      prope  same shape: RoPE table row (NULL ok)
+ *   ctok  int32 [sum(rcap+1)]  compact -> image row | -2 (representative) | -1 (unused)
+ *   cinv / crope (NULL ok)     compact -> packed position (-1 unused) / RoPE table row
+ *   rep_row int32 [nW]         compact row of the representative. */
 int toc3d_compact_rows(const int32_t* tok_map, const int32_t* rope_rows, const int32_t* coff, const int32_t* rcap,
                        int32_t nW, int32_t k, int32_t* cmap, int32_t* ctok, int32_t* rep_row, int32_t* cinv,
-                       int32_t* crope, void* stream);
+                       int32_t* crope, int32_t* prope, void* stream);
 
 /* Accelerated blocks pad BEFORE norm1 (toc3d_eva_vit.py:412-415 then :369), so a pad slot selected as a slow token
  * is the vector norm1(0) = beta: key = RoPE(W_k beta, slot), value = W_v beta + v_bias.  kpad / vpad fp32 [C] are

@@ -492,15 +492,22 @@ def test_compact_rows_and_pad_fill(lib):
     rcap = torch.minimum(real, torch.tensor(k, dtype=torch.int32))
     coff = torch.cumsum(rcap + 1, 0, dtype=torch.int32) - (rcap + 1)
     Mc = int((rcap + 1).sum())
+    rope = torch.empty(nW * (k + 1), **i32)
+    lib.window_topk(s.to(DEV), V, H, W, ws, k, tok_map=tok, rope_rows=rope)
     cmap = torch.full((nW * (k + 1),), -7, **i32); ctok = torch.full((Mc,), -7, **i32); rep_row = torch.full((nW,), -7, **i32)
-    lib.compact_rows(tok, coff.to(DEV), rcap.to(DEV), nW, k, cmap, ctok, rep_row)
-    tok_c, cmap_c, ctok_c = tok.cpu().view(nW, k + 1), cmap.cpu().view(nW, k + 1), ctok.cpu()
+    cinv = torch.full((Mc,), -7, **i32); crope = torch.full((Mc,), -7, **i32); prope = torch.full((nW * (k + 1),), -7, **i32)
+    lib.compact_rows(tok, coff.to(DEV), rcap.to(DEV), nW, k, cmap, ctok, rep_row, rope_rows=rope, cinv=cinv, crope=crope, prope=prope)
+    tok_c, rope_c = tok.cpu().view(nW, k + 1), rope.cpu().view(nW, k + 1)
+    cmap_c, prope_c, ctok_c, cinv_c, crope_c = cmap.cpu().view(nW, k + 1), prope.cpu().view(nW, k + 1), ctok.cpu(), cinv.cpu(), crope.cpu()
     for w in range(nW):
         r = int(rcap[w]); c0 = int(coff[w])
         assert (tok_c[w, :r] >= 0).all() and (tok_c[w, r:k] == -1).all()          # real rows outrank pads
-        assert cmap_c[w, :r].tolist() == list(range(c0, c0 + r)) and (cmap_c[w, r:k] == -1).all()
-        assert cmap_c[w, k] == c0 + r and rep_row[w].item() == c0 + r and ctok_c[c0 + r] == -2
-        assert torch.equal(ctok_c[c0:c0 + r], tok_c[w, :r])
+        # packed layout [real | rep | pads]
+        assert cmap_c[w, :r].tolist() == list(range(c0, c0 + r)) and cmap_c[w, r] == c0 + r and (cmap_c[w, r + 1:] == -1).all()
+        assert torch.equal(prope_c[w, :r], rope_c[w, :r]) and prope_c[w, r] == k and torch.equal(prope_c[w, r + 1:], rope_c[w, r:k])
+        assert rep_row[w].item() == c0 + r and ctok_c[c0 + r] == -2
+        assert torch.equal(ctok_c[c0:c0 + r], tok_c[w, :r]) and torch.equal(crope_c[c0:c0 + r], rope_c[w, :r]) and crope_c[c0 + r] == k
+        assert cinv_c[c0:c0 + r + 1].tolist() == list(range(w * (k + 1), w * (k + 1) + r + 1))
     # dense pad slots
     C = 128
     qkv = torch.full((40, 3 * C), 7.0, device=DEV, dtype=torch.bfloat16)
@@ -538,6 +545,29 @@ def test_fill_pad_kv_rope_matches_qkv_gemm(lib, ft):
     pad = cmap == -1
     assert (got[~pad] == 9).all() and (got[pad][:, :C] == 9).all()
     assert (got[pad][:, C:] - want[pad][:, C:]).abs().max().item() <= 2 ** -7 * want[pad][:, C:].abs().max().item()
+
+
+@pytest.mark.parametrize("seq", [77, 180, 256, 300, 401, 500])
+def test_attention_q_rows_prefix(lib, seq):
+    """q_rows: only the leading query rows of each window are computed / stored; all rows remain keys."""
+    g = torch.Generator().manual_seed(seq)
+    nW, heads = 6, 2
+    C = heads * 64
+    qkv = bf16_round(torch.randn(nW * seq, 3 * C, generator=g))
+    q, k, v = qkv.reshape(nW, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(nW, seq, C)
+    qr = torch.tensor([1, seq, min(seq, 128), min(seq, 129), seq // 2, min(seq, 65)], dtype=torch.int32)
+    out = torch.full((nW * seq, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib.window_attention(qkv.to(DEV).bfloat16(), out, nW, seq, heads, q_rows=qr.to(DEV))
+    got = out.float().cpu().view(nW, seq, C)
+    for w in range(nW):
+        n = int(qr[w])
+        assert torch.isfinite(got[w, :n]).all()
+        assert (got[w, :n] - ref[w, :n]).abs().max().item() < 2e-2
+        # whole 128-row (64 for the fallback kernel) query tiles beyond the prefix are skipped
+        tile = 128 if seq <= 448 else 64
+        first_skipped = -(-n // tile) * tile
+        assert torch.isnan(got[w, first_skipped:]).all()
 
 
 def test_attention_and_qkv_row_maps(lib):

@@ -59,6 +59,14 @@ except Exception:
 
 
 # ------------------------------------------------------------------------------- weight repacking
+def balanced_item_order(q_rows, heads):
+    """(window, head) items of the persistent attention kernel, heaviest (most 128-row query tiles) first, so that
+    dealing them round-robin to the CTAs balances the tile units.  q_rows: int tensor [nW] on the host."""
+    tiles = (q_rows.to(torch.int64) + 127) // 128
+    per_item = tiles.repeat_interleave(heads)
+    return torch.sort(per_item, descending=True, stable=True).indices.to(torch.int32)
+
+
 def hidden_pad(hd):
     """SwiGLU hidden width padded to the GEMM K block (2730 -> 2752): TMA needs 16-byte row strides."""
     return (hd + 63) // 64 * 64
@@ -217,15 +225,25 @@ class _Workspace:
             idx = torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W)
             idx = F.pad(idx, (0, nWw * ws - W, 0, nWh * ws - H), value=-1.0)
             idx = idx.reshape(V, nWh, ws, nWw, ws).permute(0, 1, 3, 2, 4).reshape(-1)
-            m = idx.to(torch.int32)
+            m0 = idx.to(torch.int32).view(nW, n)               # row-major window slot -> image row | -1 (pad)
+            real0 = m0 >= 0
+            # storage order of a window in the qkv buffer: real tokens first (row-major among themselves), pad slots
+            # after them - attention is order-free over keys, RoPE uses the original slot position, and the query
+            # rows that are needed become a prefix (query tiles of pure padding are skipped)
+            order = torch.sort((~real0).to(torch.int8), dim=1, stable=True).indices        # [nW, n] original slot per storage slot
+            m = torch.gather(m0, 1, order).reshape(-1)
+            pos = order.to(torch.int32).reshape(-1)            # storage slot -> original position inside the window
             slots = torch.arange(nW * n, dtype=torch.int32)
             real = m >= 0
             inv = torch.empty(V * H * W, dtype=torch.int32)
-            inv[m[real].long()] = slots[real]                  # image row -> window slot (global slot index)
+            inv[m[real].long()] = slots[real]                  # image row -> storage slot (global index)
+            rope_of_row = torch.empty(V * H * W, dtype=torch.int32)
+            rope_of_row[m[real].long()] = pos[real]
             self.win[ws] = dict(nW=nW, n=n, map=m.to(dev),
                                 # dense blocks run q/k/v only over real tokens and scatter them to their window slots
-                                slot_of_row=inv.to(dev), rope_slot=(inv % n).to(dev), pad_rows=slots[~real].to(dev),
-                                real_per_window=real.view(nW, n).sum(1).to(torch.int32))
+                                slot_of_row=inv.to(dev), rope_slot=rope_of_row.to(dev), pad_rows=slots[~real].to(dev),
+                                real_per_window=real0.sum(1).to(torch.int32), q_rows=real0.sum(1).to(torch.int32).to(dev),
+                                item_order=balanced_item_order(real0.sum(1), eng.heads).to(dev))
             rows = max(rows, nW * n)
         self.rows = rows
         bf = dict(device=dev, dtype=torch.bfloat16)
@@ -367,14 +385,16 @@ class _Engine:
         the SwiGLU GEMM), their row statistics, and the zeroing of the sub-LN accumulator."""
         return dict(a_out=wsp.a, row_stats=wsp.stats2, zero_stats=wsp.stats) if self.fold_norm2 else {}
 
-    def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots, qkv_out_map=None, attn_out_map=None):
+    def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots, qkv_out_map=None, attn_out_map=None, q_rows=None,
+                  item_order=None):
         """q/k/v for the M rows of wsp.a (scattered to window slots through qkv_out_map when given), then attention
         over nW windows of seq slots; attn_out_map sends the rows that are used afterwards to compact positions."""
         C = self.C
         L.gemm(wsp.a, bp["wqkv"], L.EPI_QKV_ROPE, M=M, bias=bp["bqkv"], out=wsp.qkv, rope_rows=rope_rows,
                rope_slots=rope_slots, rope_ft=bp["ft"], rope_cols=2 * C, q_scale=64 ** -0.5,
                cos_axis=bp["cos"], sin_axis=bp["sin"], out_map=qkv_out_map)
-        L.window_attention(wsp.qkv, wsp.ao, nW, seq, self.heads, out_map=attn_out_map)
+        L.window_attention(wsp.qkv, wsp.ao, nW, seq, self.heads, out_map=attn_out_map, q_rows=q_rows,
+                           item_order=item_order)
 
     def dense_block(self, i, X, wsp):
         """eva_vit.py:247-268.  The reference pads the normalised map to whole windows and runs q/k/v, attention and
@@ -386,7 +406,8 @@ class _Engine:
         VN = wsp.V * wsp.N
         L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None)
         L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
-        self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"])
+        self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"],
+                       q_rows=w["q_rows"], item_order=w["item_order"])
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X, **self._proj_kw(wsp))
         if not self.fold_norm2:
             L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
@@ -416,12 +437,13 @@ class _Engine:
                          fast_score=torch.empty(nW, n - k, device=dev), rep=torch.empty(nW, self.C, device=dev),
                          Mc=Mc, rcap=rcap.to(dev), coff=coff.to(dev), cmap=torch.empty(nW * (k + 1), **i32),
                          ctok=torch.empty(Mc, **i32), rep_row=torch.empty(nW, **i32), cinv=torch.empty(Mc, **i32),
-                         crope=torch.empty(Mc, **i32))
+                         crope=torch.empty(Mc, **i32), prope=torch.empty(nW * (k + 1), **i32), q_rows=(rcap + 1).to(dev),
+                         item_order=balanced_item_order(rcap + 1, self.heads).to(dev))
                 wsp.stage[(stage, ws)] = t
             L.window_topk(score, wsp.V, wsp.H, wsp.W, ws, k, fast_score=t["fast_score"], tok_map=t["tok_map"],
                           rope_rows=t["rope_rows"], fast_map=t["fast_map"])
             L.compact_rows(t["tok_map"], t["coff"], t["rcap"], nW, k, t["cmap"], t["ctok"], t["rep_row"],
-                           rope_rows=t["rope_rows"], cinv=t["cinv"], crope=t["crope"])
+                           rope_rows=t["rope_rows"], cinv=t["cinv"], crope=t["crope"], prope=t["prope"])
 
     def toc3d_block(self, i, X, wsp, stage):
         """toc3d_eva_vit.py:395-473 (accelerated branch).  The packed set of a window (k slow rows + rep) contains pad
@@ -439,8 +461,9 @@ class _Engine:
         L.ln_gather_merge(X, t["ctok"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
                           wsp.T, nW, k, nf, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None,
                           rep_row=t["rep_row"], compact_rows=Mc,
-                          pad_fill=(wsp.qkv, t["cmap"], t["rope_rows"], Mp, bp["kpad"], bp["vpad"], bp["cos"], bp["sin"], bp["ft"]))
-        self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"])
+                          pad_fill=(wsp.qkv, t["cmap"], t["prope"], Mp, bp["kpad"], bp["vpad"], bp["cos"], bp["sin"], bp["ft"]))
+        self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"],
+                       q_rows=t["q_rows"], item_order=t["item_order"])
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
                resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
         if not self.fold_norm2:

@@ -46,10 +46,11 @@ __device__ __forceinline__ void load_tile(__nv_bfloat16 (*dst)[LDS], const __nv_
 
 __global__ void __launch_bounds__(NTHREADS)
 window_attention_kernel(const __nv_bfloat16* __restrict__ qkv, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                        const int* __restrict__ out_map) {
+                        const int* __restrict__ out_map, const int* __restrict__ q_rows) {
   __shared__ __align__(16) Smem sm;
   pdl_wait();
   pdl_launch_dependents();
+  if (q_rows != nullptr && (int)blockIdx.x * BQ >= q_rows[blockIdx.z]) return;      // padding-only query tile
   const int C = heads * D;
   const int64_t ld = 3 * (int64_t)C;
   const int qt = blockIdx.x, h = blockIdx.y, w = blockIdx.z;
@@ -358,19 +359,21 @@ enum { BAR_QK = 0, BAR_V, BAR_S, BAR_P, BAR_O, BAR_OFREE, NUM_BARS };
 // Single-slot kernel (256 < seq <= 448, or any seq): one CTA per (window, head), query tiles in sequence.
 __global__ void __launch_bounds__(NTHREADS)
 window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                           int tmem_cols, const int* __restrict__ out_map) {
+                           int tmem_cols, const int* __restrict__ out_map, const int* __restrict__ q_rows) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int T = (seq + 127) >> 7;               // 128-row query tiles
+  const int Tmax = (seq + 127) >> 7;            // 128-row query tiles (smem layout)
   const int nb = (seq + BOX_ROWS - 1) / BOX_ROWS;   // 64-row boxes of K / V
   uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 2 * T * BOX_BYTES;
+  uint8_t* sK = sQ + 2 * Tmax * BOX_BYTES;
   uint8_t* sV = sK + nb * BOX_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(sV + nb * BOX_BYTES);
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, w = blockIdx.y;
+  // only the leading q_rows[w] query rows are needed afterwards (the rest are window padding = keys / values only)
+  const int T = ((q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq) + 127) >> 7;
   const int C = heads * D;
   const int row0 = w * seq;
 
@@ -460,7 +463,8 @@ enum { PB_FULL = 0 /* +nbuf */, PB_EMPTY = 4, PB_S = 8 /* +slot */, PB_P = 10, P
 
 __global__ void __launch_bounds__(PP_THREADS, 1)
 window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                           int n_items, int nbuf, const int* __restrict__ out_map) {
+                           int n_items, int nbuf, const int* __restrict__ out_map, const int* __restrict__ q_rows,
+                           const int* __restrict__ item_order) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int T = (seq + 127) >> 7;               // 1 or 2 query tiles
@@ -474,7 +478,18 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   const int spad = (seq + 15) & ~15;
   const uint32_t o_off = 192u;                  // O columns inside a 256-column slot (aliases dead S columns if spad > 192)
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  const int n_units = my_items * T;
+  // query tiles of item i: only the leading q_rows[w] query rows of a window are needed afterwards (the rest are
+  // window padding, used as keys / values only), so a window may need fewer tiles than its key count suggests
+  auto item_tiles = [&](int i, int& w, int& h) {
+    // item_order (optional): (window, head) items sorted by query-tile count, so that the round-robin deal to the
+    // persistent CTAs balances the tile units
+    const int idx = (int)blockIdx.x + i * (int)gridDim.x;
+    const int it = item_order != nullptr ? item_order[idx] : idx;
+    w = it / heads;
+    h = it - w * heads;
+    const int need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;
+    return (need + 127) >> 7;
+  };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm);
@@ -502,8 +517,8 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     if (lane == 0) {
       // ------------------------------------------------------------------ TMA producer: ring of item buffers
       for (int i = 0; i < my_items; ++i) {
-        const int it = (int)blockIdx.x + i * (int)gridDim.x;
-        const int w = it / heads, h = it - w * heads;
+        int w, h;
+        const int Ti = item_tiles(i, w, h);
         const int row0 = w * seq;
         const int buf = i % nbuf;
         const uint32_t round = (uint32_t)(i / nbuf);
@@ -511,64 +526,68 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
         uint8_t* base = smem + buf * item_bytes;
         uint8_t* sK = base + 2 * T * BOX_BYTES;
         uint8_t* sV = sK + nb * BOX_BYTES;
-        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)item_bytes);
+        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)((2 * Ti + 2 * nb) * BOX_BYTES));
         for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
-        for (int b = 0; b < 2 * T; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
+        for (int b = 0; b < 2 * Ti; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
         for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       // ------------------------------------------------------------------ MMA issuer
-      auto unit_ptrs = [&](int u, const uint8_t*& q_tile, const uint8_t*& sK, const uint8_t*& sV) {
-        const int i = u / T, t = u - i * T;
-        const uint8_t* base = smem + (i % nbuf) * item_bytes;
-        q_tile = base + t * 2 * BOX_BYTES;
-        sK = base + 2 * T * BOX_BYTES;
-        sV = sK + nb * BOX_BYTES;
-      };
-      auto do_pv = [&](int u) {
-        const int s = u & 1;
-        const uint32_t n = (uint32_t)(u >> 1);              // how many units this slot has seen before
-        const uint8_t *q_tile, *sK, *sV;
-        unit_ptrs(u, q_tile, sK, sV);
-        mbar_wait(&bars[PB_P + s], n & 1);
+      // unit u = (item, query tile), enumerated item by item; unit u runs on slot u & 1.  Software pipeline of
+      // depth 1: issue S(u), then P V of unit u - 1.
+      struct Unit { int s; uint32_t n; const uint8_t* sV; int last_buf; };   // last_buf >= 0: last tile of its item
+      auto do_pv = [&](const Unit& un) {
+        mbar_wait(&bars[PB_P + un.s], un.n & 1);
         tcgen05_fence_after();
-        issue_pv(tmem_base + (uint32_t)(s * 256) + o_off, tmem_base + (uint32_t)(s * 256), sV, spad);
-        tcgen05_commit(&bars[PB_O + s]);
-        const int i = u / T;
-        if (u - i * T == T - 1) tcgen05_commit(&bars[PB_EMPTY + i % nbuf]);   // all MMAs reading this item are issued
+        issue_pv(tmem_base + (uint32_t)(un.s * 256) + o_off, tmem_base + (uint32_t)(un.s * 256), un.sV, spad);
+        tcgen05_commit(&bars[PB_O + un.s]);
+        if (un.last_buf >= 0) tcgen05_commit(&bars[PB_EMPTY + un.last_buf]);   // all MMAs reading this item are issued
       };
-      for (int u = 0; u < n_units; ++u) {
-        const int s = u & 1;
-        const uint32_t n = (uint32_t)(u >> 1);
-        const int i = u / T;
-        const uint8_t *q_tile, *sK, *sV;
-        unit_ptrs(u, q_tile, sK, sV);
-        if (u - i * T == 0) mbar_wait(&bars[PB_FULL + i % nbuf], (uint32_t)((i / nbuf) & 1));
-        if (n > 0) mbar_wait(&bars[PB_OFREE + s], (n - 1) & 1);               // slot drained by its softmax warps
-        tcgen05_fence_after();
-        issue_qk(tmem_base + (uint32_t)(s * 256), q_tile, sK, spad);
-        tcgen05_commit(&bars[PB_S + s]);
-        if (u > 0) do_pv(u - 1);
+      Unit prev{0, 0, nullptr, -1};
+      bool have_prev = false;
+      int u = 0;
+      for (int i = 0; i < my_items; ++i) {
+        int w, h;
+        const int Ti = item_tiles(i, w, h);
+        const int buf = i % nbuf;
+        const uint8_t* base = smem + buf * item_bytes;
+        const uint8_t* sK = base + 2 * T * BOX_BYTES;
+        const uint8_t* sV = sK + nb * BOX_BYTES;
+        for (int t = 0; t < Ti; ++t, ++u) {
+          const int s = u & 1;
+          const uint32_t n = (uint32_t)(u >> 1);              // how many units this slot has seen before
+          if (t == 0) mbar_wait(&bars[PB_FULL + buf], (uint32_t)((i / nbuf) & 1));
+          if (n > 0) mbar_wait(&bars[PB_OFREE + s], (n - 1) & 1);             // slot drained by its softmax warps
+          tcgen05_fence_after();
+          issue_qk(tmem_base + (uint32_t)(s * 256), base + t * 2 * BOX_BYTES, sK, spad);
+          tcgen05_commit(&bars[PB_S + s]);
+          if (have_prev) do_pv(prev);
+          prev = Unit{s, n, sV, t == Ti - 1 ? buf : -1};
+          have_prev = true;
+        }
       }
-      if (n_units > 0) do_pv(n_units - 1);
+      if (have_prev) do_pv(prev);
     }
   } else {
     // -------------------------------------------------------------------- softmax warps: slot = (warp - 2) / 4
     const int slot = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 256);
-    for (int u = slot; u < n_units; u += 2) {
-      const int i = u / T, t = u - i * T;
-      const int it = (int)blockIdx.x + i * (int)gridDim.x;
-      const int w = it / heads, h = it - w * heads;
-      const int q = t * 128 + quarter * 32 + lane;
-      int dst = q < seq ? w * seq + q : -1;
-      if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
-      softmax_tile(lane_base, o_off, seq, t * 128 + quarter * 32 < seq, dst >= 0,
-                   out + (size_t)(dst < 0 ? 0 : dst) * C + h * D, &bars[PB_S + slot], &bars[PB_P + slot], &bars[PB_O + slot],
-                   &bars[PB_OFREE + slot], (uint32_t)((u >> 1) & 1));
+    int u = 0;
+    for (int i = 0; i < my_items; ++i) {
+      int w, h;
+      const int Ti = item_tiles(i, w, h);
+      for (int t = 0; t < Ti; ++t, ++u) {
+        if ((u & 1) != slot) continue;
+        const int q = t * 128 + quarter * 32 + lane;
+        int dst = q < seq ? w * seq + q : -1;
+        if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
+        softmax_tile(lane_base, o_off, seq, t * 128 + quarter * 32 < seq, dst >= 0,
+                     out + (size_t)(dst < 0 ? 0 : dst) * C + h * D, &bars[PB_S + slot], &bars[PB_P + slot], &bars[PB_O + slot],
+                     &bars[PB_OFREE + slot], (uint32_t)((u >> 1) & 1));
+      }
     }
   }
 
@@ -584,7 +603,8 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
 }  // namespace toc3d
 
 extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
-                                      const int32_t* out_map, void* stream) {
+                                      const int32_t* out_map, const int32_t* q_rows, const int32_t* item_order,
+                                      void* stream) {
   using namespace toc3d;
   TOC3D_REQUIRE(qkv && out, kErrBadArg, "toc3d_window_attention: null pointer");
   TOC3D_REQUIRE(n_windows > 0 && seq_len > 0 && seq_len <= 1024 && heads > 0 && heads <= 65535, kErrBadArg,
@@ -618,18 +638,18 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
       const int grid = n_items < n_sm ? n_items : n_sm;
       const size_t smem = (size_t)nbuf * item_bytes + 1024 + 256;
       TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1, tm, o,
-                                  seq_len, heads, n_items, nbuf, out_map));
+                                  seq_len, heads, n_items, nbuf, out_map, q_rows, item_order));
       return 0;
     }
     const int spad = (seq_len + 15) & ~15;
     const int tmem_cols = spad <= 256 ? 256 : 512;     // <= 256 keys: two CTAs per SM (O may alias the tail of S)
     const size_t smem = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128;
     TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc_kernel, dim3(heads, n_windows), dim3(attn_tc::NTHREADS), smem, st,
-                                1, tm, o, seq_len, heads, tmem_cols, out_map));
+                                1, tm, o, seq_len, heads, tmem_cols, out_map, q_rows));
     return 0;
   }
   dim3 grid((seq_len + attn::BQ - 1) / attn::BQ, heads, n_windows);
   TOC3D_CHECK_CUDA(launch_pdl(attn::window_attention_kernel, grid, dim3(attn::NTHREADS), 0, st, 1,
-                              reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads, out_map));
+                              reinterpret_cast<const __nv_bfloat16*>(qkv), reinterpret_cast<__nv_bfloat16*>(out), seq_len, heads, out_map, q_rows));
   return 0;
 }

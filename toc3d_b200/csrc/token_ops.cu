@@ -206,17 +206,20 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
   }
 }
 
-// Compact row space of an accelerated block.  The packed set of a window is [k slow rows in rank order | rep];
+// Compact row space of an accelerated block.  The selected set of a window is [k slow rows in rank order | rep];
 // slow rows that are PAD slots (tok_map = -1) matter only as attention keys / values: everything after the
 // attention (proj, norm2, SwiGLU) is row-wise and their results are cropped by window_unpartition
-// (toc3d_eva_vit.py:459-461), so those GEMMs run on the compact rows = real slow rows + rep only.
+// (toc3d_eva_vit.py:459-461), so those GEMMs (and norm1 / q,k,v) run on the compact rows = real slow rows + rep.
 // coff[w] / rcap[w] (host-static: rcap = min(k, #real tokens of the window)) give the window's compact range.
-//   cmap[w*(k+1)+r] = compact row of packed row r (or -1 for a pad), ctok[c] = image row | -2 (rep) | -1 (unused),
-//   rep_row[w] = compact row of the representative token.  One CTA per window.
+// The window-packed qkv buffer the attention reads is laid out [real slow rows | rep | pad rows] per window, so the
+// query rows that are needed form a prefix and whole query tiles of padding can be skipped (keys are order-free).
+//   cmap[w*(k+1)+p]  = compact row of packed position p (or -1 for a pad)     prope[..] = RoPE table row of p
+//   ctok[c] = image row | -2 (rep) | -1 (unused)        cinv[c] = packed position        crope[c] = RoPE row
+//   rep_row[w] = compact row of the representative token.                     One CTA per window.
 __global__ void __launch_bounds__(1024)
 compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ rope_rows, const int* __restrict__ coff,
                     const int* __restrict__ rcap, int k, int* __restrict__ cmap, int* __restrict__ ctok,
-                    int* __restrict__ rep_row, int* __restrict__ cinv, int* __restrict__ crope) {
+                    int* __restrict__ rep_row, int* __restrict__ cinv, int* __restrict__ crope, int* __restrict__ prope) {
   __shared__ int s_warp[32];
   pdl_wait();
   pdl_launch_dependents();
@@ -224,11 +227,12 @@ compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ rop
   const int lane = t & 31, wid = t >> 5;
   const size_t base = (size_t)w * (k + 1);
   const int src = t < k ? tok_map[base + t] : -1;
+  const int rope = (t < k && rope_rows != nullptr) ? rope_rows[base + t] : 0;
   const bool real = t < k && src >= 0;
   const unsigned bal = __ballot_sync(0xffffffffu, real);
   if (lane == 0) s_warp[wid] = __popc(bal);
   __syncthreads();
-  int before = __popc(bal & ((1u << lane) - 1u));
+  int before = __popc(bal & ((1u << lane) - 1u));          // real rows ranking before this one
   int total = 0;
   for (int i = 0; i < (int)(blockDim.x >> 5); ++i) {
     const int c = s_warp[i];
@@ -238,11 +242,13 @@ compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ rop
   const int c0 = coff[w], cap = rcap[w];
   if (t < k) {
     const bool ok = real && before < cap;
-    cmap[base + t] = ok ? c0 + before : -1;
+    const int pos = ok ? before : total + 1 + (t - before);      // pads (and overflow rows) go after the rep
+    cmap[base + pos] = ok ? c0 + before : -1;
+    if (prope) prope[base + pos] = rope;
     if (ok) {
       ctok[c0 + before] = src;
-      if (cinv) cinv[c0 + before] = (int)(base + t);
-      if (crope) crope[c0 + before] = rope_rows ? rope_rows[base + t] : 0;
+      if (cinv) cinv[c0 + before] = (int)(base + pos);
+      if (crope) crope[c0 + before] = rope;
     }
   }
   if (t >= total && t < cap) {                             // degenerate: fewer real slow rows than the static capacity
@@ -251,11 +257,13 @@ compact_rows_kernel(const int* __restrict__ tok_map, const int* __restrict__ rop
     if (crope) crope[c0 + t] = 0;
   }
   if (t == 0) {
-    cmap[base + k] = c0 + cap;
+    const int rrope = rope_rows != nullptr ? rope_rows[base + k] : k;
+    cmap[base + total] = c0 + cap;
+    if (prope) prope[base + total] = rrope;
     ctok[c0 + cap] = -2;
     rep_row[w] = c0 + cap;
-    if (cinv) cinv[c0 + cap] = (int)(base + k);
-    if (crope) crope[c0 + cap] = rope_rows ? rope_rows[base + k] : k;
+    if (cinv) cinv[c0 + cap] = (int)(base + total);
+    if (crope) crope[c0 + cap] = rrope;
   }
 }
 
@@ -881,12 +889,12 @@ extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int3
 
 extern "C" int toc3d_compact_rows(const int32_t* tok_map, const int32_t* rope_rows, const int32_t* coff, const int32_t* rcap,
                                   int32_t nW, int32_t k, int32_t* cmap, int32_t* ctok, int32_t* rep_row, int32_t* cinv,
-                                  int32_t* crope, void* stream) {
+                                  int32_t* crope, int32_t* prope, void* stream) {
   TOC3D_REQUIRE(tok_map && coff && rcap && cmap && ctok && rep_row, kErrBadArg, "toc3d_compact_rows: null pointer");
   TOC3D_REQUIRE(nW > 0 && k >= 1 && k <= 1023, kErrBadArg, "toc3d_compact_rows: bad shape nW=%d k=%d", nW, k);
   const int threads = ((k + 1 + 31) / 32) * 32;
   TOC3D_CHECK_CUDA(launch_pdl(compact_rows_kernel, dim3(nW), dim3(threads), 0, ST(stream), 1, tok_map, rope_rows, coff, rcap, k, cmap, ctok, rep_row,
-                              cinv, crope));
+                              cinv, crope, prope));
   return 0;
 }
 

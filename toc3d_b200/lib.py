@@ -40,7 +40,7 @@ _SIGS = {
     "toc3d_last_error": ([], ctypes.c_char_p),
     "toc3d_gemm_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int,
                          ctypes.POINTER(Epilogue), _c_void_p], _c_int),
-    "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
+    "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                               _c_float, _c_int, _c_void_p, _c_void_p], _c_int),
     "toc3d_subln_bf16": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
@@ -48,7 +48,7 @@ _SIGS = {
     "toc3d_window_topk": ([_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
                            _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_compact_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
-                            _c_void_p, _c_void_p], _c_int),
+                            _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_fill_pad_kv_rope": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                                 _c_void_p], _c_int),
     "toc3d_fill_pad_kv": ([_c_void_p, _c_void_p, _c_int, _c_void_p, _c_int, _c_void_p], _c_int),
@@ -90,7 +90,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 8:
+        if lib.toc3d_abi_version() != 10:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -143,9 +143,10 @@ def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, ac
     return out
 
 
-def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None):
+def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None, q_rows=None, item_order=None):
     _want(qkv, torch.bfloat16, "qkv"); _want(out, torch.bfloat16, "out")
-    _check(load().toc3d_window_attention(_p(qkv), _p(out), n_windows, seq_len, heads, _p(out_map), _stream()),
+    _check(load().toc3d_window_attention(_p(qkv), _p(out), n_windows, seq_len, heads, _p(out_map), _p(q_rows), _p(item_order),
+                                         _stream()),
            "toc3d_window_attention")
     return out
 
@@ -180,9 +181,9 @@ def merge_fast_tokens(x, fast_map, fast_score, nW, n_fast, k, C, rep_out, packed
                                           _p(packed), _stream()), "toc3d_merge_fast_tokens")
 
 
-def compact_rows(tok_map, coff, rcap, nW, k, cmap, ctok, rep_row, rope_rows=None, cinv=None, crope=None):
+def compact_rows(tok_map, coff, rcap, nW, k, cmap, ctok, rep_row, rope_rows=None, cinv=None, crope=None, prope=None):
     _check(load().toc3d_compact_rows(_p(tok_map), _p(rope_rows), _p(coff), _p(rcap), nW, k, _p(cmap), _p(ctok), _p(rep_row),
-                                     _p(cinv), _p(crope), _stream()), "toc3d_compact_rows")
+                                     _p(cinv), _p(crope), _p(prope), _stream()), "toc3d_compact_rows")
 
 
 def fill_pad_kv_rope(qkv, cmap, rope_rows, Mp, kpad, vpad, cos_axis, sin_axis, ft, C):
