@@ -344,11 +344,13 @@ def forward_dense(p, cfg, img, tap=None):
 
 
 def forward_toc3d(p, cfg, img, temp_queries, temp_ref_points, temp_vel, temp_timestamp, temp_ego_pose,
-                  ego_pose_inv, prev_exists=True, gumbel_noise=None, tap=None):
+                  ego_pose_inv, prev_exists=True, gumbel_noise=None, tap=None, forced_scores=None):
     """ToC3DEVAViT.forward toc3d_eva_vit.py:230-310 in eval mode.
 
     gumbel_noise: list of 3 tensors (V,N,2) (pin 2).  Returns a dict with
     last_feat (V,C,H,W), token_masks [3x(V,H,W,1)], keep_idx, drop_idx, scores [3x(V,H,W)].
+    forced_scores (test hook, mirrors the plugin's teacher_scores): per-stage (V,H,W) scores that replace the
+    predicted ones for the sort / window selection (the masks still come from the predicted scores).
     """
     c = _cfg(cfg)
     assert not set(c["pruning_loc"]) & set(c["global_attn_indexes"])          # toc3d_eva_vit.py:141
@@ -374,9 +376,10 @@ def forward_toc3d(p, cfg, img, temp_queries, temp_ref_points, temp_vel, temp_tim
                 pred = query_based_score(x, masks, q, p, stage)
             else:
                 pred = first_frame_score(x, masks, p, stage)
-            _, _, keep_idx, drop_idx = sample(pred[:, :, 0], c["token_ratio"][stage])
+            sel = pred[:, :, 0] if forced_scores is None else forced_scores[stage].reshape(V, H * W).float()
+            _, _, keep_idx, drop_idx = sample(sel, c["token_ratio"][stage])
             masks = gumbel_mask(pred, gumbel_noise[stage].reshape(pred.shape)).reshape(V, H, W, 1)
-            scores = pred[:, :, 0].reshape(V, H, W)
+            scores = sel.reshape(V, H, W)
             out["token_masks"].append(masks)
             out["keep_idx"].append(keep_idx)
             out["drop_idx"].append(drop_idx)
