@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 10
+#define TOC3D_B200_ABI_VERSION 11
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -234,7 +234,11 @@ int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t*
                           const int32_t* rep_row /* row of `packed` for the representative; NULL: w*(k+1)+k */,
                           int32_t compact_rows /* > 0: tok_map lists that many COMPACT rows (ctok; -1 skipped) and the
                                                   LayerNorm output uses compact rows (rep at rep_row[w]); 0: packed */,
-                          const toc3d_pad_fill* pad_fill /* host pointer or NULL */, void* stream);
+                          const toc3d_pad_fill* pad_fill /* host pointer or NULL */,
+                          int32_t* counters /* int32 [nW], zeroed once by the caller: the representative token of a window
+                                               is merged by C/256 thread blocks (256-channel slices), the last one to
+                                               arrive normalises the row and clears the counter; NULL allowed for C = 128 */,
+                          void* stream);
 
 /* ------------------------------------------------------------------ history-query scorer
  * toc3d_utils.py:232-252 is linear in the token up to the LogSoftmax, so the query bank is

@@ -469,7 +469,10 @@ def test_ln_gather_merge_fused(lib, C, ws, ratio):
     out = torch.full((nW * (k + 1), C), float("nan"), device=DEV, dtype=torch.bfloat16)
     rep = torch.empty(nW, C, device=DEV); packed = torch.zeros(nW * (k + 1), C, device=DEV)
     stats = torch.ones(nW * (k + 1), 2, device=DEV, dtype=torch.int64)
-    lib.ln_gather_merge(xd, tok, fm, fs, gamma.to(DEV), beta.to(DEV), out, rep, packed, nW, k, nf, C, 1e-6, zero_stats=stats)
+    cnt = torch.zeros(nW, device=DEV, dtype=torch.int32)
+    lib.ln_gather_merge(xd, tok, fm, fs, gamma.to(DEV), beta.to(DEV), out, rep, packed, nW, k, nf, C, 1e-6, zero_stats=stats,
+                        counters=cnt)
+    assert (cnt == 0).all()
     assert (rep.cpu() - rep_ref[:, 0]).abs().max().item() < 1e-5 * max(1.0, rep_ref.abs().max().item())
     assert torch.equal(packed.reshape(nW, k + 1, C)[:, k], rep)
     got = out.float().cpu()

@@ -255,6 +255,7 @@ class _Workspace:
         self.T = torch.empty(rows, C, device=dev, dtype=torch.float32)   # packed slow+rep residual stream
         self.stats = torch.zeros(rows, 2, device=dev, dtype=torch.int64)   # sub-LN fixed-point [sum, sum sq] per MLP row
         self.stats2 = torch.zeros(rows, 2, device=dev, dtype=torch.int64)  # norm2 statistics of the post-attention rows
+        self.merge_cnt = torch.zeros(max(v["nW"] for v in self.win.values()), device=dev, dtype=torch.int32)
         self.stage = {}                                # (stage, ws) -> selection tables
 
 
@@ -461,7 +462,8 @@ class _Engine:
         L.ln_gather_merge(X, t["ctok"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
                           wsp.T, nW, k, nf, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None,
                           rep_row=t["rep_row"], compact_rows=Mc,
-                          pad_fill=(wsp.qkv, t["cmap"], t["prope"], Mp, bp["kpad"], bp["vpad"], bp["cos"], bp["sin"], bp["ft"]))
+                          pad_fill=(wsp.qkv, t["cmap"], t["prope"], Mp, bp["kpad"], bp["vpad"], bp["cos"], bp["sin"], bp["ft"]),
+                          counters=wsp.merge_cnt)
         self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"],
                        q_rows=t["q_rows"], item_order=t["item_order"])
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,

@@ -462,9 +462,12 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
                        const float* __restrict__ fast_score, const float* __restrict__ gamma,
                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, float* __restrict__ rep_out,
                        float* __restrict__ packed, int nW, int k, int n_fast, float eps, long long* __restrict__ zero_stats,
-                       const int* __restrict__ rep_row, int ln_rows, int compact, const PadFill fill) {
+                       const int* __restrict__ rep_row, int ln_rows, int compact, const PadFill fill,
+                       int* __restrict__ counters) {
   constexpr int C = VPL * 128;
-  __shared__ __align__(16) float s_acc[8][C];
+  constexpr int MSLICES = C >= 256 ? C / 256 : 1;
+  const int mblocks = nW * MSLICES;       // merge blocks come first (they are the long pole), then LN, then pad fill
+  __shared__ __align__(16) float s_acc[8][C >= 256 ? 256 : 128];
   __shared__ float s_wgt[1024];
   __shared__ int s_row[1024];
   __shared__ float s_red[8];
@@ -472,16 +475,16 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
   pdl_launch_dependents();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int ln_blocks = (ln_rows + 7) >> 3;
-  if ((int)blockIdx.x >= nW + ln_blocks) {
+  if ((int)blockIdx.x >= mblocks + ln_blocks) {
     // ---- blocks after the LayerNorm ones: constant k / v of the pad rows of the packed qkv buffer
-    fill_pad_row(fill, ((int)blockIdx.x - nW - ln_blocks) * 8 + warp, lane, C);
+    fill_pad_row(fill, ((int)blockIdx.x - mblocks - ln_blocks) * 8 + warp, lane, C);
     return;
   }
-  if ((int)blockIdx.x >= nW) {
+  if ((int)blockIdx.x >= mblocks) {
     // ---- LayerNorm of gathered slow rows (pad slots are zero vectors -> beta), rep rows belong to the merge blocks
     // compact = 0: tok_map lists the packed rows (-1 = pad slot -> LN(0) = beta, -2 = rep, handled by a merge block);
     // compact = 1: tok_map lists the compact rows (ctok; -1 = unused row, skipped), out / packed use compact rows
-    const int m = ((int)blockIdx.x - nW) * 8 + warp;
+    const int m = ((int)blockIdx.x - mblocks) * 8 + warp;
     if (m >= ln_rows) return;
     if (zero_stats != nullptr && lane == 0) *reinterpret_cast<longlong2*>(zero_stats + 2 * (size_t)m) = make_longlong2(0, 0);
     const int src = tok_map[m];
@@ -514,64 +517,81 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
     }
     return;
   }
-  // ---- representative token of window w
-  const int w = blockIdx.x;
+  // ---- representative token of window w: MS channel slices per window (one CTA each), the last one to finish
+  //      normalises the whole row
+  constexpr int MS = C >= 256 ? C / 256 : 1;          // slices per window
+  constexpr int SW = C / MS;                          // channels per slice (256, or 128 for C = 128)
+  constexpr int LV = SW / 128;                        // float4 per lane
+  const int w = blockIdx.x / MS, part = blockIdx.x - w * MS;
   const float* fs = fast_score + (size_t)w * n_fast;
   const int* fm = fast_map + (size_t)w * n_fast;
-  float part = 0.f;
+  float part_s = 0.f;
   for (int j = threadIdx.x; j < n_fast; j += 256) {
     const float sc = fs[j];
     s_wgt[j] = sc;
     s_row[j] = fm[j];
-    part += sc;
+    part_s += sc;
   }
-  part = warp_sum(part);
-  if (lane == 0) s_red[warp] = part;
+  part_s = warp_sum(part_s);
+  if (lane == 0) s_red[warp] = part_s;
   __syncthreads();
   const float total = ((s_red[0] + s_red[1]) + (s_red[2] + s_red[3])) + ((s_red[4] + s_red[5]) + (s_red[6] + s_red[7]));
-  float4 a[VPL];
+  float4 a[LV];
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* xb = reinterpret_cast<const float4*>(x) + lane;
-  for (int j0 = warp; j0 < n_fast; j0 += 16) {
-    float4 v[2][VPL];
-    float wg[2];
+  for (int i = 0; i < LV; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* xb = reinterpret_cast<const float4*>(x + part * SW) + lane;
+  for (int j0 = warp; j0 < n_fast; j0 += 32) {            // warp q owns rows j = q (mod 8), four rows in flight
+    float4 v[4][LV];
+    float wg[4];
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
+    for (int u = 0; u < 4; ++u) {
       const int j = j0 + 8 * u;
       const int r = j < n_fast ? s_row[j] : -1;
       wg[u] = j < n_fast ? s_wgt[j] / total : 0.f;             // weight = score / sum(score)
 #pragma unroll
-      for (int i = 0; i < VPL; ++i)
+      for (int i = 0; i < LV; ++i)
         v[u][i] = r >= 0 ? xb[(size_t)r * (C / 4) + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
     }
 #pragma unroll
-    for (int u = 0; u < 2; ++u)
+    for (int u = 0; u < 4; ++u)
 #pragma unroll
-      for (int i = 0; i < VPL; ++i) {
+      for (int i = 0; i < LV; ++i) {
         a[i].x += wg[u] * v[u][i].x; a[i].y += wg[u] * v[u][i].y;
         a[i].z += wg[u] * v[u][i].z; a[i].w += wg[u] * v[u][i].w;
       }
   }
   __syncthreads();                        // s_red is reused below
 #pragma unroll
-  for (int i = 0; i < VPL; ++i) reinterpret_cast<float4*>(s_acc[warp])[lane + 32 * i] = a[i];
+  for (int i = 0; i < LV; ++i) reinterpret_cast<float4*>(s_acc[warp])[lane + 32 * i] = a[i];
   __syncthreads();
-  // thread t owns channels t, t + 256, ... (C / 256 of them; C = 128: threads 0..127 own one)
+  const size_t prow = (size_t)(rep_row != nullptr ? rep_row[w] : w * (k + 1) + k);
+  if ((int)threadIdx.x < SW) {
+    float r = 0.f;
+#pragma unroll
+    for (int q = 0; q < 8; ++q) r += s_acc[q][threadIdx.x];
+    const int ch = part * SW + threadIdx.x;
+    rep_out[(size_t)w * C + ch] = r;
+    packed[prow * C + ch] = r;
+  }
+  if (MS > 1) {
+    __shared__ int s_last;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) s_last = atomicAdd(counters + w, 1) == MS - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) counters[w] = 0;             // clean for the next launch (CUDA-graph replays included)
+  }
+  // ---- LayerNorm of the finished row (thread t owns channels t, t + 256, ...)
   constexpr int PER = (C + 255) / 256;
   float r[PER];
   float sm = 0.f;
 #pragma unroll
   for (int e = 0; e < PER; ++e) {
     const int ch = threadIdx.x + 256 * e;
-    r[e] = 0.f;
-    if (ch < C) {
-#pragma unroll
-      for (int q = 0; q < 8; ++q) r[e] += s_acc[q][ch];
-      rep_out[(size_t)w * C + ch] = r[e];
-      packed[(size_t)(rep_row != nullptr ? rep_row[w] : w * (k + 1) + k) * C + ch] = r[e];
-      sm += r[e];
-    }
+    r[e] = ch < C ? __ldcg(rep_out + (size_t)w * C + ch) : 0.f;
+    sm += r[e];
   }
   sm = warp_sum(sm);
   if (lane == 0) s_red[warp] = sm;
@@ -962,7 +982,7 @@ extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, con
                                      const float* fast_score, const float* gamma, const float* beta, void* out,
                                      float* rep_out, float* packed, int32_t nW, int32_t k, int32_t n_fast, int32_t C,
                                      float eps, int64_t* zero_stats, const int32_t* rep_row, int32_t compact_rows,
-                                     const toc3d_pad_fill* pf, void* stream) {
+                                     const toc3d_pad_fill* pf, int32_t* counters, void* stream) {
   TOC3D_REQUIRE(x && tok_map && fast_map && fast_score && gamma && beta && out && rep_out && packed, kErrBadArg,
                 "toc3d_ln_gather_merge: null pointer");
   TOC3D_REQUIRE(nW > 0 && k >= 0 && n_fast > 0 && n_fast <= 1024, kErrBadArg,
@@ -980,11 +1000,13 @@ extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, con
                    pf->sin_axis, pf->ft};
     fill_blocks = (pf->Mp + 7) / 8;
   }
-  dim3 grid(nW + (M + 7) / 8 + fill_blocks), block(256);
+  const int mslices = C >= 256 ? C / 256 : 1;
+  TOC3D_REQUIRE(mslices == 1 || counters != nullptr, kErrBadArg, "toc3d_ln_gather_merge: counters (int32 [nW], zeroed) required for C >= 256");
+  dim3 grid(nW * mslices + (M + 7) / 8 + fill_blocks), block(256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   long long* zs = reinterpret_cast<long long*>(zero_stats);
 #define LGM_CASE(V)                                                                                                  \
-  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs, rep_row, M, compact, fill)); break;
+  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs, rep_row, M, compact, fill, counters)); break;
   switch (C % 128 == 0 ? C / 128 : 0) {
     LGM_CASE(1) LGM_CASE(2) LGM_CASE(4) LGM_CASE(6) LGM_CASE(8)
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_ln_gather_merge: C must be 128, 256, 512, 768 or 1024 (got %d)", C);

@@ -58,7 +58,7 @@ _SIGS = {
     "toc3d_fast_token_update": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                  _c_void_p, _c_void_p], _c_int),
     "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_int,
-                               ctypes.POINTER(PadFill), _c_void_p], _c_int),
+                               ctypes.POINTER(PadFill), _c_void_p, _c_void_p], _c_int),
     "toc3d_score_fold_queries": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int,
                                   _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
@@ -90,7 +90,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 10:
+        if lib.toc3d_abi_version() != 11:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -201,7 +201,7 @@ def fast_token_update(x, fast_map, packed, rep, nW, n_fast, k, C, rep_row=None):
 
 
 def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out, packed, nW, k, n_fast, C, eps,
-                    zero_stats=None, rep_row=None, compact_rows=0, pad_fill=None):
+                    zero_stats=None, rep_row=None, compact_rows=0, pad_fill=None, counters=None):
     """pad_fill = (qkv, cmap, rope_rows, Mp, kpad, vpad, cos_axis, sin_axis, ft): also write the pad rows' k / v."""
     pf = None
     if pad_fill is not None:
@@ -210,7 +210,7 @@ def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out,
     _want(x, torch.float32, "x"); _want(out, torch.bfloat16, "out")
     _check(load().toc3d_ln_gather_merge(_p(x), _p(tok_map), _p(fast_map), _p(fast_score), _p(gamma), _p(beta), _p(out),
                                         _p(rep_out), _p(packed), nW, k, n_fast, C, eps, _p(zero_stats), _p(rep_row), compact_rows,
-                                        ctypes.byref(pf) if pf is not None else None, _stream()),
+                                        ctypes.byref(pf) if pf is not None else None, _p(counters), _stream()),
            "toc3d_ln_gather_merge")
 
 
