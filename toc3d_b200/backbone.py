@@ -329,6 +329,7 @@ class _Engine:
             ))
         self.ws_cache = {}
         self._gstreams = []
+        self.fill_stream = torch.cuda.Stream(device=device)   # dense blocks: pad-slot k / v constants, beside norm1 + q/k/v
         self.side = torch.cuda.Stream(device=device)      # query folding / image-level top-k overlap the blocks
         self.seed_t = torch.zeros(1, device=device, dtype=torch.int64)   # forward counter (Gumbel seed, graph-safe)
 
@@ -387,13 +388,15 @@ class _Engine:
         return dict(a_out=wsp.a, row_stats=wsp.stats2, zero_stats=wsp.stats) if self.fold_norm2 else {}
 
     def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots, qkv_out_map=None, attn_out_map=None, q_rows=None,
-                  item_order=None):
+                  item_order=None, join=None):
         """q/k/v for the M rows of wsp.a (scattered to window slots through qkv_out_map when given), then attention
         over nW windows of seq slots; attn_out_map sends the rows that are used afterwards to compact positions."""
         C = self.C
         L.gemm(wsp.a, bp["wqkv"], L.EPI_QKV_ROPE, M=M, bias=bp["bqkv"], out=wsp.qkv, rope_rows=rope_rows,
                rope_slots=rope_slots, rope_ft=bp["ft"], rope_cols=2 * C, q_scale=64 ** -0.5,
                cos_axis=bp["cos"], sin_axis=bp["sin"], out_map=qkv_out_map)
+        if join is not None:
+            torch.cuda.current_stream().wait_stream(join)
         L.window_attention(wsp.qkv, wsp.ao, nW, seq, self.heads, out_map=attn_out_map, q_rows=q_rows,
                            item_order=item_order)
 
@@ -405,10 +408,15 @@ class _Engine:
         bp, C = self.blocks[i], self.C
         w = wsp.win[self.block_ws[i]]
         VN = wsp.V * wsp.N
+        # the pad slots' constants touch only pad rows of the qkv buffer: written on a second stream, concurrently with
+        # norm1 and the q/k/v GEMM (which writes the real slots), joined before the attention
+        cur, fs = torch.cuda.current_stream(), self.fill_stream
+        fs.wait_stream(cur)                                  # the previous attention has finished reading qkv
+        with torch.cuda.stream(fs):
+            L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
         L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None)
-        L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
         self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"],
-                       q_rows=w["q_rows"], item_order=w["item_order"])
+                       q_rows=w["q_rows"], item_order=w["item_order"], join=fs)
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X, **self._proj_kw(wsp))
         if not self.fold_norm2:
             L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
