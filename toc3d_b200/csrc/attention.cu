@@ -1,13 +1,17 @@
 // Windowed multi-head attention, head dim 64, sequence = one window (<= 401 tokens in the shipped
-// configs).  Two kernels:
-//   attn_tc  (seq <= 448): tcgen05 / TMEM / TMA.  One CTA per (window, head): Q, K, V of the window are
-//            staged once by TMA (128B swizzle); per 128-row query tile S = Q K^T is one or two
-//            tcgen05.mma into TMEM, four softmax warps (thread = row) read S with tcgen05.ld, take the
-//            exact row max over the whole window (no online rescaling needed at these lengths), write
-//            P = exp2(.) as packed bf16 back over S with tcgen05.st, and O = P V runs as tcgen05.mma with
-//            the A operand in TMEM and V as an MN-major smem operand.  Two CTAs share an SM when the
-//            window is short enough for 256 TMEM columns, so one CTA's softmax overlaps the other's MMAs.
-//   attn     (fallback, seq > 448): flash-style mma.sync kernel.
+// configs).  Three kernels behind toc3d_window_attention:
+//   attn_tc::window_attention_pp_kernel (seq <= 256): tcgen05 / TMEM / TMA, persistent, one CTA per SM looping over
+//            (window, head) items.  Q, K, V of an item are staged by TMA (64-row boxes, 128B swizzle) into a ring of
+//            smem buffers while earlier items are processed.  TMEM holds two 256-column slots; per 128-row query
+//            tile S = Q K^T is one tcgen05.mma chain into a slot, the slot's four softmax warps (thread = row) read
+//            S with tcgen05.ld, take the exact row max over the whole window (no online rescaling at these
+//            lengths), write P = exp2(.) as packed bf16 back over S with tcgen05.st, and O = P V runs as
+//            tcgen05.mma with the A operand in TMEM and V as an MN-major smem operand.  The MMA thread issues
+//            S(u) then P V(u-1), so one slot's MMAs overlap the other slot's softmax.
+//   attn_tc::window_attention_tc_kernel (256 < seq <= 448): same math, one CTA per (window, head), one slot.
+//   attn::window_attention_kernel (seq > 448, not reached by any shipped config): flash-style mma.sync fallback.
+// All take an optional out_map (rows stored in compact order, padding rows skipped) and q_rows (only the leading
+// query rows of a window are needed; the rest is padding that only serves as keys / values).
 //
 // Fallback kernel: one CTA = 64 query rows of one (window, head); K/V tiles of 64 keys are
 // double-buffered with cp.async; S = QK^T and O += PV run on mma.sync m16n8k16 (bf16 in, fp32
