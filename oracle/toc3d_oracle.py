@@ -9,9 +9,9 @@ Parity status: the reference ships NO tests or golden vectors for this path
 (SURVEY.md §4), so "parity unpinned by the reference's own tests".  Instead
 the oracle is pinned against outputs of the reference itself: tests/golden/
 holds vectors produced by importing the unmodified reference in the build
-container (tests/golden/make_golden.py), and tests/test_oracle_vs_reference.py
-re-checks the oracle against the live reference whenever /root/reference is
-present.
+container (tests/golden/make_golden.py), and tests/test_oracle_cpu.py /
+tests/test_neck.py re-check the oracle against the live reference whenever
+/root/reference is present.
 
 Two pins (choices where the reference leaves behaviour unspecified):
   pin 1  sort tie-break = (score descending, index ascending)  [torch.sort stable=True]
