@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 11
+#define TOC3D_B200_ABI_VERSION 12
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -268,6 +268,17 @@ int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint
  * im2col for the 16x16/stride-16 patch conv (eva_utils.py:283-287): img fp32 NCHW [V,3,Hi,Wi] ->
  * bf16 [V*(Hi/16)*(Wi/16), 768], column = c*256 + ky*16 + kx (= conv weight flattening). */
 int toc3d_im2col_patch16(const float* img, void* out_bf16, int32_t V, int32_t Hi, int32_t Wi, void* stream);
+
+/* Next row f3: the step before the path.  NormalizeMultiviewImage + PadMultiViewImage
+ * (datasets/pipelines/transform_3d.py:21-104, i.e. mmcv.imnormalize + impad_to_multiple; config
+ * ToC3D_fast.py:13-14,209-210) fused with the patch im2col above, so the host uploads the u8 camera crop
+ * (4x fewer bytes than the normalised fp32 NCHW image) and no fp32 image is ever materialised.
+ * img u8 HWC [V,Hs,Ws,3]; lut fp32 [3,256]: lut[c*256+b] = normalised value of byte b in output channel c
+ * (the host builds it in cv2's arithmetic: fp32(fp64(fp32(b - mean_c)) * (1/fp64(std_c)))); output channel c
+ * reads input channel (to_rgb ? 2-c : c); Hi >= Hs, Wi >= Ws are the padded dims (multiples of 16), pad = 0.
+ * Output identical (bit-exact) to toc3d_im2col_patch16 of the normalised, padded fp32 NCHW image. */
+int toc3d_preprocess_patch16_u8(const uint8_t* img, const float* lut, void* out_bf16, int32_t V, int32_t Hs,
+                                int32_t Ws, int32_t Hi, int32_t Wi, int32_t to_rgb, void* stream);
 
 /* ------------------------------------------------------------------ neck (next row: CPFPN, necks/cp_fpn.py:157-208)
  * im2col for the 3x3 / stride 1 / pad 1 fpn conv (cp_fpn.py:123-133,182-184) over an NHWC bf16 map

@@ -28,6 +28,11 @@ Reference files restated (paths under projects/mmdet3d_plugin/models/):
   backbones/eva_utils.py       window_partition/unpartition :89-133, get_abs_pos :229-258,
                                PatchEmbed :261-287, VisionRotaryEmbeddingFast(+WithSelection) :325-402
   necks/cp_fpn.py              CPFPN.forward :157-208 (shipped config: in_channels=[1024], out 256, num_outs=2)
+  datasets/pipelines/transform_3d.py  (under projects/mmdet3d_plugin/) PadMultiViewImage :21-68,
+                               NormalizeMultiviewImage :72-104 -> mmcv.imnormalize / impad_to_multiple.  mmcv is a
+                               dependency ABSENT from /root/reference and this image (README.md:52 pins mmcv-full
+                               1.6.0): normalize_pad_images restates its published algorithm and is pinned against the
+                               same OpenCV calls (cv2 is installed; tests/test_preprocess.py, tests/golden/preprocess_cv2.pt)
   utils/misc.py                MLN :154-188, transform_reference_points :191-200
   utils/positional_encoding.py pos2posemb3d :14-26, pos2posemb1d :28-37, nerf_positional_encoding :39-81
 """
@@ -411,3 +416,25 @@ def neck_cpfpn(p, last_feat, prefix=""):
     lat = F.conv2d(last_feat, p[prefix + "lateral_convs.0.conv.weight"], p[prefix + "lateral_convs.0.conv.bias"])
     out0 = F.conv2d(lat, p[prefix + "fpn_convs.0.conv.weight"], p[prefix + "fpn_convs.0.conv.bias"], padding=1)
     return [out0, F.max_pool2d(out0, 1, stride=2)]
+
+
+def normalize_pad_images(imgs_u8, mean, std, to_rgb=True, size_divisor=32):
+    """NormalizeMultiviewImage + PadMultiViewImage (transform_3d.py:38-48,95-96) + the NCHW stacking of the format
+    bundle, on uint8 HWC camera crops (V, Hs, Ws, 3) -> fp32 (V, 3, Hi, Wi).
+
+    mmcv.imnormalize_ (mmcv/image/photometric.py): mean = float64(mean), stdinv = 1/float64(std), optional BGR->RGB,
+    then cv2.subtract(img, mean, img); cv2.multiply(img, stdinv, img) on the float32 image.  OpenCV evaluates both in
+    double per element and stores float32 after each call.  mmcv.impad_to_multiple pads bottom / right with 0."""
+    import numpy as np
+    img = imgs_u8.numpy().astype(np.float32)                     # LoadMultiViewImageFromFiles(to_float32=True)
+    if to_rgb:
+        img = img[..., ::-1]
+    mean64 = np.asarray(mean, dtype=np.float32).astype(np.float64).reshape(1, 1, 1, 3)
+    stdinv = 1.0 / np.asarray(std, dtype=np.float32).astype(np.float64).reshape(1, 1, 1, 3)
+    img = (img.astype(np.float64) - mean64).astype(np.float32)
+    img = (img.astype(np.float64) * stdinv).astype(np.float32)
+    V, Hs, Ws, _ = img.shape
+    Hi, Wi = -(-Hs // size_divisor) * size_divisor, -(-Ws // size_divisor) * size_divisor
+    out = np.zeros((V, Hi, Wi, 3), dtype=np.float32)
+    out[:, :Hs, :Ws] = img
+    return torch.from_numpy(out).permute(0, 3, 1, 2).contiguous()

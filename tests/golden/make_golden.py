@@ -87,7 +87,52 @@ def build_neck_case():
                 outs=[o.contiguous() for o in outs])
 
 
+PREPROCESS_CASES = [  # (views, Hs, Ws, to_rgb)
+    (2, 64, 96, False), (2, 64, 96, True), (1, 50, 70, False), (1, 33, 40, True)]
+IMG_NORM = dict(mean=[103.530, 116.280, 123.675], std=[57.375, 57.120, 58.395])      # ToC3D_fast.py:13-14
+
+
+def preprocess_input(case):
+    """Seeded uint8 HWC crops (every byte value occurs); rebuilt identically by the tests."""
+    V, Hs, Ws, _ = case
+    g = torch.Generator(); g.manual_seed(V * 1000 + Hs * 10 + Ws)
+    x = torch.randint(0, 256, (V, Hs, Ws, 3), generator=g, dtype=torch.uint8)
+    x.view(-1)[:256] = torch.arange(256, dtype=torch.uint8)
+    return x
+
+
+def build_preprocess_case():
+    """NormalizeMultiviewImage + PadMultiViewImage through the very OpenCV calls mmcv 1.6.0 makes
+    (imnormalize_: cvtColor / cv2.subtract / cv2.multiply with float64 scalars; impad: cv2.copyMakeBorder).
+    mmcv itself is not installed; cv2 is."""
+    import cv2
+    import numpy as np
+    mean = np.array(IMG_NORM["mean"], dtype=np.float32)
+    std = np.array(IMG_NORM["std"], dtype=np.float32)
+    outs = []
+    for case in PREPROCESS_CASES:
+        x = preprocess_input(case)
+        per_view = []
+        for v in range(case[0]):
+            img = x[v].numpy().astype(np.float32)                  # to_float32=True
+            img = img.copy().astype(np.float32)                    # imnormalize
+            mean64 = np.float64(mean.reshape(1, -1))
+            stdinv = 1 / np.float64(std.reshape(1, -1))
+            if case[3]:
+                cv2.cvtColor(img, cv2.COLOR_BGR2RGB, img)
+            cv2.subtract(img, mean64, img)
+            cv2.multiply(img, stdinv, img)
+            Hi, Wi = -(-img.shape[0] // 32) * 32, -(-img.shape[1] // 32) * 32   # impad_to_multiple(32)
+            img = cv2.copyMakeBorder(img, 0, Hi - img.shape[0], 0, Wi - img.shape[1], cv2.BORDER_CONSTANT, value=0)
+            per_view.append(torch.from_numpy(img).permute(2, 0, 1))
+        outs.append(torch.stack(per_view).contiguous())
+    return dict(meta=dict(cases=PREPROCESS_CASES, cv2=cv2.__version__, **IMG_NORM), outs=outs)
+
+
 def main():
+    fx = build_preprocess_case()
+    torch.save(fx, os.path.join(HERE, "preprocess_cv2.pt"))
+    print("preprocess_cv2", [tuple(o.shape) for o in fx["outs"]])
     fx = build_neck_case()
     torch.save(fx, os.path.join(HERE, "neck_cpfpn.pt"))
     print("neck_cpfpn", [tuple(o.shape) for o in fx["outs"]])

@@ -364,10 +364,15 @@ def _adversarial_scores(V, H, W, kind, g):
         s = -torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W) * 1e-3
     elif kind == "pads_tie":
         s[:, ::2] = O.PAD_SCORE      # real tokens that tie with the pad value
+    elif kind == "special":          # NaN ranks first in torch.sort(descending=True); +-inf, denormals, +-0 ties
+        r = torch.rand(V, H, W, generator=g)
+        for lo, val in ((0.00, float("nan")), (0.08, float("inf")), (0.16, float("-inf")), (0.24, 1e-42),
+                        (0.32, -1e-42), (0.40, 0.0), (0.48, -0.0)):
+            s = torch.where((r >= lo) & (r < lo + 0.08), torch.full((), val), s)
     return s
 
 
-@pytest.mark.parametrize("kind", ["random", "equal", "dups", "zeros", "ramp_up", "ramp_down", "pads_tie"])
+@pytest.mark.parametrize("kind", ["random", "equal", "dups", "zeros", "ramp_up", "ramp_down", "pads_tie", "special"])
 @pytest.mark.parametrize("H,W,ws,ratio", [(20, 50, 16, 0.7), (20, 50, 20, 0.5), (20, 50, 20, 0.4), (20, 50, 16, 0.3),
                                           (50, 100, 16, 0.5), (50, 100, 20, 0.3), (7, 9, 16, 0.5)])
 def test_window_topk_bit_exact(lib, kind, H, W, ws, ratio):
@@ -389,7 +394,7 @@ def test_window_topk_bit_exact(lib, kind, H, W, ws, ratio):
     lib.window_topk(s.to(DEV), V, H, W, ws, k, **d)
     assert torch.equal(d["slow_idx"].cpu().long(), slow_idx)
     assert torch.equal(d["fast_idx"].cpu().long(), fast_idx)
-    assert torch.equal(d["fast_score"].cpu(), fast_s)
+    assert torch.equal(d["fast_score"].cpu().view(torch.int32), fast_s.contiguous().view(torch.int32))   # bit copy
     # derived maps: slot -> image row
     rows = torch.arange(V * H * W, dtype=torch.float32).reshape(V, H, W, 1)
     rw, _ = O.window_partition(rows, ws, pad_value=-1.0)
@@ -401,7 +406,7 @@ def test_window_topk_bit_exact(lib, kind, H, W, ws, ratio):
     assert torch.equal(d["fast_map"].cpu().long(), torch.gather(rw, 1, fast_idx))
 
 
-@pytest.mark.parametrize("kind", ["random", "equal", "dups", "zeros"])
+@pytest.mark.parametrize("kind", ["random", "equal", "dups", "zeros", "special"])
 @pytest.mark.parametrize("N,ratio", [(1000, 0.7), (1000, 0.3), (5000, 0.5), (5000, 0.4), (63, 0.5)])
 def test_topk_split_bit_exact(lib, kind, N, ratio):
     g = torch.Generator().manual_seed(N)

@@ -5,5 +5,6 @@ Public API: the two backbone plugins (registry names of the reference) and the r
 from .backbone import EVA_ViT, ToC3DEVAViT, ToC3DViTReturnType  # noqa: F401
 from .configs import CONFIGS, TINY  # noqa: F401
 from .neck import CPFPN  # noqa: F401
+from .preprocess import ImagePreprocess  # noqa: F401
 
-__all__ = ["ToC3DEVAViT", "EVA_ViT", "ToC3DViTReturnType", "CPFPN", "CONFIGS", "TINY"]
+__all__ = ["ToC3DEVAViT", "EVA_ViT", "ToC3DViTReturnType", "CPFPN", "ImagePreprocess", "CONFIGS", "TINY"]

@@ -19,6 +19,7 @@ import torch.nn as nn
 import torch.nn.functional as F
 
 from . import lib as L
+from .preprocess import ImagePreprocess
 
 LN_EPS = 1e-6
 
@@ -360,10 +361,15 @@ class _Engine:
         return self.pos_cache[(H, W)]
 
     # -- stem ------------------------------------------------------------------------------
-    def stem(self, img, wsp, X_out=None):
-        V, _, Hi, Wi = img.shape
+    def stem(self, img, wsp, X_out=None, pre=None):
+        """img: fp32 NCHW (the reference's input), or - row f3 - the u8 HWC camera crop with `pre` (ImagePreprocess)."""
+        V = img.shape[0]
         img = img if img.is_contiguous() else img.contiguous()
-        L.im2col_patch16(img, wsp.cols, V, Hi, Wi)
+        if img.dtype == torch.uint8:
+            L.preprocess_patch16_u8(img, pre.lut(self.device), wsp.cols, V, img.shape[1], img.shape[2], wsp.H * 16, wsp.W * 16,
+                                    pre.to_rgb)
+        else:
+            L.im2col_patch16(img, wsp.cols, V, wsp.H * 16, wsp.W * 16)
         X = X_out if X_out is not None else torch.empty(V * wsp.N, self.C, device=self.device, dtype=torch.float32)
         pos = self.abs_pos(wsp.H, wsp.W)
         if pos is not None:
@@ -622,11 +628,28 @@ class _EvaBase(nn.Module):
             self._engine.has_cls = self.pretrain_use_cls_token
         return self._engine
 
-    @staticmethod
-    def _prep_img(x):
+    def set_image_preprocess(self, mean, std, to_rgb=True, size_divisor=32, size=None):
+        """Row f3: take over `NormalizeMultiviewImage(**img_norm_cfg)` + `PadMultiViewImage(size_divisor=32)`
+        (transform_3d.py:21-104).  Afterwards `forward(x=...)` also accepts the uint8 HWC camera crops
+        (B*views, Hs, Ws, 3) that the reference pipeline would have normalised on the CPU."""
+        self.img_preprocess = ImagePreprocess(mean, std, to_rgb, size_divisor, size)
+        self._graphs = {}
+
+    def _prep_img(self, x):
+        """-> (x, V, Hi, Wi) with Hi x Wi the (padded) image size the patch grid is built on."""
         if x.dim() != 4:
             raise ValueError("expected images of shape (B*views, 3, H, W)")
-        return x.float().contiguous()
+        if x.dtype == torch.uint8:
+            pre = getattr(self, "img_preprocess", None)
+            if pre is None:
+                raise RuntimeError("uint8 images need set_image_preprocess(mean, std, to_rgb) (the img_norm_cfg of the config)")
+            if x.shape[-1] != 3:
+                raise ValueError("uint8 images are camera crops of shape (B*views, H, W, 3)")
+            Hi, Wi = pre.padded_hw(x.shape[1], x.shape[2])
+            return x.contiguous(), x.shape[0], Hi, Wi
+        if x.shape[2] % 16 or x.shape[3] % 16:
+            raise ValueError("image %dx%d must be a multiple of the 16x16 patch" % (x.shape[2], x.shape[3]))
+        return x.float().contiguous(), x.shape[0], x.shape[2], x.shape[3]
 
 
 @_register
@@ -658,20 +681,20 @@ class EVA_ViT(_EvaBase):
 
     @torch.no_grad()
     def forward(self, x, *args, **kwargs):
-        x = self._prep_img(x)
+        x, V, Hi, Wi = self._prep_img(x)
         eng = self._get_engine(x)
-        V, _, Hi, Wi = x.shape
+        pre = getattr(self, "img_preprocess", None)
 
         def core(t):
             wsp = eng.workspace(V, Hi // 16, Wi // 16)
-            X = eng.stem(t["x"], wsp)
+            X = eng.stem(t["x"], wsp, pre=pre)
             for i in range(len(self.blocks)):
                 eng.dense_block(i, X, wsp)
             return (X,)
 
         GLOBAL_TIMER.event_start("StreamPETR-EVA-ViT/backbone")
         if self.use_cuda_graph:
-            (X,) = self._graphed(("dense", V, Hi, Wi), {"x": x}, core)
+            (X,) = self._graphed(("dense", V, Hi, Wi, tuple(x.shape), x.dtype), {"x": x}, core)
         else:
             (X,) = core({"x": x})
         GLOBAL_TIMER.event_end("StreamPETR-EVA-ViT/backbone")
@@ -747,9 +770,8 @@ class ToC3DEVAViT(_EvaBase):
         gumbel_noise: optional list of per-stage (V,N,2) tensors (parity pin 2); default draws
         -log(-log(u)) on device.  teacher_scores / tap are test hooks (teacher forcing, intermediates).
         """
-        x = self._prep_img(x)
+        x, V, Hi, Wi = self._prep_img(x)
         eng = self._get_engine(x)
-        V, _, Hi, Wi = x.shape
         H, W = Hi // 16, Wi // 16
         prev = bool(prev_exists) if prev_exists is not None else False
         q_names = ("temp_queries", "temp_ref_points", "temp_vel", "temp_timestamp", "temp_ego_pose", "ego_pose_inv")
@@ -762,7 +784,7 @@ class ToC3DEVAViT(_EvaBase):
 
         def core(t):
             q_kw = {k: t[k] for k in q_names} if prev else None
-            return self._forward_core(eng, t["x"], q_kw, gumbel_noise, teacher_scores, tap)
+            return self._forward_core(eng, t["x"], (H, W), q_kw, gumbel_noise, teacher_scores, tap)
 
         GLOBAL_TIMER.event_start("ToC3D-StreamPETR-EVAViT/backbone")
         if self.use_cuda_graph and gumbel_noise is None and teacher_scores is None and tap is None:
@@ -777,15 +799,15 @@ class ToC3DEVAViT(_EvaBase):
         return ToC3DViTReturnType(outputs, none_if_empty([m.view(V, H, W, 1) for m in masks]), None,
                                   keep_idx=none_if_empty(keeps), drop_idx=none_if_empty(drops), aux_outputs=None)
 
-    def _forward_core(self, eng, x, q_kw, gumbel_noise, teacher_scores, tap):
+    def _forward_core(self, eng, x, grid, q_kw, gumbel_noise, teacher_scores, tap):
         """The launch sequence of one forward (toc3d_eva_vit.py:243-310); capturable in a CUDA graph.
         Returns (X, *masks, *keep_idx, *drop_idx).
 
         With view_groups = G > 1 the views are cut into G groups that run the whole block sequence on their own
         streams (every op is independent per image): the ragged tail wave / exposed epilogue of one group's
         kernel is filled by the other group's next kernel."""
-        V, _, Hi, Wi = x.shape
-        H, W = Hi // 16, Wi // 16
+        V = x.shape[0]
+        H, W = grid
         N = H * W
         cur, side = torch.cuda.current_stream(), eng.side
         nst = len(self.pruning_loc)
@@ -839,7 +861,7 @@ class ToC3DEVAViT(_EvaBase):
         H, W = wsp.H, wsp.W
         N = H * W
         cur, side = torch.cuda.current_stream(), eng.side
-        X = eng.stem(x, wsp, X_out)
+        X = eng.stem(x, wsp, X_out, pre=getattr(self, "img_preprocess", None))
         masks, keep_idxes, drop_idxes, scores_l = [], [], [], []
         mask_prev, stage = None, -1
         if tap is not None:

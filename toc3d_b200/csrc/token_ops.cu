@@ -785,6 +785,59 @@ im2col_patch16_kernel(const float* __restrict__ img, __nv_bfloat16* __restrict__
   *reinterpret_cast<uint4*>(out + row * 768 + c * 256 + ky * 16 + kx0) = u;
 }
 
+// Camera crop -> patch matrix in one pass (next row f3): NormalizeMultiviewImage + PadMultiViewImage
+// (transform_3d.py:21-104; mmcv.imnormalize / impad_to_multiple) fused with the stem im2col.
+// img u8 HWC [V,Hs,Ws,3]; lut fp32 [3,256] = normalised value of byte b in OUTPUT channel c (built on the host in
+// cv2's arithmetic); output channel c reads input channel (to_rgb ? 2-c : c); pixels outside Hs x Ws are the pad
+// value 0 of the normalised image.  Thread = 8 consecutive pixels of one image row (24 bytes in, 3 x 16 bytes out).
+__global__ void __launch_bounds__(256)
+preprocess_patch16_u8_kernel(const uint8_t* __restrict__ img, const float* __restrict__ lut, __nv_bfloat16* __restrict__ out,
+                             int V, int Hs, int Ws, int Hi, int Wi, int to_rgb) {
+  __shared__ float s_lut[3 * 256];
+  pdl_wait();
+  pdl_launch_dependents();
+  for (int j = threadIdx.x; j < 3 * 256; j += blockDim.x) s_lut[j] = lut[j];
+  __syncthreads();
+  const int Wp = Wi >> 4, Hp = Hi >> 4;
+  const int halves = Wp * 2;
+  const size_t total = (size_t)V * Hi * halves;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const int hx = (int)(idx % halves);
+  size_t r = idx / halves;
+  const int y = (int)(r % Hi);
+  const int v = (int)(r / Hi);
+  const int x0 = hx * 8;
+  uint8_t px[24];
+  if (y < Hs && x0 + 8 <= Ws && (Ws & 7) == 0 && (reinterpret_cast<uintptr_t>(img) & 7) == 0) {
+    const uint2* src = reinterpret_cast<const uint2*>(img + (((size_t)v * Hs + y) * Ws + x0) * 3);
+    const uint2 a = src[0], b = src[1], c = src[2];
+    const uint32_t w[6] = {a.x, a.y, b.x, b.y, c.x, c.y};
+#pragma unroll
+    for (int j = 0; j < 24; ++j) px[j] = (uint8_t)(w[j >> 2] >> ((j & 3) * 8));
+  } else {
+    const uint8_t* src = img + (((size_t)v * Hs + (y < Hs ? y : 0)) * Ws) * 3;
+#pragma unroll
+    for (int j = 0; j < 24; ++j) {
+      const int x = x0 + j / 3;
+      px[j] = (y < Hs && x < Ws) ? src[(size_t)x * 3 + j % 3] : 0;
+    }
+  }
+  const int pw = hx >> 1, kx0 = (hx & 1) * 8, ph = y >> 4, ky = y & 15;
+  const size_t row = ((size_t)v * Hp + ph) * Wp + pw;
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int ci = to_rgb ? 2 - c : c;
+    float f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = (y < Hs && x0 + j < Ws) ? s_lut[c * 256 + px[j * 3 + ci]] : 0.0f;
+    uint4 u;
+    u.x = pack_bf16(f[0], f[1]); u.y = pack_bf16(f[2], f[3]);
+    u.z = pack_bf16(f[4], f[5]); u.w = pack_bf16(f[6], f[7]);
+    *reinterpret_cast<uint4*>(out + row * 768 + c * 256 + ky * 16 + kx0) = u;
+  }
+}
+
 // im2col for a 3x3 / stride 1 / pad 1 convolution over an NHWC bf16 map: out[(v,y,x), (ky*3+kx)*C + c] =
 // in[v, y+ky-1, x+kx-1, c] (zero outside the image).  Thread = 8 channels (16 bytes) of one tap.
 __global__ void __launch_bounds__(256)
@@ -1054,6 +1107,18 @@ extern "C" int toc3d_im2col_patch16(const float* img, void* out, int32_t V, int3
                 "toc3d_im2col_patch16: image %dx%d must be a multiple of the 16x16 patch", Hi, Wi);
   const size_t total = (size_t)V * 3 * Hi * (Wi / 8);
   TOC3D_CHECK_CUDA(launch_pdl(im2col_patch16_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), 1, img, reinterpret_cast<__nv_bfloat16*>(out), V, Hi, Wi));
+  TOC3D_CHECK_CUDA(cudaGetLastError());
+  return 0;
+}
+
+extern "C" int toc3d_preprocess_patch16_u8(const uint8_t* img, const float* lut, void* out, int32_t V, int32_t Hs, int32_t Ws,
+                                           int32_t Hi, int32_t Wi, int32_t to_rgb, void* stream) {
+  TOC3D_REQUIRE(img && lut && out, kErrBadArg, "toc3d_preprocess_patch16_u8: null pointer");
+  TOC3D_REQUIRE(V > 0 && Hs > 0 && Ws > 0 && Hi >= Hs && Wi >= Ws && Hi % 16 == 0 && Wi % 16 == 0, kErrBadArg,
+                "toc3d_preprocess_patch16_u8: crop %dx%d must fit the padded image %dx%d (a multiple of the 16x16 patch)", Hs, Ws, Hi, Wi);
+  const size_t total = (size_t)V * Hi * (Wi / 8);
+  TOC3D_CHECK_CUDA(launch_pdl(preprocess_patch16_u8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), 1,
+                              img, lut, reinterpret_cast<__nv_bfloat16*>(out), V, Hs, Ws, Hi, Wi, to_rgb));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }

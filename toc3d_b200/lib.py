@@ -66,6 +66,7 @@ _SIGS = {
     "toc3d_score_finish": ([_c_void_p, _c_int, _c_void_p, _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                             _c_void_p], _c_int),
     "toc3d_im2col_patch16": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
+    "toc3d_preprocess_patch16_u8": ([_c_void_p, _c_void_p, _c_void_p] + [_c_int] * 6 + [_c_void_p], _c_int),
     "toc3d_im2col_3x3": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_cast_f32_to_bf16": ([_c_void_p, _c_void_p, _c_i64, _c_void_p], _c_int),
     "toc3d_mask_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p], _c_int),
@@ -90,7 +91,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 11:
+        if lib.toc3d_abi_version() != 12:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -235,6 +236,12 @@ def score_finish(logits, M, gumbel, seed, pred, score, mask_out, seed_dev=None):
 def im2col_patch16(img, out, V, Hi, Wi):
     _want(img, torch.float32, "img")
     _check(load().toc3d_im2col_patch16(_p(img), _p(out), V, Hi, Wi, _stream()), "toc3d_im2col_patch16")
+
+
+def preprocess_patch16_u8(img, lut, out, V, Hs, Ws, Hi, Wi, to_rgb):
+    _want(img, torch.uint8, "img"); _want(lut, torch.float32, "lut"); _want(out, torch.bfloat16, "out")
+    _check(load().toc3d_preprocess_patch16_u8(_p(img), _p(lut), _p(out), V, Hs, Ws, Hi, Wi, int(bool(to_rgb)), _stream()),
+           "toc3d_preprocess_patch16_u8")
 
 
 def im2col_3x3(x, out, V, H, W, C):
