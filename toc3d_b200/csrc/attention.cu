@@ -22,6 +22,19 @@
 #include "../../include/toc3d_b200.h"
 
 namespace toc3d {
+
+// Diagnostic build only (-DTOC3D_ATTN_TRACE, tools/probes/attn_trace.py): clock64 stamps of CTA 0 of the ping-pong kernel,
+// [role = slot 0 | slot 1 | MMA thread][unit of that role][8 stamps].  Compiled out of the product library.
+#ifdef TOC3D_ATTN_TRACE
+__device__ unsigned long long g_attn_trace[3 * 32 * 8];
+#define ATRACE(cond, role, unit, k)                                                                    \
+  do {                                                                                                 \
+    if ((cond) && blockIdx.x == 0 && (unit) < 32) g_attn_trace[((role) * 32 + (unit)) * 8 + (k)] = clock64(); \
+  } while (0)
+#else
+#define ATRACE(cond, role, unit, k) do {} while (0)
+#endif
+
 namespace attn {
 
 constexpr int D = 64;          // head dim
@@ -221,116 +234,150 @@ __device__ __forceinline__ float ex2_approx(float x) {
 }
 
 // Softmax of one 128-row query tile whose scores S sit in TMEM (thread = row, `lane_base` = TMEM address of
-// this warp's lane quarter at the first S column), followed by the O epilogue.
+// this warp's lane quarter at the first S column):
 //   pass 1: exact row max over the window (no online rescaling at these lengths);
-//   pass 2: p = exp2(s log2e - max log2e), fp32 row sum, packed bf16 P written over S with tcgen05.st;
-//   then P is handed to the MMA thread (bar_p), O = P V is awaited (bar_o), read, released (bar_ofree),
-//   scaled by 1 / sum and stored as bf16.  The TMEM load of chunk c+1 is in flight while chunk c is
-//   processed (two named register buffers; tcgen05.wait::ld covers every outstanding load).
-// Warps whose 32 rows are all beyond the window (`active` false, warp-uniform) keep the barrier protocol
-// but skip the arithmetic.
+//   pass 2: p = exp2(s log2e - max log2e), fp32 row sum, packed bf16 P written over S with tcgen05.st.
+// The TMEM load of chunk c+1 is in flight while chunk c is processed (two named register buffers;
+// tcgen05.wait::ld covers every outstanding load); max and sum run on four / two independent accumulators so
+// the fixed-latency FMNMX / FADD chains do not serialise a warp that shares its scheduler with one other warp.
+// Returns the row sum (0 for warps whose rows are all beyond the window: `active` false, warp-uniform).
+__device__ __forceinline__ float softmax_rows(uint32_t lane_base, int seq, bool active, int tr_role = -1, int tr_unit = 0) {
+  if (!active) return 0.f;
+  const int nchunks = (seq + 31) >> 5;
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  uint32_t va[32], vb[32];
+  auto max_chunk = [&](const uint32_t (&v)[32], int c) {
+    const int lim = seq - c * 32;                       // valid columns in this chunk (>= 1)
+    if (lim >= 32) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        m0 = fmaxf(m0, __uint_as_float(v[i]));
+        m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+        m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+        m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, i < lim ? __uint_as_float(v[i]) : -INFINITY);
+    }
+  };
+  tmem_ld_32x32(lane_base, va);
+  for (int c = 0; c < nchunks; c += 2) {
+    tmem_ld_wait();
+    if (c + 1 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 1) * 32), vb);
+    max_chunk(va, c);
+    if (c + 1 < nchunks) {
+      tmem_ld_wait();
+      if (c + 2 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 2) * 32), va);
+      max_chunk(vb, c + 1);
+    }
+  }
+  const float mneg = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * LOG2E;
+  ATRACE(tr_role >= 0, tr_role, tr_unit, 2);
+  float s0 = 0.f, s1 = 0.f;
+  auto exp_chunk = [&](const uint32_t (&v)[32], int c) {
+    uint32_t pk[16];
+    const int lim = seq - c * 32;
+    if (lim >= 32) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg));
+        s0 += p0;
+        s1 += p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = 2 * i < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg)) : 0.f;
+        const float p1 = 2 * i + 1 < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg)) : 0.f;
+        s0 += p0;
+        s1 += p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+    }
+    tmem_st_32x16(lane_base + (uint32_t)(c * 16), pk);
+  };
+  tmem_ld_32x32(lane_base, va);
+  for (int c = 0; c < nchunks; c += 2) {
+    tmem_ld_wait();
+    if (c + 1 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 1) * 32), vb);
+    exp_chunk(va, c);
+    if (c + 1 < nchunks) {
+      tmem_ld_wait();
+      if (c + 2 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 2) * 32), va);
+      exp_chunk(vb, c + 1);
+    }
+  }
+  tmem_st_wait();
+  return s0 + s1;
+}
+
+// O epilogue of a tile, in two halves so that the slot can be released between them: read the 64 fp32 O columns
+// of this thread's row from TMEM ...
+__device__ __forceinline__ void load_o(uint32_t o_addr, bool active, uint32_t (&o0)[32], uint32_t (&o1)[32]) {
+  if (active) {
+    tmem_ld_32x32(o_addr, o0);
+    tmem_ld_32x32(o_addr + 32u, o1);
+    tmem_ld_wait();
+  }
+}
+// ... and store O / sum as 64 bf16 (128 bytes of one output row).
+__device__ __forceinline__ void store_o(const uint32_t (&o0)[32], const uint32_t (&o1)[32], float sum, __nv_bfloat16* out_row) {
+  const float inv = 1.0f / sum;
+  uint4* dst = reinterpret_cast<uint4*>(out_row);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
+    u.y = pack_bf16(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
+    u.z = pack_bf16(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
+    u.w = pack_bf16(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
+    dst[j] = u;
+  }
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
+    u.y = pack_bf16(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
+    u.z = pack_bf16(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
+    u.w = pack_bf16(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
+    dst[4 + j] = u;
+  }
+}
+
+// O epilogue of a tile: await O = P V (bar_o), read it, release the O columns (bar_ofree; and bar_p when the caller
+// hands over the next P at the same moment), store the row.
+__device__ __forceinline__ void finish_tile(uint32_t o_addr, bool active, bool store, float sum, __nv_bfloat16* out_row,
+                                            uint64_t* bar_o, uint64_t* bar_ofree, uint64_t* bar_p, uint32_t parity) {
+  uint32_t o0[32], o1[32];
+  mbar_wait(bar_o, parity);
+  tcgen05_fence_after();
+  load_o(o_addr, active, o0, o1);
+  tcgen05_fence_before();
+  mbar_arrive(bar_ofree);
+  if (bar_p != nullptr) mbar_arrive(bar_p);
+  if (store) store_o(o0, o1, sum, out_row);
+}
+
+// One tile, strictly in order: S -> softmax -> P handed to the MMA thread (bar_p), O = P V awaited (bar_o), read,
+// slot released (bar_ofree), row stored.
 __device__ __forceinline__ void softmax_tile(uint32_t lane_base, uint32_t o_off, int seq, bool active, bool row_ok,
                                              __nv_bfloat16* out_row, uint64_t* bar_s, uint64_t* bar_p, uint64_t* bar_o,
                                              uint64_t* bar_ofree, uint32_t parity) {
-  const int nchunks = (seq + 31) >> 5;
   mbar_wait(bar_s, parity);
   tcgen05_fence_after();
-  float sum = 0.f;
-  if (active) {
-    float mx = -INFINITY;
-    uint32_t va[32], vb[32];
-    auto max_chunk = [&](const uint32_t (&v)[32], int c) {
-      const int lim = seq - c * 32;                       // valid columns in this chunk (>= 1)
-      if (lim >= 32) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-      } else {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) mx = fmaxf(mx, i < lim ? __uint_as_float(v[i]) : -INFINITY);
-      }
-    };
-    tmem_ld_32x32(lane_base, va);
-    for (int c = 0; c < nchunks; c += 2) {
-      tmem_ld_wait();
-      if (c + 1 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 1) * 32), vb);
-      max_chunk(va, c);
-      if (c + 1 < nchunks) {
-        tmem_ld_wait();
-        if (c + 2 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 2) * 32), va);
-        max_chunk(vb, c + 1);
-      }
-    }
-    const float mneg = -mx * LOG2E;
-    auto exp_chunk = [&](const uint32_t (&v)[32], int c) {
-      uint32_t pk[16];
-      const int lim = seq - c * 32;
-      if (lim >= 32) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg));
-          const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg));
-          sum += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-      } else {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float p0 = 2 * i < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg)) : 0.f;
-          const float p1 = 2 * i + 1 < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg)) : 0.f;
-          sum += p0 + p1;
-          pk[i] = pack_bf16(p0, p1);
-        }
-      }
-      tmem_st_32x16(lane_base + (uint32_t)(c * 16), pk);
-    };
-    tmem_ld_32x32(lane_base, va);
-    for (int c = 0; c < nchunks; c += 2) {
-      tmem_ld_wait();
-      if (c + 1 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 1) * 32), vb);
-      exp_chunk(va, c);
-      if (c + 1 < nchunks) {
-        tmem_ld_wait();
-        if (c + 2 < nchunks) tmem_ld_32x32(lane_base + (uint32_t)((c + 2) * 32), va);
-        exp_chunk(vb, c + 1);
-      }
-    }
-    tmem_st_wait();
-  }
+  const float sum = softmax_rows(lane_base, seq, active);
   tcgen05_fence_before();
   mbar_arrive(bar_p);
-  // epilogue: O / sum -> bf16 -> global
   mbar_wait(bar_o, parity);
   tcgen05_fence_after();
   uint32_t o0[32], o1[32];
-  if (active) {
-    tmem_ld_32x32(lane_base + o_off, o0);
-    tmem_ld_32x32(lane_base + o_off + 32u, o1);
-    tmem_ld_wait();
-  }
+  load_o(lane_base + o_off, active, o0, o1);
   tcgen05_fence_before();
   mbar_arrive(bar_ofree);
-  if (active && row_ok) {
-    const float inv = 1.0f / sum;
-    uint4* dst = reinterpret_cast<uint4*>(out_row);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 u;
-      u.x = pack_bf16(__uint_as_float(o0[8 * j + 0]) * inv, __uint_as_float(o0[8 * j + 1]) * inv);
-      u.y = pack_bf16(__uint_as_float(o0[8 * j + 2]) * inv, __uint_as_float(o0[8 * j + 3]) * inv);
-      u.z = pack_bf16(__uint_as_float(o0[8 * j + 4]) * inv, __uint_as_float(o0[8 * j + 5]) * inv);
-      u.w = pack_bf16(__uint_as_float(o0[8 * j + 6]) * inv, __uint_as_float(o0[8 * j + 7]) * inv);
-      dst[j] = u;
-    }
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      uint4 u;
-      u.x = pack_bf16(__uint_as_float(o1[8 * j + 0]) * inv, __uint_as_float(o1[8 * j + 1]) * inv);
-      u.y = pack_bf16(__uint_as_float(o1[8 * j + 2]) * inv, __uint_as_float(o1[8 * j + 3]) * inv);
-      u.z = pack_bf16(__uint_as_float(o1[8 * j + 4]) * inv, __uint_as_float(o1[8 * j + 5]) * inv);
-      u.w = pack_bf16(__uint_as_float(o1[8 * j + 6]) * inv, __uint_as_float(o1[8 * j + 7]) * inv);
-      dst[4 + j] = u;
-    }
-  }
+  if (active && row_ok) store_o(o0, o1, sum, out_row);
 }
 
 // S(tile) = Q_tile K^T into TMEM columns [s_col, s_col + spad): one MMA chain for the first 256 keys, a second
@@ -407,7 +454,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   const bool o_aliases_s = (uint32_t)spad > o_col;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ---------------------------------------------------------------- TMA: K + Q, then V
       mbar_arrive_expect_tx(&bars[BAR_QK], (uint32_t)((2 * T + nb) * BOX_BYTES));
       for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_QK], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
@@ -465,6 +512,7 @@ window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
 //   * the MMA thread issues S(u) and then P V of unit u-1 (software pipeline of depth 1).
 enum { PB_FULL = 0 /* +nbuf */, PB_EMPTY = 4, PB_S = 8 /* +slot */, PB_P = 10, PB_O = 12, PB_OFREE = 14, PP_NUM_BARS = 16 };
 
+template <bool deferred>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
                            int n_items, int nbuf, const int* __restrict__ out_map, const int* __restrict__ q_rows,
@@ -481,6 +529,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   const int C = heads * D;
   const int spad = (seq + 15) & ~15;
   const uint32_t o_off = 192u;                  // O columns inside a 256-column slot (aliases dead S columns if spad > 192)
+  // deferred (host: spad <= 192, O disjoint from S / P): the O epilogue runs behind the next tile's softmax
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // query tiles of item i: only the leading q_rows[w] query rows of a window are needed afterwards (the rest are
   // window padding, used as keys / values only), so a window may need fewer tiles than its key count suggests
@@ -518,7 +567,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   pdl_launch_dependents();
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ------------------------------------------------------------------ TMA producer: ring of item buffers
       for (int i = 0; i < my_items; ++i) {
         int w, h;
@@ -537,7 +586,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one_sync()) {
       // ------------------------------------------------------------------ MMA issuer
       // unit u = (item, query tile), enumerated item by item; unit u runs on slot u & 1.  Software pipeline of
       // depth 1: issue S(u), then P V of unit u - 1.
@@ -545,6 +594,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       auto do_pv = [&](const Unit& un) {
         mbar_wait(&bars[PB_P + un.s], un.n & 1);
         tcgen05_fence_after();
+        ATRACE(true, 2, (int)(2 * un.n) + un.s, 4);        // unit index of `un` = 2 n + slot
         issue_pv(tmem_base + (uint32_t)(un.s * 256) + o_off, tmem_base + (uint32_t)(un.s * 256), un.sV, spad);
         tcgen05_commit(&bars[PB_O + un.s]);
         if (un.last_buf >= 0) tcgen05_commit(&bars[PB_EMPTY + un.last_buf]);   // all MMAs reading this item are issued
@@ -562,12 +612,19 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
         for (int t = 0; t < Ti; ++t, ++u) {
           const int s = u & 1;
           const uint32_t n = (uint32_t)(u >> 1);              // how many units this slot has seen before
+          ATRACE(true, 2, u, 0);
           if (t == 0) mbar_wait(&bars[PB_FULL + buf], (uint32_t)((i / nbuf) & 1));
-          if (n > 0) mbar_wait(&bars[PB_OFREE + s], (n - 1) & 1);             // slot drained by its softmax warps
+          ATRACE(true, 2, u, 1);
+          // in-order mode: the slot (S / P and the O columns that may alias them) must be drained by its softmax
+          // warps.  Deferred mode (O never aliases S): S(u) may follow P V (u - 2) directly - the tensor pipe runs
+          // this thread's MMAs in issue order - and the O columns are guarded by the P barrier (see below)
+          if (!deferred && n > 0) mbar_wait(&bars[PB_OFREE + s], (n - 1) & 1);
           tcgen05_fence_after();
           issue_qk(tmem_base + (uint32_t)(s * 256), base + t * 2 * BOX_BYTES, sK, spad);
           tcgen05_commit(&bars[PB_S + s]);
+          ATRACE(true, 2, u, 2);
           if (have_prev) do_pv(prev);
+          ATRACE(true, 2, u, 3);
           prev = Unit{s, n, sV, t == Ti - 1 ? buf : -1};
           have_prev = true;
         }
@@ -579,6 +636,21 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     const int slot = (warp - 2) >> 2;
     const int quarter = warp & 3;
     const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 256);
+    uint64_t* bar_s = &bars[PB_S + slot];
+    uint64_t* bar_p = &bars[PB_P + slot];
+    uint64_t* bar_o = &bars[PB_O + slot];
+    uint64_t* bar_ofree = &bars[PB_OFREE + slot];
+    // In-order mode: S -> softmax -> P -> (P V) -> O epilogue, tile by tile.  Deferred mode: the epilogue of the
+    // slot's previous tile runs after the softmax of the current one, so the slot never idles through P V + O read
+    // + S(next): it only waits for S, which was issued right behind P V.
+    bool pend = false, pend_act = false, pend_ok = false;
+    float pend_sum = 0.f;
+    __nv_bfloat16* pend_row = out;
+    uint32_t pend_par = 0;
+    auto finish = [&](bool then_p) {
+      finish_tile(lane_base + o_off, pend_act, pend_act && pend_ok, pend_sum, pend_row, bar_o, bar_ofree, then_p ? bar_p : nullptr,
+                  pend_par);
+    };
     int u = 0;
     for (int i = 0; i < my_items; ++i) {
       int w, h;
@@ -588,11 +660,37 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
         const int q = t * 128 + quarter * 32 + lane;
         int dst = q < seq ? w * seq + q : -1;
         if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
-        softmax_tile(lane_base, o_off, seq, t * 128 + quarter * 32 < seq, dst >= 0,
-                     out + (size_t)(dst < 0 ? 0 : dst) * C + h * D, &bars[PB_S + slot], &bars[PB_P + slot], &bars[PB_O + slot],
-                     &bars[PB_OFREE + slot], (uint32_t)((u >> 1) & 1));
+        const bool active = t * 128 + quarter * 32 < seq;
+        const uint32_t parity = (uint32_t)((u >> 1) & 1);
+        const bool tr = quarter == 0 && lane == 0;
+        ATRACE(tr, slot, u >> 1, 0);
+        mbar_wait(bar_s, parity);
+        tcgen05_fence_after();
+        ATRACE(tr, slot, u >> 1, 1);
+        const float sum = softmax_rows(lane_base, seq, active, tr ? slot : -1, u >> 1);
+        ATRACE(tr, slot, u >> 1, 3);
+        if (deferred) {
+          if (pend) {
+            finish(true);                                // O(previous) completed long ago: its P V ran before this S
+          } else {
+            tcgen05_fence_before();
+            mbar_arrive(bar_p);
+          }
+        } else {
+          tcgen05_fence_before();
+          mbar_arrive(bar_p);
+        }
+        ATRACE(tr, slot, u >> 1, 4);
+        pend = true; pend_act = active; pend_ok = dst >= 0; pend_sum = sum; pend_par = parity;
+        pend_row = out + (size_t)(dst < 0 ? 0 : dst) * C + h * D;
+        if (!deferred) {
+          finish(false);
+          pend = false;
+        }
+        ATRACE(tr, slot, u >> 1, 5);
       }
     }
+    if (pend) finish(false);
   }
 
   tcgen05_fence_before();
@@ -604,6 +702,13 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
 }
 
 }  // namespace attn_tc
+
+#ifdef TOC3D_ATTN_TRACE
+extern "C" int toc3d_attn_trace_read(unsigned long long* host, int n) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, g_attn_trace, sizeof(unsigned long long) * (size_t)n);
+}
+#endif
 }  // namespace toc3d
 
 extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
@@ -621,8 +726,10 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
     if (!configured) {
       TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024));
-      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            227 * 1024));
+      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp_kernel<false>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp_kernel<true>,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       int dev = 0;
       cudaGetDevice(&dev);
       cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -641,8 +748,14 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
       const int n_items = n_windows * heads;
       const int grid = n_items < n_sm ? n_items : n_sm;
       const size_t smem = (size_t)nbuf * item_bytes + 1024 + 256;
-      TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1, tm, o,
-                                  seq_len, heads, n_items, nbuf, out_map, q_rows, item_order));
+      // keys (padded to 16) <= 192: the O columns do not alias S, the epilogue is deferred behind the next softmax
+      if (((seq_len + 15) & ~15) <= 192) {
+        TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel<true>, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1,
+                                    tm, o, seq_len, heads, n_items, nbuf, out_map, q_rows, item_order));
+      } else {
+        TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel<false>, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1,
+                                    tm, o, seq_len, heads, n_items, nbuf, out_map, q_rows, item_order));
+      }
       return 0;
     }
     const int spad = (seq_len + 15) & ~15;

@@ -179,6 +179,19 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, u
       : "memory");
 }
 
+// One lane of a converged warp (elect.sync).  ptxas knows that a branch on this predicate leaves exactly one active
+// thread and issues uniform-datapath instructions (UTCHMMA, UTMALDG, ...) in it directly; behind `lane == 0` it wraps
+// every one of them in an ELECT / BRA.U.ANY loop (~10 extra dependent instructions per MMA).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 // ---------------------------------------------------------------- clusters / CTA pairs (cta_group::2)
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r;

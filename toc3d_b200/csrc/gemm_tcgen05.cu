@@ -511,7 +511,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);    // bytes landing in both CTAs of the pair
@@ -553,7 +553,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0 && lane == 0) {
+    if (rank == 0 && elect_one_sync()) {
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
