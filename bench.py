@@ -453,8 +453,10 @@ def run_native(args):
                    "e2e_pipeline": "per step: pinned-host inputs -> H2D, forward, last_feat -> D2H to pinned host; copies "
                                    "double-buffered on copy streams (overlap the neighbouring steps' forward); the L2 "
                                    "flush between steps is inside the e2e timed region"},
+        # link_gbs = bytes moved per step / step time: when it sits at the host link's rate (6 GB/s both directions
+        # together on the slowest boxes of the pool) the e2e number is bound by the copies, not by the forward
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "ms_per_step": e2e_ms / args.steps},
+                "ms_per_step": e2e_ms / args.steps, "link_gbs": (h2d + d2h) / (e2e_ms / args.steps) / 1e6},
         # row f3 (context, not the headline): same pipeline fed the uint8 HWC camera crops; normalise + pad run fused
         # in the stem kernel (toc3d_preprocess_patch16_u8), so the H2D copy carries 4x fewer image bytes
         "e2e_u8_input": {"value": world * B * args.steps / (e2e_u8_ms / 1e3), "unit": UNIT,
