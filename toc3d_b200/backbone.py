@@ -18,6 +18,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from . import chain_plan
 from . import lib as L
 from .preprocess import ImagePreprocess
 
@@ -257,6 +258,8 @@ class _Workspace:
         self.stats = torch.zeros(rows, 2, device=dev, dtype=torch.int64)   # sub-LN fixed-point [sum, sum sq] per MLP row
         self.stats2 = torch.zeros(rows, 2, device=dev, dtype=torch.int64)  # norm2 statistics of the post-attention rows
         self.merge_cnt = torch.zeros(max(v["nW"] for v in self.win.values()), device=dev, dtype=torch.int32)
+        # fuse_mlp: per-row-block arrival counters of the chained MLP launch (zeroed once, the kernel leaves them zero)
+        self.chain_sync = torch.zeros(2 * ((rows + 255) // 256), device=dev, dtype=torch.int32)
         self.stage = {}                                # (stage, ws) -> selection tables
 
 
@@ -267,6 +270,10 @@ class _Engine:
         self.device = device
         m = model
         self.fold_norm2 = bool(getattr(model, "fold_norm2", False))
+        self.fuse_mlp = bool(getattr(model, "fuse_mlp", False))
+        if self.fuse_mlp and self.fold_norm2:
+            raise NotImplementedError("fuse_mlp and fold_norm2 are separate experiments; enable one of them")
+        self.chain_scheds = {}                            # M -> device schedule of the chained MLP launch
         self.C, self.heads, self.patch = m.embed_dim, m.num_heads, m.patch_size
         self.block_ws = [b.window_size for b in m.blocks]
         self.block_acc = [b.accelerate for b in m.blocks]
@@ -383,6 +390,17 @@ class _Engine:
         """eva_vit.py:44-51 (+ norm2 of :263 when folded).  wsp.a holds the bf16 A rows: LayerNorm output, or with
         fold_norm2 the un-normalised post-attention rows whose statistics are in wsp.stats2.  wsp.stats rows
         [0, M) must be zero on entry (zeroed by the norm2 launch or by the proj epilogue)."""
+        if self.fuse_mlp:
+            # both GEMMs in one persistent launch; the per-pair tile lists are planned once per M (chain_plan.py)
+            sched = self.chain_scheds.get(M)
+            if sched is None:
+                plan = chain_plan.plan_mlp_chain(M, bp["w12"].shape[0], self.C, self.C, L.gemm_chain_units())
+                sched = self.chain_scheds[M] = chain_plan.as_tensor(plan, self.device)
+            L.mlp_chain(wsp.a, bp["w12"], bp["w3"], M, sched, wsp.chain_sync,
+                        dict(bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, tile_n=256),
+                        dict(bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"], ln_n=self.Hd, ln_eps=LN_EPS,
+                             tile_n=256, **resid_kw))
+            return
         ln = dict(ln_stats=wsp.stats2, ln_u=bp["u12"], ln_n=self.C, ln_eps=LN_EPS) if self.fold_norm2 else {}
         L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, **ln)
         L.gemm(wsp.hid, bp["w3"], L.EPI_RESID, M=M, bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"],
@@ -561,6 +579,10 @@ class _EvaBase(nn.Module):
         # measured on B200 it saves 0.29 ms of LayerNorm launches but adds 0.28 ms to the (exposed, L2-bound) proj
         # epilogue - 162.9 vs 169 samples/s.  Set before the first forward (or call refresh_weights()) to change.
         self.fold_norm2 = False
+        # the two GEMMs of the SwiGLU MLP as ONE persistent launch with per-row-block dependency counters and a
+        # host-planned tile order (toc3d_mlp_chain_bf16 + chain_plan.py).  Bit-identical results by construction;
+        # OFF until it has been verified and measured on B200 (written in a session without GPU time left).
+        self.fuse_mlp = False
         # views are independent: with G > 1 the forward runs G groups of views on their own streams inside the
         # one CUDA graph, so the tail / epilogue of one group's kernels overlaps the other group's kernels
         self.view_groups = 1

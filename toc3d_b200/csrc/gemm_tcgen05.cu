@@ -112,8 +112,10 @@ __device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&f)[32]) {
 // of the quarter; nt0: first global column of the tile; bn: tile width.  full_bar/parity: the
 // "accumulator complete" barrier this warp must observe before its first TMEM load.
 // per-row LayerNorm fold coefficients from the fixed-point statistics: y = a * acc + b * u[col] + bias[col]
+// CG: read the statistics from L2 (chain kernel: they were accumulated by other SMs of the same launch).
+template <bool CG = false>
 __device__ __forceinline__ void ln_fold_coeffs(const long long* stats_row, int n, float eps, float& a, float& b) {
-  const longlong2 st = *reinterpret_cast<const longlong2*>(stats_row);
+  const longlong2 st = CG ? __ldcg(reinterpret_cast<const longlong2*>(stats_row)) : *reinterpret_cast<const longlong2*>(stats_row);
   const double inv_n = 1.0 / (double)n;
   const double mean = (double)st.x * (1.0 / STAT_SUM_SCALE) * inv_n;
   const double var = fmax((double)st.y * (1.0 / STAT_SQ_SCALE) * inv_n - mean * mean, 0.0);
@@ -121,7 +123,7 @@ __device__ __forceinline__ void ln_fold_coeffs(const long long* stats_row, int n
   b = -a * (float)mean;
 }
 
-template <int EPI, bool LNF, bool AOUT>
+template <int EPI, bool LNF, bool AOUT, bool CHAIN = false>
 __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int nt0, int bn, int half,
                                                    int M, int N, float* stage, int lane, uint64_t* full_bar,
                                                    uint32_t parity) {
@@ -219,7 +221,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       const int row = m0 + lane;
       rr_t = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
       or_t = ep.out_map ? ep.out_map[row] : row;
-      if constexpr (LNF) ln_fold_coeffs(ep.ln_stats + 2 * (size_t)row, ep.ln_n, ep.ln_eps, lnA_t, lnB_t);
+      if constexpr (LNF) ln_fold_coeffs<CHAIN>(ep.ln_stats + 2 * (size_t)row, ep.ln_n, ep.ln_eps, lnA_t, lnB_t);
     }
     // AOUT: destination row of THIS lane's row (thread = row domain) for the statistics / zeroing
     const int dst_t = !my_row_ok ? -1 : (or_t >= 0 ? or_t : (or_t == -2 ? m0 + lane : -1));
@@ -614,6 +616,256 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// GEMM chain: the two GEMMs of the SwiGLU MLP (eva_vit.py:44-51) in ONE persistent launch.
+//   problem 0: hid = silu(a W1^T + b1) * (a W2^T + b2)   (SWIGLU epilogue, sub-LN statistics accumulated per row)
+//   problem 1: out = resid + sub-LN-folded (hid W3'^T)     (RESID epilogue with ln_stats)
+// A problem-1 tile of row block m (256 rows) needs every problem-0 tile of that row block: its hid rows (read by
+// TMA) and their statistics.  Instead of a launch boundary the dependency is a per-row-block arrival counter in
+// global memory: problem-0 epilogue warps arrive on ready[m] after their stores, the TMA producer and the epilogue
+// warps of a problem-1 tile wait for ready[m] == all arrivals.  The last problem-1 epilogue warp of a row block
+// clears both counters, so the workspace is zero again when the launch ends.
+// The order in which a CTA pair works through tiles is an explicit list planned on the host (toc3d_b200/chain_plan.py):
+// sched[pair * sched_len + i] = tile id or -1 (end).  Tile id g < tiles0: problem 0, (m, n) = (g / num_n0, g % num_n0);
+// else problem 1 with j = g - tiles0, (m, n) = (j / num_n1, j % num_n1).  Progress: every pair lists each of its
+// problem-0 tiles before the problem-1 tiles that (transitively) wait on them is NOT required - the only requirement
+// is that executing the lists in order never waits on a tile that sits behind a waiting tile (checked by the planner's
+// simulation); all pairs of the grid are co-resident (grid <= toc3d_gemm_chain_units()), so a waiting pair never keeps
+// a producer from running.  A protocol bug traps after 4 s (bounded waits) instead of hanging.
+struct ChainProblem {
+  CUtensorMap tmA, tmB;
+  EpiParams ep;
+  int N, K, BN, num_n;
+};
+struct ChainParams {
+  ChainProblem p[2];
+  int M, tiles0;
+  const int* sched;
+  int sched_len;
+  int* ready;            // [ceil(M / 256)] arrivals of problem-0 epilogue warps
+  int* done;             // [ceil(M / 256)] arrivals of problem-1 epilogue warps
+  int ready_target;      // num_n0 * 2 CTAs * EPI_WARPS
+  int done_target;       // num_n1 * 2 CTAs * EPI_WARPS
+};
+
+__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
+  int v;
+  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// generic-proxy writes (st.global of hid) <-> async-proxy reads (TMA loads of hid by another CTA)
+__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
+
+__device__ __forceinline__ void chain_wait(const int* ctr, int target) {
+  uint64_t t0 = 0;
+  for (uint32_t spin = 1;; ++spin) {
+    if (ld_acquire_gpu(ctr) >= target) return;
+    __nanosleep(40);
+    if ((spin & 0xFFFu) == 0) {
+      uint64_t t1;
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+      if (t0 == 0) t0 = t1;
+      else if (t1 - t0 > 4000000000ull) {
+        printf("toc3d: chain dependency wait timed out (block %d thread %d target %d)\n", blockIdx.x, threadIdx.x, target);
+        __trap();
+      }
+    }
+  }
+}
+
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_TILES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tmem_full = empty_bar + STAGES;
+  uint64_t* tmem_empty = tmem_full + 2;
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* s_stage = reinterpret_cast<float*>(smem + SMEM_TILES + 256);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();          // rank in the pair, 0 = leader
+  const int pair = blockIdx.x >> 1;
+  const int* my_sched = cp.sched + (size_t)pair * cp.sched_len;
+  const int M = cp.M;
+
+  // tile id -> (problem, row block, column block)
+  auto decode = [&](int g, int& q, int& mb, int& nb) {
+    q = g >= cp.tiles0 ? 1 : 0;
+    const int j = q ? g - cp.tiles0 : g;
+    const int nn = q ? cp.p[1].num_n : cp.p[0].num_n;
+    mb = j / nn;
+    nb = j - mb * nn;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&cp.p[0].tmA);
+    tma_prefetch_desc(&cp.p[0].tmB);
+    tma_prefetch_desc(&cp.p[1].tmA);
+    tma_prefetch_desc(&cp.p[1].tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
+  tcgen05_fence_before();
+  cluster_sync_all();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int pre = 0;
+      {
+        // weights of the first tile: in flight before the programmatic-dependency wait
+        int q, mb, nb;
+        decode(__ldg(my_sched), q, mb, nb);
+        const ChainProblem& P = q ? cp.p[1] : cp.p[0];
+        const int b_rows = P.BN >> 1;
+        const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);
+        const int num_k = (P.K + BK - 1) / BK;
+        pre = num_k < STAGES ? num_k : STAGES;
+        for (int kb = 0; kb < pre; ++kb) {
+          if (rank == 0) mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
+          tma_load_2d_2sm(&P.tmB, smem_u32(&full_bar[kb]) & 0xFEFFFFFFu, smem + kb * STAGE_BYTES + A_BYTES, kb * BK,
+                          nb * P.BN + (int)rank * b_rows);
+        }
+      }
+      pdl_wait();
+      for (int i = 0; i < cp.sched_len; ++i) {
+        const int g = __ldg(my_sched + i);
+        if (g < 0) break;
+        int q, mb, nb;
+        decode(g, q, mb, nb);
+        const ChainProblem& P = q ? cp.p[1] : cp.p[0];
+        const int b_rows = P.BN >> 1;
+        const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);
+        const int num_k = (P.K + BK - 1) / BK;
+        const int m_idx = mb * (2 * BM) + (int)rank * BM;
+        const int n_idx = nb * P.BN + (int)rank * b_rows;
+        if (q) {
+          chain_wait(cp.ready + mb, cp.ready_target);   // the A rows (hid) of this row block are complete ...
+          fence_proxy_async_all();                      // ... and ordered before this thread's TMA reads
+        }
+        for (int kb = 0; kb < num_k; ++kb) {
+          const uint32_t lead_full = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
+          uint8_t* sa = smem + stage * STAGE_BYTES;
+          if (pre > 0) {
+            --pre;
+          } else {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
+            tma_load_2d_2sm(&P.tmB, lead_full, sa + A_BYTES, kb * BK, n_idx);
+          }
+          tma_load_2d_2sm(&P.tmA, lead_full, sa, kb * BK, m_idx);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && elect_one_sync()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      const uint16_t pair_mask = (uint16_t)3u;
+      for (int i = 0; i < cp.sched_len; ++i) {
+        const int g = __ldg(my_sched + i);
+        if (g < 0) break;
+        const int q = g >= cp.tiles0 ? 1 : 0;
+        const int bn = q ? cp.p[1].BN : cp.p[0].BN;
+        const int num_k = ((q ? cp.p[1].K : cp.p[0].K) + BK - 1) / BK;
+        const uint32_t idesc = make_idesc(bn);
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
+        tcgen05_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN_MAX);
+        for (int kb = 0; kb < num_k; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tcgen05_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
+          const uint64_t a_desc = umma_desc_k_sw128(sa);
+          const uint64_t b_desc = umma_desc_k_sw128(sa + A_BYTES);
+#pragma unroll
+          for (int k = 0; k < BK / UMMA_K; ++k)
+            umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tcgen05_commit_2sm(&empty_bar[stage], pair_mask);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        tcgen05_commit_2sm(&tmem_full[acc], pair_mask);
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (8 warps per CTA)
+    const int quarter = warp & 3;
+    const int half = (warp - 2) >> 2;
+    float* stage_buf = s_stage + (warp - 2) * STAGE_FLOATS;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    pdl_wait();
+    for (int i = 0; i < cp.sched_len; ++i) {
+      const int g = __ldg(my_sched + i);
+      if (g < 0) break;
+      int q, mb, nb;
+      decode(g, q, mb, nb);
+      const int m_idx = mb * (2 * BM) + (int)rank * BM + quarter * 32;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX);
+      if (q == 0) {
+        epilogue_warp_tile<TOC3D_EPI_SWIGLU, false, false>(cp.p[0].ep, taddr, m_idx, nb * cp.p[0].BN, cp.p[0].BN, half, M,
+                                                           cp.p[0].N, stage_buf, lane, &tmem_full[acc], acc_phase);
+      } else {
+        // the sub-LN statistics of these rows are complete once every problem-0 tile of the row block has arrived
+        if (lane == 0) chain_wait(cp.ready + mb, cp.ready_target);
+        __syncwarp();
+        epilogue_warp_tile<TOC3D_EPI_RESID, true, false, true>(cp.p[1].ep, taddr, m_idx, nb * cp.p[1].BN, cp.p[1].BN, half, M,
+                                                               cp.p[1].N, stage_buf, lane, &tmem_full[acc], acc_phase);
+      }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (q == 0) {
+        // publish this warp's hid rows + statistics: every lane orders its own writes (gpu scope, and against the
+        // async proxy that will read them), then one lane arrives
+        __threadfence();
+        fence_proxy_async_all();
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence();
+          atomicAdd(cp.ready + mb, 1);
+        }
+      } else if (lane == 0) {
+        // every poll of ready[mb] by this tile happened before this point; the last tile of the row block resets
+        if (atomicAdd(cp.done + mb, 1) == cp.done_target - 1) {
+          atomicExch(cp.done + mb, 0);
+          atomicExch(cp.ready + mb, 0);
+        }
+      }
+    }
+  }
+
+  tcgen05_fence_before();
+  cluster_sync_all();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+  }
+}
+
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -732,6 +984,79 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
 }  // namespace gemm
 }  // namespace toc3d
 
+namespace toc3d {
+namespace gemm {
+
+// C-ABI epilogue -> kernel parameters, with the argument checks shared by toc3d_gemm_bf16 and toc3d_mlp_chain_bf16
+static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, EpiParams& ep) {
+  ep.bias = e->bias; ep.out = e->out; ep.ldo = e->ldo; ep.out_f32 = e->out_f32; ep.act = e->act;
+  ep.resid = e->resid; ep.resid_map = e->resid_map; ep.resid_mod = e->resid_mod; ep.out_map = e->out_map;
+  ep.out_alt = e->out_alt; ep.rope_rows = e->rope_rows; ep.rope_slots = e->rope_slots; ep.rope_ft = e->rope_ft;
+  ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
+  ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
+  ep.ln_stats = reinterpret_cast<const long long*>(e->ln_stats);
+  ep.a_out = reinterpret_cast<__nv_bfloat16*>(e->a_out); ep.zero_stats = reinterpret_cast<long long*>(e->zero_stats);
+  const int tile_n = e->tile_n;
+  TOC3D_REQUIRE(e->cluster_pairs >= 0 && e->cluster_pairs <= 2, kErrBadArg, "%s: cluster_pairs must be 0 (auto), 1 or 2", fn);
+  TOC3D_REQUIRE(tile_n == 0 || (tile_n >= 64 && tile_n <= BN_MAX && tile_n % 32 == 0 &&
+                                (kind != TOC3D_EPI_SWIGLU || tile_n % 64 == 0)), kErrBadArg,
+                "%s: tile_n must be 0 (auto) or a multiple of 32 (64 for SWIGLU) in [64, 256], got %d", fn, tile_n);
+  const bool lnf = ep.ln_stats != nullptr;
+  if (lnf)
+    TOC3D_REQUIRE((kind == TOC3D_EPI_RESID || kind == TOC3D_EPI_SWIGLU) && ep.ln_u != nullptr && ep.ln_n > 0 &&
+                  ((uintptr_t)ep.ln_u & 15) == 0 && ((uintptr_t)ep.ln_stats & 15) == 0,
+                  kErrBadArg, "%s: folded LayerNorm (RESID / SWIGLU) needs ln_stats + ln_u (16-byte aligned), ln_n > 0", fn);
+  const bool aout = ep.a_out != nullptr;
+  if (aout)
+    TOC3D_REQUIRE(kind == TOC3D_EPI_RESID && !lnf && ep.row_stats != nullptr && ((uintptr_t)ep.a_out & 15) == 0 &&
+                  ((uintptr_t)ep.row_stats & 15) == 0 && ((uintptr_t)ep.zero_stats & 15) == 0, kErrBadArg,
+                  "%s: a_out needs RESID without ln fold, plus row_stats (16-byte aligned)", fn);
+  TOC3D_REQUIRE(ep.ldo > 0 && ep.ldo % 4 == 0 && N % 4 == 0, kErrBadArg,
+                "%s: N and ldo must be positive multiples of 4 (vector epilogue), got N=%d ldo=%d", fn, N, ep.ldo);
+  TOC3D_REQUIRE(((uintptr_t)ep.out & 15) == 0 && ((uintptr_t)ep.bias & 15) == 0 && ((uintptr_t)ep.resid & 15) == 0 &&
+                ((uintptr_t)ep.out_alt & 15) == 0, kErrBadArg, "%s: epilogue pointers must be 16-byte aligned", fn);
+  if (kind == TOC3D_EPI_QKV_ROPE) {
+    TOC3D_REQUIRE(ep.cos_axis && ep.sin_axis && ep.rope_ft > 0 && ep.rope_ft <= ROPE_MAX_FT, kErrBadArg,
+                  "%s: bad RoPE tables (ft=%d)", fn, ep.rope_ft);
+    TOC3D_REQUIRE(ep.rope_rows || ep.rope_slots > 0, kErrBadArg, "%s: rope_rows or rope_slots required", fn);
+    TOC3D_REQUIRE(ep.rope_cols % 128 == 0 && ep.rope_cols <= N, kErrBadArg, "%s: rope_cols %d", fn, ep.rope_cols);
+  }
+  if (kind == TOC3D_EPI_RESID) {
+    TOC3D_REQUIRE(ep.resid_mod > 0 ? ep.resid != nullptr : true, kErrBadArg, "%s: resid_mod needs resid", fn);
+    TOC3D_REQUIRE(ep.resid != nullptr || ep.resid_map != nullptr, kErrBadArg, "%s: RESID needs resid", fn);
+  }
+  if (kind == TOC3D_EPI_SWIGLU) TOC3D_REQUIRE(N % 64 == 0, kErrBadArg, "%s: SWIGLU needs N %% 64 == 0", fn);
+  return 0;
+}
+
+// CTA pairs of the chain kernel that can be resident at the same time (GPC boundaries can strand SMs); the chain's
+// dependency waits are only deadlock-free when the whole grid is resident, so its grid never exceeds this.
+static int chain_units() {
+  static int units = 0;
+  if (units == 0) {
+    if (cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+      cudaGetLastError();
+      return 0;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(NUM_THREADS);
+    cfg.dynamicSmemBytes = SMEM_BYTES; cfg.attrs = at; cfg.numAttrs = 1;
+    int n = 0;
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_chain_kernel, &cfg) != cudaSuccess || n <= 0) {
+      cudaGetLastError();
+      return 0;
+    }
+    units = n < sm_count() / 2 ? n : sm_count() / 2;
+  }
+  return units;
+}
+
+}  // namespace gemm
+}  // namespace toc3d
+
 extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N,
                                int32_t K, int32_t kind, const toc3d_epilogue* e, void* stream) {
   using namespace toc3d;
@@ -741,45 +1066,14 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   TOC3D_REQUIRE(K % 8 == 0 && lda % 8 == 0 && ldb % 8 == 0, kErrBadArg,
                 "toc3d_gemm_bf16: K, lda, ldb must be multiples of 8 (16-byte TMA strides)");
   TOC3D_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B & 15) == 0, kErrBadArg, "toc3d_gemm_bf16: unaligned operand");
+  TOC3D_REQUIRE(kind >= TOC3D_EPI_LINEAR && kind <= TOC3D_EPI_SWIGLU, kErrBadArg, "toc3d_gemm_bf16: unknown epilogue kind %d", kind);
   EpiParams ep;
-  ep.bias = e->bias; ep.out = e->out; ep.ldo = e->ldo; ep.out_f32 = e->out_f32; ep.act = e->act;
-  ep.resid = e->resid; ep.resid_map = e->resid_map; ep.resid_mod = e->resid_mod; ep.out_map = e->out_map;
-  ep.out_alt = e->out_alt; ep.rope_rows = e->rope_rows; ep.rope_slots = e->rope_slots; ep.rope_ft = e->rope_ft;
-  ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
-  ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
-  ep.ln_stats = reinterpret_cast<const long long*>(e->ln_stats);
-  ep.a_out = reinterpret_cast<__nv_bfloat16*>(e->a_out); ep.zero_stats = reinterpret_cast<long long*>(e->zero_stats);
+  int rc = to_params("toc3d_gemm_bf16", e, kind, N, ep);
+  if (rc) return rc;
   const int tile_n = e->tile_n;
   const int cpairs = e->cluster_pairs;
-  TOC3D_REQUIRE(cpairs >= 0 && cpairs <= 2, kErrBadArg, "toc3d_gemm_bf16: cluster_pairs must be 0 (auto), 1 or 2");
-  TOC3D_REQUIRE(tile_n == 0 || (tile_n >= 64 && tile_n <= BN_MAX && tile_n % 32 == 0 &&
-                                (kind != TOC3D_EPI_SWIGLU || tile_n % 64 == 0)), kErrBadArg,
-                "toc3d_gemm_bf16: tile_n must be 0 (auto) or a multiple of 32 (64 for SWIGLU) in [64, 256], got %d", tile_n);
   const bool lnf = ep.ln_stats != nullptr;
-  if (lnf)
-    TOC3D_REQUIRE((kind == TOC3D_EPI_RESID || kind == TOC3D_EPI_SWIGLU) && ep.ln_u != nullptr && ep.ln_n > 0 &&
-                  ((uintptr_t)ep.ln_u & 15) == 0 && ((uintptr_t)ep.ln_stats & 15) == 0,
-                  kErrBadArg, "toc3d_gemm_bf16: folded LayerNorm (RESID / SWIGLU) needs ln_stats + ln_u (16-byte aligned), ln_n > 0");
   const bool aout = ep.a_out != nullptr;
-  if (aout)
-    TOC3D_REQUIRE(kind == TOC3D_EPI_RESID && !lnf && ep.row_stats != nullptr && ((uintptr_t)ep.a_out & 15) == 0 &&
-                  ((uintptr_t)ep.row_stats & 15) == 0 && ((uintptr_t)ep.zero_stats & 15) == 0, kErrBadArg,
-                  "toc3d_gemm_bf16: a_out needs RESID without ln fold, plus row_stats (16-byte aligned)");
-  TOC3D_REQUIRE(ep.ldo > 0 && ep.ldo % 4 == 0 && N % 4 == 0, kErrBadArg,
-                "toc3d_gemm_bf16: N and ldo must be positive multiples of 4 (vector epilogue), got N=%d ldo=%d", N, ep.ldo);
-  TOC3D_REQUIRE(((uintptr_t)ep.out & 15) == 0 && ((uintptr_t)ep.bias & 15) == 0 && ((uintptr_t)ep.resid & 15) == 0 &&
-                ((uintptr_t)ep.out_alt & 15) == 0, kErrBadArg, "toc3d_gemm_bf16: epilogue pointers must be 16-byte aligned");
-  if (kind == TOC3D_EPI_QKV_ROPE) {
-    TOC3D_REQUIRE(ep.cos_axis && ep.sin_axis && ep.rope_ft > 0 && ep.rope_ft <= ROPE_MAX_FT, kErrBadArg,
-                  "toc3d_gemm_bf16: bad RoPE tables (ft=%d)", ep.rope_ft);
-    TOC3D_REQUIRE(ep.rope_rows || ep.rope_slots > 0, kErrBadArg, "toc3d_gemm_bf16: rope_rows or rope_slots required");
-    TOC3D_REQUIRE(ep.rope_cols % 128 == 0 && ep.rope_cols <= N, kErrBadArg, "toc3d_gemm_bf16: rope_cols %d", ep.rope_cols);
-  }
-  if (kind == TOC3D_EPI_RESID) {
-    TOC3D_REQUIRE(ep.resid_mod > 0 ? ep.resid != nullptr : true, kErrBadArg, "toc3d_gemm_bf16: resid_mod needs resid");
-    TOC3D_REQUIRE(ep.resid != nullptr || ep.resid_map != nullptr, kErrBadArg, "toc3d_gemm_bf16: RESID needs resid");
-  }
-  if (kind == TOC3D_EPI_SWIGLU) TOC3D_REQUIRE(N % 64 == 0, kErrBadArg, "toc3d_gemm_bf16: SWIGLU needs N %% 64 == 0");
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (kind) {
     case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
@@ -788,10 +1082,61 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
       if (aout) return launch<TOC3D_EPI_RESID, false, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
       return lnf ? launch<TOC3D_EPI_RESID, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st)
                  : launch<TOC3D_EPI_RESID, false>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
-    case TOC3D_EPI_SWIGLU:
+    default:
       return lnf ? launch<TOC3D_EPI_SWIGLU, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st)
                  : launch<TOC3D_EPI_SWIGLU, false>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
-    default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_gemm_bf16: unknown epilogue kind %d", kind);
   }
+}
+
+extern "C" int toc3d_gemm_chain_units(void) { return toc3d::gemm::chain_units(); }
+
+extern "C" int toc3d_mlp_chain_bf16(const void* A, int64_t lda, const void* B0, int64_t ldb0, int32_t N0, int32_t K0,
+                                    const toc3d_epilogue* e0, const void* B1, int64_t ldb1, int32_t N1,
+                                    const toc3d_epilogue* e1, int32_t M, const int32_t* sched, int32_t units,
+                                    int32_t sched_len, int32_t* sync, void* stream) {
+  using namespace toc3d;
+  using namespace toc3d::gemm;
+  const char* fn = "toc3d_mlp_chain_bf16";
+  TOC3D_REQUIRE(A && B0 && B1 && e0 && e1 && e0->out && e1->out && sched && sync, kErrBadArg, "%s: null pointer", fn);
+  TOC3D_REQUIRE(M > 0 && N0 > 0 && K0 > 0 && N1 > 0, kErrBadArg, "%s: empty problem M=%d N0=%d K0=%d N1=%d", fn, M, N0, K0, N1);
+  const int K1 = N0 / 2;                               // hidden width = columns of the SwiGLU output
+  const int64_t lda1 = e0->ldo;
+  TOC3D_REQUIRE(K0 % 8 == 0 && K1 % 8 == 0 && lda % 8 == 0 && lda1 % 8 == 0 && ldb0 % 8 == 0 && ldb1 % 8 == 0 && lda1 >= K1,
+                kErrBadArg, "%s: K, lda, ldb must be multiples of 8 (16-byte TMA strides) and ldo0 >= N0 / 2", fn);
+  TOC3D_REQUIRE(((uintptr_t)A & 15) == 0 && ((uintptr_t)B0 & 15) == 0 && ((uintptr_t)B1 & 15) == 0, kErrBadArg,
+                "%s: unaligned operand", fn);
+  ChainParams cp;
+  int rc = to_params(fn, e0, TOC3D_EPI_SWIGLU, N0, cp.p[0].ep);
+  if (rc) return rc;
+  rc = to_params(fn, e1, TOC3D_EPI_RESID, N1, cp.p[1].ep);
+  if (rc) return rc;
+  TOC3D_REQUIRE(cp.p[0].ep.ln_stats == nullptr && cp.p[0].ep.row_stats != nullptr, kErrBadArg,
+                "%s: problem 0 is SWIGLU with row_stats and without a folded LayerNorm", fn);
+  TOC3D_REQUIRE(cp.p[1].ep.ln_stats == cp.p[0].ep.row_stats && cp.p[1].ep.a_out == nullptr, kErrBadArg,
+                "%s: problem 1 is RESID with ln_stats = problem 0's row_stats", fn);
+  TOC3D_REQUIRE(e0->cluster_pairs != 2 && e1->cluster_pairs != 2, kErrBadArg, "%s: one CTA pair per cluster only", fn);
+  const int max_units = chain_units();
+  TOC3D_REQUIRE(max_units > 0, kErrNoDriver, "%s: occupancy query failed", fn);
+  TOC3D_REQUIRE(units > 0 && units <= max_units && sched_len > 0, kErrBadArg,
+                "%s: the schedule uses %d CTA pairs, %d can be co-resident (toc3d_gemm_chain_units)", fn, units, max_units);
+  const int bn0 = e0->tile_n > 0 ? e0->tile_n : BN_MAX, bn1 = e1->tile_n > 0 ? e1->tile_n : BN_MAX;
+  const int num_m = (M + 2 * BM - 1) / (2 * BM);
+  cp.p[0].N = N0; cp.p[0].K = K0; cp.p[0].BN = bn0; cp.p[0].num_n = (N0 + bn0 - 1) / bn0;
+  cp.p[1].N = N1; cp.p[1].K = K1; cp.p[1].BN = bn1; cp.p[1].num_n = (N1 + bn1 - 1) / bn1;
+  cp.M = M; cp.tiles0 = num_m * cp.p[0].num_n;
+  cp.sched = sched; cp.sched_len = sched_len;
+  cp.ready = sync; cp.done = sync + num_m;
+  cp.ready_target = cp.p[0].num_n * 2 * EPI_WARPS;
+  cp.done_target = cp.p[1].num_n * 2 * EPI_WARPS;
+  rc = make_tmap_bf16_2d(&cp.p[0].tmA, A, M, K0, lda, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&cp.p[0].tmB, B0, N0, K0, ldb0, bn0 / 2);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&cp.p[1].tmA, e0->out, M, K1, lda1, BM);
+  if (rc) return rc;
+  rc = make_tmap_bf16_2d(&cp.p[1].tmB, B1, N1, K1, ldb1, bn1 / 2);
+  if (rc) return rc;
+  TOC3D_CHECK_CUDA(launch_pdl(gemm_chain_kernel, dim3(2 * units), dim3(NUM_THREADS), SMEM_BYTES,
+                              reinterpret_cast<cudaStream_t>(stream), 2, cp));
   return 0;
 }

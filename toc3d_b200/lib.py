@@ -40,6 +40,9 @@ _SIGS = {
     "toc3d_last_error": ([], ctypes.c_char_p),
     "toc3d_gemm_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int,
                          ctypes.POINTER(Epilogue), _c_void_p], _c_int),
+    "toc3d_gemm_chain_units": ([], _c_int),
+    "toc3d_mlp_chain_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, ctypes.POINTER(Epilogue), _c_void_p, _c_i64,
+                              _c_int, ctypes.POINTER(Epilogue), _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
     "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                               _c_float, _c_int, _c_void_p, _c_void_p], _c_int),
@@ -91,7 +94,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 12:
+        if lib.toc3d_abi_version() != 13:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -121,15 +124,10 @@ def _want(t, dtype, name):
 
 
 # ------------------------------------------------------------------------------- wrappers
-def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, resid=None,
-         resid_map=None, resid_mod=0, out_map=None, out_alt=None, rope_rows=None, rope_slots=0, rope_ft=0,
-         rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None, row_stats=None, ln_u=None, ln_n=0, ln_eps=0.0,
-         tile_n=0, cluster_pairs=0, ln_stats=None, a_out=None, zero_stats=None):
-    """C = A[M,K] @ B[N,K]^T with fused epilogue `kind` (see include/toc3d_b200.h)."""
-    _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
-    M = A.shape[0] if M is None else M
-    N, K = B.shape
-    assert A.shape[1] == K and A.stride(1) == 1 and B.stride(1) == 1
+def _epilogue(*, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, resid=None,
+              resid_map=None, resid_mod=0, out_map=None, out_alt=None, rope_rows=None, rope_slots=0, rope_ft=0,
+              rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None, row_stats=None, ln_u=None, ln_n=0, ln_eps=0.0,
+              tile_n=0, cluster_pairs=0, ln_stats=None, a_out=None, zero_stats=None):
     e = Epilogue()
     e.bias = _p(bias); e.out = _p(out); e.ldo = out.shape[-1] if ldo is None else ldo
     e.out_f32 = int(out_f32); e.act = act
@@ -137,11 +135,49 @@ def gemm(A, B, kind, M=None, *, bias=None, out=None, ldo=None, out_f32=False, ac
     e.out_map = _p(out_map); e.out_alt = _p(out_alt)
     e.rope_rows = _p(rope_rows); e.rope_slots = rope_slots; e.rope_ft = rope_ft; e.rope_cols = rope_cols
     e.q_scale = q_scale; e.cos_axis = _p(cos_axis); e.sin_axis = _p(sin_axis)
-    e.row_stats = _p(row_stats); e.ln_stats = _p(ln_stats); e.a_out = _p(a_out); e.zero_stats = _p(zero_stats); e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps; e.tile_n = tile_n; e.cluster_pairs = cluster_pairs
+    e.row_stats = _p(row_stats); e.ln_stats = _p(ln_stats); e.a_out = _p(a_out); e.zero_stats = _p(zero_stats)
+    e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps; e.tile_n = tile_n; e.cluster_pairs = cluster_pairs
+    return e
+
+
+def gemm(A, B, kind, M=None, **epi):
+    """C = A[M,K] @ B[N,K]^T with fused epilogue `kind` (see include/toc3d_b200.h; keywords = toc3d_epilogue fields)."""
+    _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
+    M = A.shape[0] if M is None else M
+    N, K = B.shape
+    assert A.shape[1] == K and A.stride(1) == 1 and B.stride(1) == 1
+    e = _epilogue(**epi)
+    out = epi.get("out")
     rc = load().toc3d_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, kind,
                                 ctypes.byref(e), _stream())
     _check(rc, "toc3d_gemm_bf16")
     return out
+
+
+def gemm_chain_units():
+    """CTA pairs of the chain kernel that are co-resident on this device (upper bound for a schedule's `units`)."""
+    n = load().toc3d_gemm_chain_units()
+    if n <= 0:
+        raise RuntimeError("toc3d_gemm_chain_units failed: %s" % load().toc3d_last_error().decode())
+    return n
+
+
+def mlp_chain(A, B0, B1, M, sched, sync, epi0, epi1):
+    """SwiGLU MLP as one launch (toc3d_mlp_chain_bf16).  epi0 / epi1: keyword dicts of the SWIGLU / RESID epilogues
+    exactly as they would be passed to two gemm() calls; sched int32 [units, sched_len] from chain_plan.plan_mlp_chain
+    (planned for the same M and tile widths); sync int32 [>= 2 * ceil(M / 256)], zeroed once."""
+    for t, n in ((A, "A"), (B0, "B0"), (B1, "B1")):
+        _want(t, torch.bfloat16, n)
+    _want(sched, torch.int32, "sched"); _want(sync, torch.int32, "sync")
+    N0, K0 = B0.shape
+    N1, K1 = B1.shape
+    assert A.shape[1] == K0 and K1 == N0 // 2 and A.stride(1) == 1 and B0.stride(1) == 1 and B1.stride(1) == 1
+    assert sched.dim() == 2 and sync.numel() >= 2 * ((M + 255) // 256)
+    e0, e1 = _epilogue(**epi0), _epilogue(**epi1)
+    rc = load().toc3d_mlp_chain_bf16(A.data_ptr(), A.stride(0), B0.data_ptr(), B0.stride(0), N0, K0, ctypes.byref(e0),
+                                     B1.data_ptr(), B1.stride(0), N1, ctypes.byref(e1), M, _p(sched), sched.shape[0],
+                                     sched.shape[1], _p(sync), _stream())
+    _check(rc, "toc3d_mlp_chain_bf16")
 
 
 def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None, q_rows=None, item_order=None):
