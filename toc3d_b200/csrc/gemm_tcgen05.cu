@@ -33,6 +33,8 @@ constexpr int ROPE_MAX_FT = 256;
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;  // 196608
 constexpr int SMEM_AUX = 256 + 8 * 32 * 32 * 4;   // barriers + epilogue staging (8 warps x 32 rows x 32 fp32)
 constexpr int SMEM_BYTES = SMEM_TILES + SMEM_AUX + 1024;  // + alignment slack (230656 <= 232448)
+constexpr int CHAIN_MAX_SCHED = 256;                      // chain kernel: tile ids of one CTA pair, staged in smem
+constexpr int SMEM_BYTES_CHAIN = SMEM_BYTES + CHAIN_MAX_SCHED * 4;   // 231680 <= 232448
 
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10),
 // B=bf16 [10,13), A/B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).  M = 256 over the pair.
@@ -674,7 +676,15 @@ __device__ __forceinline__ void chain_wait(const int* ctr, int target) {
   }
 }
 
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// SIG = false: every epilogue warp publishes its own tile (membar.gpu + atomic per warp and tile).  Measured on B200
+// (profiles/r01zd_chain_bench_*): ~1 us per tile on the critical path - the SwiGLU epilogue is as long as its mainloop,
+// so the fence stalls the tensor pipe.  SIG = true: an 11th warp does the publishing; the epilogue warps only arrive on
+// a CTA-local mbarrier (ring of 4, one phase per tile) and never execute a gpu-scope fence.  Registers are allocated
+// per 4 warps, so the extra warp is free.
+constexpr int CHAIN_SIG_RING = 4;
+
+template <bool SIG>
+__global__ void __launch_bounds__(NUM_THREADS + (SIG ? 32 : 0), 1)
 gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -683,14 +693,18 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
   uint64_t* tmem_full = empty_bar + STAGES;
   uint64_t* tmem_empty = tmem_full + 2;
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  uint64_t* epi_done = reinterpret_cast<uint64_t*>(smem + SMEM_TILES + 192);    // SIG: [CHAIN_SIG_RING]
   float* s_stage = reinterpret_cast<float*>(smem + SMEM_TILES + 256);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();          // rank in the pair, 0 = leader
   const int pair = blockIdx.x >> 1;
-  const int* my_sched = cp.sched + (size_t)pair * cp.sched_len;
   const int M = cp.M;
+  // this pair's tile list, copied to shared memory once: the MMA thread reads the next tile id between two tiles, and
+  // a global load there (0.5-1 us) would idle the tensor pipe at every tile boundary
+  int* my_sched = reinterpret_cast<int*>(smem + SMEM_TILES + SMEM_AUX);
+  for (int i = threadIdx.x; i < cp.sched_len; i += blockDim.x) my_sched[i] = __ldg(cp.sched + (size_t)pair * cp.sched_len + i);
 
   // tile id -> (problem, row block, column block)
   auto decode = [&](int g, int& q, int& mb, int& nb) {
@@ -714,6 +728,8 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
       mbar_init(&tmem_full[a], 1);
       mbar_init(&tmem_empty[a], 2 * EPI_WARPS);
     }
+    if (SIG)
+      for (int a = 0; a < CHAIN_SIG_RING; ++a) mbar_init(&epi_done[a], EPI_WARPS);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
@@ -723,7 +739,29 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
   const uint32_t tmem_base = *tmem_ptr;
   pdl_launch_dependents();
 
-  if (warp == 0) {
+  if (SIG && warp == 2 + EPI_WARPS) {
+    // ------------------------------------------------------------------ publisher (SIG): one lane per CTA
+    if (elect_one_sync()) {
+      pdl_wait();
+      for (int i = 0; i < cp.sched_len; ++i) {
+        const int g = my_sched[i];
+        if (g < 0) break;
+        int q, mb, nb;
+        decode(g, q, mb, nb);
+        // all 8 epilogue warps of this CTA have stored their part of tile i (mbarrier: release.cta / acquire.cta) ...
+        mbar_wait(&epi_done[i & (CHAIN_SIG_RING - 1)], (uint32_t)((i / CHAIN_SIG_RING) & 1));
+        if (q == 0) {
+          // ... and this thread's gpu-scope fence is cumulative over what it has observed: publish for all 8 at once
+          fence_proxy_async_all();
+          __threadfence();
+          atomicAdd(cp.ready + mb, EPI_WARPS);
+        } else if (atomicAdd(cp.done + mb, EPI_WARPS) == cp.done_target - EPI_WARPS) {
+          atomicExch(cp.done + mb, 0);
+          atomicExch(cp.ready + mb, 0);
+        }
+      }
+    }
+  } else if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (elect_one_sync()) {
       int stage = 0;
@@ -732,7 +770,7 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
       {
         // weights of the first tile: in flight before the programmatic-dependency wait
         int q, mb, nb;
-        decode(__ldg(my_sched), q, mb, nb);
+        decode(my_sched[0], q, mb, nb);
         const ChainProblem& P = q ? cp.p[1] : cp.p[0];
         const int b_rows = P.BN >> 1;
         const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);
@@ -746,7 +784,7 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
       }
       pdl_wait();
       for (int i = 0; i < cp.sched_len; ++i) {
-        const int g = __ldg(my_sched + i);
+        const int g = my_sched[i];
         if (g < 0) break;
         int q, mb, nb;
         decode(g, q, mb, nb);
@@ -784,7 +822,7 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
       uint32_t acc_phase = 0;
       const uint16_t pair_mask = (uint16_t)3u;
       for (int i = 0; i < cp.sched_len; ++i) {
-        const int g = __ldg(my_sched + i);
+        const int g = my_sched[i];
         if (g < 0) break;
         const int q = g >= cp.tiles0 ? 1 : 0;
         const int bn = q ? cp.p[1].BN : cp.p[0].BN;
@@ -818,7 +856,7 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
     uint32_t acc_phase = 0;
     pdl_wait();
     for (int i = 0; i < cp.sched_len; ++i) {
-      const int g = __ldg(my_sched + i);
+      const int g = my_sched[i];
       if (g < 0) break;
       int q, mb, nb;
       decode(g, q, mb, nb);
@@ -836,18 +874,21 @@ gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
       }
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      if (lane == 0) {
+        // SIG: hand the tile to the publisher BEFORE releasing the accumulator, so that no warp can arrive for tile
+        // i + CHAIN_SIG_RING on the same barrier while another has not yet arrived for tile i
+        if (SIG) mbar_arrive(&epi_done[i & (CHAIN_SIG_RING - 1)]);
+        mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (SIG) continue;
       if (q == 0) {
         // publish this warp's hid rows + statistics: every lane orders its own writes (gpu scope, and against the
         // async proxy that will read them), then one lane arrives
-        __threadfence();
         fence_proxy_async_all();
+        __threadfence();
         __syncwarp();
-        if (lane == 0) {
-          __threadfence();
-          atomicAdd(cp.ready + mb, 1);
-        }
+        if (lane == 0) atomicAdd(cp.ready + mb, 1);
       } else if (lane == 0) {
         // every poll of ready[mb] by this tile happened before this point; the last tile of the row block resets
         if (atomicAdd(cp.done + mb, 1) == cp.done_target - 1) {
@@ -1031,10 +1072,16 @@ static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, E
 
 // CTA pairs of the chain kernel that can be resident at the same time (GPC boundaries can strand SMs); the chain's
 // dependency waits are only deadlock-free when the whole grid is resident, so its grid never exceeds this.
+static bool chain_publisher_warp() {       // TOC3D_CHAIN_SIG=1: the variant with the publisher warp (see gemm_chain_kernel)
+  static const bool on = getenv("TOC3D_CHAIN_SIG") != nullptr && getenv("TOC3D_CHAIN_SIG")[0] == '1';
+  return on;
+}
+
 static int chain_units() {
   static int units = 0;
   if (units == 0) {
-    if (cudaFuncSetAttribute(gemm_chain_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES) != cudaSuccess) {
+    if (cudaFuncSetAttribute(gemm_chain_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_CHAIN) != cudaSuccess ||
+        cudaFuncSetAttribute(gemm_chain_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_CHAIN) != cudaSuccess) {
       cudaGetLastError();
       return 0;
     }
@@ -1043,9 +1090,9 @@ static int chain_units() {
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(NUM_THREADS);
-    cfg.dynamicSmemBytes = SMEM_BYTES; cfg.attrs = at; cfg.numAttrs = 1;
+    cfg.dynamicSmemBytes = SMEM_BYTES_CHAIN; cfg.attrs = at; cfg.numAttrs = 1;
     int n = 0;
-    if (cudaOccupancyMaxActiveClusters(&n, gemm_chain_kernel, &cfg) != cudaSuccess || n <= 0) {
+    if (cudaOccupancyMaxActiveClusters(&n, gemm_chain_kernel<false>, &cfg) != cudaSuccess || n <= 0) {
       cudaGetLastError();
       return 0;
     }
@@ -1117,7 +1164,9 @@ extern "C" int toc3d_mlp_chain_bf16(const void* A, int64_t lda, const void* B0, 
   TOC3D_REQUIRE(e0->cluster_pairs != 2 && e1->cluster_pairs != 2, kErrBadArg, "%s: one CTA pair per cluster only", fn);
   const int max_units = chain_units();
   TOC3D_REQUIRE(max_units > 0, kErrNoDriver, "%s: occupancy query failed", fn);
-  TOC3D_REQUIRE(units > 0 && units <= max_units && sched_len > 0, kErrBadArg,
+  TOC3D_REQUIRE(sched_len > 0 && sched_len <= CHAIN_MAX_SCHED, kErrBadArg, "%s: sched_len %d not in [1, %d]", fn, sched_len,
+                CHAIN_MAX_SCHED);
+  TOC3D_REQUIRE(units > 0 && units <= max_units, kErrBadArg,
                 "%s: the schedule uses %d CTA pairs, %d can be co-resident (toc3d_gemm_chain_units)", fn, units, max_units);
   const int bn0 = e0->tile_n > 0 ? e0->tile_n : BN_MAX, bn1 = e1->tile_n > 0 ? e1->tile_n : BN_MAX;
   const int num_m = (M + 2 * BM - 1) / (2 * BM);
@@ -1136,7 +1185,11 @@ extern "C" int toc3d_mlp_chain_bf16(const void* A, int64_t lda, const void* B0, 
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&cp.p[1].tmB, B1, N1, K1, ldb1, bn1 / 2);
   if (rc) return rc;
-  TOC3D_CHECK_CUDA(launch_pdl(gemm_chain_kernel, dim3(2 * units), dim3(NUM_THREADS), SMEM_BYTES,
-                              reinterpret_cast<cudaStream_t>(stream), 2, cp));
+  if (chain_publisher_warp())
+    TOC3D_CHECK_CUDA(launch_pdl(gemm_chain_kernel<true>, dim3(2 * units), dim3(NUM_THREADS + 32), SMEM_BYTES_CHAIN,
+                                reinterpret_cast<cudaStream_t>(stream), 2, cp));
+  else
+    TOC3D_CHECK_CUDA(launch_pdl(gemm_chain_kernel<false>, dim3(2 * units), dim3(NUM_THREADS), SMEM_BYTES_CHAIN,
+                                reinterpret_cast<cudaStream_t>(stream), 2, cp));
   return 0;
 }
