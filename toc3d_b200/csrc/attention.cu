@@ -701,6 +701,297 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// Split-softmax variant of the ping-pong kernel (OPT-IN: TOC3D_ATTN_SPLIT=1; written without GPU time left in its
+// round, default off).  Why: in the kernel above a slot's softmax is ONE warp per TMEM lane quarter, so every SM
+// sub-partition hosts two softmax warps; the ex2 pass is latency-bound (MUFU 33 % busy).  Here TWO warps
+// share a lane quarter of a slot (warp_id % 4 selects both the TMEM lane quarter and the scheduler, so they sit on the
+// same sub-partition and fill each other's MUFU / TMEM-load latencies) and split the KEY columns:
+//   half 0: 32-key chunks [0, c0) in ascending order,  P chunk c packed at columns [16 c, 16 c + 16)
+//   half 1: chunks [c0, n) in DESCENDING order,         P chunk c packed at columns [16 (n + c), 16 (n + c) + 16)
+// (n = ceil(seq / 32), c0 = ceil(n / 2)).  A P chunk always lands on score columns its own warp has already read
+// (half 0: below 32 (c + 1); half 1: at or above 32 c) and never in the other half's score range, so the two warps
+// need no ordering between their passes except the exchange of the row max (and of the row sum) through shared
+// memory + a 64-thread named barrier.  O sits at columns [192, 256) when the keys fit below it (deferred mode), else
+// at [64, 128) between the two P blocks (n >= 7: P = [0, 64) and [16 n + 64, 32 n)).  Each half reads and stores 32 of
+// the 64 O columns of its rows.
+constexpr int PP2_THREADS = 64 + 16 * 32;       // warp 0 TMA, warp 1 MMA issue, warps 2-17 softmax
+constexpr int PP2_XCH_BYTES = 2 * 2 * 4 * 2 * 32 * 4;   // {max, sum} x slot x quarter x half x lane, fp32
+
+__device__ __forceinline__ uint32_t p_col_split(int c, int c0, int n) { return c < c0 ? 16u * (uint32_t)c : 16u * (uint32_t)(n + c); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// O = P V with the split P layout: k-step kk covers keys [16 kk, 16 kk + 16) = half a 32-key chunk
+__device__ __forceinline__ void issue_pv_split(uint32_t o_addr, uint32_t slot_addr, const uint8_t* v_base, int spad, int c0, int n) {
+  const uint64_t v_desc = umma_desc_k_sw128(smem_u32(v_base));
+  const uint32_t id = idesc_m128(D, 1);
+  const int ksteps = spad >> 4;
+  for (int kk = 0; kk < ksteps; ++kk)
+    umma_bf16_ts(o_addr, slot_addr + p_col_split(kk >> 1, c0, n) + (uint32_t)(8 * (kk & 1)), v_desc + (uint64_t)(128 * kk), id, kk);
+}
+
+// One warp's share of the softmax of a 128-row tile (thread = row): its key chunks only; row max and row sum are
+// combined with the partner warp of the lane quarter through xmax / xsum (indexed [half][lane]) and barrier bar_id.
+// Returns the full row sum.  `active` is the same for both partners (same rows).
+__device__ __forceinline__ float softmax_half(uint32_t lane_base, int seq, int n, int c0, int half, int lane, bool active,
+                                              float* xmax, float* xsum, int bar_id) {
+  if (!active) return 0.f;
+  const int cb = half ? c0 : 0, ce = half ? n : c0;
+  uint32_t v[32];
+  float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
+  for (int c = cb; c < ce; ++c) {
+    tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    const int lim = seq - c * 32;
+    if (lim >= 32) {
+#pragma unroll
+      for (int i = 0; i < 32; i += 4) {
+        m0 = fmaxf(m0, __uint_as_float(v[i]));
+        m1 = fmaxf(m1, __uint_as_float(v[i + 1]));
+        m2 = fmaxf(m2, __uint_as_float(v[i + 2]));
+        m3 = fmaxf(m3, __uint_as_float(v[i + 3]));
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 32; ++i) m0 = fmaxf(m0, i < lim ? __uint_as_float(v[i]) : -INFINITY);
+    }
+  }
+  float mx = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  xmax[half * 32 + lane] = mx;
+  named_bar_sync(bar_id, 64);
+  mx = fmaxf(mx, xmax[(half ^ 1) * 32 + lane]);          // finite: chunk 0 holds at least one valid key
+  const float mneg = -mx * LOG2E;
+  float s0 = 0.f, s1 = 0.f;
+  for (int j = cb; j < ce; ++j) {
+    const int c = half ? (ce - 1 - (j - cb)) : j;        // half 1 walks its chunks from the top
+    tmem_ld_32x32(lane_base + (uint32_t)(c * 32), v);
+    tmem_ld_wait();
+    uint32_t pk[16];
+    const int lim = seq - c * 32;
+    if (lim >= 32) {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg));
+        const float p1 = ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg));
+        s0 += p0;
+        s1 += p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 16; ++i) {
+        const float p0 = 2 * i < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i]), LOG2E, mneg)) : 0.f;
+        const float p1 = 2 * i + 1 < lim ? ex2_approx(fmaf(__uint_as_float(v[2 * i + 1]), LOG2E, mneg)) : 0.f;
+        s0 += p0;
+        s1 += p1;
+        pk[i] = pack_bf16(p0, p1);
+      }
+    }
+    tmem_st_32x16(lane_base + p_col_split(c, c0, n), pk);
+  }
+  tmem_st_wait();
+  const float sum = s0 + s1;
+  xsum[half * 32 + lane] = sum;
+  named_bar_sync(bar_id, 64);                           // also: both halves of P are in TMEM
+  return sum + xsum[(half ^ 1) * 32 + lane];
+}
+
+// this warp's 32 of the 64 O columns of a row -> 64 bytes of the output row
+__device__ __forceinline__ void store_o_half(const uint32_t (&o)[32], float sum, __nv_bfloat16* out_half_row) {
+  const float inv = 1.0f / sum;
+  uint4* dst = reinterpret_cast<uint4*>(out_half_row);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    uint4 u;
+    u.x = pack_bf16(__uint_as_float(o[8 * j + 0]) * inv, __uint_as_float(o[8 * j + 1]) * inv);
+    u.y = pack_bf16(__uint_as_float(o[8 * j + 2]) * inv, __uint_as_float(o[8 * j + 3]) * inv);
+    u.z = pack_bf16(__uint_as_float(o[8 * j + 4]) * inv, __uint_as_float(o[8 * j + 5]) * inv);
+    u.w = pack_bf16(__uint_as_float(o[8 * j + 6]) * inv, __uint_as_float(o[8 * j + 7]) * inv);
+    dst[j] = u;
+  }
+}
+
+template <bool deferred>
+__global__ void __launch_bounds__(PP2_THREADS, 1)
+window_attention_pp2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
+                            int n_items, int nbuf, const int* __restrict__ out_map, const int* __restrict__ q_rows,
+                            const int* __restrict__ item_order) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int T = (seq + 127) >> 7;
+  const int nb = (seq + BOX_ROWS - 1) / BOX_ROWS;
+  const int item_bytes = (2 * T + 2 * nb) * BOX_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nbuf * item_bytes);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + PP_NUM_BARS);
+  float* xch = reinterpret_cast<float*>(smem + nbuf * item_bytes + 256);     // [max | sum][slot][quarter][half][lane]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int C = heads * D;
+  const int spad = (seq + 15) & ~15;
+  const int n = (seq + 31) >> 5;                // 32-key chunks
+  const int c0 = (n + 1) >> 1;                  // chunks of half 0
+  const uint32_t o_off = deferred ? 192u : 64u; // host: deferred <=> spad <= 192; otherwise n >= 7 and [64, 128) is free of P
+  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  auto item_tiles = [&](int i, int& w, int& h) {
+    const int idx = (int)blockIdx.x + i * (int)gridDim.x;
+    const int it = item_order != nullptr ? item_order[idx] : idx;
+    w = it / heads;
+    h = it - w * heads;
+    const int need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;
+    return (need + 127) >> 7;
+  };
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    for (int b = 0; b < 4; ++b) {
+      mbar_init(&bars[PB_FULL + b], 1);
+      mbar_init(&bars[PB_EMPTY + b], 1);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&bars[PB_S + s], 1);
+      mbar_init(&bars[PB_P + s], 256);          // both halves of every row arrive
+      mbar_init(&bars[PB_O + s], 1);
+      mbar_init(&bars[PB_OFREE + s], 256);
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, 512);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      // ------------------------------------------------------------------ TMA producer (as in the kernel above)
+      for (int i = 0; i < my_items; ++i) {
+        int w, h;
+        const int Ti = item_tiles(i, w, h);
+        const int row0 = w * seq;
+        const int buf = i % nbuf;
+        const uint32_t round = (uint32_t)(i / nbuf);
+        mbar_wait(&bars[PB_EMPTY + buf], (round & 1) ^ 1);
+        uint8_t* base = smem + buf * item_bytes;
+        uint8_t* sK = base + 2 * T * BOX_BYTES;
+        uint8_t* sV = sK + nb * BOX_BYTES;
+        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)((2 * Ti + 2 * nb) * BOX_BYTES));
+        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
+        for (int b = 0; b < 2 * Ti; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
+        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one_sync()) {
+      // ------------------------------------------------------------------ MMA issuer (as above, split P layout)
+      struct Unit { int s; uint32_t n; const uint8_t* sV; int last_buf; };
+      auto do_pv = [&](const Unit& un) {
+        mbar_wait(&bars[PB_P + un.s], un.n & 1);
+        tcgen05_fence_after();
+        issue_pv_split(tmem_base + (uint32_t)(un.s * 256) + o_off, tmem_base + (uint32_t)(un.s * 256), un.sV, spad, c0, n);
+        tcgen05_commit(&bars[PB_O + un.s]);
+        if (un.last_buf >= 0) tcgen05_commit(&bars[PB_EMPTY + un.last_buf]);
+      };
+      Unit prev{0, 0, nullptr, -1};
+      bool have_prev = false;
+      int u = 0;
+      for (int i = 0; i < my_items; ++i) {
+        int w, h;
+        const int Ti = item_tiles(i, w, h);
+        const int buf = i % nbuf;
+        const uint8_t* base = smem + buf * item_bytes;
+        const uint8_t* sK = base + 2 * T * BOX_BYTES;
+        const uint8_t* sV = sK + nb * BOX_BYTES;
+        for (int t = 0; t < Ti; ++t, ++u) {
+          const int s = u & 1;
+          const uint32_t nu = (uint32_t)(u >> 1);
+          if (t == 0) mbar_wait(&bars[PB_FULL + buf], (uint32_t)((i / nbuf) & 1));
+          if (!deferred && nu > 0) mbar_wait(&bars[PB_OFREE + s], (nu - 1) & 1);
+          tcgen05_fence_after();
+          issue_qk(tmem_base + (uint32_t)(s * 256), base + t * 2 * BOX_BYTES, sK, spad);
+          tcgen05_commit(&bars[PB_S + s]);
+          if (have_prev) do_pv(prev);
+          prev = Unit{s, nu, sV, t == Ti - 1 ? buf : -1};
+          have_prev = true;
+        }
+      }
+      if (have_prev) do_pv(prev);
+    }
+  } else {
+    // -------------------------------------------------------------------- softmax warps 2..17
+    const int idx = warp - 2;
+    const int quarter = warp & 3;                 // TMEM lane quarter (and scheduler) of this warp
+    const int slot = (idx >> 2) & 1;
+    const int half = idx >> 3;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 256);
+    uint64_t* bar_s = &bars[PB_S + slot];
+    uint64_t* bar_p = &bars[PB_P + slot];
+    uint64_t* bar_o = &bars[PB_O + slot];
+    uint64_t* bar_ofree = &bars[PB_OFREE + slot];
+    float* xmax = xch + ((slot * 4 + quarter) * 2) * 32;
+    float* xsum = xmax + 2 * 4 * 2 * 32;
+    const int bar_id = 1 + slot * 4 + quarter;    // named barriers 1..8 (0 = __syncthreads)
+    bool pend = false, pend_act = false, pend_ok = false;
+    float pend_sum = 0.f;
+    __nv_bfloat16* pend_row = out;
+    uint32_t pend_par = 0;
+    // O epilogue of the pending tile: this warp's 32 columns
+    auto finish = [&](bool then_p) {
+      uint32_t o[32];
+      mbar_wait(bar_o, pend_par);
+      tcgen05_fence_after();
+      if (pend_act) {
+        tmem_ld_32x32(lane_base + o_off + (uint32_t)(half * 32), o);
+        tmem_ld_wait();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(bar_ofree);
+      if (then_p) mbar_arrive(bar_p);
+      if (pend_act && pend_ok) store_o_half(o, pend_sum, pend_row + half * 32);
+    };
+    int u = 0;
+    for (int i = 0; i < my_items; ++i) {
+      int w, h;
+      const int Ti = item_tiles(i, w, h);
+      for (int t = 0; t < Ti; ++t, ++u) {
+        if ((u & 1) != slot) continue;
+        const int q = t * 128 + quarter * 32 + lane;
+        int dst = q < seq ? w * seq + q : -1;
+        if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
+        const bool active = t * 128 + quarter * 32 < seq;
+        const uint32_t parity = (uint32_t)((u >> 1) & 1);
+        mbar_wait(bar_s, parity);
+        tcgen05_fence_after();
+        const float sum = softmax_half(lane_base, seq, n, c0, half, lane, active, xmax, xsum, bar_id);
+        if (deferred && pend) {
+          finish(true);                                 // O(previous) completed long ago: its P V ran before this S
+        } else {
+          tcgen05_fence_before();
+          mbar_arrive(bar_p);
+        }
+        pend = true; pend_act = active; pend_ok = dst >= 0; pend_sum = sum; pend_par = parity;
+        pend_row = out + (size_t)(dst < 0 ? 0 : dst) * C + h * D;
+        if (!deferred) {
+          finish(false);
+          pend = false;
+        }
+      }
+    }
+    if (pend) finish(false);
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
 }  // namespace attn_tc
 
 #ifdef TOC3D_ATTN_TRACE
@@ -743,10 +1034,33 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
     __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
     if (seq_len <= attn_tc::PP_MAX_SEQ) {
       const int item_bytes = (2 * T + 2 * nb) * attn_tc::BOX_BYTES;
-      int nbuf = (226 * 1024 - 1024 - 256) / item_bytes;
-      nbuf = nbuf > 4 ? 4 : nbuf;                       // >= 2 for seq <= 256 (96 KB per item)
       const int n_items = n_windows * heads;
       const int grid = n_items < n_sm ? n_items : n_sm;
+      // opt-in experiment: two softmax warps per lane quarter and slot, key columns split between them
+      static const bool split = getenv("TOC3D_ATTN_SPLIT") != nullptr && getenv("TOC3D_ATTN_SPLIT")[0] == '1';
+      if (split) {
+        static bool configured2 = false;
+        if (!configured2) {
+          TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp2_kernel<false>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp2_kernel<true>,
+                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+          configured2 = true;
+        }
+        int nbuf2 = (226 * 1024 - 1024 - 256 - attn_tc::PP2_XCH_BYTES) / item_bytes;
+        nbuf2 = nbuf2 > 4 ? 4 : nbuf2;
+        const size_t smem2 = (size_t)nbuf2 * item_bytes + 1024 + 256 + attn_tc::PP2_XCH_BYTES;
+        if (((seq_len + 15) & ~15) <= 192) {
+          TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp2_kernel<true>, dim3(grid), dim3(attn_tc::PP2_THREADS), smem2, st,
+                                      1, tm, o, seq_len, heads, n_items, nbuf2, out_map, q_rows, item_order));
+        } else {
+          TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp2_kernel<false>, dim3(grid), dim3(attn_tc::PP2_THREADS), smem2, st,
+                                      1, tm, o, seq_len, heads, n_items, nbuf2, out_map, q_rows, item_order));
+        }
+        return 0;
+      }
+      int nbuf = (226 * 1024 - 1024 - 256) / item_bytes;
+      nbuf = nbuf > 4 ? 4 : nbuf;                       // >= 2 for seq <= 256 (96 KB per item)
       const size_t smem = (size_t)nbuf * item_bytes + 1024 + 256;
       // keys (padded to 16) <= 192: the O columns do not alias S, the epilogue is deferred behind the next softmax
       if (((seq_len + 15) & ~15) <= 192) {
