@@ -108,26 +108,38 @@ typedef struct toc3d_epilogue {
 int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
                     int32_t epilogue_kind, const toc3d_epilogue* epi /* host */, void* stream);
 
-/* SwiGLU MLP (eva_vit.py:44-51: w3(ffn_ln(silu(w1 x) * (w2 x)))) as ONE persistent launch of two chained GEMMs -
- * OPT-IN (plugin option fuse_mlp, default off; results are bit-identical to the two toc3d_gemm_bf16 launches it
- * replaces):
- *   problem 0: SWIGLU  hid[M, N0/2] = epilogue e0 of A[M,K0] * B0[N0,K0]^T   (e0->out = hid, e0->row_stats required)
- *   problem 1: RESID   epilogue e1 of hid[M, N0/2] * B1[N1, N0/2]^T          (e1->ln_stats == e0->row_stats)
- * A problem-1 tile of a 256-row block starts as soon as the problem-0 tiles of that row block have been stored
- * (arrival counters in `sync`), so there is no launch boundary, no second prologue, and the ragged last wave of
- * either GEMM is filled with tiles of the other.  The order in which each CTA pair works through the tiles is planned
- * on the host (toc3d_b200/chain_plan.py) and passed as
- *   sched int32 [units, sched_len]: tile ids, -1 terminated.  id g < tiles0 = ceil(M/256) * ceil(N0/tile_n0):
- *        problem 0, row block g / num_n0, column block g % num_n0; else j = g - tiles0: problem 1, row block
- *        j / num_n1, column block j % num_n1.  Every tile exactly once.  Lists must be executable in order without
- *        a cyclic wait (the planner simulates this); a violated schedule traps after 4 s.
- *   units <= toc3d_gemm_chain_units() (all pairs co-resident);  tile widths: e0->tile_n / e1->tile_n (0 = 256).
- *   sync  int32 [2 * ceil(M/256)], zeroed ONCE by the caller; the kernel leaves it zeroed. */
+/* Consecutive GEMMs of a block as ONE persistent launch - OPT-IN (plugin options fuse_mlp / fuse_block_tail,
+ * default off; same tiles, same k order and integer statistics as the separate toc3d_gemm_bf16 launches, so the
+ * results are bit-identical to them):
+ *   nprob = 2, the SwiGLU MLP (eva_vit.py:44-51: w3(ffn_ln(silu(w1 x) * (w2 x)))):
+ *     problem 0: SWIGLU  hid[M, N0/2] = epilogue of A[M,K0] * B0[N0,K0]^T   (out = hid, row_stats required)
+ *     problem 1: RESID   epilogue of hid[M, N0/2] * B1[N1, N0/2]^T          (ln_stats == problem 0's row_stats)
+ *   nprob = 3, the attention output projection with norm2 folded (eva_vit.py:113,263) in front of it:
+ *     problem 0: RESID with a_out + row_stats (+ zero_stats), no out_map;  problem 1: SWIGLU with ln_stats ==
+ *     problem 0's row_stats and A == problem 0's a_out;  problem 2: as problem 1 of the 2-chain.
+ * Problem q's A / lda / K must be the bf16 output of problem q-1.  A problem-q tile of a 256-row block starts as
+ * soon as the problem-(q-1) tiles of that row block have been stored (arrival counters in `sync`), so there is no
+ * launch boundary, no further prologue, and the ragged last wave of one GEMM is filled with tiles of the next.  The
+ * order in which each CTA pair works through the tiles is planned on the host (toc3d_b200/chain_plan.py):
+ *   sched int32 [units, sched_len <= 256]: tile ids, -1 terminated.  Problem q owns the ids [base_q, base_q+1),
+ *        base_0 = 0, base_q+1 = base_q + ceil(M/256) * ceil(N_q / tile_n_q); (row block, column block) =
+ *        divmod(id - base_q, ceil(N_q / tile_n_q)).  Every tile exactly once.  Lists must be executable in order
+ *        without a cyclic wait (the planner proves this); a violated schedule traps after 4 s.
+ *   units <= toc3d_gemm_chain_units() (all pairs co-resident);  tile widths: epi->tile_n (0 = 256).
+ *   sync  int32 [2 * (nprob - 1) * ceil(M/256)], zeroed ONCE by the caller; the kernel leaves it zeroed. */
+typedef struct toc3d_chain_problem {
+  const void* A;             /* bf16 [M, K], leading dimension lda */
+  int64_t lda;
+  const void* B;             /* bf16 [N, K] (nn.Linear layout), leading dimension ldb */
+  int64_t ldb;
+  int32_t N, K;
+  int32_t kind;              /* toc3d_epilogue_kind */
+  const toc3d_epilogue* epi; /* host */
+} toc3d_chain_problem;
+
 int toc3d_gemm_chain_units(void);
-int toc3d_mlp_chain_bf16(const void* A, int64_t lda, const void* B0, int64_t ldb0, int32_t N0, int32_t K0,
-                         const toc3d_epilogue* e0 /* host */, const void* B1, int64_t ldb1, int32_t N1,
-                         const toc3d_epilogue* e1 /* host */, int32_t M, const int32_t* sched, int32_t units,
-                         int32_t sched_len, int32_t* sync, void* stream);
+int toc3d_gemm_chain_bf16(const toc3d_chain_problem* probs /* host */, int32_t nprob, int32_t M, const int32_t* sched,
+                          int32_t units, int32_t sched_len, int32_t* sync, void* stream);
 
 /* ------------------------------------------------------------------ windowed attention
  * softmax(q k^T) v per (window, head); q already rotated and scaled by the QKV epilogue.

@@ -91,6 +91,53 @@ def test_mlp_chain_with_few_pairs(lib, units):
         assert torch.equal(r, g), name
 
 
+def _tail_case(M, C, Hd, seed):
+    """proj (norm2 folded) + MLP: the operands of _mlp_case plus the proj weights and the norm2-fold vectors."""
+    c = _mlp_case(M, C, Hd, False, seed)
+    g = torch.Generator().manual_seed(seed + 1)
+    c["ao"] = torch.randn(M, C, generator=g).to(DEV).bfloat16()
+    c["wp"] = (torch.randn(C, C, generator=g) * 0.05).to(DEV).bfloat16()
+    c["bp"] = (torch.randn(C, generator=g) * 0.1).to(DEV)
+    c["u12"] = torch.randn(2 * c["Hp"], generator=g).to(DEV)
+    return c
+
+
+def _run_tail(lib, c, M, C, Hd, chained):
+    x = c["x"][:M].clone()
+    a = torch.zeros(M, C, device=DEV, dtype=torch.bfloat16)
+    hid = torch.zeros(M, c["Hp"], device=DEV, dtype=torch.bfloat16)
+    st, st2 = torch.ones(M, 2, device=DEV, dtype=torch.int64), torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+    e0 = dict(bias=c["bp"], out=x, ldo=C, resid=x, a_out=a, row_stats=st2, zero_stats=st, tile_n=256)
+    e1 = dict(bias=c["b12"], out=hid, row_stats=st, ln_stats=st2, ln_u=c["u12"], ln_n=C, ln_eps=1e-6, tile_n=256)
+    e2 = dict(bias=c["b3"], out=x, ldo=C, resid=x, ln_stats=st, ln_u=c["u3"], ln_n=Hd, ln_eps=1e-6, tile_n=256)
+    if chained:
+        probs = [(C, C, 256), (2 * c["Hp"], C, 256), (C, c["Hp"], 256)]
+        plan = chain_plan.plan_chain(M, probs, lib.gemm_chain_units())
+        sync = torch.zeros(4 * ((M + 255) // 256), device=DEV, dtype=torch.int32)
+        sched = chain_plan.as_tensor(plan, DEV)
+        for _ in range(2):
+            x.copy_(c["x"][:M]); st.fill_(1); st2.zero_()
+            lib.gemm_chain([(c["ao"], c["wp"], lib.EPI_RESID, e0), (a, c["w12"], lib.EPI_SWIGLU, e1),
+                            (hid, c["w3"], lib.EPI_RESID, e2)], M, sched, sync)
+        torch.cuda.synchronize()
+        assert int(sync.abs().sum()) == 0, "chain counters not reset"
+    else:
+        lib.gemm(c["ao"], c["wp"], lib.EPI_RESID, M=M, **e0)
+        lib.gemm(a, c["w12"], lib.EPI_SWIGLU, M=M, **e1)
+        lib.gemm(hid, c["w3"], lib.EPI_RESID, M=M, **e2)
+    torch.cuda.synchronize()
+    return x, a, hid, st, st2
+
+
+@pytest.mark.parametrize("M,C,Hd", [(300, 256, 341), (1000, 128, 200), (513, 1024, 2730), (4662, 1024, 2730), (6000, 1024, 2730)])
+def test_block_tail_chain_is_bit_identical_to_three_launches(lib, M, C, Hd):
+    c = _tail_case(M, C, Hd, seed=M + 7)
+    ref = _run_tail(lib, c, M, C, Hd, chained=False)
+    got = _run_tail(lib, c, M, C, Hd, chained=True)
+    for name, r, g in zip(("x", "a", "hid", "stats", "stats2"), ref, got):
+        assert torch.equal(r, g), name
+
+
 def test_mlp_chain_rejects_oversubscribed_grid(lib):
     M, C, Hd = 300, 256, 341
     c = _mlp_case(M, C, Hd, False, seed=1)
@@ -104,8 +151,10 @@ def test_mlp_chain_rejects_oversubscribed_grid(lib):
 
 
 @pytest.mark.parametrize("case", ["tiny_prev_small", "tiny_dense"])
-def test_fuse_mlp_forward_is_bit_identical(case):
-    """fuse_mlp=True through the whole plugin (eager and CUDA-graph replay): same features, masks and indices."""
+@pytest.mark.parametrize("option", ["fuse_mlp", "fuse_block_tail"])
+def test_chained_forward_is_bit_identical(case, option):
+    """fuse_mlp / fuse_block_tail through the whole plugin (eager and CUDA-graph replay): same features, masks and
+    indices as the separate launches with the same arithmetic (fuse_block_tail <-> fold_norm2)."""
     fx, kind, cfg, model, sd, inp, gn = case_setup(case)
     ref = run_oracle(kind, cfg, sd, inp, gn)
     kw = dict(gumbel_noise=gn, teacher_scores=ref["scores"]) if kind != "dense" else {}
@@ -113,7 +162,10 @@ def test_fuse_mlp_forward_is_bit_identical(case):
     for fuse in (False, True):
         m = build_model(kind, cfg)
         m.load_state_dict(sd)
-        m.fuse_mlp = fuse
+        if fuse:
+            setattr(m, option, True)
+        elif option == "fuse_block_tail":
+            m.fold_norm2 = True
         m = m.cuda()
         args = dict(x=inp["x"].cuda()) if kind == "dense" else to_cuda(inp)
         with torch.no_grad():

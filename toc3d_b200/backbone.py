@@ -259,7 +259,7 @@ class _Workspace:
         self.stats2 = torch.zeros(rows, 2, device=dev, dtype=torch.int64)  # norm2 statistics of the post-attention rows
         self.merge_cnt = torch.zeros(max(v["nW"] for v in self.win.values()), device=dev, dtype=torch.int32)
         # fuse_mlp: per-row-block arrival counters of the chained MLP launch (zeroed once, the kernel leaves them zero)
-        self.chain_sync = torch.zeros(2 * ((rows + 255) // 256), device=dev, dtype=torch.int32)
+        self.chain_sync = torch.zeros(4 * ((rows + 255) // 256), device=dev, dtype=torch.int32)
         self.stage = {}                                # (stage, ws) -> selection tables
 
 
@@ -269,11 +269,13 @@ class _Engine:
     def __init__(self, model, device):
         self.device = device
         m = model
-        self.fold_norm2 = bool(getattr(model, "fold_norm2", False))
-        self.fuse_mlp = bool(getattr(model, "fuse_mlp", False))
+        self.fuse_block_tail = bool(getattr(model, "fuse_block_tail", False))
+        # the 3-problem chain starts with the proj GEMM in its norm2-fold form (a_out + statistics)
+        self.fold_norm2 = bool(getattr(model, "fold_norm2", False)) or self.fuse_block_tail
+        self.fuse_mlp = bool(getattr(model, "fuse_mlp", False)) and not self.fuse_block_tail
         if self.fuse_mlp and self.fold_norm2:
-            raise NotImplementedError("fuse_mlp and fold_norm2 are separate experiments; enable one of them")
-        self.chain_scheds = {}                            # M -> device schedule of the chained MLP launch
+            raise NotImplementedError("fuse_mlp runs the MLP without the norm2 fold; use fuse_block_tail with fold_norm2")
+        self.chain_scheds = {}                            # (problems, M) -> device schedule of a chained launch
         self.C, self.heads, self.patch = m.embed_dim, m.num_heads, m.patch_size
         self.block_ws = [b.window_size for b in m.blocks]
         self.block_acc = [b.accelerate for b in m.blocks]
@@ -392,19 +394,36 @@ class _Engine:
         [0, M) must be zero on entry (zeroed by the norm2 launch or by the proj epilogue)."""
         if self.fuse_mlp:
             # both GEMMs in one persistent launch; the per-pair tile lists are planned once per M (chain_plan.py)
-            sched = self.chain_scheds.get(M)
-            if sched is None:
-                plan = chain_plan.plan_mlp_chain(M, bp["w12"].shape[0], self.C, self.C, L.gemm_chain_units())
-                sched = self.chain_scheds[M] = chain_plan.as_tensor(plan, self.device)
-            L.mlp_chain(wsp.a, bp["w12"], bp["w3"], M, sched, wsp.chain_sync,
-                        dict(bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, tile_n=256),
-                        dict(bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"], ln_n=self.Hd, ln_eps=LN_EPS,
-                             tile_n=256, **resid_kw))
+            L.gemm_chain(self._mlp_problems(bp, wsp, resid_kw), M, self._chain_sched(2, bp, M), wsp.chain_sync)
             return
         ln = dict(ln_stats=wsp.stats2, ln_u=bp["u12"], ln_n=self.C, ln_eps=LN_EPS) if self.fold_norm2 else {}
         L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, **ln)
         L.gemm(wsp.hid, bp["w3"], L.EPI_RESID, M=M, bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"],
                ln_n=self.Hd, ln_eps=LN_EPS, **resid_kw)
+
+    def _mlp_problems(self, bp, wsp, resid_kw):
+        """The two MLP GEMMs as problems of a chained launch (same epilogue keywords as the separate launches)."""
+        ln = dict(ln_stats=wsp.stats2, ln_u=bp["u12"], ln_n=self.C, ln_eps=LN_EPS) if self.fold_norm2 else {}
+        return [(wsp.a, bp["w12"], L.EPI_SWIGLU, dict(bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, tile_n=256, **ln)),
+                (wsp.hid, bp["w3"], L.EPI_RESID, dict(bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"],
+                                                      ln_n=self.Hd, ln_eps=LN_EPS, tile_n=256, **resid_kw))]
+
+    def _chain_sched(self, nprob, bp, M):
+        key = (nprob, M)
+        if key not in self.chain_scheds:
+            probs = chain_plan.mlp_probs(bp["w12"].shape[0], self.C, self.C)
+            if nprob == 3:
+                probs = [(self.C, self.C, 256)] + probs
+            plan = chain_plan.plan_chain(M, probs, L.gemm_chain_units())
+            self.chain_scheds[key] = chain_plan.as_tensor(plan, self.device)
+        return self.chain_scheds[key]
+
+    def _block_tail_chain(self, bp, wsp, M, proj_kw, mlp_kw):
+        """fuse_block_tail: proj (+ residual, norm2 folded) -> w1/w2 + SwiGLU -> w3 (+ residual), eva_vit.py:113,261-266,
+        as ONE chained launch of three problems (no norm2 launch either)."""
+        proj = (wsp.ao, bp["wproj"], L.EPI_RESID, dict(bias=bp["bproj"], ldo=self.C, tile_n=256, **proj_kw,
+                                                       **self._proj_kw(wsp)))
+        L.gemm_chain([proj] + self._mlp_problems(bp, wsp, mlp_kw), M, self._chain_sched(3, bp, M), wsp.chain_sync)
 
     def _proj_kw(self, wsp):
         """Extra outputs of the proj GEMM when norm2 is folded: bf16 copy of the new residual rows (A operand of
@@ -441,6 +460,9 @@ class _Engine:
         L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None)
         self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"],
                        q_rows=w["q_rows"], item_order=w["item_order"], join=fs)
+        if self.fuse_block_tail:
+            self._block_tail_chain(bp, wsp, VN, dict(out=X, resid=X), dict(out=X, resid=X))
+            return
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X, **self._proj_kw(wsp))
         if not self.fold_norm2:
             L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
@@ -498,11 +520,15 @@ class _Engine:
                           counters=wsp.merge_cnt)
         self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"],
                        q_rows=t["q_rows"], item_order=t["item_order"])
-        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
-               resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
-        if not self.fold_norm2:
-            L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
-        self._mlp(bp, wsp, Mc, out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T)     # t2 -> image rows
+        if self.fuse_block_tail:
+            self._block_tail_chain(bp, wsp, Mc, dict(out=wsp.T, resid=X, resid_map=t["ctok"], out_alt=wsp.T),
+                                   dict(out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T))
+        else:
+            L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
+                   resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
+            if not self.fold_norm2:
+                L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
+            self._mlp(bp, wsp, Mc, out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T)     # t2 -> image rows
         L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C, rep_row=t["rep_row"])
 
     # -- scorers ----------------------------------------------------------------------------
@@ -583,6 +609,9 @@ class _EvaBase(nn.Module):
         # host-planned tile order (toc3d_mlp_chain_bf16 + chain_plan.py).  Bit-identical results by construction;
         # OFF until it has been verified and measured on B200 (written in a session without GPU time left).
         self.fuse_mlp = False
+        # proj (norm2 folded) + both MLP GEMMs as one chained launch of three problems; implies the fold_norm2 weights.
+        # Compile-checked only (written after the last GPU minute of round 1); numerics = the tested fold_norm2 option.
+        self.fuse_block_tail = False
         # views are independent: with G > 1 the forward runs G groups of views on their own streams inside the
         # one CUDA graph, so the tail / epilogue of one group's kernels overlaps the other group's kernels
         self.view_groups = 1

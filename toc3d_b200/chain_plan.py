@@ -1,16 +1,17 @@
-"""Host-side planner for toc3d_mlp_chain_bf16 (include/toc3d_b200.h): which CTA pair runs which tile, in what order.
+"""Host-side planner for toc3d_gemm_chain_bf16 (include/toc3d_b200.h): which CTA pair runs which tile, in what order.
 
-The chain kernel runs the two GEMMs of the SwiGLU MLP (eva_vit.py:44-51) in one persistent launch.  Tiles of problem 1
-(w3) wait for the problem-0 tiles (w1/w2 + SwiGLU) of their 256-row block.  The shapes of this path are static per
+The chain kernel runs consecutive GEMMs of a block in one persistent launch: the two GEMMs of the SwiGLU MLP
+(eva_vit.py:44-51), optionally preceded by the attention output projection with norm2 folded (eva_vit.py:113,263).
+A tile of problem q > 0 waits for all problem q-1 tiles of its 256-row block.  The shapes of this path are static per
 (token grid, stage, window size), so the work list of every CTA pair is planned here once and uploaded:
 
-  * tile ids as in the header: g < tiles0 -> problem 0, (row block, column block) = divmod(g, num_n0);
-    else problem 1 with divmod(g - tiles0, num_n1);
+  * tile ids as in the header: problem q owns ids [base[q], base[q+1]); (row block, column block) =
+    divmod(id - base[q], num_n[q]);
   * cost model in k-block units (one 256 x BN x 64 MMA step of a pair): a tile costs num_k + c_fix, its results are
     visible e_lat units after its last MMA (the epilogue runs under the next tile's mainloop);
-  * candidates: "sequential" (all problem-0 tiles round-robin, then all problem-1 tiles - what two launches do, minus
-    the launch boundary) and greedy list schedules that keep `reserve` problem-1 tiles back for full final waves and
-    start the others as soon as their row block is complete; the candidate with the smallest simulated makespan wins.
+  * candidates: "sequential" (problem after problem, round-robin - what separate launches do, minus the launch
+    boundaries) and greedy list schedules that keep `reserve` tiles of the last problem back for full final waves and
+    start every other dependent tile as soon as its row block is complete; the smallest simulated makespan wins.
 
 Deadlock freedom does not depend on the cost model: verify() checks that every tile appears exactly once and that
 list order + dependencies form a DAG, i.e. the lists can always be executed in order whatever the real timing is.
@@ -21,30 +22,41 @@ from collections import namedtuple
 
 BM_PAIR = 256          # rows of a pair tile (gemm_tcgen05.cu: 2 * BM)
 BK = 64
+E_LAT = 12.0           # k-block units between a tile's last MMA and its results being visible to other pairs
 
-Shape = namedtuple("Shape", "num_m num_n0 num_n1 k0 k1 tiles0 tiles1")
+Shape = namedtuple("Shape", "num_m num_n k tiles base")          # num_n / k / tiles: one entry per problem
 Plan = namedtuple("Plan", "lists units sched_len makespan strategy shape")
 
 
-def chain_shape(M, N0, K0, N1, bn0=256, bn1=256):
+def chain_shape(M, probs):
+    """probs: [(N, K, tile_n), ...] in chain order."""
     num_m = (M + BM_PAIR - 1) // BM_PAIR
-    num_n0 = (N0 + bn0 - 1) // bn0
-    num_n1 = (N1 + bn1 - 1) // bn1
-    k0 = (K0 + BK - 1) // BK
-    k1 = (N0 // 2 + BK - 1) // BK
-    return Shape(num_m, num_n0, num_n1, k0, k1, num_m * num_n0, num_m * num_n1)
+    num_n = tuple((N + bn - 1) // bn for N, _, bn in probs)
+    k = tuple((K + BK - 1) // BK for _, K, _ in probs)
+    tiles = tuple(num_m * n for n in num_n)
+    base = [0]
+    for t in tiles:
+        base.append(base[-1] + t)
+    return Shape(num_m, num_n, k, tiles, tuple(base))
+
+
+def mlp_probs(N0, K0, N1, bn0=256, bn1=256):
+    """The SwiGLU MLP: [M,K0] x [N0,K0]^T (interleaved w1|w2) -> hidden N0/2 -> [N1, N0/2]^T."""
+    return [(N0, K0, bn0), (N1, N0 // 2, bn1)]
 
 
 def tile_info(sh, g):
     """-> (problem, row block, column block)"""
-    if g < sh.tiles0:
-        return (0,) + divmod(g, sh.num_n0)
-    return (1,) + divmod(g - sh.tiles0, sh.num_n1)
+    q = 0
+    while g >= sh.base[q + 1]:
+        q += 1
+    return (q,) + divmod(g - sh.base[q], sh.num_n[q])
 
 
 def verify(sh, lists):
     """Every tile exactly once; list order + row-block dependencies acyclic (executable in order).  Raises ValueError."""
-    total = sh.tiles0 + sh.tiles1
+    total = sh.base[-1]
+    nq = len(sh.tiles)
     seen = [0] * total
     for l in lists:
         for g in l:
@@ -53,18 +65,20 @@ def verify(sh, lists):
             seen[g] += 1
     if any(c != 1 for c in seen):
         raise ValueError("schedule does not cover every tile exactly once")
-    # Kahn on: predecessor in the same list -> tile; every problem-0 tile of row block m -> every problem-1 tile of m.
-    # Row-block nodes keep the edge count linear: A(m, *) -> R(m) -> B(m, *).
-    indeg = [0] * (total + sh.num_m)
+    # Kahn on: predecessor in the same list -> tile; every problem q-1 tile of row block m -> every problem q tile of m.
+    # Row-block nodes R(q, m) keep the edge count linear: tiles(q-1, m, *) -> R(q, m) -> tiles(q, m, *).
+    rnode = lambda q, m: total + (q - 1) * sh.num_m + m            # q in [1, nq)
+    indeg = [0] * (total + (nq - 1) * sh.num_m)
     nxt = [-1] * total
     for l in lists:
         for a, b in zip(l, l[1:]):
             nxt[a] = b
             indeg[b] += 1
-    for g in range(sh.tiles0, total):
-        indeg[g] += 1                                  # from its row-block node
-    for m in range(sh.num_m):
-        indeg[total + m] = sh.num_n0
+    for g in range(sh.base[1], total):
+        indeg[g] += 1                                              # from its row-block node
+    for q in range(1, nq):
+        for m in range(sh.num_m):
+            indeg[rnode(q, m)] = sh.num_n[q - 1]
     ready = [g for g in range(total) if indeg[g] == 0]
     done = 0
     while ready:
@@ -74,65 +88,66 @@ def verify(sh, lists):
         if g < total:
             if nxt[g] >= 0:
                 succ.append(nxt[g])
-            if g < sh.tiles0:
-                succ.append(total + g // sh.num_n0)
+            q, m, _ = tile_info(sh, g)
+            if q + 1 < nq:
+                succ.append(rnode(q + 1, m))
         else:
-            m = g - total
-            succ.extend(sh.tiles0 + m * sh.num_n1 + n for n in range(sh.num_n1))
+            q, m = divmod(g - total, sh.num_m)
+            q += 1
+            succ.extend(sh.base[q] + m * sh.num_n[q] + n for n in range(sh.num_n[q]))
         for s in succ:
             indeg[s] -= 1
             if indeg[s] == 0:
                 ready.append(s)
-    if done != total + sh.num_m:
+    if done != len(indeg):
         raise ValueError("schedule has a cyclic wait (would deadlock)")
 
 
-def simulate(sh, lists, c_fix=1.5, e_lat=(12.0, 10.0), cost_scale=None):
+def simulate(sh, lists, c_fix=1.5, e_lat=E_LAT, cost_scale=None):
     """Makespan of executing `lists` in order under the cost model (k-block units).  cost_scale: optional
     callable(g) -> factor, to test robustness against a wrong model."""
-    total = sh.tiles0 + sh.tiles1
-    row_ready = [0.0] * sh.num_m               # time the last problem-0 result of a row block is visible
-    row_left = [sh.num_n0] * sh.num_m
+    nq = len(sh.tiles)
+    row_ready = [[0.0] * sh.num_m for _ in range(nq)]      # time the last result of (problem, row block) is visible
+    row_left = [[sh.num_n[q]] * sh.num_m for q in range(nq)]
     pos = [0] * len(lists)
     free = [0.0] * len(lists)
     end = 0.0
     heap = [(0.0, p) for p in range(len(lists)) if lists[p]]
     heapq.heapify(heap)
-    blocked = {}                               # row block -> pairs waiting for it
+    blocked = {}                                           # (problem, row block) -> pairs waiting for it
     executed = 0
     while heap:
         t, p = heapq.heappop(heap)
         g = lists[p][pos[p]]
         q, m, _ = tile_info(sh, g)
-        if q == 1 and row_left[m] > 0:
-            blocked.setdefault(m, []).append(p)
+        if q > 0 and row_left[q - 1][m] > 0:
+            blocked.setdefault((q - 1, m), []).append(p)
             continue
-        start = max(t, row_ready[m]) if q == 1 else t
-        cost = (sh.k1 if q else sh.k0) + c_fix
+        start = max(t, row_ready[q - 1][m]) if q > 0 else t
+        cost = sh.k[q] + c_fix
         if cost_scale is not None:
             cost *= cost_scale(g)
         fin = start + cost
         executed += 1
-        end = max(end, fin + e_lat[q])
-        if q == 0:
-            row_ready[m] = max(row_ready[m], fin + e_lat[0])
-            row_left[m] -= 1
-            if row_left[m] == 0:
-                for w in blocked.pop(m, []):
-                    heapq.heappush(heap, (free[w], w))
+        end = max(end, fin + e_lat)
+        row_ready[q][m] = max(row_ready[q][m], fin + e_lat)
+        row_left[q][m] -= 1
+        if row_left[q][m] == 0:
+            for w in blocked.pop((q, m), []):
+                heapq.heappush(heap, (free[w], w))
         pos[p] += 1
         free[p] = fin
         if pos[p] < len(lists[p]):
             heapq.heappush(heap, (fin, p))
-    if executed != total:
+    if executed != sh.base[-1]:
         raise ValueError("schedule deadlocks in simulation")
     return end
 
 
 def _sequential(sh, units):
-    """Problem 0 column-major round-robin (the order of the stand-alone GEMM), then problem 1 row-major."""
-    order = [m * sh.num_n0 + n for n in range(sh.num_n0) for m in range(sh.num_m)]
-    order += [sh.tiles0 + j for j in range(sh.tiles1)]
+    """Problem 0 column-major round-robin (the order of the stand-alone GEMM), then the other problems row-major."""
+    order = [m * sh.num_n[0] + n for n in range(sh.num_n[0]) for m in range(sh.num_m)]
+    order += list(range(sh.base[1], sh.base[-1]))
     lists = [[] for _ in range(units)]
     for i, g in enumerate(order):
         lists[i % units].append(g)
@@ -140,55 +155,61 @@ def _sequential(sh, units):
 
 
 def _greedy(sh, units, reserve, c_fix, e_lat):
-    """Event-driven list schedule: a free pair takes (1) an 'early' problem-1 tile whose row block is complete, else
-    (2) the next problem-0 tile (row-major, so row blocks complete one after the other), else (3) the next remaining
-    problem-1 tile.  The last `reserve` problem-1 tiles (by row) are never taken early."""
-    n_early = max(0, sh.tiles1 - reserve)
-    a_next, b_next = 0, 0                      # next problem-0 / problem-1 tile (both in row-major id order)
-    row_ready = [0.0] * sh.num_m
-    row_left = [sh.num_n0] * sh.num_m
+    """Event-driven list schedule.  A free pair takes, deepest problem first, a dependent tile whose row block is
+    complete and visible; else the next problem-0 tile (row-major, so row blocks complete one after the other); else,
+    when problem 0 is used up, the next tile of the shallowest unfinished problem (all its producers are placed then)
+    and waits for it.  The last `reserve` tiles of the last problem are only taken once every other problem is used
+    up, so that they form whole waves at the end."""
+    nq = len(sh.tiles)
+    last = nq - 1
+    n_early = max(0, sh.tiles[last] - reserve)
+    nxt = [0] * nq                                         # next tile of each problem (row-major order)
+    row_ready = [[0.0] * sh.num_m for _ in range(nq)]
+    row_left = [[sh.num_n[q]] * sh.num_m for q in range(nq)]
     lists = [[] for _ in range(units)]
     heap = [(0.0, p) for p in range(units)]
     heapq.heapify(heap)
-    cA, cB = sh.k0 + c_fix, sh.k1 + c_fix
-    while heap and (a_next < sh.tiles0 or b_next < sh.tiles1):
+    remaining = sh.base[-1]
+    while remaining:
         t, p = heapq.heappop(heap)
-        take_b = False
-        if b_next < sh.tiles1:
-            mb = b_next // sh.num_n1
-            complete = row_left[mb] == 0
-            if a_next >= sh.tiles0:
-                take_b = True                   # (3): only problem-1 tiles are left; all their producers are placed
-            elif b_next < n_early and complete and row_ready[mb] <= t:
-                take_b = True                   # (1)
-        if take_b:
-            mb = b_next // sh.num_n1
-            start = max(t, row_ready[mb])
-            lists[p].append(sh.tiles0 + b_next)
-            b_next += 1
-            heapq.heappush(heap, (start + cB, p))
-        else:
-            m = a_next // sh.num_n0
-            lists[p].append(a_next)
-            a_next += 1
-            fin = t + cA
-            row_left[m] -= 1
-            row_ready[m] = max(row_ready[m], fin + e_lat[0])
-            heapq.heappush(heap, (fin, p))
+        pick = None
+        for q in range(last, 0, -1):
+            if nxt[q] >= sh.tiles[q]:
+                continue
+            m = nxt[q] // sh.num_n[q]
+            if row_left[q - 1][m] or row_ready[q - 1][m] > t:
+                continue
+            if q == last and nxt[q] >= n_early and any(nxt[r] < sh.tiles[r] for r in range(last)):
+                continue
+            pick = q
+            break
+        if pick is None:
+            pick = next(q for q in range(nq) if nxt[q] < sh.tiles[q])      # shallowest unfinished problem
+        q = pick
+        m = nxt[q] // sh.num_n[q]
+        assert q == 0 or row_left[q - 1][m] == 0
+        start = max(t, row_ready[q - 1][m]) if q else t
+        lists[p].append(sh.base[q] + nxt[q])
+        nxt[q] += 1
+        remaining -= 1
+        fin = start + sh.k[q] + c_fix
+        row_left[q][m] -= 1
+        row_ready[q][m] = max(row_ready[q][m], fin + e_lat)
+        heapq.heappush(heap, (fin, p))
     return lists
 
 
-def plan_mlp_chain(M, N0, K0, N1, max_units, bn0=256, bn1=256, c_fix=1.5, e_lat=(12.0, 10.0)):
+def plan_chain(M, probs, max_units, c_fix=1.5, e_lat=E_LAT):
     """-> Plan.  lists[p] = tile ids of CTA pair p in execution order; units = pairs used (<= max_units)."""
-    sh = chain_shape(M, N0, K0, N1, bn0, bn1)
-    units = max(1, min(max_units, sh.tiles0 + sh.tiles1))
+    sh = chain_shape(M, probs)
+    units = max(1, min(max_units, sh.base[-1]))
     cands = [("sequential", _sequential(sh, units))]
-    reserves = {0, sh.tiles1}
+    tl = sh.tiles[-1]
+    reserves = {0, tl, tl % units}
     w = 1
-    while w * units <= sh.tiles1:
+    while w * units <= tl:
         reserves.add(w * units)
         w += 1
-    reserves.add(sh.tiles1 % units)
     for r in sorted(reserves):
         cands.append(("greedy(reserve=%d)" % r, _greedy(sh, units, r, c_fix, e_lat)))
     best = None
@@ -202,17 +223,22 @@ def plan_mlp_chain(M, N0, K0, N1, max_units, bn0=256, bn1=256, c_fix=1.5, e_lat=
     return Plan(lists, len(lists), max(len(l) for l in lists) + 1, t, name, sh)
 
 
-def two_launch_makespan(M, N0, K0, N1, units, bn0=256, bn1=256, c_fix=1.5, e_lat=(12.0, 10.0), launch=6.0):
-    """The same cost model for the two separate launches the chain replaces (round-robin waves per GEMM, plus the
-    exposed epilogue and prologue at the launch boundary) - for reporting the expected gain only."""
-    sh = chain_shape(M, N0, K0, N1, bn0, bn1)
-    w0 = -(-sh.tiles0 // units)
-    w1 = -(-sh.tiles1 // units)
-    return w0 * (sh.k0 + c_fix) + e_lat[0] + launch + w1 * (sh.k1 + c_fix) + e_lat[1]
+def plan_mlp_chain(M, N0, K0, N1, max_units, bn0=256, bn1=256, **kw):
+    return plan_chain(M, mlp_probs(N0, K0, N1, bn0, bn1), max_units, **kw)
+
+
+def separate_launch_makespan(M, probs, units, c_fix=1.5, e_lat=E_LAT, launch=6.0):
+    """The same cost model for the separate launches the chain replaces (round-robin waves per GEMM, plus the exposed
+    epilogue and prologue at every launch boundary) - for reporting the expected gain only."""
+    sh = chain_shape(M, probs)
+    t = 0.0
+    for q in range(len(sh.tiles)):
+        t += -(-sh.tiles[q] // units) * (sh.k[q] + c_fix) + e_lat + (launch if q else 0.0)
+    return t
 
 
 def as_tensor(plan, device=None):
-    """int32 [units, sched_len] tensor, -1 padded (the `sched` argument of toc3d_mlp_chain_bf16)."""
+    """int32 [units, sched_len] tensor, -1 padded (the `sched` argument of toc3d_gemm_chain_bf16)."""
     import torch
     t = torch.full((plan.units, plan.sched_len), -1, dtype=torch.int32)
     for p, l in enumerate(plan.lists):

@@ -30,6 +30,11 @@ class Epilogue(ctypes.Structure):
     ]
 
 
+class ChainProblem(ctypes.Structure):
+    _fields_ = [("A", _c_void_p), ("lda", _c_i64), ("B", _c_void_p), ("ldb", _c_i64), ("N", _c_int), ("K", _c_int),
+                ("kind", _c_int), ("epi", ctypes.POINTER(Epilogue))]
+
+
 class PadFill(ctypes.Structure):
     _fields_ = [("qkv", _c_void_p), ("cmap", _c_void_p), ("rope_rows", _c_void_p), ("Mp", _c_int), ("kpad", _c_void_p),
                 ("vpad", _c_void_p), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p), ("ft", _c_int)]
@@ -41,8 +46,8 @@ _SIGS = {
     "toc3d_gemm_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int,
                          ctypes.POINTER(Epilogue), _c_void_p], _c_int),
     "toc3d_gemm_chain_units": ([], _c_int),
-    "toc3d_mlp_chain_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, ctypes.POINTER(Epilogue), _c_void_p, _c_i64,
-                              _c_int, ctypes.POINTER(Epilogue), _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p], _c_int),
+    "toc3d_gemm_chain_bf16": ([ctypes.POINTER(ChainProblem), _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p],
+                              _c_int),
     "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                               _c_float, _c_int, _c_void_p, _c_void_p], _c_int),
@@ -162,22 +167,30 @@ def gemm_chain_units():
     return n
 
 
-def mlp_chain(A, B0, B1, M, sched, sync, epi0, epi1):
-    """SwiGLU MLP as one launch (toc3d_mlp_chain_bf16).  epi0 / epi1: keyword dicts of the SWIGLU / RESID epilogues
-    exactly as they would be passed to two gemm() calls; sched int32 [units, sched_len] from chain_plan.plan_mlp_chain
-    (planned for the same M and tile widths); sync int32 [>= 2 * ceil(M / 256)], zeroed once."""
-    for t, n in ((A, "A"), (B0, "B0"), (B1, "B1")):
-        _want(t, torch.bfloat16, n)
+def gemm_chain(probs, M, sched, sync):
+    """Consecutive GEMMs as one launch (toc3d_gemm_chain_bf16).  probs: [(A, B, kind, epilogue keywords), ...] exactly
+    as they would be passed to separate gemm() calls, in chain order (2: SWIGLU, RESID; 3: RESID + a_out, SWIGLU, RESID);
+    sched int32 [units, sched_len] from chain_plan.plan_chain (planned for the same M, shapes and tile widths);
+    sync int32 [>= 2 * (len(probs) - 1) * ceil(M / 256)], zeroed once."""
     _want(sched, torch.int32, "sched"); _want(sync, torch.int32, "sync")
-    N0, K0 = B0.shape
-    N1, K1 = B1.shape
-    assert A.shape[1] == K0 and K1 == N0 // 2 and A.stride(1) == 1 and B0.stride(1) == 1 and B1.stride(1) == 1
-    assert sched.dim() == 2 and sync.numel() >= 2 * ((M + 255) // 256)
-    e0, e1 = _epilogue(**epi0), _epilogue(**epi1)
-    rc = load().toc3d_mlp_chain_bf16(A.data_ptr(), A.stride(0), B0.data_ptr(), B0.stride(0), N0, K0, ctypes.byref(e0),
-                                     B1.data_ptr(), B1.stride(0), N1, ctypes.byref(e1), M, _p(sched), sched.shape[0],
-                                     sched.shape[1], _p(sync), _stream())
-    _check(rc, "toc3d_mlp_chain_bf16")
+    assert sched.dim() == 2 and sync.numel() >= 2 * (len(probs) - 1) * ((M + 255) // 256)
+    arr = (ChainProblem * len(probs))()
+    keep = []
+    for i, (A, B, kind, epi) in enumerate(probs):
+        _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
+        N, K = B.shape
+        assert A.shape[1] >= K and A.stride(1) == 1 and B.stride(1) == 1
+        e = _epilogue(**epi)
+        keep.append(e)
+        arr[i].A = A.data_ptr(); arr[i].lda = A.stride(0); arr[i].B = B.data_ptr(); arr[i].ldb = B.stride(0)
+        arr[i].N = N; arr[i].K = K; arr[i].kind = kind; arr[i].epi = ctypes.pointer(e)
+    rc = load().toc3d_gemm_chain_bf16(arr, len(probs), M, _p(sched), sched.shape[0], sched.shape[1], _p(sync), _stream())
+    _check(rc, "toc3d_gemm_chain_bf16")
+
+
+def mlp_chain(A, B0, B1, M, sched, sync, epi0, epi1):
+    """The SwiGLU MLP as one launch: gemm_chain over [SWIGLU(A, B0), RESID(hid, B1)]."""
+    gemm_chain([(A, B0, EPI_SWIGLU, epi0), (epi0["out"], B1, EPI_RESID, epi1)], M, sched, sync)
 
 
 def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None, q_rows=None, item_order=None):

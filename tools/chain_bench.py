@@ -57,6 +57,38 @@ def main():
             t1.record()
             torch.cuda.synchronize()
             res[name] = t0.elapsed_time(t1) / n * 1e3
+        # block tail: proj (norm2 folded) + MLP as three launches vs one chain of three problems
+        ao = torch.randn(M, C, generator=g).to(DEV).bfloat16()
+        wp = (torch.randn(C, C, generator=g) * 0.02).to(DEV).bfloat16()
+        bp = torch.zeros(C, device=DEV); u12 = torch.ones(2 * Hp, device=DEV)
+        stats2 = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
+        t0p = dict(bias=bp, out=x, ldo=C, resid=x, a_out=a, row_stats=stats2, zero_stats=stats, tile_n=256)
+        t1p = dict(e0, ln_stats=stats2, ln_u=u12, ln_n=C, ln_eps=1e-6)
+        plan3 = chain_plan.plan_chain(M, [(C, C, 256)] + chain_plan.mlp_probs(2 * Hp, C, C), units)
+        sched3 = chain_plan.as_tensor(plan3, DEV)
+        sync3 = torch.zeros(4 * ((M + 255) // 256), device=DEV, dtype=torch.int32)
+
+        def three():
+            lib.gemm(ao, wp, lib.EPI_RESID, M=M, **t0p)
+            lib.gemm(a, w12, lib.EPI_SWIGLU, M=M, **t1p)
+            lib.gemm(hid, w3, lib.EPI_RESID, M=M, **e1)
+
+        def chain3():
+            lib.gemm_chain([(ao, wp, lib.EPI_RESID, t0p), (a, w12, lib.EPI_SWIGLU, t1p), (hid, w3, lib.EPI_RESID, e1)], M, sched3, sync3)
+
+        for name, fn in (("three", three), ("chain3", chain3)):
+            for _ in range(3):
+                fn()
+            torch.cuda.synchronize()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(20):
+                fn()
+            t1.record()
+            torch.cuda.synchronize()
+            res[name] = t0.elapsed_time(t1) / 20 * 1e3
+        print("         proj+MLP: three launches %.1f us, chain of three %.1f us (%+.1f %%)  plan=%s" % (
+            res["three"], res["chain3"], (res["chain3"] / res["three"] - 1) * 100, plan3.strategy))
         fl = 2.0 * M * C * (2 * Hp) + 2.0 * M * Hp * C
         print("M=%5d  two %.1f us (%.0f TF/s)  chain %.1f us (%.0f TF/s)  %+.1f %%  [sequential order %.1f us]  plan=%s model %.0f -> %.0f" % (
             M, res["two"], fl / res["two"] * 1e-6, res["chain"], fl / res["chain"] * 1e-6,

@@ -15,11 +15,13 @@ done
 TOC3D_ATTN_SPLIT=1 timeout 600 python -m pytest tests/test_backbone_gpu.py -m gpu -x -q --no-header -p no:cacheprovider --timeout=600 2>&1 | tail -4 | tee gpurun_out/backbone_split1.log
 timeout 400 python bench.py > gpurun_out/bench_default.json 2> gpurun_out/bench_default.err
 timeout 400 python bench.py --fuse-mlp > gpurun_out/bench_fuse_mlp.json 2> gpurun_out/bench_fuse_mlp.err
+timeout 400 python bench.py --fuse-block-tail > gpurun_out/bench_fuse_tail.json 2> gpurun_out/bench_fuse_tail.err
+TOC3D_CHAIN_SIG=1 timeout 400 python bench.py --fuse-block-tail > gpurun_out/bench_fuse_tail_sig.json 2> gpurun_out/bench_fuse_tail_sig.err
 TOC3D_CHAIN_SIG=1 timeout 400 python bench.py --fuse-mlp > gpurun_out/bench_fuse_mlp_sig.json 2> gpurun_out/bench_fuse_mlp_sig.err
 TOC3D_ATTN_SPLIT=1 timeout 400 python bench.py > gpurun_out/bench_attn_split.json 2> gpurun_out/bench_attn_split.err
 python - <<'PY'
 import json
-for n in ("default", "fuse_mlp", "fuse_mlp_sig", "attn_split"):
+for n in ("default", "fuse_mlp", "fuse_mlp_sig", "fuse_tail", "fuse_tail_sig", "attn_split"):
     try:
         d = json.load(open("gpurun_out/bench_%s.json" % n))
         b = d["roofline"]["breakdown"]
