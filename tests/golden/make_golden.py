@@ -28,6 +28,8 @@ CASES = {
     "tiny_dense": ("dense", {k: v for k, v in TINY.items() if k in CONFIGS["eva_vit_l"][1]},
                    (160, 352), 1, 0.1, True, 3, 1),
     "vitl_faster_1view": ("toc3d", CONFIGS["toc3d_faster"][1], (320, 800), 1, 0.1, True, 4, 16),
+    # the 1600x800 token grid (50 x 100: 28 ragged ws16 windows and 15 ws20 windows per view, N = 5000)
+    "tiny_prev_1600": ("toc3d", dict(TINY, token_ratio=[0.5, 0.4, 0.3]), (800, 1600), 1, 0.1, True, 5, 8),
 }
 
 
