@@ -606,7 +606,7 @@ class _EvaBase(nn.Module):
         # epilogue - 162.9 vs 169 samples/s.  Set before the first forward (or call refresh_weights()) to change.
         self.fold_norm2 = False
         # the two GEMMs of the SwiGLU MLP as ONE persistent launch with per-row-block dependency counters and a
-        # host-planned tile order (toc3d_mlp_chain_bf16 + chain_plan.py).  Bit-identical results by construction;
+        # host-planned tile order (toc3d_gemm_chain_bf16 + chain_plan.py).  Bit-identical results by construction;
         # OFF until it has been verified and measured on B200 (written in a session without GPU time left).
         self.fuse_mlp = False
         # proj (norm2 folded) + both MLP GEMMs as one chained launch of three problems; implies the fold_norm2 weights.

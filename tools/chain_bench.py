@@ -1,4 +1,4 @@
-"""Kernel-level timing of the SwiGLU MLP: two toc3d_gemm_bf16 launches vs the chained launch (toc3d_mlp_chain_bf16),
+"""Kernel-level timing of the SwiGLU MLP: two toc3d_gemm_bf16 launches vs the chained launch (toc3d_gemm_chain_bf16),
 EVA-ViT-L shapes, CUDA events over trains of launches (warm L2, like tools/gemm_bench.py)."""
 import sys
 import os
@@ -93,7 +93,7 @@ def main():
         print("M=%5d  two %.1f us (%.0f TF/s)  chain %.1f us (%.0f TF/s)  %+.1f %%  [sequential order %.1f us]  plan=%s model %.0f -> %.0f" % (
             M, res["two"], fl / res["two"] * 1e-6, res["chain"], fl / res["chain"] * 1e-6,
             (res["chain"] / res["two"] - 1) * 100, res["seq"], plan.strategy,
-            chain_plan.two_launch_makespan(M, 2 * Hp, C, C, units), plan.makespan))
+            chain_plan.separate_launch_makespan(M, chain_plan.mlp_probs(2 * Hp, C, C), units), plan.makespan))
 
 
 if __name__ == "__main__":
