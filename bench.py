@@ -475,6 +475,39 @@ def run_native(args):
         "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
         "clocks": clocks, "roofline": roofline,
     }
+    if world > 1 and args.overlap_gather:
+        # experiment (not the headline): the all-gather of step i runs on its own stream behind forward(i) and overlaps
+        # forward(i+1) - what a pipelined deployment would do; the timed region ends when the last gather has landed.
+        # The L2 flushes are inside this region (they are outside the per-step events of `value`).
+        gs = torch.cuda.Stream(device=dev)
+        gbuf = [gathered, torch.empty_like(gathered)]
+        main = torch.cuda.current_stream()
+
+        def run_overlapped(steps):
+            for i in range(steps):
+                flush.zero_()
+                out = model(**res)
+                lf = out["last_feat"] if isinstance(out, dict) else out.img_feats["last_feat"]
+                ev = torch.cuda.Event()
+                ev.record(main)
+                with torch.cuda.stream(gs):
+                    gs.wait_event(ev)
+                    dist.all_gather_into_tensor(gbuf[i % 2], lf.permute(0, 2, 3, 1))
+                    lf.record_stream(gs)
+            main.wait_stream(gs)
+
+        run_overlapped(3)
+        barrier()
+        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        o0.record()
+        run_overlapped(args.steps)
+        o1.record()
+        barrier()
+        ot = torch.tensor([o0.elapsed_time(o1)], device=dev, dtype=torch.float64)
+        dist.all_reduce(ot, op=dist.ReduceOp.MAX)
+        line["overlap_gather"] = {"value": world * B * args.steps / (ot.item() * 1e-3), "unit": UNIT,
+                                  "ms_per_step": ot.item() / args.steps,
+                                  "note": "all-gather of step i overlaps forward(i+1); L2 flushes inside the region; not the headline"}
     if world == 1 and args.batch == 1 and not args.no_batch4:
         # context, not the headline: the same forward with 4 samples (24 views) per launch - at batch 1 the 200-odd
         # kernels of a 5 ms step are latency bound, a serving deployment with several streams would batch them
@@ -534,6 +567,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch4", action="store_true", help="skip the extra batch-4 throughput line")
     ap.add_argument("--view-groups", type=int, default=None, help="override the plugin's view_groups (streams of views)")
+    ap.add_argument("--overlap-gather", action="store_true", help="experiment (N > 1): extra line with the all-gather overlapped")
     ap.add_argument("--fuse-mlp", action="store_true", help="experiment: both MLP GEMMs of a block as one chained launch")
     ap.add_argument("--fuse-block-tail", action="store_true", help="experiment: proj (norm2 folded) + MLP as one chained launch")
     args = ap.parse_args()
