@@ -113,3 +113,14 @@ def test_dense_model_sequences():
 
 TINY_DENSE = {k: v for k, v in TINY.items() if k not in ("pc_range", "pruning_num_queries", "pruning_loc", "accelerate_global",
                                                          "token_ratio", "token_selection_loss", "rope_acc")}
+
+
+def test_chained_launches_refuse_concurrent_view_groups():
+    """A chained launch is deadlock-free only when its whole grid is co-resident: two of them on concurrent streams
+    (view_groups > 1) are refused before anything is launched."""
+    import pytest
+    m = _toc3d()
+    with pytest.raises(NotImplementedError, match="co-resident"):
+        dryrun.run(m, _inputs(), fuse_mlp=True, view_groups=2)
+    m = _toc3d()
+    assert "gemm_chain:2" not in dryrun.names(dryrun.run(m, _inputs(), view_groups=2))      # default path still runs

@@ -873,6 +873,10 @@ class ToC3DEVAViT(_EvaBase):
             ev_q = torch.cuda.Event()
             ev_q.record(side)
         G = self.view_groups if (tap is None and self.view_groups > 1 and V % self.view_groups == 0) else 1
+        if G > 1 and (eng.fuse_mlp or eng.fuse_block_tail):
+            # two chained launches on concurrent streams could each be partially resident and wait for each other's SMs
+            raise NotImplementedError("chained launches (fuse_mlp / fuse_block_tail) need the whole grid co-resident; "
+                                      "they cannot be combined with view_groups > 1")
         if G > 1 and q_kw is not None:
             Bf = q_kw["temp_queries"].shape[0]
             vg = V // G
