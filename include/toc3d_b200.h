@@ -126,6 +126,9 @@ int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int3
  *        divmod(id - base_q, ceil(N_q / tile_n_q)).  Every tile exactly once.  Lists must be executable in order
  *        without a cyclic wait (the planner proves this); a violated schedule traps after 4 s.
  *   units <= toc3d_gemm_chain_units() (all pairs co-resident);  tile widths: epi->tile_n (0 = 256).
+ *        Two chained launches must not run CONCURRENTLY on one device (different streams): each could be partially
+ *        resident and wait for tiles of pairs that the other one keeps off the SMs.  Kernels that finish on their
+ *        own (everything else in this library, NCCL) may overlap a chained launch.
  *   sync  int32 [2 * (nprob - 1) * ceil(M/256)], zeroed ONCE by the caller; the kernel leaves it zeroed. */
 typedef struct toc3d_chain_problem {
   const void* A;             /* bf16 [M, K], leading dimension lda */
