@@ -9,13 +9,15 @@ def p_col_split(c, c0, n):
     return 16 * c if c < c0 else 16 * (n + c)
 
 
-@pytest.mark.parametrize("seq", list(range(1, 257)))
+@pytest.mark.parametrize("seq", list(range(1, 449)))
 def test_split_layout_is_hazard_free(seq):
+    """seq <= 256: ping-pong kernel (256-column slots); 256 < seq <= 448: single-slot kernel (512 columns, O last)."""
     spad = (seq + 15) // 16 * 16
     n = (seq + 31) // 32
     c0 = (n + 1) // 2
-    deferred = spad <= 192
-    o_cols = set(range(192, 256)) if deferred else set(range(64, 128))
+    slot = 256 if seq <= 256 else 512
+    deferred = spad <= 192 or slot == 512                      # O disjoint from the scores
+    o_cols = set(range(slot - 64, slot)) if deferred else set(range(64, 128))
     s_cols = set(range(spad))                                  # written by S = Q K^T
     chunks = {0: list(range(0, c0)), 1: list(range(n - 1, c0 - 1, -1))}     # exp-pass order of each half
     region = {h: set(col for c in chunks[h] for col in range(32 * c, 32 * c + 32)) for h in (0, 1)}
@@ -28,7 +30,7 @@ def test_split_layout_is_hazard_free(seq):
             w = set(range(p_col_split(c, c0, n), p_col_split(c, c0, n) + 16))
             assert w.isdisjoint(unread), "P chunk %d overwrites unread scores of its own half" % c
             assert w.isdisjoint(region[1 - h]), "P chunk %d lands in the other half's score range" % c
-            assert max(w) < 256 and w.isdisjoint(o_cols), "P chunk %d outside the slot or on O" % c
+            assert max(w) < slot and w.isdisjoint(o_cols), "P chunk %d outside the slot or on O" % c
             for col in w:
                 assert col not in p_cols, "two P chunks share column %d" % col
                 p_cols[col] = (c, col - p_col_split(c, c0, n))

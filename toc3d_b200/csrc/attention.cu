@@ -992,6 +992,120 @@ window_attention_pp2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat1
   }
 }
 
+
+// Split-softmax variant of the single-slot kernel (256 < seq <= 448; same opt-in switch).  The single-slot kernel has
+// ONE softmax warp per scheduler - the least latency hiding of all - so here too two warps share a lane quarter and
+// split the key columns (layout and exchange as above); S occupies [0, spad) <= 448 and O the last 64 of the 512
+// columns, so nothing aliases.  warp 0: TMA + MMA issue; warps 1-4: half 0; warps 5-8: half 1.
+constexpr int TC2_THREADS = 32 + 8 * 32;
+constexpr int TC2_XCH_BYTES = 2 * 4 * 2 * 32 * 4;   // {max, sum} x quarter x half x lane
+
+__global__ void __launch_bounds__(TC2_THREADS)
+window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
+                            const int* __restrict__ out_map, const int* __restrict__ q_rows) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  const int Tmax = (seq + 127) >> 7;
+  const int nb = (seq + BOX_ROWS - 1) / BOX_ROWS;
+  uint8_t* sQ = smem;
+  uint8_t* sK = sQ + 2 * Tmax * BOX_BYTES;
+  uint8_t* sV = sK + nb * BOX_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + nb * BOX_BYTES);
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
+  float* xch = reinterpret_cast<float*>(sV + nb * BOX_BYTES + 128);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int h = blockIdx.x, w = blockIdx.y;
+  const int T = ((q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq) + 127) >> 7;
+  const int C = heads * D;
+  const int row0 = w * seq;
+  constexpr int tmem_cols = 512;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tm);
+    mbar_init(&bars[BAR_QK], 1);
+    mbar_init(&bars[BAR_V], 1);
+    mbar_init(&bars[BAR_S], 1);
+    mbar_init(&bars[BAR_P], 256);
+    mbar_init(&bars[BAR_O], 1);
+    mbar_init(&bars[BAR_OFREE], 256);
+    fence_barrier_init();
+  }
+  if (warp == 0) tmem_alloc(tmem_ptr, (uint32_t)tmem_cols);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+  pdl_wait();
+  pdl_launch_dependents();
+
+  const int spad = (seq + 15) & ~15;
+  const int n = (seq + 31) >> 5;
+  const int c0 = (n + 1) >> 1;
+  const uint32_t o_col = (uint32_t)tmem_cols - 64u;          // host: spad <= 448, so O never aliases S / P
+
+  if (warp == 0) {
+    if (elect_one_sync()) {
+      mbar_arrive_expect_tx(&bars[BAR_QK], (uint32_t)((2 * T + nb) * BOX_BYTES));
+      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_QK], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
+      for (int b = 0; b < 2 * T; ++b) tma_load_2d(&tm, &bars[BAR_QK], sQ + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
+      mbar_arrive_expect_tx(&bars[BAR_V], (uint32_t)(nb * BOX_BYTES));
+      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_V], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
+      mbar_wait(&bars[BAR_QK], 0);
+      tcgen05_fence_after();
+      issue_qk(tmem_base, sQ, sK, spad);
+      tcgen05_commit(&bars[BAR_S]);
+      for (int t = 0; t < T; ++t) {
+        mbar_wait(&bars[BAR_P], t & 1);                     // both halves of P(t) are in TMEM (over S(t))
+        if (t == 0) mbar_wait(&bars[BAR_V], 0);
+        else mbar_wait(&bars[BAR_OFREE], (t - 1) & 1);      // O(t-1) has been read out
+        tcgen05_fence_after();
+        issue_pv_split(tmem_base + o_col, tmem_base, sV, spad, c0, n);
+        tcgen05_commit(&bars[BAR_O]);
+        if (t + 1 < T) {
+          issue_qk(tmem_base, sQ + (t + 1) * 2 * BOX_BYTES, sK, spad);   // executes after PV(t): may overwrite P(t)
+          tcgen05_commit(&bars[BAR_S]);
+        }
+      }
+    }
+  } else {
+    const int quarter = warp & 3;
+    const int half = (warp - 1) >> 2;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
+    float* xmax = xch + (quarter * 2) * 32;
+    float* xsum = xmax + 4 * 2 * 32;
+    for (int t = 0; t < T; ++t) {
+      const int q = t * 128 + quarter * 32 + lane;
+      int dst = q < seq ? row0 + q : -1;
+      if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
+      const bool active = t * 128 + quarter * 32 < seq;
+      const uint32_t parity = (uint32_t)(t & 1);
+      mbar_wait(&bars[BAR_S], parity);
+      tcgen05_fence_after();
+      const float sum = softmax_half(lane_base, seq, n, c0, half, lane, active, xmax, xsum, 1 + quarter);
+      tcgen05_fence_before();
+      mbar_arrive(&bars[BAR_P]);
+      mbar_wait(&bars[BAR_O], parity);
+      tcgen05_fence_after();
+      uint32_t o[32];
+      if (active) {
+        tmem_ld_32x32(lane_base + o_col + (uint32_t)(half * 32), o);
+        tmem_ld_wait();
+      }
+      tcgen05_fence_before();
+      mbar_arrive(&bars[BAR_OFREE]);
+      if (active && dst >= 0) store_o_half(o, sum, out + (size_t)dst * C + h * D + half * 32);
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 0) {
+    tcgen05_fence_after();
+    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
+  }
+}
+
 }  // namespace attn_tc
 
 #ifdef TOC3D_ATTN_TRACE
@@ -1073,6 +1187,21 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
       return 0;
     }
     const int spad = (seq_len + 15) & ~15;
+    {
+      static const bool split = getenv("TOC3D_ATTN_SPLIT") != nullptr && getenv("TOC3D_ATTN_SPLIT")[0] == '1';
+      if (split) {
+        static bool configured3 = false;
+        if (!configured3) {
+          TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                227 * 1024));
+          configured3 = true;
+        }
+        const size_t smem2 = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128 + attn_tc::TC2_XCH_BYTES;
+        TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc2_kernel, dim3(heads, n_windows), dim3(attn_tc::TC2_THREADS), smem2,
+                                    st, 1, tm, o, seq_len, heads, out_map, q_rows));
+        return 0;
+      }
+    }
     const int tmem_cols = spad <= 256 ? 256 : 512;     // <= 256 keys: two CTAs per SM (O may alias the tail of S)
     const size_t smem = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128;
     TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc_kernel, dim3(heads, n_windows), dim3(attn_tc::NTHREADS), smem, st,
