@@ -131,7 +131,17 @@ def build_preprocess_case():
     return dict(meta=dict(cases=PREPROCESS_CASES, cv2=cv2.__version__, **IMG_NORM), outs=outs)
 
 
+def build_vis_case():
+    """Row f4: the arrays the reference's token_selection_vis (models/utils/token_select_vis.py:8-79) hands to
+    mmcv.imwrite for the seeded case of tests/test_vis.py (mmcv stubbed through the cv2 calls it makes)."""
+    from tests.test_vis import run_reference, vis_case
+    return run_reference(*vis_case())
+
+
 def main():
+    import numpy as np
+    np.savez_compressed(os.path.join(HERE, "token_vis.npz"), **build_vis_case())
+    print("token_vis written")
     fx = build_preprocess_case()
     torch.save(fx, os.path.join(HERE, "preprocess_cv2.pt"))
     print("preprocess_cv2", [tuple(o.shape) for o in fx["outs"]])
