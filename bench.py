@@ -160,18 +160,55 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- reference arm (CPU)
-def oracle_step_fn(name, views_sample):
-    """The oracle port of the reference forward on the host cores, on `views_sample` views of the
-    workload (bounded sample).  bench.py is one of the two places allowed to execute oracle/."""
+def workload_config(name, batch, world):
+    """The `config` object of the JSON line - identical in both arms (the driver compares them)."""
+    kind, cfg, hw = CONFIGS[name]
+    return {"workload": name, "backbone": kind, "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": batch,
+            "prev_exists": True, "weights": "random-init EVA-ViT-L + ToC3D selectors (seed 0)",
+            "parallelism": "dp%d (views x batch sharded, all-gather of the feature list)" % world}
+
+
+def reference_step_fn(name, views, device="cpu", autocast=False, batch=1):
+    """One forward of the reference on `batch` samples of `views` views.  Prefers the reference's OWN modules
+    (unmodified sources from /root/reference or the staged baseline/_ref/, imported by tests/golden/ref_import.py with
+    its third-party stubs; the stable-sort / injected-noise pins do not change the work done); falls back to the
+    oracle port when the sources are not present.  bench.py is one of the two places allowed to execute oracle/.
+    -> (step, kind) with kind in {"reference", "port"}."""
+    import contextlib
+    import io
+    kind, cfg, hw = CONFIGS[name]
+    inp = make_inputs(batch, views, hw, seed=0)
+    gn = make_gumbel(batch * views, (hw[0] // 16) * (hw[1] // 16))
+    try:
+        from tests.golden.ref_import import load_reference, reference_available
+        have_ref = reference_available()
+    except Exception:
+        have_ref = False
+    if have_ref:
+        ns = load_reference()
+        torch.manual_seed(0)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = (ns.ToC3DEVAViT if kind == "ToC3DEVAViT" else ns.EVA_ViT)(**cfg).eval()
+        m.load_state_dict(randomize_state_dict(m.state_dict(), seed=0, bias_std=0.02))
+        m = m.to(device)
+        d = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in inp.items()}
+        gnd = [g.to(device) for g in gn]
+
+        def step():
+            ns.set_gumbel(gnd)
+            with torch.no_grad(), torch.autocast(device_type=torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
+                if kind == "EVA_ViT":
+                    return m(d["x"])["last_feat"]
+                return m(**d).img_feats["last_feat"]
+        return step, "reference"
+    if device != "cpu":
+        raise RuntimeError("the oracle port is a CPU checker; the GPU-eager reference leg needs baseline/_ref (tools/stage_ref.sh)")
     from oracle import toc3d_oracle as O
     from toc3d_b200 import EVA_ViT, ToC3DEVAViT
-    kind, cfg, hw = CONFIGS[name]
     torch.manual_seed(0)
     model = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
     sd = randomize_state_dict(model.state_dict(), seed=0, bias_std=0.02)
     del model
-    inp = make_inputs(1, views_sample, hw, seed=0)
-    gn = make_gumbel(views_sample, (hw[0] // 16) * (hw[1] // 16))
 
     def step():
         with torch.no_grad():
@@ -179,7 +216,13 @@ def oracle_step_fn(name, views_sample):
                 return O.forward_dense(sd, cfg, inp["x"])
             return O.forward_toc3d(sd, cfg, inp["x"], inp["temp_queries"], inp["temp_ref_points"], inp["temp_vel"],
                                    inp["temp_timestamp"], inp["temp_ego_pose"], inp["ego_pose_inv"], True, gn)
-    return step
+    return step, "port"
+
+
+def reference_views(name):
+    """Views per CPU step: the whole 6-view sample at 800x320 (a few seconds per step); one view at 1600x800, where a
+    6-view step takes the best part of a minute on the host cores - reported as extrapolated."""
+    return VIEWS if CONFIGS[name][2][0] * CONFIGS[name][2][1] <= 320 * 800 else 1
 
 
 def run_reference(args):
@@ -188,26 +231,31 @@ def run_reference(args):
         return
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    views_sample = 1
-    step = oracle_step_fn(args.config, views_sample)
-    for _ in range(max(1, min(args.warmup, 2))):
+    views = reference_views(args.config)
+    step, rkind = reference_step_fn(args.config, views)
+    for _ in range(args.warmup):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = (time.perf_counter() - t0) / args.steps
-    value = 1.0 / (dt * VIEWS / views_sample)
-    sample = "%d of %d views per step (fp32 oracle port of the reference forward, %d torch threads); scaled x%d" % (
-        views_sample, VIEWS, cores, VIEWS // views_sample)
-    kind, cfg, hw = CONFIGS[args.config]
-    emit({
+    scale = VIEWS // views
+    value = 1.0 / (dt * scale)
+    what = {"reference": "the reference's own ToC3DEVAViT / EVA_ViT modules (unmodified sources, third-party imports stubbed)",
+            "port": "fp32 oracle port of the reference forward (reference sources not present)"}[rkind]
+    sample = "%d of %d views per step, fp32, torch.no_grad, %d torch threads: %s%s" % (
+        views, VIEWS, cores, what, "" if scale == 1 else "; scaled x%d (extrapolated)" % scale)
+    line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": dt * 1e3 * VIEWS / views_sample, "higher_is_better": True,
+        "warmup": args.warmup, "ms_per_step": dt * 1e3 * scale, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": {"workload": args.config, "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": 1},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+        "config": workload_config(args.config, 1, args.gpus),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": rkind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    })
+    }
+    if scale != 1:
+        line["extrapolated"] = True
+    emit(line)
 
 
 # ------------------------------------------------------------------------------- native arm (B200)
@@ -454,15 +502,13 @@ def run_native(args):
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
         "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
         "data": "synthetic",
-        "config": {"workload": args.config, "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": B,
-                   "prev_exists": True, "weights": "random-init EVA-ViT-L + ToC3D selectors (seed 0)",
-                   "parallelism": "dp%d (views x batch sharded, all-gather of last_feat)" % world,
-                   "l2": "256 MiB buffer zeroed between timed steps (L2 flush)",
-                   "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate",
-                   "launch": "whole forward replayed as one CUDA graph per call",
-                   "e2e_pipeline": "per step: pinned-host inputs -> H2D, forward, last_feat -> D2H to pinned host; copies "
-                                   "double-buffered on copy streams (overlap the neighbouring steps' forward); the L2 "
-                                   "flush between steps is inside the e2e timed region"},
+        "config": workload_config(args.config, B, world),
+        "native_details": {"l2": "256 MiB buffer zeroed between timed steps (L2 flush)",
+                           "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate",
+                           "launch": "whole forward replayed as one CUDA graph per call",
+                           "e2e_pipeline": "per step: pinned-host inputs -> H2D, forward, last_feat -> D2H to pinned host; copies "
+                                           "double-buffered on copy streams (overlap the neighbouring steps' forward); the L2 "
+                                           "flush between steps is inside the e2e timed region"},
         # link_gbs = bytes moved per step / step time: when it sits at the host link's rate (6 GB/s both directions
         # together on the slowest boxes of the pool) the e2e number is bound by the copies, not by the forward
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -520,16 +566,36 @@ def run_native(args):
                                      "note": "4 samples per launch, device-resident inputs; not the headline"}
         del res4
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # the reference on the same box: its own modules on the B200 in PyTorch eager, fp32 and bf16
+        # autocast - the number the native result should be read against; then on the host cores (cpu_baseline)
+        try:
+            gpu_ref = {}
+            for label, ac in (("fp32", False), ("bf16_autocast", True)):
+                step, rkind = reference_step_fn(args.config, VIEWS, device=dev, autocast=ac)
+                for _ in range(3):
+                    step()
+                t_ms, _ = timed(step, 5)
+                gpu_ref[label] = {"value": 5 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / 5}
+                del step
+                torch.cuda.empty_cache()
+            gpu_ref["what"] = ("the reference's own module (.cuda(), torch %s eager, ATen/cuBLAS/cuDNN kernels), same weights and "
+                               "inputs, 6 views, batch 1, L2 flushed between steps" % torch.__version__)
+            line["reference_gpu_eager"] = gpu_ref
+        except Exception as ex:  # reference sources not staged: say so, do not guess
+            line["reference_gpu_eager"] = {"unavailable": str(ex)[:200]}
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
-        step = oracle_step_fn(args.config, 1)
+        views = reference_views(args.config)
+        step, rkind = reference_step_fn(args.config, views)
         step()
         t0 = time.perf_counter(); n = 0
         while n < 3 or (time.perf_counter() - t0 < 10 and n < 10):
             step(); n += 1
         dt = (time.perf_counter() - t0) / n
-        line["cpu_baseline"] = {"value": 1.0 / (dt * VIEWS), "unit": UNIT, "cores": cores, "kind": "port",
-                                "sample": "1 of 6 views x %d runs, fp32 oracle port of the reference, scaled x6" % n}
+        scale = VIEWS // views
+        line["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": UNIT, "cores": cores, "kind": rkind,
+                                "sample": "%d of 6 views x %d forwards after 1 warm-up, fp32, %d torch threads%s" % (
+                                    views, n, cores, "" if scale == 1 else ", scaled x%d (extrapolated)" % scale)}
     if rank == 0:
         emit(line)
     if world > 1:

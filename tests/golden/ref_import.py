@@ -15,9 +15,11 @@ unspecified:
          image-level calls (last dim 2) and returns ones for the window-level
          calls (last dim 1, result discarded by the caller).
 
-This file is never imported by the product and cannot run on the GPU box
-(/root/reference is absent there); it exists to generate tests/golden/*.pt
-and to validate oracle/ against the real reference in this container.
+This file is never imported by the product.  It exists to generate
+tests/golden/*.pt, to validate oracle/ against the real reference in this
+container, and - through the staged copy baseline/_ref/ (tools/stage_ref.sh,
+git-ignored, travels with the gpurun snapshot) - to let bench.py time the
+reference's own modules on the GPU box, where /root/reference is absent.
 """
 import importlib
 import os
@@ -27,11 +29,24 @@ import types
 import torch
 import torch.nn as nn
 
-REF_ROOT = os.environ.get("TOC3D_REFERENCE_ROOT", "/root/reference")
+_REPO = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+
+def _find_root():
+    """TOC3D_REFERENCE_ROOT, else /root/reference (build container), else the git-ignored staged copy
+    baseline/_ref/ (tools/stage_ref.sh; travels to the GPU box with the gpurun snapshot)."""
+    cands = [os.environ.get("TOC3D_REFERENCE_ROOT"), "/root/reference", os.path.join(_REPO, "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "projects", "mmdet3d_plugin", "models", "backbones")):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REF_ROOT, "projects", "mmdet3d_plugin"))
+    return os.path.isdir(os.path.join(REF_ROOT, "projects", "mmdet3d_plugin", "models", "backbones"))
 
 
 class _Registry:
