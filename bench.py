@@ -282,8 +282,8 @@ def run_native(args):
     model.set_image_preprocess(**IMG_NORM)       # row f3: lets forward() take the uint8 camera crops as well
     if args.view_groups is not None and hasattr(model, "view_groups"):
         model.view_groups = args.view_groups
-    if args.fuse_mlp or args.fuse_block_tail:    # opt-in chained launches; default off
-        model.fuse_mlp, model.fuse_block_tail = bool(args.fuse_mlp), bool(args.fuse_block_tail)
+    if args.fold_norm2:                          # tested option (norm2 inside the proj / SwiGLU epilogues); default off
+        model.fold_norm2 = True
         model.refresh_weights()
     B = args.batch
     V = B * VIEWS
@@ -403,8 +403,8 @@ def run_native(args):
     #     device-side sleep is queued first so the host runs ahead and the events bracket kernels, not launch gaps.
     work = algorithmic_work(cfg, kind, hw, V)
     recs = []
-    names = ["gemm", "gemm_chain", "window_attention", "layernorm_rows", "ln_gather_merge", "fill_pad_kv", "fill_pad_kv_rope", "compact_rows", "subln", "window_topk", "topk_split", "merge_fast_tokens",
-             "fast_token_update", "score_fold_queries", "score_tokens", "score_finish", "im2col_patch16", "mask_rows",
+    names = ["gemm", "window_attention", "layernorm_rows", "ln_gather_merge", "fill_pad_kv", "fill_pad_kv_rope", "compact_rows", "subln", "window_topk", "topk_split", "merge_fast_tokens",
+             "fast_token_update", "motion_queries_fold", "score_tokens", "score_finish", "im2col_patch16", "mask_rows",
              "global_half_mean"]
     saved = {n: getattr(L, n) for n in names}
     kind_names = {L.EPI_LINEAR: "linear", L.EPI_QKV_ROPE: "qkv_rope", L.EPI_RESID: "resid", L.EPI_SWIGLU: "swiglu"}
@@ -425,15 +425,9 @@ def run_native(args):
                 # algorithmic bytes: A + B once, output once (+ fp32 residual for RESID, half-width bf16 for SWIGLU)
                 by = 2.0 * m * k_ + 2.0 * n_ * k_ + {L.EPI_RESID: 8.0 * m * n_, L.EPI_SWIGLU: 1.0 * m * n_}.get(
                     a[2], (4.0 if kw.get("out_f32") else 2.0) * m * n_)
-            elif name == "gemm_chain":                    # (probs, M, sched, sync): chained GEMMs in one launch
-                m = a[1]
-                label = "gemm_chain%d" % len(a[0])
-                for _, Bw, kd, _ in a[0]:
-                    n_, k_ = Bw.shape
-                    fl += 2.0 * m * n_ * k_
-                    by += 2.0 * m * k_ + 2.0 * n_ * k_ + (8.0 if kd == L.EPI_RESID else 1.0) * m * n_
             elif name == "window_attention":              # (qkv, out, nW, seq, heads): QK^T + PV, head dim 64
                 fl = 4.0 * a[2] * a[4] * a[3] * a[3] * 64
+                label = "window_attention_%dx%d" % (a[2], a[3])
             elif name == "layernorm_rows":                # (x, gamma, beta, out, M, C, ...): fp32 in, bf16 out
                 by = a[4] * a[5] * 6.0
             elif name == "ln_gather_merge":               # (..., nW, k, n_fast, C, eps): packed rows LN + fast rows read
@@ -634,8 +628,7 @@ def main():
     ap.add_argument("--no-batch4", action="store_true", help="skip the extra batch-4 throughput line")
     ap.add_argument("--view-groups", type=int, default=None, help="override the plugin's view_groups (streams of views)")
     ap.add_argument("--overlap-gather", action="store_true", help="experiment (N > 1): extra line with the all-gather overlapped")
-    ap.add_argument("--fuse-mlp", action="store_true", help="experiment: both MLP GEMMs of a block as one chained launch")
-    ap.add_argument("--fuse-block-tail", action="store_true", help="experiment: proj (norm2 folded) + MLP as one chained launch")
+    ap.add_argument("--fold-norm2", action="store_true", help="tested option: norm2 folded into the proj / SwiGLU GEMM epilogues")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":

@@ -26,7 +26,7 @@
 extern "C" {
 #endif
 
-#define TOC3D_B200_ABI_VERSION 13
+#define TOC3D_B200_ABI_VERSION 14
 
 int toc3d_abi_version(void);
 /* Thread-local message of the last failing call ("" if none). Host pointer. */
@@ -107,42 +107,6 @@ typedef struct toc3d_epilogue {
 
 int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,
                     int32_t epilogue_kind, const toc3d_epilogue* epi /* host */, void* stream);
-
-/* Consecutive GEMMs of a block as ONE persistent launch - OPT-IN (plugin options fuse_mlp / fuse_block_tail,
- * default off; same tiles, same k order and integer statistics as the separate toc3d_gemm_bf16 launches, so the
- * results are bit-identical to them):
- *   nprob = 2, the SwiGLU MLP (eva_vit.py:44-51: w3(ffn_ln(silu(w1 x) * (w2 x)))):
- *     problem 0: SWIGLU  hid[M, N0/2] = epilogue of A[M,K0] * B0[N0,K0]^T   (out = hid, row_stats required)
- *     problem 1: RESID   epilogue of hid[M, N0/2] * B1[N1, N0/2]^T          (ln_stats == problem 0's row_stats)
- *   nprob = 3, the attention output projection with norm2 folded (eva_vit.py:113,263) in front of it:
- *     problem 0: RESID with a_out + row_stats (+ zero_stats), no out_map;  problem 1: SWIGLU with ln_stats ==
- *     problem 0's row_stats and A == problem 0's a_out;  problem 2: as problem 1 of the 2-chain.
- * Problem q's A / lda / K must be the bf16 output of problem q-1.  A problem-q tile of a 256-row block starts as
- * soon as the problem-(q-1) tiles of that row block have been stored (arrival counters in `sync`), so there is no
- * launch boundary, no further prologue, and the ragged last wave of one GEMM is filled with tiles of the next.  The
- * order in which each CTA pair works through the tiles is planned on the host (toc3d_b200/chain_plan.py):
- *   sched int32 [units, sched_len <= 256]: tile ids, -1 terminated.  Problem q owns the ids [base_q, base_q+1),
- *        base_0 = 0, base_q+1 = base_q + ceil(M/256) * ceil(N_q / tile_n_q); (row block, column block) =
- *        divmod(id - base_q, ceil(N_q / tile_n_q)).  Every tile exactly once.  Lists must be executable in order
- *        without a cyclic wait (the planner proves this); a violated schedule traps after 4 s.
- *   units <= toc3d_gemm_chain_units() (all pairs co-resident);  tile widths: epi->tile_n (0 = 256).
- *        Two chained launches must not run CONCURRENTLY on one device (different streams): each could be partially
- *        resident and wait for tiles of pairs that the other one keeps off the SMs.  Kernels that finish on their
- *        own (everything else in this library, NCCL) may overlap a chained launch.
- *   sync  int32 [2 * (nprob - 1) * ceil(M/256)], zeroed ONCE by the caller; the kernel leaves it zeroed. */
-typedef struct toc3d_chain_problem {
-  const void* A;             /* bf16 [M, K], leading dimension lda */
-  int64_t lda;
-  const void* B;             /* bf16 [N, K] (nn.Linear layout), leading dimension ldb */
-  int64_t ldb;
-  int32_t N, K;
-  int32_t kind;              /* toc3d_epilogue_kind */
-  const toc3d_epilogue* epi; /* host */
-} toc3d_chain_problem;
-
-int toc3d_gemm_chain_units(void);
-int toc3d_gemm_chain_bf16(const toc3d_chain_problem* probs /* host */, int32_t nprob, int32_t M, const int32_t* sched,
-                          int32_t units, int32_t sched_len, int32_t* sync, void* stream);
 
 /* ------------------------------------------------------------------ windowed attention
  * softmax(q k^T) v per (window, head); q already rotated and scaled by the QKV epilogue.
@@ -277,13 +241,29 @@ int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t*
                           void* stream);
 
 /* ------------------------------------------------------------------ history-query scorer
- * toc3d_utils.py:232-252 is linear in the token up to the LogSoftmax, so the query bank is
- * folded once per frame into A[f] (2 x C) and c[f] (2):
- *   A = scale * W_agg (2xQ) * queries[f] (QxCq) * W_in (CqxC),  c = scale * W_agg * queries * b_in + b_agg
- * queries fp32 [Bf,Q,Cq]; w_in fp32 [Cq,C]; b_in [Cq]; w_agg [2,Q]; b_agg [2]; A_out [Bf,2,C]; c_out [Bf,2]. */
-int toc3d_score_fold_queries(const float* queries, const float* w_in, const float* b_in, const float* w_agg,
-                             const float* b_agg, float scale, int32_t Bf, int32_t Q, int32_t Cq, int32_t C,
-                             float* A_out, float* c_out, void* stream);
+ * Motion-aware query encoder + scorer folding for ALL S selector stages of one forward (row a12 + a13), two launches.
+ * Replaces MotionAwareQueryGuidedTokenSelector.get_motion_aware_queries (toc3d_utils.py:334-360) with its helpers
+ * transform_reference_points (misc.py:191-200), MLN (misc.py:154-188), pos2posemb3d / pos2posemb1d /
+ * nerf_positional_encoding (positional_encoding.py:14-81), fp32 throughout (the timestamp embedding in fp64 when the
+ * timestamps are fp64, as in the reference), and folds the result: toc3d_utils.py:232-252 is linear in the token up
+ * to the LogSoftmax, so per (stage, frame)
+ *   A = scale * W_agg (2xQ) * q (Qx256) * W_in (256xC),   c = scale * W_agg * q * b_in + b_agg.
+ * blob: fp32 [S, blob_stride] per-stage parameters, packed by the caller in this order (Linear weights TRANSPOSED to
+ *   [in][out]; D = 256):  dimt128[128] dimt256[256] (temperature ** (2 * (i // 2) / F), positional_encoding.py:17,31)
+ *   pc_range[8: 6 used]  query_embedding.0 wT[384][D] b[D]  query_embedding.2 wT[D][D] b[D]
+ *   ego_pose_pe:      reduce.0 wT[180][D] b[D]  gamma wT[D][D] b[D]  beta wT[D][D] b[D]
+ *   ego_pose_queries: reduce.0 wT[180][D] b[D]  gamma wT[D][D] b[D]  beta wT[D][D] b[D]
+ *   time_embedding.0 wT[D][D] b[D]  time_embedding.1 weight[D] bias[D]
+ *   input_proj.0 weight[D][C] (NOT transposed) bias[D]  aggregate.0 weight[2][Q] bias[4: 2 used];
+ *   toc3d_motion_blob_floats(Q, C) returns the number of floats (host-only helper, no CUDA call).
+ * temp_queries fp32 [Bf,Q,256]; ref_points [Bf,Q,3]; vel [Bf,Q,2]; timestamp [Bf,Q] fp32 or fp64 (timestamp_is_f64);
+ * ego_pose [Bf,Q,4,4]; ego_pose_inv [Bf,4,4].  Outputs: q_out [S,Bf,Q,256] (the encoded queries), A_out [S,Bf,2,C],
+ * c_out [S,Bf,2].  Q even, C % 4 == 0. */
+int64_t toc3d_motion_blob_floats(int32_t Q, int32_t C);
+int toc3d_motion_queries_fold(const float* blob, int64_t blob_stride, int32_t S, int32_t Bf, int32_t Q, int32_t C,
+                              const float* temp_queries, const float* ref_points, const float* vel, const void* timestamp,
+                              int32_t timestamp_is_f64, const float* ego_pose, const float* ego_pose_inv, float scale,
+                              float* q_out, float* A_out, float* c_out, void* stream);
 
 /* Per token: logit = mask_in * (x . A[f]) + c[f]; pred = log_softmax(logit) (fp32 [V*N,2]);
  * mask_out = softmax(pred + g)[0] (toc3d_utils.py:147, pin 2) with g = gumbel [V*N,2] or, when
@@ -295,8 +275,8 @@ int toc3d_score_tokens(const float* x, const float* mask_in, const float* A, con
                        int32_t C, int32_t views_per_frame, const float* gumbel, uint64_t seed,
                        const uint64_t* seed_dev, float* pred, float* score, float* mask_out, void* stream);
 
-/* Same tail for the first-frame scorer (toc3d_utils.py:114-129) whose logits come from the MLP
- * GEMM chain: logits fp32 [M,2] -> pred, score, mask_out. */
+/* Same tail for the first-frame scorer (toc3d_utils.py:114-129) whose logits come from its four MLP
+ * GEMMs: logits fp32 [M,2] -> pred, score, mask_out. */
 int toc3d_score_finish(const float* logits, int32_t M, const float* gumbel, uint64_t seed,
                        const uint64_t* seed_dev, float* pred, float* score, float* mask_out, void* stream);
 

@@ -341,6 +341,8 @@ def forward_dense(p, cfg, img, tap=None):
     win, glb = _ropes(c)
     for i in range(c["depth"]):
         g = i in c["global_attn_indexes"]
+        if tap is not None:
+            tap.setdefault("block_in", []).append(x)
         x = dense_block(x, p, i, c["global_window_size"] if g else c["window_size"], c["num_heads"],
                         glb if g else win)
         if tap is not None:

@@ -9,7 +9,6 @@ import torch
 from toc3d_b200 import backbone as BB
 from toc3d_b200 import lib as L
 
-_NO_RECORD = {"load", "gemm_chain_units"}
 
 
 class _Stream:
@@ -42,7 +41,7 @@ def _describe(v):
 
 
 @contextlib.contextmanager
-def recording(units=74):
+def recording():
     """Patches toc3d_b200.lib + torch.cuda inside the block; yields the list of (name, args, kwargs) records."""
     calls = []
     wrappers = [n for n in dir(L) if not n.startswith("_") and callable(getattr(L, n)) and not isinstance(getattr(L, n), type)
@@ -58,8 +57,9 @@ def recording(units=74):
         for n in wrappers:
             if n == "load":
                 st.enter_context(mock.patch.object(L, n, lambda: None))
-            elif n == "gemm_chain_units":
-                st.enter_context(mock.patch.object(L, n, lambda: units))
+            elif n == "motion_blob_floats":          # host-only size helper of the C-ABI (include/toc3d_b200.h layout)
+                st.enter_context(mock.patch.object(L, n, lambda Q, C: 392 + 384 * 256 + 256 + 2 * 256 + 6 * (256 * 256 + 256)
+                                                   + 2 * (180 * 256 + 256) + 256 * C + 256 + 2 * Q + 4))
             else:
                 st.enter_context(mock.patch.object(L, n, recorder(n)))
         st.enter_context(mock.patch.object(torch.cuda, "Stream", _Stream))
@@ -71,7 +71,7 @@ def recording(units=74):
 
 def run(model, inputs, **options):
     """One eager forward of `model` (CPU tensors) under recording(); options are set as model attributes
-    (fuse_mlp, fuse_block_tail, fold_norm2, ...).  -> list of records."""
+    (fold_norm2, view_groups, ...).  -> list of records."""
     for k, v in options.items():
         setattr(model, k, v)
     model.refresh_weights()
@@ -105,8 +105,6 @@ def names(calls):
     for name, a, k, _ in calls:
         if name == "gemm":
             out.append("gemm:%d" % a[2])
-        elif name == "gemm_chain":
-            out.append("gemm_chain:%d" % len(a[0]))
         else:
             out.append(name)
     return out

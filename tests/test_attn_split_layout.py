@@ -1,7 +1,8 @@
-"""TMEM column layout of the split-softmax attention variant (attention.cu: window_attention_pp2_kernel, opt-in
-TOC3D_ATTN_SPLIT=1), replayed on the CPU: for every window length the two warps of a lane quarter must never overwrite
-a score column that either of them still has to read, P must not touch O, and the P V k-steps must address the
-columns where the keys' probabilities were packed.  Mirrors p_col_split / softmax_half / issue_pv_split."""
+"""TMEM column layout of the split-softmax attention kernel for 256 < seq <= 448 (attention.cu:
+window_attention_tc2_kernel), replayed on the CPU: for every window length the two warps of a lane quarter must never
+overwrite a score column that either of them still has to read, P must not touch O, and the P V k-steps must address
+the columns where the keys' probabilities were packed.  Mirrors p_col_split / softmax_half / issue_pv_split.  (The same
+layout rule was measured on the 256-column ping-pong slots too - slower there, removed; the replay still covers it.)"""
 import pytest
 
 

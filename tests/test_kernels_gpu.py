@@ -608,25 +608,69 @@ def test_attention_and_qkv_row_maps(lib):
 
 
 # ------------------------------------------------------------------------------------ scorer
+def _selector_case(seed, Bf, Q=64, C=1024, f64_time=True, bias_std=0.1):
+    """A randomised MotionAwareQueryGuidedTokenSelector parameter set + history-query inputs (rigid random poses)."""
+    from toc3d_b200.backbone import _Selector, pack_motion_blob
+    from toc3d_b200.configs import PC_RANGE
+    from toc3d_b200.synthetic import make_inputs, randomize_state_dict
+    torch.manual_seed(seed)
+    sel = _Selector(C, Q, 0.7, PC_RANGE)
+    sd = randomize_state_dict(sel.state_dict(), seed=seed, bias_std=bias_std, weight_std=0.05)
+    sd["ego_pose_pe.gamma.weight"] = sd["ego_pose_pe.gamma.weight"] * 2          # zero-init in the reference: make them count
+    sel.load_state_dict(sd)
+    p = {"score_predictor.0." + k: v for k, v in sel.state_dict().items()}
+    inp = make_inputs(Bf, 1, (32, 32), seed=seed, num_queries=Q, pose="random")
+    if not f64_time:
+        inp["temp_timestamp"] = inp["temp_timestamp"].float()
+    inp["temp_timestamp"] = inp["temp_timestamp"] * 3.0 - 0.5                     # beyond [0, 1): several periods of the embedding
+    return sel, p, inp, pack_motion_blob(sel, Q, C)
+
+
+@pytest.mark.parametrize("Bf,Q,f64_time", [(1, 64, True), (2, 64, False), (3, 30, True)])
+def test_motion_queries_and_fold(lib, Bf, Q, f64_time):
+    """toc3d_motion_queries_fold (row a12): encoded queries against the oracle's get_motion_aware_queries restatement
+    (toc3d_utils.py:334-360) at 1e-5 relative, folded (A, c) against the fp64 product; two stages in one call."""
+    C = 1024
+    sel0, p0, inp, blob0 = _selector_case(41, Bf, Q, C, f64_time)
+    sel1, p1, _, blob1 = _selector_case(42, Bf, Q, C, f64_time)
+    blob = torch.stack([blob0, blob1]).to(DEV)
+    q_out = torch.empty(2, Bf, Q, 256, device=DEV); A = torch.empty(2, Bf, 2, C, device=DEV); c = torch.empty(2, Bf, 2, device=DEV)
+    d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    lib.motion_queries_fold(blob, d["temp_queries"], d["temp_ref_points"], d["temp_vel"], d["temp_timestamp"], d["temp_ego_pose"],
+                            d["ego_pose_inv"], sel0.scale, C, q_out, A, c)
+    for j, p in enumerate((p0, p1)):
+        ref = O.motion_aware_queries(p, 0, inp["temp_queries"], inp["temp_ref_points"], inp["temp_vel"], inp["temp_timestamp"],
+                                     inp["temp_ego_pose"], inp["ego_pose_inv"])
+        err = (q_out[j].cpu() - ref).abs().max().item() / ref.abs().max().item()
+        print("motion queries stage %d: max-abs %.3g rel %.3g (|ref| max %.2f)" % (j, (q_out[j].cpu() - ref).abs().max().item(), err, ref.abs().max().item()))
+        assert err < 1e-5, err
+        pre = "score_predictor.0."
+        P = p[pre + "aggregate.0.weight"].double() @ q_out[j].cpu().double()                           # [Bf, 2, 256]
+        A_ref = sel0.scale * (P @ p[pre + "input_proj.0.weight"].double())
+        c_ref = sel0.scale * (P @ p[pre + "input_proj.0.bias"].double()) + p[pre + "aggregate.0.bias"].double()
+        assert (A[j].cpu().double() - A_ref).abs().max().item() < 1e-5 * max(1.0, A_ref.abs().max().item())
+        assert (c[j].cpu().double() - c_ref).abs().max().item() < 1e-5 * max(1.0, c_ref.abs().max().item())
+
+
 def test_scorer_fold_and_tokens(lib):
+    """Folded query scorer end to end (rows a12 + a13): toc3d_motion_queries_fold + toc3d_score_tokens against the oracle's
+    motion_aware_queries + query_based_score (toc3d_utils.py:232-252, 334-360), fp32, 2e-4 on the log-probabilities."""
     g = torch.Generator().manual_seed(5)
-    Bf, views, H, W, C, Q, Cq = 2, 3, 10, 22, 1024, 64, 256
+    Bf, views, H, W, C, Q = 2, 3, 10, 22, 1024, 64
     V, N = Bf * views, H * W
-    p = {"score_predictor.0.input_proj.0.weight": torch.randn(Cq, C, generator=g) * 0.02,
-         "score_predictor.0.input_proj.0.bias": torch.randn(Cq, generator=g) * 0.1,
-         "score_predictor.0.aggregate.0.weight": torch.randn(2, Q, generator=g) * 0.1,
-         "score_predictor.0.aggregate.0.bias": torch.randn(2, generator=g) * 0.1}
+    sel, p, inp, blob = _selector_case(43, Bf, Q, C)
     x = torch.randn(V, H, W, C, generator=g) * 2
     mask = torch.rand(V, H, W, 1, generator=g)
-    queries = torch.randn(Bf, Q, Cq, generator=g)
     gn = -torch.log(-torch.log(torch.rand(V, N, 2, generator=g).clamp(1e-9, 1 - 1e-7)))
+    queries = O.motion_aware_queries(p, 0, inp["temp_queries"], inp["temp_ref_points"], inp["temp_vel"], inp["temp_timestamp"],
+                                     inp["temp_ego_pose"], inp["ego_pose_inv"])
     pred_ref = O.query_based_score(x, mask, queries, p, 0)
     mask_ref = O.gumbel_mask(pred_ref, gn)[..., 0]
-    A = torch.empty(Bf, 2, C, device=DEV); c = torch.empty(Bf, 2, device=DEV)
-    lib.score_fold_queries(queries.to(DEV), p["score_predictor.0.input_proj.0.weight"].to(DEV),
-                           p["score_predictor.0.input_proj.0.bias"].to(DEV),
-                           p["score_predictor.0.aggregate.0.weight"].to(DEV),
-                           p["score_predictor.0.aggregate.0.bias"].to(DEV), Cq ** -0.5, A, c)
+    q_out = torch.empty(1, Bf, Q, 256, device=DEV); A = torch.empty(1, Bf, 2, C, device=DEV); c = torch.empty(1, Bf, 2, device=DEV)
+    d = {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    lib.motion_queries_fold(blob[None].to(DEV), d["temp_queries"], d["temp_ref_points"], d["temp_vel"], d["temp_timestamp"],
+                            d["temp_ego_pose"], d["ego_pose_inv"], sel.scale, C, q_out, A, c)
+    A, c = A[0].contiguous(), c[0].contiguous()
     pred = torch.empty(V, N, 2, device=DEV); score = torch.empty(V, N, device=DEV); mo = torch.empty(V, N, device=DEV)
     lib.score_tokens(x.to(DEV), mask.reshape(V, N).to(DEV).contiguous(), A, c, V, N, C, views, gn.to(DEV), 0, pred, score, mo)
     assert (pred.cpu() - pred_ref).abs().max().item() < 2e-4       # fp32, re-associated (folded) product
@@ -637,6 +681,84 @@ def test_scorer_fold_and_tokens(lib):
     lib.score_tokens(x.to(DEV), None, A, c, V, N, C, views, None, 1, None, None, m1)
     lib.score_tokens(x.to(DEV), None, A, c, V, N, C, views, None, 2, None, None, m2)
     assert ((m1 > 0) & (m1 < 1)).all() and not torch.equal(m1, m2)
+
+
+def test_mask_rows(lib):
+    """x * mask (toc3d_utils.py:117,234: the previous stage's soft mask multiplies the scorer input), fp32, exact."""
+    g = torch.Generator().manual_seed(21)
+    M, C = 6000, 1024
+    x = torch.randn(M, C, generator=g) * 3
+    m = torch.rand(M, generator=g)
+    out = torch.full((M, C), float("nan"), device=DEV)
+    lib.mask_rows(x.to(DEV), m.to(DEV), out, M, C)
+    assert torch.equal(out.cpu(), x * m[:, None])
+
+
+@pytest.mark.parametrize("V,N,C", [(1, 77, 256), (2, 1000, 1024), (1, 5000, 1024)])
+def test_global_half_mean(lib, V, N, C):
+    """cat[y[:, :, :C/2], mean_N(y[:, :, C/2:])] (toc3d_utils.py:122-126) in place on the bf16 activations: the lower half
+    is untouched bit for bit, the upper half holds the token mean (fp32 accumulation, one bf16 rounding)."""
+    g = torch.Generator().manual_seed(V + N + C)
+    y = bf16_round(torch.randn(V, N, C, generator=g) + 0.3)
+    d = y.to(DEV).bfloat16().contiguous()
+    lib.global_half_mean(d, V, N, C)
+    got = d.float().cpu()
+    assert torch.equal(got[:, :, : C // 2], y[:, :, : C // 2])
+    mean = y[:, :, C // 2:].double().mean(dim=1, keepdim=True).float()
+    assert (got[:, :, C // 2:] - mean).abs().max().item() <= 2.0 ** -8 * mean.abs().max().item() + 1e-6
+    assert (got[:, :, C // 2:] == got[:, :1, C // 2:]).all()          # one value per (view, channel)
+
+
+def test_score_finish(lib):
+    """LogSoftmax over the 2 logits + pinned Gumbel mask (toc3d_utils.py:112,147): fp32, against the oracle."""
+    g = torch.Generator().manual_seed(23)
+    M = 6000
+    logits = torch.randn(M, 2, generator=g) * 4
+    logits[::97] = torch.tensor([60.0, -60.0]); logits[1::97] = torch.tensor([-80.0, 75.0])     # saturated rows
+    gn = -torch.log(-torch.log(torch.rand(M, 2, generator=g).clamp(1e-9, 1 - 1e-7)))
+    pred_ref = torch.log_softmax(logits, -1)
+    mask_ref = O.gumbel_mask(pred_ref, gn)[..., 0]
+    pred = torch.empty(M, 2, device=DEV); score = torch.empty(M, device=DEV); mo = torch.empty(M, device=DEV)
+    lib.score_finish(logits.to(DEV), M, gn.to(DEV), 0, pred, score, mo)
+    assert (pred.cpu() - pred_ref).abs().max().item() < 1e-5
+    assert torch.equal(score.cpu(), pred.cpu()[:, 0])
+    assert (mo.cpu() - mask_ref).abs().max().item() < 1e-5
+    m1 = torch.empty(M, device=DEV); m2 = torch.empty(M, device=DEV)       # device-drawn noise
+    lib.score_finish(logits.to(DEV), M, None, 1, None, None, m1)
+    lib.score_finish(logits.to(DEV), M, None, 2, None, None, m2)
+    assert ((m1 >= 0) & (m1 <= 1)).all() and not torch.equal(m1, m2)
+
+
+def test_first_frame_scorer_full_width(lib):
+    """The first-frame scorer (ScoreBasedTokenSelector.score, toc3d_utils.py:114-129) at EVA-ViT-L width through the
+    engine's launch sequence (mask_rows, LayerNorm 1e-5, 1024x1024 GELU GEMM, global_half_mean, 1024-512-256-2 GEMMs,
+    score_finish) against the oracle on identical fp32 input.  bf16 GEMM operands: log-prob tolerance 2e-2."""
+    from toc3d_b200 import CONFIGS, ToC3DEVAViT
+    from toc3d_b200.synthetic import randomize_state_dict
+    from toc3d_b200.backbone import _Engine
+    kind, cfg, hw = CONFIGS["toc3d_fast"]
+    torch.manual_seed(0)
+    model = ToC3DEVAViT(**dict(cfg, depth=6, global_attn_indexes=(2, 5), pruning_loc=[3], token_ratio=[0.7])).eval()
+    sd = randomize_state_dict(model.state_dict(), seed=31, bias_std=0.1)
+    model.load_state_dict(sd)
+    g = torch.Generator().manual_seed(32)
+    V, H, W, C = 2, 20, 50, 1024
+    x = torch.randn(V, H, W, C, generator=g) * 2.5
+    mask = torch.rand(V, H, W, 1, generator=g)
+    gn = -torch.log(-torch.log(torch.rand(V, H * W, 2, generator=g).clamp(1e-9, 1 - 1e-7)))
+    pred_ref = O.first_frame_score(x, mask, sd, 0)
+    lib.load()
+    eng = _Engine(model, torch.device("cuda", 0))
+    wsp = eng.workspace(V, H, W)
+    for mk in (None, mask):
+        ref = pred_ref if mk is not None else O.first_frame_score(x, torch.ones_like(mask), sd, 0)
+        pred, score, m_out = eng.score_stage(0, x.reshape(V * H * W, C).to(DEV), None if mk is None else mk.reshape(-1).to(DEV),
+                                             wsp, None, gn.to(DEV))
+        d = (pred.cpu() - ref).abs().max().item()
+        print("first-frame scorer full width max-abs log-prob diff %.5f (|ref| max %.2f)" % (d, ref.abs().max().item()))
+        assert d < 2e-2, d
+        assert torch.equal(score.cpu().reshape(-1), pred.cpu()[..., 0].reshape(-1))
+        assert (m_out.cpu().reshape(-1) - O.gumbel_mask(ref, gn)[..., 0].reshape(-1)).abs().max().item() < 1e-2
 
 
 def test_im2col_patch_embed(lib):

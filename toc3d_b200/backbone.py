@@ -18,7 +18,6 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import chain_plan
 from . import lib as L
 from .preprocess import ImagePreprocess
 
@@ -86,6 +85,29 @@ def interleave_w12(w1, b1, w2, b2, hp):
     return W.reshape(2 * hp, k).contiguous(), B.reshape(2 * hp).contiguous()
 
 
+def pack_motion_blob(sel, Q, C):
+    """Per-stage parameter blob of toc3d_motion_queries_fold (layout: include/toc3d_b200.h).  Linear weights are
+    transposed to [in][out]; the positional-encoding temperature tables are computed with torch exactly as the
+    reference does (positional_encoding.py:17,31: temperature ** (2 * (i // 2) / F) in fp32)."""
+    f = lambda t: t.detach().to(torch.float32).cpu().reshape(-1)
+    wT = lambda lin: lin.weight.detach().to(torch.float32).cpu().t().contiguous().reshape(-1)
+
+    def dim_t(n):
+        d = torch.arange(n, dtype=torch.float32)
+        return 10000 ** (2 * torch.div(d, 2, rounding_mode="floor") / n)
+
+    def mln(m):
+        return [wT(m.reduce[0]), f(m.reduce[0].bias), wT(m.gamma), f(m.gamma.bias), wT(m.beta), f(m.beta.bias)]
+    parts = [dim_t(128), dim_t(256), F.pad(f(sel.pc_range), (0, 2)),
+             wT(sel.query_embedding[0]), f(sel.query_embedding[0].bias), wT(sel.query_embedding[2]), f(sel.query_embedding[2].bias)]
+    parts += mln(sel.ego_pose_pe) + mln(sel.ego_pose_queries)
+    parts += [wT(sel.time_embedding[0]), f(sel.time_embedding[0].bias), f(sel.time_embedding[1].weight), f(sel.time_embedding[1].bias),
+              f(sel.input_proj[0].weight), f(sel.input_proj[0].bias), f(sel.aggregate[0].weight), F.pad(f(sel.aggregate[0].bias), (0, 2))]
+    blob = torch.cat(parts)
+    assert blob.numel() == L.motion_blob_floats(Q, C), (blob.numel(), L.motion_blob_floats(Q, C))
+    return blob
+
+
 # ------------------------------------------------------------------------------- parameter containers
 class _Rope(nn.Module):
     """eva_utils.py:325-371 buffers (freqs_cos/freqs_sin of shape (ft*ft, 2*dim))."""
@@ -146,7 +168,7 @@ class _PatchEmbed(nn.Module):
 
 
 class _MLN(nn.Module):
-    """misc.py:154-188."""
+    """Parameters of misc.py:154-188 (the arithmetic runs in toc3d_motion_queries_fold)."""
 
     def __init__(self, c_dim, f_dim=256):
         super().__init__()
@@ -156,26 +178,10 @@ class _MLN(nn.Module):
         nn.init.zeros_(self.gamma.weight); nn.init.zeros_(self.beta.weight)
         nn.init.ones_(self.gamma.bias); nn.init.zeros_(self.beta.bias)
 
-    def forward(self, x, c):
-        x = F.layer_norm(x, (x.shape[-1],))
-        c = self.reduce(c)
-        return self.gamma(c) * x + self.beta(c)
-
-
-def _posemb(pos, feats, temperature=10000):
-    pos = pos * (2 * math.pi)
-    dim_t = torch.arange(feats, dtype=torch.float32, device=pos.device)
-    dim_t = temperature ** (2 * torch.div(dim_t, 2, rounding_mode="floor") / feats)
-    out = []
-    for c in range(pos.shape[-1]):
-        a = pos[..., c, None] / dim_t
-        out.append(torch.stack((a[..., 0::2].sin(), a[..., 1::2].cos()), dim=-1).flatten(-2))
-    return out
-
 
 class _Selector(nn.Module):
-    """Parameter container of MotionAwareQueryGuidedTokenSelector (toc3d_utils.py:92-112,196-230,294-332)
-    plus the tiny per-frame query encoder (toc3d_utils.py:334-360; 64 queries x 256 channels)."""
+    """Parameter container of MotionAwareQueryGuidedTokenSelector (toc3d_utils.py:92-112,196-230,294-332).  The per-frame
+    query encoder (toc3d_utils.py:334-360) runs in toc3d_motion_queries_fold from a packed copy (pack_motion_blob)."""
 
     def __init__(self, embed_dim, num_queries, ratio, pc_range, query_dim=256):
         super().__init__()
@@ -194,22 +200,6 @@ class _Selector(nn.Module):
         self.ego_pose_pe = _MLN(180)
         self.ego_pose_queries = _MLN(180)
         self.time_embedding = nn.Sequential(nn.Linear(query_dim, query_dim), nn.LayerNorm(query_dim))
-
-    @torch.no_grad()
-    def motion_aware_queries(self, temp_queries, temp_ref_points, temp_vel, temp_timestamp, temp_ego_pose,
-                             ego_pose_inv):
-        assert ego_pose_inv is not None                                          # toc3d_utils.py:345
-        ref = torch.cat([temp_ref_points, torch.ones_like(temp_ref_points[..., :1])], dim=-1)
-        ref = (ego_pose_inv.unsqueeze(1) @ ref.unsqueeze(-1)).squeeze(-1)[..., :3]
-        ref = (ref - self.pc_range[:3]) / (self.pc_range[3:6] - self.pc_range[0:3])
-        ex, ey, ez = _posemb(ref, 128)
-        pos = self.query_embedding(torch.cat((ey, ex, ez), dim=-1))
-        motion = torch.cat([temp_vel, temp_timestamp, temp_ego_pose[..., :3, :].flatten(-2)], dim=-1).float()
-        bands = 2.0 ** torch.linspace(0.0, 5.0, 6, dtype=motion.dtype, device=motion.device)
-        motion = torch.cat([fn(motion * f) for f in bands for fn in (torch.sin, torch.cos)], dim=-1)
-        pos = self.ego_pose_pe(pos, motion)
-        pos = pos + self.time_embedding(_posemb(temp_timestamp[..., :1], 256)[0].float())
-        return (self.ego_pose_queries(temp_queries, motion) + pos).contiguous()
 
 
 # ------------------------------------------------------------------------------- device engine
@@ -258,8 +248,6 @@ class _Workspace:
         self.stats = torch.zeros(rows, 2, device=dev, dtype=torch.int64)   # sub-LN fixed-point [sum, sum sq] per MLP row
         self.stats2 = torch.zeros(rows, 2, device=dev, dtype=torch.int64)  # norm2 statistics of the post-attention rows
         self.merge_cnt = torch.zeros(max(v["nW"] for v in self.win.values()), device=dev, dtype=torch.int32)
-        # fuse_mlp: per-row-block arrival counters of the chained MLP launch (zeroed once, the kernel leaves them zero)
-        self.chain_sync = torch.zeros(4 * ((rows + 255) // 256), device=dev, dtype=torch.int32)
         self.stage = {}                                # (stage, ws) -> selection tables
 
 
@@ -269,13 +257,7 @@ class _Engine:
     def __init__(self, model, device):
         self.device = device
         m = model
-        self.fuse_block_tail = bool(getattr(model, "fuse_block_tail", False))
-        # the 3-problem chain starts with the proj GEMM in its norm2-fold form (a_out + statistics)
-        self.fold_norm2 = bool(getattr(model, "fold_norm2", False)) or self.fuse_block_tail
-        self.fuse_mlp = bool(getattr(model, "fuse_mlp", False)) and not self.fuse_block_tail
-        if self.fuse_mlp and self.fold_norm2:
-            raise NotImplementedError("fuse_mlp runs the MLP without the norm2 fold; use fuse_block_tail with fold_norm2")
-        self.chain_scheds = {}                            # (problems, M) -> device schedule of a chained launch
+        self.fold_norm2 = bool(getattr(model, "fold_norm2", False))
         self.C, self.heads, self.patch = m.embed_dim, m.num_heads, m.patch_size
         self.block_ws = [b.window_size for b in m.blocks]
         self.block_acc = [b.accelerate for b in m.blocks]
@@ -337,6 +319,12 @@ class _Engine:
                 w_o4=F.pad(b16(s.out_conv[4].weight), (0, 0, 0, 6)).contiguous(),
                 b_o4=F.pad(f32(s.out_conv[4].bias), (0, 6)).contiguous(),
             ))
+        self.sel_blob = self.sel_scale = None
+        if len(self.sel):
+            preds = list(m.score_predictor)
+            self.sel_Q = preds[0].num_queries
+            self.sel_blob = torch.stack([pack_motion_blob(s, self.sel_Q, C) for s in preds]).to(device).contiguous()
+            self.sel_scale = preds[0].scale
         self.ws_cache = {}
         self._gstreams = []
         self.fill_stream = torch.cuda.Stream(device=device)   # dense blocks: pad-slot k / v constants, beside norm1 + q/k/v
@@ -392,38 +380,10 @@ class _Engine:
         """eva_vit.py:44-51 (+ norm2 of :263 when folded).  wsp.a holds the bf16 A rows: LayerNorm output, or with
         fold_norm2 the un-normalised post-attention rows whose statistics are in wsp.stats2.  wsp.stats rows
         [0, M) must be zero on entry (zeroed by the norm2 launch or by the proj epilogue)."""
-        if self.fuse_mlp:
-            # both GEMMs in one persistent launch; the per-pair tile lists are planned once per M (chain_plan.py)
-            L.gemm_chain(self._mlp_problems(bp, wsp, resid_kw), M, self._chain_sched(2, bp, M), wsp.chain_sync)
-            return
         ln = dict(ln_stats=wsp.stats2, ln_u=bp["u12"], ln_n=self.C, ln_eps=LN_EPS) if self.fold_norm2 else {}
         L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, **ln)
         L.gemm(wsp.hid, bp["w3"], L.EPI_RESID, M=M, bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"],
                ln_n=self.Hd, ln_eps=LN_EPS, **resid_kw)
-
-    def _mlp_problems(self, bp, wsp, resid_kw):
-        """The two MLP GEMMs as problems of a chained launch (same epilogue keywords as the separate launches)."""
-        ln = dict(ln_stats=wsp.stats2, ln_u=bp["u12"], ln_n=self.C, ln_eps=LN_EPS) if self.fold_norm2 else {}
-        return [(wsp.a, bp["w12"], L.EPI_SWIGLU, dict(bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, tile_n=256, **ln)),
-                (wsp.hid, bp["w3"], L.EPI_RESID, dict(bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"],
-                                                      ln_n=self.Hd, ln_eps=LN_EPS, tile_n=256, **resid_kw))]
-
-    def _chain_sched(self, nprob, bp, M):
-        key = (nprob, M)
-        if key not in self.chain_scheds:
-            probs = chain_plan.mlp_probs(bp["w12"].shape[0], self.C, self.C)
-            if nprob == 3:
-                probs = [(self.C, self.C, 256)] + probs
-            plan = chain_plan.plan_chain(M, probs, L.gemm_chain_units())
-            self.chain_scheds[key] = chain_plan.as_tensor(plan, self.device)
-        return self.chain_scheds[key]
-
-    def _block_tail_chain(self, bp, wsp, M, proj_kw, mlp_kw):
-        """fuse_block_tail: proj (+ residual, norm2 folded) -> w1/w2 + SwiGLU -> w3 (+ residual), eva_vit.py:113,261-266,
-        as ONE chained launch of three problems (no norm2 launch either)."""
-        proj = (wsp.ao, bp["wproj"], L.EPI_RESID, dict(bias=bp["bproj"], ldo=self.C, tile_n=256, **proj_kw,
-                                                       **self._proj_kw(wsp)))
-        L.gemm_chain([proj] + self._mlp_problems(bp, wsp, mlp_kw), M, self._chain_sched(3, bp, M), wsp.chain_sync)
 
     def _proj_kw(self, wsp):
         """Extra outputs of the proj GEMM when norm2 is folded: bf16 copy of the new residual rows (A operand of
@@ -460,9 +420,6 @@ class _Engine:
         L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None)
         self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"],
                        q_rows=w["q_rows"], item_order=w["item_order"], join=fs)
-        if self.fuse_block_tail:
-            self._block_tail_chain(bp, wsp, VN, dict(out=X, resid=X), dict(out=X, resid=X))
-            return
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X, **self._proj_kw(wsp))
         if not self.fold_norm2:
             L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
@@ -520,28 +477,32 @@ class _Engine:
                           counters=wsp.merge_cnt)
         self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"],
                        q_rows=t["q_rows"], item_order=t["item_order"])
-        if self.fuse_block_tail:
-            self._block_tail_chain(bp, wsp, Mc, dict(out=wsp.T, resid=X, resid_map=t["ctok"], out_alt=wsp.T),
-                                   dict(out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T))
-        else:
-            L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
-                   resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
-            if not self.fold_norm2:
-                L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
-            self._mlp(bp, wsp, Mc, out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T)     # t2 -> image rows
+        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
+               resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
+        if not self.fold_norm2:
+            L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
+        self._mlp(bp, wsp, Mc, out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T)     # t2 -> image rows
         L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C, rep_row=t["rep_row"])
 
     # -- scorers ----------------------------------------------------------------------------
-    def fold_queries(self, j, sel_mod, q_kw, V):
-        """Motion-aware query encoding + folding of the query bank into (A, c) for stage j.  Depends only
-        on the history queries, not on the image, so the caller runs it on the side stream."""
-        sp = self.sel[j]
-        q = sel_mod.motion_aware_queries(**q_kw)
-        Bf = q.shape[0]
+    def fold_all_queries(self, q_kw, V):
+        """Motion-aware query encoding (toc3d_utils.py:334-360) + folding of the query bank into (A, c) for ALL stages in
+        one C-ABI call (two launches).  Depends only on the history queries, not on the image, so the caller runs it on
+        the side stream.  -> ([(A_j, c_j)], q_all [S,Bf,Q,256])."""
+        tq = q_kw["temp_queries"]
+        Bf, Q = tq.shape[0], tq.shape[1]
         assert V % Bf == 0, "views*batch must be a multiple of the query batch (toc3d_utils.py:240)"
-        A = torch.empty(Bf, 2, self.C, device=self.device); c = torch.empty(Bf, 2, device=self.device)
-        L.score_fold_queries(q.float(), sp["w_in"], sp["b_in"], sp["w_agg"], sp["b_agg"], sel_mod.scale, A, c)
-        return A, c
+        assert Q == self.sel_Q and tq.shape[2] == 256
+        S = len(self.sel)
+        dev = self.device
+        f32c = lambda t: t.to(torch.float32).contiguous()
+        ts = q_kw["temp_timestamp"]
+        ts = ts.contiguous() if ts.dtype == torch.float64 else f32c(ts)
+        q_all = torch.empty(S, Bf, Q, 256, device=dev)
+        A = torch.empty(S, Bf, 2, self.C, device=dev); c = torch.empty(S, Bf, 2, device=dev)
+        L.motion_queries_fold(self.sel_blob, f32c(tq), f32c(q_kw["temp_ref_points"]), f32c(q_kw["temp_vel"]), ts,
+                              f32c(q_kw["temp_ego_pose"]), f32c(q_kw["ego_pose_inv"]), self.sel_scale, self.C, q_all, A, c)
+        return [(A[j], c[j]) for j in range(S)], q_all
 
     def score_stage(self, j, X, mask_prev, wsp, folded, gumbel, seed=None):
         """folded = (A, c) from fold_queries when the previous frame exists, else None (first-frame scorer)."""
@@ -605,13 +566,6 @@ class _EvaBase(nn.Module):
         # measured on B200 it saves 0.29 ms of LayerNorm launches but adds 0.28 ms to the (exposed, L2-bound) proj
         # epilogue - 162.9 vs 169 samples/s.  Set before the first forward (or call refresh_weights()) to change.
         self.fold_norm2 = False
-        # the two GEMMs of the SwiGLU MLP as ONE persistent launch with per-row-block dependency counters and a
-        # host-planned tile order (toc3d_gemm_chain_bf16 + chain_plan.py).  Bit-identical results by construction;
-        # OFF until it has been verified and measured on B200 (written in a session without GPU time left).
-        self.fuse_mlp = False
-        # proj (norm2 folded) + both MLP GEMMs as one chained launch of three problems; implies the fold_norm2 weights.
-        # Compile-checked only (written after the last GPU minute of round 1); numerics = the tested fold_norm2 option.
-        self.fuse_block_tail = False
         # views are independent: with G > 1 the forward runs G groups of views on their own streams inside the
         # one CUDA graph, so the tail / epilogue of one group's kernels overlaps the other group's kernels
         self.view_groups = 1
@@ -731,7 +685,8 @@ class EVA_ViT(_EvaBase):
         self._init_weights()
 
     @torch.no_grad()
-    def forward(self, x, *args, **kwargs):
+    def forward(self, x, *args, tap=None, **kwargs):
+        """tap: test hook (dict) - collects per-block outputs; tap["inject_block_in"] replaces each block's input."""
         x, V, Hi, Wi = self._prep_img(x)
         eng = self._get_engine(x)
         pre = getattr(self, "img_preprocess", None)
@@ -739,12 +694,19 @@ class EVA_ViT(_EvaBase):
         def core(t):
             wsp = eng.workspace(V, Hi // 16, Wi // 16)
             X = eng.stem(t["x"], wsp, pre=pre)
+            if tap is not None:
+                tap["stem"] = X.clone()
+                tap["block_out"] = []
             for i in range(len(self.blocks)):
+                if tap is not None and "inject_block_in" in tap:
+                    X.copy_(tap["inject_block_in"][i].reshape(X.shape))
                 eng.dense_block(i, X, wsp)
+                if tap is not None:
+                    tap["block_out"].append(X.clone())
             return (X,)
 
         GLOBAL_TIMER.event_start("StreamPETR-EVA-ViT/backbone")
-        if self.use_cuda_graph:
+        if self.use_cuda_graph and tap is None:
             (X,) = self._graphed(("dense", V, Hi, Wi, tuple(x.shape), x.dtype), {"x": x}, core)
         else:
             (X,) = core({"x": x})
@@ -819,7 +781,8 @@ class ToC3DEVAViT(_EvaBase):
         """Same keyword contract as the reference (extra kwargs such as gt_bboxes are ignored).
 
         gumbel_noise: optional list of per-stage (V,N,2) tensors (parity pin 2); default draws
-        -log(-log(u)) on device.  teacher_scores / tap are test hooks (teacher forcing, intermediates).
+        -log(-log(u)) on device.  teacher_scores / tap are test hooks (teacher forcing, intermediates;
+        tap["inject_block_in"] = per-block inputs replaces the residual stream before every block).
         """
         x, V, Hi, Wi = self._prep_img(x)
         eng = self._get_engine(x)
@@ -868,15 +831,12 @@ class ToC3DEVAViT(_EvaBase):
         with torch.cuda.stream(side):
             eng.seed_t.add_(1)
             if q_kw is not None:
-                for j in range(nst):
-                    folded[j] = eng.fold_queries(j, self.score_predictor[j], q_kw, V)
+                folded, q_all = eng.fold_all_queries(q_kw, V)
+                if tap is not None:
+                    tap["motion_queries"] = q_all
             ev_q = torch.cuda.Event()
             ev_q.record(side)
         G = self.view_groups if (tap is None and self.view_groups > 1 and V % self.view_groups == 0) else 1
-        if G > 1 and (eng.fuse_mlp or eng.fuse_block_tail):
-            # two chained launches on concurrent streams could each be partially resident and wait for each other's SMs
-            raise NotImplementedError("chained launches (fuse_mlp / fuse_block_tail) need the whole grid co-resident; "
-                                      "they cannot be combined with view_groups > 1")
         if G > 1 and q_kw is not None:
             Bf = q_kw["temp_queries"].shape[0]
             vg = V // G
@@ -930,6 +890,8 @@ class ToC3DEVAViT(_EvaBase):
                     g = gumbel_noise[stage].to(device=x.device, dtype=torch.float32).contiguous()
                 if stage == 0:
                     cur.wait_event(ev_q)
+                if tap is not None and "inject_block_in" in tap:      # test hook: per-block isolation (block i starts from
+                    X.copy_(tap["inject_block_in"][i].reshape(X.shape))  # the checker's input, so errors do not accumulate)
                 pred, score, mask = eng.score_stage(stage, X, mask_prev, wsp, folded[stage], g, seed=stage + 16 * group)
                 if tap is not None:
                     tap.setdefault("scores_raw", []).append(score.view(V, H, W).clone())
@@ -948,6 +910,8 @@ class ToC3DEVAViT(_EvaBase):
                 keep_idxes.append(keep)
                 drop_idxes.append(drop)
                 scores_l.append(score.view(V, H, W))
+            if tap is not None and "inject_block_in" in tap:
+                X.copy_(tap["inject_block_in"][i].reshape(X.shape))
             if blk.accelerate:
                 eng.toc3d_block(i, X, wsp, stage)
             else:

@@ -8,7 +8,8 @@
 //            lengths), write P = exp2(.) as packed bf16 back over S with tcgen05.st, and O = P V runs as
 //            tcgen05.mma with the A operand in TMEM and V as an MN-major smem operand.  The MMA thread issues
 //            S(u) then P V(u-1), so one slot's MMAs overlap the other slot's softmax.
-//   attn_tc::window_attention_tc_kernel (256 < seq <= 448): same math, one CTA per (window, head), one slot.
+//   attn_tc::window_attention_tc2_kernel (256 < seq <= 448): same math, one CTA per (window, head), one slot, two
+//            softmax warps per TMEM lane quarter splitting the key columns.
 //   attn::window_attention_kernel (seq > 448, not reached by any shipped config): flash-style mma.sync fallback.
 // All take an optional out_map (rows stored in compact order, padding rows skipped) and q_rows (only the leading
 // query rows of a window are needed; the rest is padding that only serves as keys / values).
@@ -216,7 +217,6 @@ namespace attn_tc {
 constexpr int D = 64;
 constexpr int BOX_ROWS = 64;                    // TMA box: 64 rows x 64 bf16 (128 B) = 8 KB
 constexpr int BOX_BYTES = BOX_ROWS * D * 2;
-constexpr int NTHREADS = 160;                   // single-tile kernel: warp 0 TMA + MMA issue; warps 1-4 softmax / epilogue
 constexpr int MAX_SEQ = 448;                    // S (<= 448 fp32 columns) + O (64) fill the 512 TMEM columns
 constexpr int PP_MAX_SEQ = 256;                 // ping-pong kernel: two 256-column slots
 constexpr int PP_THREADS = 320;                 // warp 0 TMA, warp 1 MMA issue, warps 2-5 / 6-9 softmax of slot 0 / 1
@@ -361,25 +361,6 @@ __device__ __forceinline__ void finish_tile(uint32_t o_addr, bool active, bool s
   if (store) store_o(o0, o1, sum, out_row);
 }
 
-// One tile, strictly in order: S -> softmax -> P handed to the MMA thread (bar_p), O = P V awaited (bar_o), read,
-// slot released (bar_ofree), row stored.
-__device__ __forceinline__ void softmax_tile(uint32_t lane_base, uint32_t o_off, int seq, bool active, bool row_ok,
-                                             __nv_bfloat16* out_row, uint64_t* bar_s, uint64_t* bar_p, uint64_t* bar_o,
-                                             uint64_t* bar_ofree, uint32_t parity) {
-  mbar_wait(bar_s, parity);
-  tcgen05_fence_after();
-  const float sum = softmax_rows(lane_base, seq, active);
-  tcgen05_fence_before();
-  mbar_arrive(bar_p);
-  mbar_wait(bar_o, parity);
-  tcgen05_fence_after();
-  uint32_t o0[32], o1[32];
-  load_o(lane_base + o_off, active, o0, o1);
-  tcgen05_fence_before();
-  mbar_arrive(bar_ofree);
-  if (active && row_ok) store_o(o0, o1, sum, out_row);
-}
-
 // S(tile) = Q_tile K^T into TMEM columns [s_col, s_col + spad): one MMA chain for the first 256 keys, a second
 // for the rest.
 __device__ __forceinline__ void issue_qk(uint32_t s_addr, const uint8_t* q_tile, const uint8_t* k_base, int spad) {
@@ -405,103 +386,6 @@ __device__ __forceinline__ void issue_pv(uint32_t o_addr, uint32_t p_addr, const
 }
 
 enum { BAR_QK = 0, BAR_V, BAR_S, BAR_P, BAR_O, BAR_OFREE, NUM_BARS };
-
-// ---------------------------------------------------------------------------------------------------
-// Single-slot kernel (256 < seq <= 448, or any seq): one CTA per (window, head), query tiles in sequence.
-__global__ void __launch_bounds__(NTHREADS)
-window_attention_tc_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                           int tmem_cols, const int* __restrict__ out_map, const int* __restrict__ q_rows) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int Tmax = (seq + 127) >> 7;            // 128-row query tiles (smem layout)
-  const int nb = (seq + BOX_ROWS - 1) / BOX_ROWS;   // 64-row boxes of K / V
-  uint8_t* sQ = smem;
-  uint8_t* sK = sQ + 2 * Tmax * BOX_BYTES;
-  uint8_t* sV = sK + nb * BOX_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sV + nb * BOX_BYTES);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + NUM_BARS);
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int h = blockIdx.x, w = blockIdx.y;
-  // only the leading q_rows[w] query rows are needed afterwards (the rest are window padding = keys / values only)
-  const int T = ((q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq) + 127) >> 7;
-  const int C = heads * D;
-  const int row0 = w * seq;
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm);
-    mbar_init(&bars[BAR_QK], 1);
-    mbar_init(&bars[BAR_V], 1);
-    mbar_init(&bars[BAR_S], 1);
-    mbar_init(&bars[BAR_P], 128);
-    mbar_init(&bars[BAR_O], 1);
-    mbar_init(&bars[BAR_OFREE], 128);
-    fence_barrier_init();
-  }
-  if (warp == 0) tmem_alloc(tmem_ptr, (uint32_t)tmem_cols);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();
-  pdl_launch_dependents();
-
-  const int spad = (seq + 15) & ~15;            // keys rounded up to the MMA K / N granularity
-  // O (64 fp32 columns) sits in the last 64 allocated columns.  With 256 columns and more than 192 keys it
-  // overlaps the tail of S, which is dead once P (packed, <= 128 columns) has been written; S(t+1) must then
-  // wait until O(t) has been read out.
-  const uint32_t o_col = (uint32_t)tmem_cols - 64u;
-  const bool o_aliases_s = (uint32_t)spad > o_col;
-
-  if (warp == 0) {
-    if (elect_one_sync()) {
-      // ---------------------------------------------------------------- TMA: K + Q, then V
-      mbar_arrive_expect_tx(&bars[BAR_QK], (uint32_t)((2 * T + nb) * BOX_BYTES));
-      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_QK], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
-      for (int b = 0; b < 2 * T; ++b) tma_load_2d(&tm, &bars[BAR_QK], sQ + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
-      mbar_arrive_expect_tx(&bars[BAR_V], (uint32_t)(nb * BOX_BYTES));
-      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_V], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
-      // ---------------------------------------------------------------- MMA issue
-      mbar_wait(&bars[BAR_QK], 0);
-      tcgen05_fence_after();
-      issue_qk(tmem_base, sQ, sK, spad);
-      tcgen05_commit(&bars[BAR_S]);
-      for (int t = 0; t < T; ++t) {
-        mbar_wait(&bars[BAR_P], t & 1);                     // P(t) is in TMEM (over S(t))
-        if (t == 0) mbar_wait(&bars[BAR_V], 0);
-        else if (!o_aliases_s) mbar_wait(&bars[BAR_OFREE], (t - 1) & 1);      // O(t-1) has been read out
-        tcgen05_fence_after();
-        issue_pv(tmem_base + o_col, tmem_base, sV, spad);
-        tcgen05_commit(&bars[BAR_O]);
-        if (t + 1 < T) {
-          if (o_aliases_s) {
-            mbar_wait(&bars[BAR_OFREE], t & 1);
-            tcgen05_fence_after();
-          }
-          issue_qk(tmem_base, sQ + (t + 1) * 2 * BOX_BYTES, sK, spad);   // executes after PV(t): may overwrite P(t)
-          tcgen05_commit(&bars[BAR_S]);
-        }
-      }
-    }
-  } else {
-    const int quarter = warp & 3;                           // TMEM lane quarter this warp may access
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16);
-    for (int t = 0; t < T; ++t) {
-      const int q = t * 128 + quarter * 32 + lane;
-      int dst = q < seq ? row0 + q : -1;
-      if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
-      softmax_tile(lane_base, o_col, seq, t * 128 + quarter * 32 < seq, dst >= 0, out + (size_t)(dst < 0 ? 0 : dst) * C + h * D,
-                   &bars[BAR_S], &bars[BAR_P], &bars[BAR_O], &bars[BAR_OFREE], (uint32_t)(t & 1));
-    }
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 0) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_base, (uint32_t)tmem_cols);
-  }
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Ping-pong kernel (seq <= 256): persistent CTAs, one per SM, looping over (window, head) items.
@@ -703,21 +587,19 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
 
 
 // ---------------------------------------------------------------------------------------------------
-// Split-softmax variant of the ping-pong kernel (OPT-IN: TOC3D_ATTN_SPLIT=1; written without GPU time left in its
-// round, default off).  Why: in the kernel above a slot's softmax is ONE warp per TMEM lane quarter, so every SM
-// sub-partition hosts two softmax warps; the ex2 pass is latency-bound (MUFU 33 % busy).  Here TWO warps
-// share a lane quarter of a slot (warp_id % 4 selects both the TMEM lane quarter and the scheduler, so they sit on the
-// same sub-partition and fill each other's MUFU / TMEM-load latencies) and split the KEY columns:
+// Split softmax (used by the single-slot kernel below).  With ONE softmax warp per TMEM lane quarter the ex2 pass is
+// latency-bound (MUFU 33 % busy).  Here TWO warps share a lane quarter (warp_id % 4 selects both the TMEM
+// lane quarter and the scheduler, so they sit on the same sub-partition and fill each other's MUFU / TMEM-load
+// latencies) and split the KEY columns:
 //   half 0: 32-key chunks [0, c0) in ascending order,  P chunk c packed at columns [16 c, 16 c + 16)
 //   half 1: chunks [c0, n) in DESCENDING order,         P chunk c packed at columns [16 (n + c), 16 (n + c) + 16)
 // (n = ceil(seq / 32), c0 = ceil(n / 2)).  A P chunk always lands on score columns its own warp has already read
 // (half 0: below 32 (c + 1); half 1: at or above 32 c) and never in the other half's score range, so the two warps
 // need no ordering between their passes except the exchange of the row max (and of the row sum) through shared
-// memory + a 64-thread named barrier.  O sits at columns [192, 256) when the keys fit below it (deferred mode), else
-// at [64, 128) between the two P blocks (n >= 7: P = [0, 64) and [16 n + 64, 32 n)).  Each half reads and stores 32 of
-// the 64 O columns of its rows.
-constexpr int PP2_THREADS = 64 + 16 * 32;       // warp 0 TMA, warp 1 MMA issue, warps 2-17 softmax
-constexpr int PP2_XCH_BYTES = 2 * 2 * 4 * 2 * 32 * 4;   // {max, sum} x slot x quarter x half x lane, fp32
+// memory + a 64-thread named barrier.  Each half reads and stores 32 of the 64 O columns of its rows.  (Measured on
+// B200, profiles/r02a_attn_bench_*.txt: 18 x 400 keys 55.5 -> 42.6 us, 18 x 281 33.0 -> 26.6 us.  The same split on the
+// two 256-column slots of the ping-pong kernel was 0-12 % SLOWER - two slots already give each scheduler two softmax
+// warps - and was removed.)
 
 __device__ __forceinline__ uint32_t p_col_split(int c, int c0, int n) { return c < c0 ? 16u * (uint32_t)c : 16u * (uint32_t)(n + c); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
@@ -814,189 +696,9 @@ __device__ __forceinline__ void store_o_half(const uint32_t (&o)[32], float sum,
   }
 }
 
-template <bool deferred>
-__global__ void __launch_bounds__(PP2_THREADS, 1)
-window_attention_pp2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                            int n_items, int nbuf, const int* __restrict__ out_map, const int* __restrict__ q_rows,
-                            const int* __restrict__ item_order) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  const int T = (seq + 127) >> 7;
-  const int nb = (seq + BOX_ROWS - 1) / BOX_ROWS;
-  const int item_bytes = (2 * T + 2 * nb) * BOX_BYTES;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + nbuf * item_bytes);
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + PP_NUM_BARS);
-  float* xch = reinterpret_cast<float*>(smem + nbuf * item_bytes + 256);     // [max | sum][slot][quarter][half][lane]
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int C = heads * D;
-  const int spad = (seq + 15) & ~15;
-  const int n = (seq + 31) >> 5;                // 32-key chunks
-  const int c0 = (n + 1) >> 1;                  // chunks of half 0
-  const uint32_t o_off = deferred ? 192u : 64u; // host: deferred <=> spad <= 192; otherwise n >= 7 and [64, 128) is free of P
-  const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
-  auto item_tiles = [&](int i, int& w, int& h) {
-    const int idx = (int)blockIdx.x + i * (int)gridDim.x;
-    const int it = item_order != nullptr ? item_order[idx] : idx;
-    w = it / heads;
-    h = it - w * heads;
-    const int need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;
-    return (need + 127) >> 7;
-  };
-
-  if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&tm);
-    for (int b = 0; b < 4; ++b) {
-      mbar_init(&bars[PB_FULL + b], 1);
-      mbar_init(&bars[PB_EMPTY + b], 1);
-    }
-    for (int s = 0; s < 2; ++s) {
-      mbar_init(&bars[PB_S + s], 1);
-      mbar_init(&bars[PB_P + s], 256);          // both halves of every row arrive
-      mbar_init(&bars[PB_O + s], 1);
-      mbar_init(&bars[PB_OFREE + s], 256);
-    }
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc(tmem_ptr, 512);
-  tcgen05_fence_before();
-  __syncthreads();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_wait();
-  pdl_launch_dependents();
-
-  if (warp == 0) {
-    if (elect_one_sync()) {
-      // ------------------------------------------------------------------ TMA producer (as in the kernel above)
-      for (int i = 0; i < my_items; ++i) {
-        int w, h;
-        const int Ti = item_tiles(i, w, h);
-        const int row0 = w * seq;
-        const int buf = i % nbuf;
-        const uint32_t round = (uint32_t)(i / nbuf);
-        mbar_wait(&bars[PB_EMPTY + buf], (round & 1) ^ 1);
-        uint8_t* base = smem + buf * item_bytes;
-        uint8_t* sK = base + 2 * T * BOX_BYTES;
-        uint8_t* sV = sK + nb * BOX_BYTES;
-        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)((2 * Ti + 2 * nb) * BOX_BYTES));
-        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
-        for (int b = 0; b < 2 * Ti; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
-        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one_sync()) {
-      // ------------------------------------------------------------------ MMA issuer (as above, split P layout)
-      struct Unit { int s; uint32_t n; const uint8_t* sV; int last_buf; };
-      auto do_pv = [&](const Unit& un) {
-        mbar_wait(&bars[PB_P + un.s], un.n & 1);
-        tcgen05_fence_after();
-        issue_pv_split(tmem_base + (uint32_t)(un.s * 256) + o_off, tmem_base + (uint32_t)(un.s * 256), un.sV, spad, c0, n);
-        tcgen05_commit(&bars[PB_O + un.s]);
-        if (un.last_buf >= 0) tcgen05_commit(&bars[PB_EMPTY + un.last_buf]);
-      };
-      Unit prev{0, 0, nullptr, -1};
-      bool have_prev = false;
-      int u = 0;
-      for (int i = 0; i < my_items; ++i) {
-        int w, h;
-        const int Ti = item_tiles(i, w, h);
-        const int buf = i % nbuf;
-        const uint8_t* base = smem + buf * item_bytes;
-        const uint8_t* sK = base + 2 * T * BOX_BYTES;
-        const uint8_t* sV = sK + nb * BOX_BYTES;
-        for (int t = 0; t < Ti; ++t, ++u) {
-          const int s = u & 1;
-          const uint32_t nu = (uint32_t)(u >> 1);
-          if (t == 0) mbar_wait(&bars[PB_FULL + buf], (uint32_t)((i / nbuf) & 1));
-          if (!deferred && nu > 0) mbar_wait(&bars[PB_OFREE + s], (nu - 1) & 1);
-          tcgen05_fence_after();
-          issue_qk(tmem_base + (uint32_t)(s * 256), base + t * 2 * BOX_BYTES, sK, spad);
-          tcgen05_commit(&bars[PB_S + s]);
-          if (have_prev) do_pv(prev);
-          prev = Unit{s, nu, sV, t == Ti - 1 ? buf : -1};
-          have_prev = true;
-        }
-      }
-      if (have_prev) do_pv(prev);
-    }
-  } else {
-    // -------------------------------------------------------------------- softmax warps 2..17
-    const int idx = warp - 2;
-    const int quarter = warp & 3;                 // TMEM lane quarter (and scheduler) of this warp
-    const int slot = (idx >> 2) & 1;
-    const int half = idx >> 3;
-    const uint32_t lane_base = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(slot * 256);
-    uint64_t* bar_s = &bars[PB_S + slot];
-    uint64_t* bar_p = &bars[PB_P + slot];
-    uint64_t* bar_o = &bars[PB_O + slot];
-    uint64_t* bar_ofree = &bars[PB_OFREE + slot];
-    float* xmax = xch + ((slot * 4 + quarter) * 2) * 32;
-    float* xsum = xmax + 2 * 4 * 2 * 32;
-    const int bar_id = 1 + slot * 4 + quarter;    // named barriers 1..8 (0 = __syncthreads)
-    bool pend = false, pend_act = false, pend_ok = false;
-    float pend_sum = 0.f;
-    __nv_bfloat16* pend_row = out;
-    uint32_t pend_par = 0;
-    // O epilogue of the pending tile: this warp's 32 columns
-    auto finish = [&](bool then_p) {
-      uint32_t o[32];
-      mbar_wait(bar_o, pend_par);
-      tcgen05_fence_after();
-      if (pend_act) {
-        tmem_ld_32x32(lane_base + o_off + (uint32_t)(half * 32), o);
-        tmem_ld_wait();
-      }
-      tcgen05_fence_before();
-      mbar_arrive(bar_ofree);
-      if (then_p) mbar_arrive(bar_p);
-      if (pend_act && pend_ok) store_o_half(o, pend_sum, pend_row + half * 32);
-    };
-    int u = 0;
-    for (int i = 0; i < my_items; ++i) {
-      int w, h;
-      const int Ti = item_tiles(i, w, h);
-      for (int t = 0; t < Ti; ++t, ++u) {
-        if ((u & 1) != slot) continue;
-        const int q = t * 128 + quarter * 32 + lane;
-        int dst = q < seq ? w * seq + q : -1;
-        if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
-        const bool active = t * 128 + quarter * 32 < seq;
-        const uint32_t parity = (uint32_t)((u >> 1) & 1);
-        mbar_wait(bar_s, parity);
-        tcgen05_fence_after();
-        const float sum = softmax_half(lane_base, seq, n, c0, half, lane, active, xmax, xsum, bar_id);
-        if (deferred && pend) {
-          finish(true);                                 // O(previous) completed long ago: its P V ran before this S
-        } else {
-          tcgen05_fence_before();
-          mbar_arrive(bar_p);
-        }
-        pend = true; pend_act = active; pend_ok = dst >= 0; pend_sum = sum; pend_par = parity;
-        pend_row = out + (size_t)(dst < 0 ? 0 : dst) * C + h * D;
-        if (!deferred) {
-          finish(false);
-          pend = false;
-        }
-      }
-    }
-    if (pend) finish(false);
-  }
-
-  tcgen05_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc(tmem_base, 512);
-  }
-}
-
-
-// Split-softmax variant of the single-slot kernel (256 < seq <= 448; same opt-in switch).  The single-slot kernel has
-// ONE softmax warp per scheduler - the least latency hiding of all - so here too two warps share a lane quarter and
-// split the key columns (layout and exchange as above); S occupies [0, spad) <= 448 and O the last 64 of the 512
-// columns, so nothing aliases.  warp 0: TMA + MMA issue; warps 1-4: half 0; warps 5-8: half 1.
+// Single-slot kernel (256 < seq <= 448): one CTA per (window, head), query tiles in sequence, split softmax: two warps
+// share a lane quarter and split the key columns (layout and exchange as above); S occupies [0, spad) <= 448 and O the
+// last 64 of the 512 columns, so nothing aliases.  warp 0: TMA + MMA issue; warps 1-4: half 0; warps 5-8: half 1.
 constexpr int TC2_THREADS = 32 + 8 * 32;
 constexpr int TC2_XCH_BYTES = 2 * 4 * 2 * 32 * 4;   // {max, sum} x quarter x half x lane
 
@@ -1129,7 +831,7 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
     static bool configured = false;
     static int n_sm = 148;
     if (!configured) {
-      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024));
       TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp_kernel<false>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -1150,29 +852,6 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
       const int item_bytes = (2 * T + 2 * nb) * attn_tc::BOX_BYTES;
       const int n_items = n_windows * heads;
       const int grid = n_items < n_sm ? n_items : n_sm;
-      // opt-in experiment: two softmax warps per lane quarter and slot, key columns split between them
-      static const bool split = getenv("TOC3D_ATTN_SPLIT") != nullptr && getenv("TOC3D_ATTN_SPLIT")[0] == '1';
-      if (split) {
-        static bool configured2 = false;
-        if (!configured2) {
-          TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp2_kernel<false>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp2_kernel<true>,
-                                                cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-          configured2 = true;
-        }
-        int nbuf2 = (226 * 1024 - 1024 - 256 - attn_tc::PP2_XCH_BYTES) / item_bytes;
-        nbuf2 = nbuf2 > 4 ? 4 : nbuf2;
-        const size_t smem2 = (size_t)nbuf2 * item_bytes + 1024 + 256 + attn_tc::PP2_XCH_BYTES;
-        if (((seq_len + 15) & ~15) <= 192) {
-          TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp2_kernel<true>, dim3(grid), dim3(attn_tc::PP2_THREADS), smem2, st,
-                                      1, tm, o, seq_len, heads, n_items, nbuf2, out_map, q_rows, item_order));
-        } else {
-          TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp2_kernel<false>, dim3(grid), dim3(attn_tc::PP2_THREADS), smem2, st,
-                                      1, tm, o, seq_len, heads, n_items, nbuf2, out_map, q_rows, item_order));
-        }
-        return 0;
-      }
       int nbuf = (226 * 1024 - 1024 - 256) / item_bytes;
       nbuf = nbuf > 4 ? 4 : nbuf;                       // >= 2 for seq <= 256 (96 KB per item)
       const size_t smem = (size_t)nbuf * item_bytes + 1024 + 256;
@@ -1186,26 +865,9 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
       }
       return 0;
     }
-    const int spad = (seq_len + 15) & ~15;
-    {
-      static const bool split = getenv("TOC3D_ATTN_SPLIT") != nullptr && getenv("TOC3D_ATTN_SPLIT")[0] == '1';
-      if (split) {
-        static bool configured3 = false;
-        if (!configured3) {
-          TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                                227 * 1024));
-          configured3 = true;
-        }
-        const size_t smem2 = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128 + attn_tc::TC2_XCH_BYTES;
-        TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc2_kernel, dim3(heads, n_windows), dim3(attn_tc::TC2_THREADS), smem2,
-                                    st, 1, tm, o, seq_len, heads, out_map, q_rows));
-        return 0;
-      }
-    }
-    const int tmem_cols = spad <= 256 ? 256 : 512;     // <= 256 keys: two CTAs per SM (O may alias the tail of S)
-    const size_t smem = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128;
-    TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc_kernel, dim3(heads, n_windows), dim3(attn_tc::NTHREADS), smem, st,
-                                1, tm, o, seq_len, heads, tmem_cols, out_map, q_rows));
+    const size_t smem2 = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128 + attn_tc::TC2_XCH_BYTES;
+    TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc2_kernel, dim3(heads, n_windows), dim3(attn_tc::TC2_THREADS), smem2,
+                                st, 1, tm, o, seq_len, heads, out_map, q_rows));
     return 0;
   }
   dim3 grid((seq_len + attn::BQ - 1) / attn::BQ, heads, n_windows);

@@ -33,9 +33,6 @@ constexpr int ROPE_MAX_FT = 256;
 constexpr int SMEM_TILES = STAGES * STAGE_BYTES;  // 196608
 constexpr int SMEM_AUX = 256 + 8 * 32 * 32 * 4;   // barriers + epilogue staging (8 warps x 32 rows x 32 fp32)
 constexpr int SMEM_BYTES = SMEM_TILES + SMEM_AUX + 1024;  // + alignment slack (230656 <= 232448)
-constexpr int CHAIN_MAX_SCHED = 256;                      // chain kernel: tile ids of one CTA pair, staged in smem
-constexpr int CHAIN_EPI_COPY = 640;                       // 3-chain: EpiParams of the three problems, copied to smem
-constexpr int SMEM_BYTES_CHAIN = SMEM_BYTES + CHAIN_MAX_SCHED * 4 + CHAIN_EPI_COPY;   // 232320 <= 232448
 
 // kind::f16 instruction descriptor (cute::UMMA::InstrDescriptor): D=f32 [4,6), A=bf16 [7,10),
 // B=bf16 [10,13), A/B K-major (bits 15,16 = 0), N>>3 [17,23), M>>4 [24,29).  M = 256 over the pair.
@@ -115,10 +112,8 @@ __device__ __forceinline__ void tmem_ld_f32x32(uint32_t taddr, float (&f)[32]) {
 // of the quarter; nt0: first global column of the tile; bn: tile width.  full_bar/parity: the
 // "accumulator complete" barrier this warp must observe before its first TMEM load.
 // per-row LayerNorm fold coefficients from the fixed-point statistics: y = a * acc + b * u[col] + bias[col]
-// CG: read the statistics from L2 (chain kernel: they were accumulated by other SMs of the same launch).
-template <bool CG = false>
 __device__ __forceinline__ void ln_fold_coeffs(const long long* stats_row, int n, float eps, float& a, float& b) {
-  const longlong2 st = CG ? __ldcg(reinterpret_cast<const longlong2*>(stats_row)) : *reinterpret_cast<const longlong2*>(stats_row);
+  const longlong2 st = *reinterpret_cast<const longlong2*>(stats_row);
   const double inv_n = 1.0 / (double)n;
   const double mean = (double)st.x * (1.0 / STAT_SUM_SCALE) * inv_n;
   const double var = fmax((double)st.y * (1.0 / STAT_SQ_SCALE) * inv_n - mean * mean, 0.0);
@@ -126,7 +121,7 @@ __device__ __forceinline__ void ln_fold_coeffs(const long long* stats_row, int n
   b = -a * (float)mean;
 }
 
-template <int EPI, bool LNF, bool AOUT, bool CHAIN = false>
+template <int EPI, bool LNF, bool AOUT>
 __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int nt0, int bn, int half,
                                                    int M, int N, float* stage, int lane, uint64_t* full_bar,
                                                    uint32_t parity) {
@@ -143,7 +138,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
     long long st_sum = 0, st_sq = 0;
     float la = 1.0f, lb = 0.0f;          // LNF: LayerNorm of the A rows folded in (norm2 before w1/w2, eva_vit.py:263)
     if constexpr (LNF) {
-      if (my_row_ok) ln_fold_coeffs<CHAIN>(ep.ln_stats + 2 * (size_t)(m0 + lane), ep.ln_n, ep.ln_eps, la, lb);
+      if (my_row_ok) ln_fold_coeffs(ep.ln_stats + 2 * (size_t)(m0 + lane), ep.ln_n, ep.ln_eps, la, lb);
     }
     mbar_wait(full_bar, parity);
     tcgen05_fence_after();
@@ -224,7 +219,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       const int row = m0 + lane;
       rr_t = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
       or_t = ep.out_map ? ep.out_map[row] : row;
-      if constexpr (LNF) ln_fold_coeffs<CHAIN>(ep.ln_stats + 2 * (size_t)row, ep.ln_n, ep.ln_eps, lnA_t, lnB_t);
+      if constexpr (LNF) ln_fold_coeffs(ep.ln_stats + 2 * (size_t)row, ep.ln_n, ep.ln_eps, lnA_t, lnB_t);
     }
     // AOUT: destination row of THIS lane's row (thread = row domain) for the statistics / zeroing
     const int dst_t = !my_row_ok ? -1 : (or_t >= 0 ? or_t : (or_t == -2 ? m0 + lane : -1));
@@ -455,15 +450,6 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
   }
 }
 
-// Out-of-line form for kernels that host several epilogue kinds (the 3-problem chain): three inlined bodies in one
-// kernel share one register allocation and spill ~1 KB per thread; as calls each body gets the full budget.  `ep`
-// points to a copy of the parameters in shared memory.
-template <int EPI, bool LNF, bool AOUT, bool CHAIN>
-__device__ __noinline__ void epilogue_warp_tile_call(const EpiParams* ep, uint32_t taddr, int m0, int nt0, int bn, int half,
-                                                     int M, int N, float* stage, int lane, uint64_t* full_bar, uint32_t parity) {
-  epilogue_warp_tile<EPI, LNF, AOUT, CHAIN>(*ep, taddr, m0, nt0, bn, half, M, N, stage, lane, full_bar, parity);
-}
-
 // (registers are allocated per 4 warps: 10 warps count as 12, hence the 168-register cap)
 template <int EPI, bool LNF, bool AOUT>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
@@ -629,332 +615,6 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 }
 
 
-// ---------------------------------------------------------------------------------------------
-// GEMM chain: consecutive GEMMs of a block in ONE persistent launch.
-//   NPROB = 2 (SwiGLU MLP, eva_vit.py:44-51):
-//     problem 0: hid = silu(a W1^T + b1) * (a W2^T + b2)   SWIGLU epilogue, sub-LN statistics accumulated per row
-//     problem 1: out = resid + sub-LN-folded (hid W3'^T)     RESID epilogue with ln_stats
-//   NPROB = 3 (attention output projection with norm2 folded, eva_vit.py:113,263, in front of the MLP):
-//     problem 0: t1 = resid + ao Wp^T + bp                   RESID epilogue + a_out (bf16 rows) + norm2 statistics
-//     problem 1: SWIGLU with the norm2 fold (ln_stats),  problem 2: as problem 1 above
-// A problem-q tile of row block m (256 rows) needs every problem-(q-1) tile of that row block: its bf16 rows (read by
-// TMA) and their statistics.  Instead of a launch boundary the dependency is a per-row-block arrival counter in global
-// memory: problem-(q-1) epilogue warps arrive on ready[q-1][m] after their stores, the TMA producer and the epilogue
-// warps of a problem-q tile wait for ready[q-1][m] == all arrivals.  The last problem-q epilogue warp of a row block
-// clears the counters of that boundary, so the workspace is zero again when the launch ends.
-// The order in which a CTA pair works through tiles is an explicit list planned on the host (toc3d_b200/chain_plan.py):
-// sched[pair * sched_len + i] = tile id or -1 (end); problem q owns the ids [base[q], base[q+1]) and
-// (row block, column block) = divmod(id - base[q], num_n[q]).  The lists must be executable in order without a cyclic
-// wait (checked by the planner: list order + dependencies form a DAG); all pairs of the grid are co-resident (grid <=
-// toc3d_gemm_chain_units()), so a waiting pair never keeps a producer from running.  A protocol bug traps after 4 s
-// (bounded waits) instead of hanging.
-constexpr int CHAIN_MAX_PROBS = 3;
-struct ChainProblem {
-  CUtensorMap tmA, tmB;
-  EpiParams ep;
-  int N, K, BN, num_n;
-  int target;            // arrivals of one row block of this problem: num_n * 2 CTAs * EPI_WARPS
-};
-struct ChainParams {
-  ChainProblem p[CHAIN_MAX_PROBS];
-  int M, num_m;
-  int base[CHAIN_MAX_PROBS + 1];
-  const int* sched;
-  int sched_len;
-  // boundary b (between problem b and b + 1): ready[b][m] = sync[b * num_m + m] counts problem-b epilogue warps,
-  // done[b][m] = sync[(NPROB - 1 + b) * num_m + m] counts problem-(b+1) epilogue warps
-  int* sync;
-};
-
-__device__ __forceinline__ int ld_acquire_gpu(const int* p) {
-  int v;
-  asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-// generic-proxy writes (st.global of bf16 rows) <-> async-proxy reads (TMA loads of them by another CTA)
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
-
-__device__ __forceinline__ void chain_wait(const int* ctr, int target) {
-  uint64_t t0 = 0;
-  for (uint32_t spin = 1;; ++spin) {
-    if (ld_acquire_gpu(ctr) >= target) return;
-    __nanosleep(40);
-    if ((spin & 0xFFFu) == 0) {
-      uint64_t t1;
-      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-      if (t0 == 0) t0 = t1;
-      else if (t1 - t0 > 4000000000ull) {
-        printf("toc3d: chain dependency wait timed out (block %d thread %d target %d)\n", blockIdx.x, threadIdx.x, target);
-        __trap();
-      }
-    }
-  }
-}
-
-// SIG = false: every epilogue warp publishes its own tile (membar.gpu + atomic per warp and tile).  Measured on B200
-// (profiles/r01zd_chain_bench_*): ~1 us per tile on the critical path - the SwiGLU epilogue is as long as its mainloop,
-// so the fence stalls the tensor pipe.  SIG = true: an 11th warp does the publishing; the epilogue warps only arrive on
-// a CTA-local mbarrier (ring of 4, one phase per tile) and never execute a gpu-scope fence.  Registers are allocated
-// per 4 warps, so the extra warp is free.
-constexpr int CHAIN_SIG_RING = 4;
-
-template <bool SIG, int NPROB>
-__global__ void __launch_bounds__(NUM_THREADS + (SIG ? 32 : 0), 1)
-gemm_chain_kernel(const __grid_constant__ ChainParams cp) {
-  static_assert(NPROB == 2 || NPROB == 3, "chains of 2 or 3 GEMMs");
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + SMEM_TILES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tmem_full = empty_bar + STAGES;
-  uint64_t* tmem_empty = tmem_full + 2;
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
-  uint64_t* epi_done = reinterpret_cast<uint64_t*>(smem + SMEM_TILES + 192);    // SIG: [CHAIN_SIG_RING]
-  float* s_stage = reinterpret_cast<float*>(smem + SMEM_TILES + 256);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t rank = cluster_ctarank();          // rank in the pair, 0 = leader
-  const int pair = blockIdx.x >> 1;
-  const int M = cp.M;
-  // this pair's tile list, copied to shared memory once: the MMA thread reads the next tile id between two tiles, and
-  // a global load there (0.5-1 us) would idle the tensor pipe at every tile boundary
-  int* my_sched = reinterpret_cast<int*>(smem + SMEM_TILES + SMEM_AUX);
-  for (int i = threadIdx.x; i < cp.sched_len; i += blockDim.x) my_sched[i] = __ldg(cp.sched + (size_t)pair * cp.sched_len + i);
-  // NPROB == 3: the epilogues run as calls (see epilogue_warp_tile_call) and read their parameters from this copy
-  static_assert(CHAIN_MAX_PROBS * sizeof(EpiParams) <= CHAIN_EPI_COPY && sizeof(EpiParams) % 4 == 0, "EpiParams copy");
-  EpiParams* s_ep = reinterpret_cast<EpiParams*>(smem + SMEM_TILES + SMEM_AUX + CHAIN_MAX_SCHED * 4);
-  if constexpr (NPROB == 3) {
-    constexpr int words = (int)(sizeof(EpiParams) / 4);
-    for (int w = threadIdx.x; w < NPROB * words; w += blockDim.x) {
-      const int q = w / words;
-      reinterpret_cast<uint32_t*>(s_ep)[w] = reinterpret_cast<const uint32_t*>(&cp.p[q].ep)[w - q * words];
-    }
-  }
-
-  auto prob = [&](int q) -> const ChainProblem& {
-    if (NPROB == 3 && q == 2) return cp.p[NPROB - 1];
-    return q ? cp.p[1] : cp.p[0];
-  };
-  auto which = [&](int g) { return (g >= cp.base[1] ? 1 : 0) + ((NPROB == 3 && g >= cp.base[2]) ? 1 : 0); };
-  // tile id -> (problem, row block, column block)
-  auto decode = [&](int g, int& q, int& mb, int& nb) {
-    q = which(g);
-    const int j = g - cp.base[q];
-    const int nn = prob(q).num_n;
-    mb = j / nn;
-    nb = j - mb * nn;
-  };
-  auto ready_ctr = [&](int b, int mb) { return cp.sync + b * cp.num_m + mb; };
-  auto done_ctr = [&](int b, int mb) { return cp.sync + (NPROB - 1 + b) * cp.num_m + mb; };
-  // publish `n` epilogue-warp arrivals of tile (q, mb); the caller has made the tile's stores visible (see call sites)
-  auto publish = [&](int q, int mb, int n) {
-    if (q < NPROB - 1) atomicAdd(ready_ctr(q, mb), n);
-    if (q > 0) {
-      // every poll of ready[q-1][mb] by this tile happened before this point; the last tile of the row block resets
-      if (atomicAdd(done_ctr(q - 1, mb), n) == prob(q).target - n) {
-        atomicExch(done_ctr(q - 1, mb), 0);
-        atomicExch(ready_ctr(q - 1, mb), 0);
-      }
-    }
-  };
-
-  if (warp == 0 && lane == 0) {
-    for (int q = 0; q < NPROB; ++q) {
-      tma_prefetch_desc(&cp.p[q].tmA);
-      tma_prefetch_desc(&cp.p[q].tmB);
-    }
-    for (int s = 0; s < STAGES; ++s) {
-      mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], 1);
-    }
-    for (int a = 0; a < 2; ++a) {
-      mbar_init(&tmem_full[a], 1);
-      mbar_init(&tmem_empty[a], 2 * EPI_WARPS);
-    }
-    if (SIG)
-      for (int a = 0; a < CHAIN_SIG_RING; ++a) mbar_init(&epi_done[a], EPI_WARPS);
-    fence_barrier_init();
-  }
-  if (warp == 1) tmem_alloc_2sm(tmem_ptr, TMEM_COLS);
-  tcgen05_fence_before();
-  cluster_sync_all();
-  tcgen05_fence_after();
-  const uint32_t tmem_base = *tmem_ptr;
-  pdl_launch_dependents();
-
-  if (SIG && warp == 2 + EPI_WARPS) {
-    // ------------------------------------------------------------------ publisher (SIG): one lane per CTA
-    if (elect_one_sync()) {
-      pdl_wait();
-      for (int i = 0; i < cp.sched_len; ++i) {
-        const int g = my_sched[i];
-        if (g < 0) break;
-        int q, mb, nb;
-        decode(g, q, mb, nb);
-        // all 8 epilogue warps of this CTA have stored their part of tile i (mbarrier: release.cta / acquire.cta) ...
-        mbar_wait(&epi_done[i & (CHAIN_SIG_RING - 1)], (uint32_t)((i / CHAIN_SIG_RING) & 1));
-        if (q < NPROB - 1) {
-          // ... and this thread's gpu-scope fence is cumulative over what it has observed: publish for all 8 at once
-          fence_proxy_async_all();
-          __threadfence();
-        }
-        publish(q, mb, EPI_WARPS);
-      }
-    }
-  } else if (warp == 0) {
-    // ------------------------------------------------------------------ TMA producer (both CTAs)
-    if (elect_one_sync()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int pre = 0;
-      {
-        // weights of the first tile: in flight before the programmatic-dependency wait
-        int q, mb, nb;
-        decode(my_sched[0], q, mb, nb);
-        const ChainProblem& P = prob(q);
-        const int b_rows = P.BN >> 1;
-        const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);
-        const int num_k = (P.K + BK - 1) / BK;
-        pre = num_k < STAGES ? num_k : STAGES;
-        for (int kb = 0; kb < pre; ++kb) {
-          if (rank == 0) mbar_arrive_expect_tx(&full_bar[kb], stage_tx);
-          tma_load_2d_2sm(&P.tmB, smem_u32(&full_bar[kb]) & 0xFEFFFFFFu, smem + kb * STAGE_BYTES + A_BYTES, kb * BK,
-                          nb * P.BN + (int)rank * b_rows);
-        }
-      }
-      pdl_wait();
-      for (int i = 0; i < cp.sched_len; ++i) {
-        const int g = my_sched[i];
-        if (g < 0) break;
-        int q, mb, nb;
-        decode(g, q, mb, nb);
-        const ChainProblem& P = prob(q);
-        const int b_rows = P.BN >> 1;
-        const uint32_t stage_tx = 2u * (uint32_t)(A_BYTES + b_rows * BK * 2);
-        const int num_k = (P.K + BK - 1) / BK;
-        const int m_idx = mb * (2 * BM) + (int)rank * BM;
-        const int n_idx = nb * P.BN + (int)rank * b_rows;
-        if (q) {
-          chain_wait(ready_ctr(q - 1, mb), prob(q - 1).target);   // the A rows of this row block are complete ...
-          fence_proxy_async_all();                                // ... and ordered before this thread's TMA reads
-        }
-        for (int kb = 0; kb < num_k; ++kb) {
-          const uint32_t lead_full = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
-          uint8_t* sa = smem + stage * STAGE_BYTES;
-          if (pre > 0) {
-            --pre;
-          } else {
-            mbar_wait(&empty_bar[stage], phase ^ 1);
-            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
-            tma_load_2d_2sm(&P.tmB, lead_full, sa + A_BYTES, kb * BK, n_idx);
-          }
-          tma_load_2d_2sm(&P.tmA, lead_full, sa, kb * BK, m_idx);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0 && elect_one_sync()) {
-      int stage = 0;
-      uint32_t phase = 0;
-      int acc = 0;
-      uint32_t acc_phase = 0;
-      const uint16_t pair_mask = (uint16_t)3u;
-      for (int i = 0; i < cp.sched_len; ++i) {
-        const int g = my_sched[i];
-        if (g < 0) break;
-        const ChainProblem& P = prob(which(g));
-        const int num_k = (P.K + BK - 1) / BK;
-        const uint32_t idesc = make_idesc(P.BN);
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
-        tcgen05_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN_MAX);
-        for (int kb = 0; kb < num_k; ++kb) {
-          mbar_wait(&full_bar[stage], phase);
-          tcgen05_fence_after();
-          const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
-          const uint64_t a_desc = umma_desc_k_sw128(sa);
-          const uint64_t b_desc = umma_desc_k_sw128(sa + A_BYTES);
-#pragma unroll
-          for (int k = 0; k < BK / UMMA_K; ++k)
-            umma_bf16_ss_2sm(d_tmem, a_desc + (uint64_t)(2 * k), b_desc + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          tcgen05_commit_2sm(&empty_bar[stage], pair_mask);
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        tcgen05_commit_2sm(&tmem_full[acc], pair_mask);
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      }
-    }
-  } else {
-    // ------------------------------------------------------------------ epilogue (8 warps per CTA)
-    const int quarter = warp & 3;
-    const int half = (warp - 2) >> 2;
-    float* stage_buf = s_stage + (warp - 2) * STAGE_FLOATS;
-    int acc = 0;
-    uint32_t acc_phase = 0;
-    pdl_wait();
-    for (int i = 0; i < cp.sched_len; ++i) {
-      const int g = my_sched[i];
-      if (g < 0) break;
-      int q, mb, nb;
-      decode(g, q, mb, nb);
-      const int m_idx = mb * (2 * BM) + (int)rank * BM + quarter * 32;
-      const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX);
-      if (q > 0) {
-        // the statistics (and, for a residual written by an earlier problem, the rows) of this row block are complete
-        // once every tile of the previous problem has arrived
-        if (lane == 0) chain_wait(ready_ctr(q - 1, mb), prob(q - 1).target);
-        __syncwarp();
-      }
-      uint64_t* fb = &tmem_full[acc];
-      // every branch names its problem statically: the epilogue parameters then come straight from the constant bank
-#define TOC3D_CHAIN_EPI(IDX, ...) \
-  epilogue_warp_tile<__VA_ARGS__>(cp.p[IDX].ep, taddr, m_idx, nb * cp.p[IDX].BN, cp.p[IDX].BN, half, M, cp.p[IDX].N, stage_buf, \
-                                  lane, fb, acc_phase)
-      if constexpr (NPROB == 2) {
-        if (q == 0) TOC3D_CHAIN_EPI(0, TOC3D_EPI_SWIGLU, false, false);
-        else TOC3D_CHAIN_EPI(1, TOC3D_EPI_RESID, true, false, true);
-      } else {
-#define TOC3D_CHAIN_CALL(IDX, ...) \
-  epilogue_warp_tile_call<__VA_ARGS__>(s_ep + IDX, taddr, m_idx, nb * cp.p[IDX].BN, cp.p[IDX].BN, half, M, cp.p[IDX].N, \
-                                       stage_buf, lane, fb, acc_phase)
-        if (q == 0) TOC3D_CHAIN_CALL(0, TOC3D_EPI_RESID, false, true, false);
-        else if (q == 1) TOC3D_CHAIN_CALL(1, TOC3D_EPI_SWIGLU, true, false, true);
-        else TOC3D_CHAIN_CALL(NPROB - 1, TOC3D_EPI_RESID, true, false, true);
-#undef TOC3D_CHAIN_CALL
-      }
-#undef TOC3D_CHAIN_EPI
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) {
-        // SIG: hand the tile to the publisher BEFORE releasing the accumulator, so that no warp can arrive for tile
-        // i + CHAIN_SIG_RING on the same barrier while another has not yet arrived for tile i
-        if (SIG) mbar_arrive(&epi_done[i & (CHAIN_SIG_RING - 1)]);
-        mbar_arrive_cluster(mapa_u32(smem_u32(&tmem_empty[acc]), 0));
-      }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
-      if (SIG) continue;
-      if (q < NPROB - 1) {
-        // publish this warp's rows + statistics: every lane orders its own writes (against the async proxy that will
-        // read them, and at gpu scope), then one lane arrives
-        fence_proxy_async_all();
-        __threadfence();
-        __syncwarp();
-      }
-      if (lane == 0) publish(q, mb, 1);
-    }
-  }
-
-  tcgen05_fence_before();
-  cluster_sync_all();
-  if (warp == 1) {
-    tcgen05_fence_after();
-    tmem_dealloc_2sm(tmem_base, TMEM_COLS);
-  }
-}
-
 // ---------------------------------------------------------------------------- host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
@@ -1076,7 +736,7 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
 namespace toc3d {
 namespace gemm {
 
-// C-ABI epilogue -> kernel parameters, with the argument checks shared by toc3d_gemm_bf16 and toc3d_mlp_chain_bf16
+// C-ABI epilogue -> kernel parameters, with the argument checks of toc3d_gemm_bf16
 static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, EpiParams& ep) {
   ep.bias = e->bias; ep.out = e->out; ep.ldo = e->ldo; ep.out_f32 = e->out_f32; ep.act = e->act;
   ep.resid = e->resid; ep.resid_map = e->resid_map; ep.resid_mod = e->resid_mod; ep.out_map = e->out_map;
@@ -1118,48 +778,6 @@ static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, E
   return 0;
 }
 
-// CTA pairs of the chain kernel that can be resident at the same time (GPC boundaries can strand SMs); the chain's
-// dependency waits are only deadlock-free when the whole grid is resident, so its grid never exceeds this.
-static bool chain_publisher_warp() {       // TOC3D_CHAIN_SIG=1: the variant with the publisher warp (see gemm_chain_kernel)
-  static const bool on = getenv("TOC3D_CHAIN_SIG") != nullptr && getenv("TOC3D_CHAIN_SIG")[0] == '1';
-  return on;
-}
-
-typedef void (*ChainKernel)(const ChainParams);
-static ChainKernel chain_kernel(bool sig, int nprob) {
-  if (nprob == 2) return sig ? gemm_chain_kernel<true, 2> : gemm_chain_kernel<false, 2>;
-  return sig ? gemm_chain_kernel<true, 3> : gemm_chain_kernel<false, 3>;
-}
-
-// CTA pairs of the chain kernel that can be resident at the same time (GPC boundaries can strand SMs); the chain's
-// dependency waits are only deadlock-free when the whole grid is resident, so its grid never exceeds this.
-static int chain_units() {
-  static int units = 0;
-  if (units == 0) {
-    int least = sm_count() / 2;
-    for (int v = 0; v < 4; ++v) {
-      ChainKernel k = chain_kernel(v & 1, 2 + (v >> 1));
-      if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES_CHAIN) != cudaSuccess) {
-        cudaGetLastError();
-        return 0;
-      }
-      cudaLaunchConfig_t cfg = {};
-      cudaLaunchAttribute at[1];
-      at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(NUM_THREADS + ((v & 1) ? 32 : 0));
-      cfg.dynamicSmemBytes = SMEM_BYTES_CHAIN; cfg.attrs = at; cfg.numAttrs = 1;
-      int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, k, &cfg) != cudaSuccess || n <= 0) {
-        cudaGetLastError();
-        return 0;
-      }
-      least = n < least ? n : least;
-    }
-    units = least;
-  }
-  return units;
-}
 
 }  // namespace gemm
 }  // namespace toc3d
@@ -1193,73 +811,4 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
       return lnf ? launch<TOC3D_EPI_SWIGLU, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st)
                  : launch<TOC3D_EPI_SWIGLU, false>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
   }
-}
-
-extern "C" int toc3d_gemm_chain_units(void) { return toc3d::gemm::chain_units(); }
-
-extern "C" int toc3d_gemm_chain_bf16(const toc3d_chain_problem* probs, int32_t nprob, int32_t M, const int32_t* sched,
-                                     int32_t units, int32_t sched_len, int32_t* sync, void* stream) {
-  using namespace toc3d;
-  using namespace toc3d::gemm;
-  const char* fn = "toc3d_gemm_chain_bf16";
-  TOC3D_REQUIRE(probs && sched && sync, kErrBadArg, "%s: null pointer", fn);
-  TOC3D_REQUIRE(nprob == 2 || nprob == 3, kErrBadArg, "%s: chains of 2 (SWIGLU, RESID) or 3 (RESID, SWIGLU, RESID) problems", fn);
-  TOC3D_REQUIRE(M > 0, kErrBadArg, "%s: empty problem M=%d", fn, M);
-  ChainParams cp;
-  const int num_m = (M + 2 * BM - 1) / (2 * BM);
-  cp.M = M; cp.num_m = num_m; cp.base[0] = 0;
-  for (int q = 0; q < nprob; ++q) {
-    const toc3d_chain_problem& pq = probs[q];
-    const toc3d_epilogue* e = pq.epi;
-    TOC3D_REQUIRE(pq.A && pq.B && e && e->out, kErrBadArg, "%s: problem %d: null pointer", fn, q);
-    TOC3D_REQUIRE(pq.N > 0 && pq.K > 0, kErrBadArg, "%s: problem %d: empty N=%d K=%d", fn, q, pq.N, pq.K);
-    TOC3D_REQUIRE(pq.K % 8 == 0 && pq.lda % 8 == 0 && pq.ldb % 8 == 0 && pq.lda >= pq.K, kErrBadArg,
-                  "%s: problem %d: K, lda, ldb must be multiples of 8 (16-byte TMA strides), lda >= K", fn, q);
-    TOC3D_REQUIRE(((uintptr_t)pq.A & 15) == 0 && ((uintptr_t)pq.B & 15) == 0, kErrBadArg, "%s: problem %d: unaligned operand", fn, q);
-    const int want = nprob == 2 ? (q == 0 ? TOC3D_EPI_SWIGLU : TOC3D_EPI_RESID) : (q == 1 ? TOC3D_EPI_SWIGLU : TOC3D_EPI_RESID);
-    TOC3D_REQUIRE(pq.kind == want, kErrBadArg, "%s: problem %d must have epilogue kind %d, got %d", fn, q, want, pq.kind);
-    int rc = to_params(fn, e, pq.kind, pq.N, cp.p[q].ep);
-    if (rc) return rc;
-    TOC3D_REQUIRE(e->cluster_pairs != 2, kErrBadArg, "%s: one CTA pair per cluster only", fn);
-    const EpiParams& ep = cp.p[q].ep;
-    if (nprob == 3 && q == 0)
-      TOC3D_REQUIRE(ep.a_out != nullptr && ep.out_map == nullptr, kErrBadArg,
-                    "%s: problem 0 of a 3-chain is RESID with a_out + row_stats (norm2 fold) and without out_map", fn);
-    else
-      TOC3D_REQUIRE(ep.a_out == nullptr, kErrBadArg, "%s: problem %d: a_out only on problem 0 of a 3-chain", fn, q);
-    if (pq.kind == TOC3D_EPI_SWIGLU)
-      TOC3D_REQUIRE(ep.row_stats != nullptr && (ep.ln_stats != nullptr) == (nprob == 3), kErrBadArg,
-                    "%s: SWIGLU needs row_stats, and the norm2 fold (ln_stats) exactly in a 3-chain", fn);
-    if (q > 0) {
-      // the A operand and the folded statistics are what the previous problem produced, row for row
-      const toc3d_epilogue* ePrev = probs[q - 1].epi;
-      const bool prev_swiglu = probs[q - 1].kind == TOC3D_EPI_SWIGLU;
-      const void* a_want = prev_swiglu ? ePrev->out : ePrev->a_out;
-      const int k_want = prev_swiglu ? probs[q - 1].N / 2 : probs[q - 1].N;
-      TOC3D_REQUIRE(pq.A == a_want && pq.lda == ePrev->ldo && pq.K == k_want, kErrBadArg,
-                    "%s: problem %d: A / lda / K must be the bf16 output of problem %d", fn, q, q - 1);
-      TOC3D_REQUIRE(ep.ln_stats != nullptr && (const void*)ep.ln_stats == (const void*)ePrev->row_stats, kErrBadArg,
-                    "%s: problem %d: ln_stats must be problem %d's row_stats", fn, q, q - 1);
-    }
-    const int bn = e->tile_n > 0 ? e->tile_n : BN_MAX;
-    cp.p[q].N = pq.N; cp.p[q].K = pq.K; cp.p[q].BN = bn; cp.p[q].num_n = (pq.N + bn - 1) / bn;
-    cp.p[q].target = cp.p[q].num_n * 2 * EPI_WARPS;
-    cp.base[q + 1] = cp.base[q] + num_m * cp.p[q].num_n;
-    rc = make_tmap_bf16_2d(&cp.p[q].tmA, pq.A, M, pq.K, pq.lda, BM);
-    if (rc) return rc;
-    rc = make_tmap_bf16_2d(&cp.p[q].tmB, pq.B, pq.N, pq.K, pq.ldb, bn / 2);
-    if (rc) return rc;
-  }
-  for (int q = nprob; q < CHAIN_MAX_PROBS; ++q) cp.base[q + 1] = cp.base[nprob];
-  const int max_units = chain_units();
-  TOC3D_REQUIRE(max_units > 0, kErrNoDriver, "%s: occupancy query failed", fn);
-  TOC3D_REQUIRE(sched_len > 0 && sched_len <= CHAIN_MAX_SCHED, kErrBadArg, "%s: sched_len %d not in [1, %d]", fn, sched_len,
-                CHAIN_MAX_SCHED);
-  TOC3D_REQUIRE(units > 0 && units <= max_units, kErrBadArg,
-                "%s: the schedule uses %d CTA pairs, %d can be co-resident (toc3d_gemm_chain_units)", fn, units, max_units);
-  cp.sched = sched; cp.sched_len = sched_len; cp.sync = sync;
-  const bool sig = chain_publisher_warp();
-  TOC3D_CHECK_CUDA(launch_pdl(chain_kernel(sig, nprob), dim3(2 * units), dim3(NUM_THREADS + (sig ? 32 : 0)), SMEM_BYTES_CHAIN,
-                              reinterpret_cast<cudaStream_t>(stream), 2, cp));
-  return 0;
 }

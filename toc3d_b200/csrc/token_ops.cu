@@ -648,46 +648,7 @@ fast_update_kernel(float* __restrict__ x, const int* __restrict__ fast_map, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// Scorer folding: P = w_agg (2xQ) * queries[f] (QxCq); A[f] = scale * P * w_in (CqxC);
-// c[f] = scale * P . b_in + b_agg.   grid (Bf, C/128), 128 threads.
-__global__ void __launch_bounds__(128)
-score_fold_kernel(const float* __restrict__ queries, const float* __restrict__ w_in, const float* __restrict__ b_in,
-                  const float* __restrict__ w_agg, const float* __restrict__ b_agg, float scale, int Q, int Cq, int C,
-                  float* __restrict__ A_out, float* __restrict__ c_out) {
-  pdl_wait();
-  pdl_launch_dependents();
-  extern __shared__ float s_p[];  // [2][Cq]
-  const int f = blockIdx.x;
-  const float* q = queries + (size_t)f * Q * Cq;
-  for (int c = threadIdx.x; c < Cq; c += blockDim.x) {
-    float p0 = 0.f, p1 = 0.f;
-    for (int j = 0; j < Q; ++j) {
-      const float qv = q[(size_t)j * Cq + c];
-      p0 += w_agg[j] * qv;
-      p1 += w_agg[Q + j] * qv;
-    }
-    s_p[c] = p0;
-    s_p[Cq + c] = p1;
-  }
-  __syncthreads();
-  const int ch = blockIdx.y * 128 + threadIdx.x;
-  if (ch < C) {
-    float a0 = 0.f, a1 = 0.f;
-    for (int c = 0; c < Cq; ++c) {
-      const float wv = w_in[(size_t)c * C + ch];
-      a0 += s_p[c] * wv;
-      a1 += s_p[Cq + c] * wv;
-    }
-    A_out[((size_t)f * 2 + 0) * C + ch] = a0 * scale;
-    A_out[((size_t)f * 2 + 1) * C + ch] = a1 * scale;
-  }
-  if (blockIdx.y == 0 && threadIdx.x < 2) {
-    float acc = 0.f;
-    for (int c = 0; c < Cq; ++c) acc += s_p[threadIdx.x * Cq + c] * b_in[c];
-    c_out[f * 2 + threadIdx.x] = acc * scale + b_agg[threadIdx.x];
-  }
-}
-
+// (the query encoder and the scorer folding live in motion_queries.cu)
 __device__ __forceinline__ float gumbel_from_hash(uint64_t seed, uint64_t idx) {
   uint64_t z = seed + (idx + 1) * 0x9E3779B97F4A7C15ull;   // splitmix64
   z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
@@ -1065,18 +1026,6 @@ extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, con
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_ln_gather_merge: C must be 128, 256, 512, 768 or 1024 (got %d)", C);
   }
 #undef LGM_CASE
-  return 0;
-}
-
-extern "C" int toc3d_score_fold_queries(const float* queries, const float* w_in, const float* b_in, const float* w_agg,
-                                        const float* b_agg, float scale, int32_t Bf, int32_t Q, int32_t Cq, int32_t C,
-                                        float* A_out, float* c_out, void* stream) {
-  TOC3D_REQUIRE(queries && w_in && b_in && w_agg && b_agg && A_out && c_out, kErrBadArg, "toc3d_score_fold_queries: null pointer");
-  TOC3D_REQUIRE(Bf > 0 && Q > 0 && Cq > 0 && Cq <= 4096 && C > 0, kErrBadArg, "toc3d_score_fold_queries: bad shape");
-  dim3 grid(Bf, (C + 127) / 128);
-  TOC3D_CHECK_CUDA(launch_pdl(score_fold_kernel, dim3(grid), dim3(128), 2 * Cq * sizeof(float), ST(stream), 1, queries, w_in, b_in, w_agg, b_agg, scale, Q, Cq, C,
-                                                                        A_out, c_out));
-  TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
 

@@ -30,11 +30,6 @@ class Epilogue(ctypes.Structure):
     ]
 
 
-class ChainProblem(ctypes.Structure):
-    _fields_ = [("A", _c_void_p), ("lda", _c_i64), ("B", _c_void_p), ("ldb", _c_i64), ("N", _c_int), ("K", _c_int),
-                ("kind", _c_int), ("epi", ctypes.POINTER(Epilogue))]
-
-
 class PadFill(ctypes.Structure):
     _fields_ = [("qkv", _c_void_p), ("cmap", _c_void_p), ("rope_rows", _c_void_p), ("Mp", _c_int), ("kpad", _c_void_p),
                 ("vpad", _c_void_p), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p), ("ft", _c_int)]
@@ -45,9 +40,6 @@ _SIGS = {
     "toc3d_last_error": ([], ctypes.c_char_p),
     "toc3d_gemm_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int,
                          ctypes.POINTER(Epilogue), _c_void_p], _c_int),
-    "toc3d_gemm_chain_units": ([], _c_int),
-    "toc3d_gemm_chain_bf16": ([ctypes.POINTER(ChainProblem), _c_int, _c_int, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p],
-                              _c_int),
     "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                               _c_float, _c_int, _c_void_p, _c_void_p], _c_int),
@@ -67,8 +59,9 @@ _SIGS = {
                                  _c_void_p, _c_void_p], _c_int),
     "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_int,
                                ctypes.POINTER(PadFill), _c_void_p, _c_void_p], _c_int),
-    "toc3d_score_fold_queries": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_float, _c_int, _c_int,
-                                  _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_motion_blob_floats": ([_c_int, _c_int], _c_i64),
+    "toc3d_motion_queries_fold": ([_c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                   _c_int, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_tokens": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p,
                             _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_score_finish": ([_c_void_p, _c_int, _c_void_p, _c_u64, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
@@ -99,7 +92,7 @@ def load():
             fn = getattr(lib, name)
             fn.argtypes = args
             fn.restype = res
-        if lib.toc3d_abi_version() != 13:
+        if lib.toc3d_abi_version() != 14:
             raise RuntimeError("toc3d_b200: ABI version mismatch")
         _lib = lib
     return _lib
@@ -157,40 +150,6 @@ def gemm(A, B, kind, M=None, **epi):
                                 ctypes.byref(e), _stream())
     _check(rc, "toc3d_gemm_bf16")
     return out
-
-
-def gemm_chain_units():
-    """CTA pairs of the chain kernel that are co-resident on this device (upper bound for a schedule's `units`)."""
-    n = load().toc3d_gemm_chain_units()
-    if n <= 0:
-        raise RuntimeError("toc3d_gemm_chain_units failed: %s" % load().toc3d_last_error().decode())
-    return n
-
-
-def gemm_chain(probs, M, sched, sync):
-    """Consecutive GEMMs as one launch (toc3d_gemm_chain_bf16).  probs: [(A, B, kind, epilogue keywords), ...] exactly
-    as they would be passed to separate gemm() calls, in chain order (2: SWIGLU, RESID; 3: RESID + a_out, SWIGLU, RESID);
-    sched int32 [units, sched_len] from chain_plan.plan_chain (planned for the same M, shapes and tile widths);
-    sync int32 [>= 2 * (len(probs) - 1) * ceil(M / 256)], zeroed once."""
-    _want(sched, torch.int32, "sched"); _want(sync, torch.int32, "sync")
-    assert sched.dim() == 2 and sync.numel() >= 2 * (len(probs) - 1) * ((M + 255) // 256)
-    arr = (ChainProblem * len(probs))()
-    keep = []
-    for i, (A, B, kind, epi) in enumerate(probs):
-        _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
-        N, K = B.shape
-        assert A.shape[1] >= K and A.stride(1) == 1 and B.stride(1) == 1
-        e = _epilogue(**epi)
-        keep.append(e)
-        arr[i].A = A.data_ptr(); arr[i].lda = A.stride(0); arr[i].B = B.data_ptr(); arr[i].ldb = B.stride(0)
-        arr[i].N = N; arr[i].K = K; arr[i].kind = kind; arr[i].epi = ctypes.pointer(e)
-    rc = load().toc3d_gemm_chain_bf16(arr, len(probs), M, _p(sched), sched.shape[0], sched.shape[1], _p(sync), _stream())
-    _check(rc, "toc3d_gemm_chain_bf16")
-
-
-def mlp_chain(A, B0, B1, M, sched, sync, epi0, epi1):
-    """The SwiGLU MLP as one launch: gemm_chain over [SWIGLU(A, B0), RESID(hid, B1)]."""
-    gemm_chain([(A, B0, EPI_SWIGLU, epi0), (epi0["out"], B1, EPI_RESID, epi1)], M, sched, sync)
 
 
 def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None, q_rows=None, item_order=None):
@@ -264,11 +223,32 @@ def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out,
            "toc3d_ln_gather_merge")
 
 
-def score_fold_queries(queries, w_in, b_in, w_agg, b_agg, scale, A_out, c_out):
-    Bf, Q, Cq = queries.shape
-    C = w_in.shape[1]
-    _check(load().toc3d_score_fold_queries(_p(queries), _p(w_in), _p(b_in), _p(w_agg), _p(b_agg), scale, Bf, Q, Cq,
-                                           C, _p(A_out), _p(c_out), _stream()), "toc3d_score_fold_queries")
+def motion_blob_floats(Q, C):
+    n = load().toc3d_motion_blob_floats(Q, C)
+    if n <= 0:
+        raise RuntimeError("toc3d_motion_blob_floats: bad shape Q=%d C=%d" % (Q, C))
+    return n
+
+
+def motion_queries_fold(blob, temp_queries, ref_points, vel, timestamp, ego_pose, ego_pose_inv, scale, C, q_out, A_out, c_out):
+    """Motion-aware query encoder + scorer folding of all stages (toc3d_motion_queries_fold).  blob fp32 [S, stride]
+    (layout: include/toc3d_b200.h); timestamp fp32 or fp64 [Bf, Q(, 1)]; outputs q_out [S,Bf,Q,256], A_out [S,Bf,2,C],
+    c_out [S,Bf,2]."""
+    for t, n in ((blob, "blob"), (temp_queries, "temp_queries"), (ref_points, "ref_points"), (vel, "vel"),
+                 (ego_pose, "ego_pose"), (ego_pose_inv, "ego_pose_inv"), (q_out, "q_out"), (A_out, "A_out"), (c_out, "c_out")):
+        _want(t, torch.float32, n)
+    assert timestamp.dtype in (torch.float32, torch.float64), "timestamp must be fp32 or fp64"
+    S, stride = blob.shape
+    Bf, Q, D = temp_queries.shape
+    assert D == 256 and tuple(q_out.shape) == (S, Bf, Q, 256) and tuple(A_out.shape) == (S, Bf, 2, C)
+    assert timestamp.numel() == Bf * Q and ref_points.numel() == Bf * Q * 3 and vel.numel() == Bf * Q * 2
+    assert ego_pose.numel() == Bf * Q * 16 and ego_pose_inv.numel() == Bf * 16 and c_out.numel() == S * Bf * 2
+    rc = load().toc3d_motion_queries_fold(_p(blob), stride, S, Bf, Q, C, _p(temp_queries), _p(ref_points), _p(vel), _p(timestamp),
+                                          int(timestamp.dtype == torch.float64), _p(ego_pose), _p(ego_pose_inv), scale,
+                                          _p(q_out), _p(A_out), _p(c_out), _stream())
+    _check(rc, "toc3d_motion_queries_fold")
+    global launch_count
+    launch_count += 1          # two kernels behind this entry point (encoder, fold)
 
 
 def score_tokens(x, mask_in, A, c, V, N, C, views_per_frame, gumbel, seed, pred, score, mask_out, seed_dev=None):

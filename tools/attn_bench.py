@@ -6,8 +6,10 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from toc3d_b200 import lib as L  # noqa: E402
+from bench import ClockSampler  # noqa: E402
 
 L.load()
+clk = ClockSampler(0).__enter__()      # same nvidia-smi sampler as bench.py
 dev = "cuda"
 heads, C = 16, 1024
 for nW, seq in [(48, 256), (18, 400), (48, 180), (18, 281), (48, 129), (18, 201), (48, 103), (18, 161), (168, 256), (90, 400)]:
@@ -28,3 +30,5 @@ for nW, seq in [(48, 256), (18, 400), (48, 180), (18, 281), (48, 129), (18, 201)
     ts.sort()
     fl = 4.0 * nW * heads * seq * seq * 64
     print("nW=%3d seq=%3d  %7.1f us  %6.1f TF/s" % (nW, seq, ts[3], fl / ts[3] / 1e6), flush=True)
+clk.__exit__()
+print("clocks:", clk.summary(), flush=True)

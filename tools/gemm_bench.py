@@ -11,6 +11,7 @@ import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from toc3d_b200 import lib as L  # noqa: E402
+from bench import ClockSampler  # noqa: E402
 from toc3d_b200.backbone import hidden_pad, interleave_w12  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -63,6 +64,7 @@ def report(name, M, N, K, fn):
     print("%-22s M=%6d N=%5d K=%5d  %s" % (name, M, N, K, " | ".join(cells)), flush=True)
 
 
+clk = ClockSampler(0).__enter__()      # same nvidia-smi sampler as bench.py: the clocks the numbers were taken at
 C, Hd = 1024, 2730
 Hp = hidden_pad(Hd)
 g = torch.Generator(device=dev); g.manual_seed(0)
@@ -90,3 +92,5 @@ for n in ((4096, 8192) if args.square else ()):
     A = rn(n, n).bfloat16(); B = rn(n, n).bfloat16(); o = torch.empty(n, n, device=dev, dtype=torch.bfloat16)
     report("square linear", n, n, n, lambda t: L.gemm(A, B, L.EPI_LINEAR, out=o, tile_n=t, cluster_pairs=args.cp))
     report("torch.matmul (cuBLAS)", n, n, n, lambda t: torch.matmul(A, B.t()))
+clk.__exit__()
+print("clocks:", clk.summary(), flush=True)
