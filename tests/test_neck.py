@@ -80,3 +80,46 @@ def test_backbone_then_neck_contract():
     feats = neck(list(out.img_feats.values()))
     assert feats[0].shape == (2, 64, 10, 22) and feats[1].shape == (2, 64, 5, 11)
     assert all(torch.isfinite(f).all() for f in feats)
+
+
+@pytest.mark.gpu
+def test_fused_neck_matches_separate_call_and_keeps_state_dict():
+    """fuse_neck: the neck's launches run inside the backbone's CUDA graph; `neck(list(img_feats.values()))` returns those
+    maps (bit-identical to the separate call), the backbone's state-dict keys are unchanged, reloading the neck's
+    weights invalidates the captured graph."""
+    from toc3d_b200 import TINY, EVA_ViT, ToC3DEVAViT
+    from toc3d_b200 import lib as L
+    from toc3d_b200.synthetic import make_gumbel, make_inputs
+    torch.manual_seed(0)
+    bb = ToC3DEVAViT(**TINY).eval().cuda()
+    keys = sorted(bb.state_dict().keys())
+    neck = CPFPN(in_channels=[TINY["embed_dim"]], out_channels=64, num_outs=2).eval().cuda()
+    inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in make_inputs(1, 2, (160, 352), seed=3).items()}
+    gn = make_gumbel(2, 220, seed=4)
+    out = bb(**inp, gumbel_noise=gn)
+    sep = neck(list(out.img_feats.values()))
+    bb.fuse_neck(neck)
+    assert sorted(bb.state_dict().keys()) == keys
+    out2 = bb(**inp, gumbel_noise=gn)                       # eager path (injected noise)
+    n0 = L.launch_count
+    fused = neck(list(out2.img_feats.values()))
+    assert L.launch_count == n0, "the fused neck must not launch anything in its own forward"
+    assert torch.equal(out.img_feats["last_feat"], out2.img_feats["last_feat"])
+    assert all(torch.equal(a, b) for a, b in zip(sep, fused)) and fused[1].shape == (2, 64, 5, 11)
+    # graph path: replay twice, results finite and identical in shape; a plain tensor (not from this backbone) still works
+    o3 = bb(**inp); f3 = neck(list(o3.img_feats.values()))
+    o4 = bb(**inp); f4 = neck(list(o4.img_feats.values()))
+    assert f3[0].shape == sep[0].shape and torch.isfinite(f4[0]).all() and f3[0].data_ptr() != f4[0].data_ptr()
+    again = neck([out.img_feats["last_feat"].clone()])
+    assert all(torch.equal(a, b) for a, b in zip(sep, again))
+    assert len(bb._graphs) > 0
+    neck.load_state_dict(neck.state_dict())
+    assert len(bb._graphs) == 0
+    # dense backbone
+    d = EVA_ViT(**{k: v for k, v in TINY.items() if k not in ("pc_range", "pruning_num_queries", "pruning_loc", "accelerate_global",
+                                                               "token_ratio", "token_selection_loss", "rope_acc")}).eval().cuda()
+    x = inp["x"]
+    a = neck([d(x)["last_feat"]])
+    d.fuse_neck(neck)
+    b = neck([d(x)["last_feat"]])
+    assert all(torch.equal(u, v) for u, v in zip(a, b))

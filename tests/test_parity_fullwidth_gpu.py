@@ -24,9 +24,9 @@ pytestmark = pytest.mark.gpu
 
 REL_TOL = 2e-2            # last_feat rel-l2 after 24 blocks of bf16-operand GEMMs (fp32 accumulate, fp32 residual stream)
 SCORE_TOL = 0.08          # device scorer vs oracle scorer, log-prob units, residual-stream error included
-SCORE_TOL_ISO = 2e-3      # same, isolated (identical fp32 input): the scorer kernels' own arithmetic
+SCORE_TOL_ISO = 1e-4      # same, isolated (identical fp32 input): the folded fp32 scorer's own arithmetic (measured 2e-6)
 MASK_TOL = 2e-2           # token mask = softmax(logp + g)[..., 0]
-BLOCK_ABS_TOL = 0.15      # one block in isolation, max-abs at |x| up to ~30 (bf16 operand rounding: 2^-9 relative)
+BLOCK_ABS_TOL = 0.05      # one block in isolation, max-abs at |x| up to ~30 (bf16 operand rounding; measured 0.021 - 0.026)
 BLOCK_REL_TOL = 4e-3      # one block in isolation, rel-l2 of the block output
 
 
@@ -84,7 +84,7 @@ def _check_toc3d(name, frames, views, seed, prev=True, isolated=True, label=None
     for j, (s_c, s_o) in enumerate(zip(tap2["scores_raw"], ref["scores"])):
         d = (s_c.cpu().reshape(-1) - s_o.reshape(-1)).abs().max().item()
         print("%s: stage %d ISOLATED score max-abs diff %.6f" % (label, j, d))
-        assert d <= (SCORE_TOL_ISO if prev else 3e-2), (label, j, d)   # first-frame scorer: 4 bf16-operand GEMMs
+        assert d <= (SCORE_TOL_ISO if prev else 2e-3), (label, j, d)   # first-frame scorer: 4 bf16-operand GEMMs (measured 1.5e-4)
     iso = [_stats(a.cpu().view_as(b), b) for a, b in zip(tap2["block_out"], tap_o["block_out"])]
     mags = [b.abs().max().item() for b in tap_o["block_out"]]
     print("%s: ISOLATED per-block max-abs: %s" % (label, " ".join("%.4f" % e[0] for e in iso)))

@@ -633,6 +633,29 @@ class _EvaBase(nn.Module):
             self._engine.has_cls = self.pretrain_use_cls_token
         return self._engine
 
+    def fuse_neck(self, neck):
+        """Run `neck` (toc3d_b200.CPFPN) at the end of this backbone's own launch sequence / CUDA graph.  The plugin
+        boundary is unchanged: forward returns what it always returns, and `neck(list(img_feats.values()))` - the call
+        Petr3D makes (petr3d.py:188-190) - hands back the maps computed here instead of launching anything.  None undoes it."""
+        import weakref
+        object.__setattr__(self, "_fused_neck", neck)      # NOT a sub-module: the state-dict keys stay the reference's
+        if neck is not None:
+            if not hasattr(neck, "_fused_into"):
+                neck._fused_into = []
+            neck._fused_into.append(weakref.ref(self))
+        self._graphs = {}
+
+    def _neck_tail(self, X, V, H, W):
+        """-> tuple with the fused neck's level-0 rows (fp32 [V*H*W, out_channels]) or ()."""
+        neck = getattr(self, "_fused_neck", None)
+        return () if neck is None else (neck.launch(X, V, H, W),)
+
+    def _attach_neck(self, last_feat, extra, V, H, W):
+        neck = getattr(self, "_fused_neck", None)
+        if neck is not None:
+            last_feat._toc3d_fused_neck = (neck, neck.levels(extra[0], V, H, W))
+        return last_feat
+
     def set_image_preprocess(self, mean, std, to_rgb=True, size_divisor=32, size=None):
         """Row f3: take over `NormalizeMultiviewImage(**img_norm_cfg)` + `PadMultiViewImage(size_divisor=32)`
         (transform_3d.py:21-104).  Afterwards `forward(x=...)` also accepts the uint8 HWC camera crops
@@ -703,15 +726,16 @@ class EVA_ViT(_EvaBase):
                 eng.dense_block(i, X, wsp)
                 if tap is not None:
                     tap["block_out"].append(X.clone())
-            return (X,)
+            return (X,) + self._neck_tail(X, V, Hi // 16, Wi // 16)
 
         GLOBAL_TIMER.event_start("StreamPETR-EVA-ViT/backbone")
         if self.use_cuda_graph and tap is None:
-            (X,) = self._graphed(("dense", V, Hi, Wi, tuple(x.shape), x.dtype), {"x": x}, core)
+            X, *extra = self._graphed(("dense", V, Hi, Wi, tuple(x.shape), x.dtype), {"x": x}, core)
         else:
-            (X,) = core({"x": x})
+            X, *extra = core({"x": x})
         GLOBAL_TIMER.event_end("StreamPETR-EVA-ViT/backbone")
-        return {self._out_features[0]: X.view(V, Hi // 16, Wi // 16, -1).permute(0, 3, 1, 2)}
+        lf = X.view(V, Hi // 16, Wi // 16, -1).permute(0, 3, 1, 2)
+        return {self._out_features[0]: self._attach_neck(lf, extra, V, Hi // 16, Wi // 16)}
 
 
 @_register
@@ -798,7 +822,8 @@ class ToC3DEVAViT(_EvaBase):
 
         def core(t):
             q_kw = {k: t[k] for k in q_names} if prev else None
-            return self._forward_core(eng, t["x"], (H, W), q_kw, gumbel_noise, teacher_scores, tap)
+            flat = self._forward_core(eng, t["x"], (H, W), q_kw, gumbel_noise, teacher_scores, tap)
+            return tuple(flat) + self._neck_tail(flat[0], V, H, W)
 
         GLOBAL_TIMER.event_start("ToC3D-StreamPETR-EVAViT/backbone")
         if self.use_cuda_graph and gumbel_noise is None and teacher_scores is None and tap is None:
@@ -807,8 +832,8 @@ class ToC3DEVAViT(_EvaBase):
         else:
             flat = core(tensors)
         GLOBAL_TIMER.event_end("ToC3D-StreamPETR-EVAViT/backbone")
-        X, masks, keeps, drops = flat[0], list(flat[1:1 + nst]), list(flat[1 + nst:1 + 2 * nst]), list(flat[1 + 2 * nst:])
-        outputs = {self._out_features[0]: X.view(V, H, W, -1).permute(0, 3, 1, 2)}
+        X, masks, keeps, drops = flat[0], list(flat[1:1 + nst]), list(flat[1 + nst:1 + 2 * nst]), list(flat[1 + 2 * nst:1 + 3 * nst])
+        outputs = {self._out_features[0]: self._attach_neck(X.view(V, H, W, -1).permute(0, 3, 1, 2), flat[1 + 3 * nst:], V, H, W)}
         none_if_empty = lambda l: l if len(l) else None
         return ToC3DViTReturnType(outputs, none_if_empty([m.view(V, H, W, 1) for m in masks]), None,
                                   keep_idx=none_if_empty(keeps), drop_idx=none_if_empty(drops), aux_outputs=None)

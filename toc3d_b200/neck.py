@@ -52,12 +52,19 @@ class CPFPN(nn.Module):
         self.fpn_convs = nn.ModuleList([_ConvModule(out_channels, out_channels, 3, padding=1)])
         self._packed = None
 
-    def _apply(self, fn, *a, **k):
+    def _invalidate(self):
         self._packed = None
+        for ref in getattr(self, "_fused_into", []):       # backbones whose captured graphs hold pointers to the packed weights
+            bb = ref()
+            if bb is not None:
+                bb._graphs = {}
+
+    def _apply(self, fn, *a, **k):
+        self._invalidate()
         return super()._apply(fn, *a, **k)
 
     def load_state_dict(self, *a, **k):
-        self._packed = None
+        self._invalidate()
         return super().load_state_dict(*a, **k)
 
     def _weights(self, dev):
@@ -71,33 +78,49 @@ class CPFPN(nn.Module):
                                 b3=self.fpn_convs[0].conv.bias.detach().to(dev).float().contiguous())
         return self._packed
 
+    def launch(self, x2d, V, H, W):
+        """The neck's launch sequence on the residual-stream buffer itself: x2d = fp32 (or bf16) [V*H*W, C] NHWC rows.
+        -> level-0 output, fp32 [V*H*W, out_channels] (NHWC rows).  Stream-ordered, allocation-only host work, so the
+        backbone can run it inside its own CUDA graph (ToC3DEVAViT.fuse_neck)."""
+        M, C = x2d.shape
+        co = self.out_channels
+        p = self._weights(x2d.device)
+        bf = dict(device=x2d.device, dtype=torch.bfloat16)
+        if x2d.dtype == torch.bfloat16:
+            a = x2d
+        else:
+            a = torch.empty(M, C, **bf)
+            L.cast_bf16(x2d, a)
+        lat = torch.empty(M, co, **bf)
+        L.gemm(a, p["w1"], L.EPI_LINEAR, bias=p["b1"], out=lat)                            # lateral 1x1 (cp_fpn.py:163-166)
+        cols = torch.empty(M, 9 * co, **bf)
+        L.im2col_3x3(lat, cols, V, H, W, co)
+        out0 = torch.empty(M, co, device=x2d.device, dtype=torch.float32)
+        L.gemm(cols, p["w3"], L.EPI_LINEAR, bias=p["b3"], out=out0, out_f32=True)          # fpn 3x3 (cp_fpn.py:182-184)
+        return out0
+
+    def levels(self, out0, V, H, W):
+        """NCHW views of the output pyramid: level 0 and its stride-2 subsamples (F.max_pool2d(x, 1, stride=2),
+        cp_fpn.py:190-191)."""
+        outs = [out0.view(V, H, W, self.out_channels).permute(0, 3, 1, 2)]
+        for _ in range(self.num_outs - 1):
+            outs.append(outs[-1][:, :, ::2, ::2])
+        return tuple(outs)
+
     @torch.no_grad()
     def forward(self, inputs):
         assert len(inputs) == len(self.in_channels)                                       # cp_fpn.py:160
         x = inputs[0]
+        fused = getattr(x, "_toc3d_fused_neck", None)
+        if fused is not None and fused[0] is self:
+            return fused[1]                 # computed inside the backbone's CUDA graph (ToC3DEVAViT.fuse_neck)
         if not x.is_cuda:
             raise RuntimeError("toc3d_b200 CPFPN runs on CUDA (sm_100a) only; there is no CPU fallback")
         if self.training:
             raise RuntimeError("toc3d_b200 CPFPN is inference-only; call .eval()")
         V, C, H, W = x.shape
-        co = self.out_channels
-        p = self._weights(x.device)
         nhwc = x.permute(0, 2, 3, 1)                        # the backbone hands out a permuted view of NHWC storage
         nhwc = nhwc if nhwc.is_contiguous() else nhwc.contiguous()
-        M = V * H * W
-        bf = dict(device=x.device, dtype=torch.bfloat16)
-        if nhwc.dtype == torch.bfloat16:
-            a = nhwc.reshape(M, C)
-        else:
-            a = torch.empty(M, C, **bf)
-            L.cast_bf16(nhwc.float().reshape(M, C), a)
-        lat = torch.empty(M, co, **bf)
-        L.gemm(a, p["w1"], L.EPI_LINEAR, bias=p["b1"], out=lat)                            # lateral 1x1 (cp_fpn.py:163-166)
-        cols = torch.empty(M, 9 * co, **bf)
-        L.im2col_3x3(lat, cols, V, H, W, co)
-        out0 = torch.empty(M, co, device=x.device, dtype=torch.float32)
-        L.gemm(cols, p["w3"], L.EPI_LINEAR, bias=p["b3"], out=out0, out_f32=True)          # fpn 3x3 (cp_fpn.py:182-184)
-        outs = [out0.view(V, H, W, co).permute(0, 3, 1, 2)]
-        for _ in range(self.num_outs - 1):
-            outs.append(outs[-1][:, :, ::2, ::2])           # F.max_pool2d(x, 1, stride=2) (cp_fpn.py:190-191)
-        return tuple(outs)
+        if nhwc.dtype != torch.bfloat16:
+            nhwc = nhwc.float()
+        return self.levels(self.launch(nhwc.reshape(V * H * W, C), V, H, W), V, H, W)
