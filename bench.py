@@ -282,9 +282,6 @@ def run_native(args):
     model.set_image_preprocess(**IMG_NORM)       # row f3: lets forward() take the uint8 camera crops as well
     if args.view_groups is not None and hasattr(model, "view_groups"):
         model.view_groups = args.view_groups
-    if args.fold_norm2:                          # tested option (norm2 inside the proj / SwiGLU epilogues); default off
-        model.fold_norm2 = True
-        model.refresh_weights()
     B = args.batch
     V = B * VIEWS
     H, W = hw[0] // 16, hw[1] // 16
@@ -628,7 +625,6 @@ def main():
     ap.add_argument("--no-batch4", action="store_true", help="skip the extra batch-4 throughput line")
     ap.add_argument("--view-groups", type=int, default=None, help="override the plugin's view_groups (streams of views)")
     ap.add_argument("--overlap-gather", action="store_true", help="experiment (N > 1): extra line with the all-gather overlapped")
-    ap.add_argument("--fold-norm2", action="store_true", help="tested option: norm2 folded into the proj / SwiGLU GEMM epilogues")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":

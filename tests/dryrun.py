@@ -71,7 +71,7 @@ def recording():
 
 def run(model, inputs, **options):
     """One eager forward of `model` (CPU tensors) under recording(); options are set as model attributes
-    (fold_norm2, view_groups, ...).  -> list of records."""
+    (view_groups, ...).  -> list of records."""
     for k, v in options.items():
         setattr(model, k, v)
     model.refresh_weights()

@@ -244,53 +244,6 @@ def test_gemm_swiglu_folded_subln(lib, M, Hd, C):
 
 
 # ------------------------------------------------------------------------------------ attention
-@pytest.mark.parametrize("M,C,Hd,scatter", [(300, 256, 341, False), (1000, 128, 200, True), (513, 1024, 2730, False)])
-def test_gemm_norm2_fold_chain(lib, M, C, Hd, scatter):
-    """norm2 folded into the GEMMs (eva_vit.py:262-266): the proj epilogue emits the bf16 copy of the new residual
-    rows and their fixed-point row statistics, the SwiGLU epilogue applies the LayerNorm from those statistics."""
-    from toc3d_b200.backbone import interleave_w12, hidden_pad
-    g = torch.Generator().manual_seed(M + C)
-    K0, eps = 128, 1e-6
-    Hp = hidden_pad(Hd)
-    A0 = bf16_round(torch.randn(M, K0, generator=g))
-    Wp = bf16_round(torch.randn(C, K0, generator=g) * 0.2); bp = torch.randn(C, generator=g) * 0.1
-    resid = torch.randn(M, C, generator=g) * 3 + 0.7
-    g2 = 1 + 0.1 * torch.randn(C, generator=g); be2 = 0.1 * torch.randn(C, generator=g)
-    w1 = torch.randn(Hd, C, generator=g) * 0.05; w2 = torch.randn(Hd, C, generator=g) * 0.05
-    b1 = torch.randn(Hd, generator=g) * 0.1; b2 = torch.randn(Hd, generator=g) * 0.1
-    # fp32 reference
-    t1 = resid + A0 @ Wp.t() + bp
-    y = torch.nn.functional.layer_norm(t1, (C,), g2, be2, eps)
-    h_ref = torch.nn.functional.silu(y @ w1.t() + b1) * (y @ w2.t() + b2)
-    # device: proj with a_out + statistics (optionally scattered through an out_map like the dense block)
-    perm = torch.randperm(M, generator=g).int() if scatter else None
-    t1_d = torch.empty(M, C, device=DEV)
-    a_d = torch.full((M, C), float("nan"), device=DEV, dtype=torch.bfloat16)
-    st2 = torch.zeros(M, 2, device=DEV, dtype=torch.int64)
-    st = torch.ones(M, 2, device=DEV, dtype=torch.int64)
-    lib.gemm(A0.to(DEV).bfloat16(), Wp.to(DEV).bfloat16(), lib.EPI_RESID, bias=bp.to(DEV), out=t1_d, resid=resid.to(DEV),
-             out_map=perm.to(DEV) if scatter else None, a_out=a_d, row_stats=st2, zero_stats=st)
-    torch.cuda.synchronize()
-    dst = perm.long() if scatter else torch.arange(M)
-    assert (t1_d.cpu()[dst] - t1).abs().max().item() < 2e-3
-    assert torch.equal(a_d.float().cpu(), bf16_round(t1_d.cpu()))
-    assert (st == 0).all()
-    mean_dev = st2[:, 0].double().cpu() / 2 ** 30 / C
-    var_dev = st2[:, 1].double().cpu() / 2 ** 26 / C - mean_dev ** 2
-    assert (mean_dev[dst] - t1.double().mean(1)).abs().max().item() < 1e-4
-    assert (var_dev[dst] - t1.double().var(1, unbiased=False)).abs().max().item() < 1e-3 * t1.var(1).max().item()
-    # SwiGLU GEMM with the LayerNorm folded in: W' = W * gamma, u = W gamma, c = W beta + b
-    W12, c12 = interleave_w12(w1 * g2[None], w1 @ be2 + b1, w2 * g2[None], w2 @ be2 + b2, Hp)
-    _, u12 = interleave_w12(w1, w1 @ g2, w2, w2 @ g2, Hp)
-    hid = torch.full((M, Hp), float("nan"), device=DEV, dtype=torch.bfloat16)
-    lib.gemm(a_d, W12.to(DEV).bfloat16(), lib.EPI_SWIGLU, bias=c12.to(DEV), out=hid, row_stats=st, ln_stats=st2,
-             ln_u=u12.to(DEV), ln_n=C, ln_eps=eps)
-    got = hid.float().cpu()[dst]
-    assert torch.isfinite(got).all()
-    assert rel_err(got[:, :Hd], h_ref) < 2e-2, rel_err(got[:, :Hd], h_ref)
-    assert (got[:, Hd:] == 0).all()
-
-
 @pytest.mark.parametrize("seq", [1, 16, 64, 77, 103, 121, 129, 161, 180, 192, 193, 201, 256, 257, 281, 400, 401, 448, 449, 600])
 def test_window_attention(lib, seq):
     """seq <= 448: tcgen05/TMEM kernel (256 or 512 TMEM columns, 1 or 2 S halves); above: mma.sync fallback."""

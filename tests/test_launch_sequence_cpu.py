@@ -1,5 +1,5 @@
 """Host logic of the plugin without a GPU (tests/dryrun.py): the launch sequence of the default path and of the tested
-options (fold_norm2, view_groups)."""
+options (view_groups)."""
 import torch
 
 from tests import dryrun
@@ -42,8 +42,6 @@ def test_dense_model_sequences():
     seq = dryrun.names(dryrun.run(m, inp))
     depth = len(m.blocks)
     assert seq.count("window_attention") == depth and seq.count("layernorm_rows") == 2 * depth
-    seq2 = dryrun.names(dryrun.run(m, inp, fold_norm2=True))
-    assert seq2.count("layernorm_rows") == depth                                   # norm2 lives in the GEMM epilogues
 
 
 TINY_DENSE = {k: v for k, v in TINY.items() if k not in ("pc_range", "pruning_num_queries", "pruning_loc", "accelerate_global",

@@ -246,7 +246,6 @@ class _Workspace:
         self.hid = torch.empty(rows, eng.Hp, **bf)
         self.T = torch.empty(rows, C, device=dev, dtype=torch.float32)   # packed slow+rep residual stream
         self.stats = torch.zeros(rows, 2, device=dev, dtype=torch.int64)   # sub-LN fixed-point [sum, sum sq] per MLP row
-        self.stats2 = torch.zeros(rows, 2, device=dev, dtype=torch.int64)  # norm2 statistics of the post-attention rows
         self.merge_cnt = torch.zeros(max(v["nW"] for v in self.win.values()), device=dev, dtype=torch.int32)
         self.stage = {}                                # (stage, ws) -> selection tables
 
@@ -257,7 +256,6 @@ class _Engine:
     def __init__(self, model, device):
         self.device = device
         m = model
-        self.fold_norm2 = bool(getattr(model, "fold_norm2", False))
         self.C, self.heads, self.patch = m.embed_dim, m.num_heads, m.patch_size
         self.block_ws = [b.window_size for b in m.blocks]
         self.block_acc = [b.accelerate for b in m.blocks]
@@ -276,16 +274,8 @@ class _Engine:
             zeros = torch.zeros(C, device=device)
             qb = f32(a.q_bias) if a.q_bias is not None else zeros
             vb = f32(a.v_bias) if a.v_bias is not None else zeros
-            w1, w2, g2, be2 = f32(b.mlp.w1.weight), f32(b.mlp.w2.weight), f32(b.norm2.weight), f32(b.norm2.bias)
-            if self.fold_norm2:
-                # norm2 (eva_vit.py:263) folded into the w1/w2 GEMM: W' = W * gamma2 (columns), u = W gamma2,
-                # c = W beta2 + b; the SwiGLU epilogue applies rstd * acc - rstd * mean * u + c per row
-                w12, b12 = interleave_w12(w1 * g2[None, :], w1 @ be2 + f32(b.mlp.w1.bias), w2 * g2[None, :],
-                                          w2 @ be2 + f32(b.mlp.w2.bias), self.Hp)
-                _, u12 = interleave_w12(w1, w1 @ g2, w2, w2 @ g2, self.Hp)
-            else:
-                w12, b12 = interleave_w12(w1, f32(b.mlp.w1.bias), w2, f32(b.mlp.w2.bias), self.Hp)
-                u12 = None
+            w1, w2 = f32(b.mlp.w1.weight), f32(b.mlp.w2.weight)
+            w12, b12 = interleave_w12(w1, f32(b.mlp.w1.bias), w2, f32(b.mlp.w2.bias), self.Hp)
             ft = a.rope.ft
             self.blocks.append(dict(
                 n1w=f32(b.norm1.weight), n1b=f32(b.norm1.bias), n2w=f32(b.norm2.weight), n2b=f32(b.norm2.bias),
@@ -296,7 +286,7 @@ class _Engine:
                 kpad=(b16(a.k_proj.weight).float() @ b16(b.norm1.bias).float()).contiguous(),
                 vpad=(b16(a.v_proj.weight).float() @ b16(b.norm1.bias).float() + vb).contiguous(),
                 wproj=b16(a.proj.weight), bproj=f32(a.proj.bias),
-                w12=w12.to(torch.bfloat16).contiguous(), b12=b12, u12=u12,
+                w12=w12.to(torch.bfloat16).contiguous(), b12=b12,
                 # SwiGLU sub-LN (eva_vit.py:48) folded into the w3 GEMM: w3g = W3 * gamma (columns),
                 # u3 = W3 gamma, c3 = W3 beta + b3; the epilogue applies rstd * acc - rstd * mean * u3 + c3
                 w3=F.pad(f32(b.mlp.w3.weight) * f32(b.mlp.ffn_ln.weight)[None, :],
@@ -377,18 +367,11 @@ class _Engine:
 
     # -- MLP shared by both block kinds ----------------------------------------------------------
     def _mlp(self, bp, wsp, M, **resid_kw):
-        """eva_vit.py:44-51 (+ norm2 of :263 when folded).  wsp.a holds the bf16 A rows: LayerNorm output, or with
-        fold_norm2 the un-normalised post-attention rows whose statistics are in wsp.stats2.  wsp.stats rows
-        [0, M) must be zero on entry (zeroed by the norm2 launch or by the proj epilogue)."""
-        ln = dict(ln_stats=wsp.stats2, ln_u=bp["u12"], ln_n=self.C, ln_eps=LN_EPS) if self.fold_norm2 else {}
-        L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats, **ln)
+        """eva_vit.py:44-51.  wsp.a holds the bf16 norm2 rows; wsp.stats rows [0, M) must be zero on entry (zeroed by the
+        norm2 launch)."""
+        L.gemm(wsp.a, bp["w12"], L.EPI_SWIGLU, M=M, bias=bp["b12"], out=wsp.hid, row_stats=wsp.stats)
         L.gemm(wsp.hid, bp["w3"], L.EPI_RESID, M=M, bias=bp["b3"], ldo=self.C, ln_stats=wsp.stats, ln_u=bp["u3"],
                ln_n=self.Hd, ln_eps=LN_EPS, **resid_kw)
-
-    def _proj_kw(self, wsp):
-        """Extra outputs of the proj GEMM when norm2 is folded: bf16 copy of the new residual rows (A operand of
-        the SwiGLU GEMM), their row statistics, and the zeroing of the sub-LN accumulator."""
-        return dict(a_out=wsp.a, row_stats=wsp.stats2, zero_stats=wsp.stats) if self.fold_norm2 else {}
 
     def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots, qkv_out_map=None, attn_out_map=None, q_rows=None,
                   item_order=None, join=None):
@@ -417,12 +400,11 @@ class _Engine:
         fs.wait_stream(cur)                                  # the previous attention has finished reading qkv
         with torch.cuda.stream(fs):
             L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
-        L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None)
+        L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS)
         self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"],
                        q_rows=w["q_rows"], item_order=w["item_order"], join=fs)
-        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X, **self._proj_kw(wsp))
-        if not self.fold_norm2:
-            L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
+        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X)
+        L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
         self._mlp(bp, wsp, VN, out=X, resid=X)
 
     def select_windows(self, stage, score, ratio, wsp):
@@ -471,16 +453,15 @@ class _Engine:
         Mp = nW * (k + 1)
         # one launch: representative token (-> T[rep_row]) + norm1 of the compact rows + k / v of the pad rows
         L.ln_gather_merge(X, t["ctok"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
-                          wsp.T, nW, k, nf, C, LN_EPS, zero_stats=wsp.stats2 if self.fold_norm2 else None,
+                          wsp.T, nW, k, nf, C, LN_EPS,
                           rep_row=t["rep_row"], compact_rows=Mc,
                           pad_fill=(wsp.qkv, t["cmap"], t["prope"], Mp, bp["kpad"], bp["vpad"], bp["cos"], bp["sin"], bp["ft"]),
                           counters=wsp.merge_cnt)
         self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"],
                        q_rows=t["q_rows"], item_order=t["item_order"])
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
-               resid_map=t["ctok"], out_alt=wsp.T, **self._proj_kw(wsp))                # t1 = t + attn
-        if not self.fold_norm2:
-            L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
+               resid_map=t["ctok"], out_alt=wsp.T)                                      # t1 = t + attn
+        L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
         self._mlp(bp, wsp, Mc, out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T)     # t2 -> image rows
         L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C, rep_row=t["rep_row"])
 
@@ -562,10 +543,6 @@ class _EvaBase(nn.Module):
         self._engine = None
         self._graphs = {}
         self.use_cuda_graph = True     # replay the whole forward as one CUDA graph per (shape, prev_exists)
-        # norm2 folded into the proj / SwiGLU GEMM epilogues (no LayerNorm launch).  Tested option, OFF by default:
-        # measured on B200 it saves 0.29 ms of LayerNorm launches but adds 0.28 ms to the (exposed, L2-bound) proj
-        # epilogue - 162.9 vs 169 samples/s.  Set before the first forward (or call refresh_weights()) to change.
-        self.fold_norm2 = False
         # views are independent: with G > 1 the forward runs G groups of views on their own streams inside the
         # one CUDA graph, so the tail / epilogue of one group's kernels overlaps the other group's kernels
         self.view_groups = 1

@@ -58,13 +58,11 @@ struct EpiParams {
   float q_scale;
   const float* cos_axis;
   const float* sin_axis;
-  long long* row_stats;          // OUTPUT statistics accumulator (SWIGLU: hidden rows; RESID + a_out: result rows)
-  const long long* ln_stats;     // INPUT statistics of the A rows for a folded LayerNorm (RESID, SWIGLU)
+  long long* row_stats;          // OUTPUT statistics accumulator (SWIGLU: per-row sum / sum of squares of the hidden rows)
+  const long long* ln_stats;     // INPUT statistics of the A rows for a folded LayerNorm (RESID)
   const float* ln_u;
   int ln_n;
   float ln_eps;
-  __nv_bfloat16* a_out;          // RESID: bf16 copy of the result rows (A operand of the next GEMM)
-  long long* zero_stats;         // RESID + a_out: statistics rows zeroed for the GEMM after the next one
 };
 
 // Folded-LayerNorm row statistics are accumulated as int64 fixed point: sum * 2^30 (|sum| < 8.6e9,
@@ -121,7 +119,7 @@ __device__ __forceinline__ void ln_fold_coeffs(const long long* stats_row, int n
   b = -a * (float)mean;
 }
 
-template <int EPI, bool LNF, bool AOUT>
+template <int EPI, bool LNF>
 __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int nt0, int bn, int half,
                                                    int M, int N, float* stage, int lane, uint64_t* full_bar,
                                                    uint32_t parity) {
@@ -136,10 +134,6 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
     // this row's sum / sum of squares of the bf16-rounded hidden values, accumulated per 32-column block
     // in fixed point so that the result does not depend on the tile width or on which warp owns a block
     long long st_sum = 0, st_sq = 0;
-    float la = 1.0f, lb = 0.0f;          // LNF: LayerNorm of the A rows folded in (norm2 before w1/w2, eva_vit.py:263)
-    if constexpr (LNF) {
-      if (my_row_ok) ln_fold_coeffs(ep.ln_stats + 2 * (size_t)(m0 + lane), ep.ln_n, ep.ln_eps, la, lb);
-    }
     mbar_wait(full_bar, parity);
     tcgen05_fence_after();
 #pragma unroll 1
@@ -159,16 +153,10 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
             b1 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1) + j);
             b2 = __ldg(reinterpret_cast<const float4*>(ep.bias + col1 + 32) + j);
           }
-          if constexpr (LNF) {
-            const float4 u1 = __ldg(reinterpret_cast<const float4*>(ep.ln_u + col1) + j);
-            const float4 u2 = __ldg(reinterpret_cast<const float4*>(ep.ln_u + col1 + 32) + j);
-            b1.x = fmaf(lb, u1.x, b1.x); b1.y = fmaf(lb, u1.y, b1.y); b1.z = fmaf(lb, u1.z, b1.z); b1.w = fmaf(lb, u1.w, b1.w);
-            b2.x = fmaf(lb, u2.x, b2.x); b2.y = fmaf(lb, u2.y, b2.y); b2.z = fmaf(lb, u2.z, b2.z); b2.w = fmaf(lb, u2.w, b2.w);
-          }
-          h[4 * j + 0] = silu(fmaf(la, __uint_as_float(v1[4 * j + 0]), b1.x)) * fmaf(la, __uint_as_float(v2[4 * j + 0]), b2.x);
-          h[4 * j + 1] = silu(fmaf(la, __uint_as_float(v1[4 * j + 1]), b1.y)) * fmaf(la, __uint_as_float(v2[4 * j + 1]), b2.y);
-          h[4 * j + 2] = silu(fmaf(la, __uint_as_float(v1[4 * j + 2]), b1.z)) * fmaf(la, __uint_as_float(v2[4 * j + 2]), b2.z);
-          h[4 * j + 3] = silu(fmaf(la, __uint_as_float(v1[4 * j + 3]), b1.w)) * fmaf(la, __uint_as_float(v2[4 * j + 3]), b2.w);
+          h[4 * j + 0] = silu(__uint_as_float(v1[4 * j + 0]) + b1.x) * (__uint_as_float(v2[4 * j + 0]) + b2.x);
+          h[4 * j + 1] = silu(__uint_as_float(v1[4 * j + 1]) + b1.y) * (__uint_as_float(v2[4 * j + 1]) + b2.y);
+          h[4 * j + 2] = silu(__uint_as_float(v1[4 * j + 2]) + b1.z) * (__uint_as_float(v2[4 * j + 2]) + b2.z);
+          h[4 * j + 3] = silu(__uint_as_float(v1[4 * j + 3]) + b1.w) * (__uint_as_float(v2[4 * j + 3]) + b2.w);
         }
       }
       if (ep.row_stats != nullptr) {
@@ -220,13 +208,6 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       rr_t = ep.resid_mod > 0 ? (row % ep.resid_mod) : (ep.resid_map ? ep.resid_map[row] : row);
       or_t = ep.out_map ? ep.out_map[row] : row;
       if constexpr (LNF) ln_fold_coeffs(ep.ln_stats + 2 * (size_t)row, ep.ln_n, ep.ln_eps, lnA_t, lnB_t);
-    }
-    // AOUT: destination row of THIS lane's row (thread = row domain) for the statistics / zeroing
-    const int dst_t = !my_row_ok ? -1 : (or_t >= 0 ? or_t : (or_t == -2 ? m0 + lane : -1));
-    long long st_sum = 0, st_sq = 0;
-    if constexpr (AOUT) {
-      if (dst_t >= 0 && ep.zero_stats != nullptr && nt0 == 0 && half == 0)
-        *reinterpret_cast<longlong2*>(ep.zero_stats + 2 * (size_t)dst_t) = make_longlong2(0, 0);
     }
     // 32-bit row indices + masks instead of 16 pointers (register pressure)
     int o_row[8], r_row[8];
@@ -307,44 +288,14 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
           o.w = r_cur[it].w + (fmaf(la[it], a.w, lb[it] * u4.w) + b.w);
           float* base = ((o_alt >> it) & 1u) ? ep.out_alt : reinterpret_cast<float*>(ep.out);
           __stcg(reinterpret_cast<float4*>(base + (size_t)o_row[it] * ep.ldo + col), o);
-          if constexpr (AOUT) {
-            uint2 u;
-            u.x = pack_bf16(o.x, o.y);
-            u.y = pack_bf16(o.z, o.w);
-            *reinterpret_cast<uint2*>(ep.a_out + (size_t)o_row[it] * ep.ldo + col) = u;
-            stage_write(stage, it * 4 + rin, cseg, o);     // back to the staging tile for the row statistics
-          }
-        } else if constexpr (AOUT) {
-          stage_write(stage, it * 4 + rin, cseg, make_float4(0.f, 0.f, 0.f, 0.f));
         }
       }
       __syncwarp();
-      if constexpr (AOUT) {
-        // thread = row again: sum / sum of squares of this row's 32 result columns, fixed point per chunk
-        float bs = 0.f, bq = 0.f;
-        const float4* srow = reinterpret_cast<const float4*>(stage) + lane * 8;
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const float4 t = srow[j ^ (lane & 7)];
-          bs += (t.x + t.y) + (t.z + t.w);
-          bq += (t.x * t.x + t.y * t.y) + (t.z * t.z + t.w * t.w);
-        }
-        st_sum += __float2ll_rn(bs * (float)STAT_SUM_SCALE);
-        st_sq += __float2ll_rn(bq * (float)STAT_SQ_SCALE);
-        __syncwarp();
-      }
       if (more) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) r_cur[it] = r_nxt[it];
         b = b_nxt;
         u4 = u_nxt;
-      }
-    }
-    if constexpr (AOUT) {
-      if (dst_t >= 0) {
-        unsigned long long* dst = reinterpret_cast<unsigned long long*>(ep.row_stats + 2 * (size_t)dst_t);
-        atomicAdd(dst, (unsigned long long)st_sum);
-        atomicAdd(dst + 1, (unsigned long long)st_sq);
       }
     }
     return;
@@ -451,7 +402,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
 }
 
 // (registers are allocated per 4 warps: 10 warps count as 12, hence the 168-register cap)
-template <int EPI, bool LNF, bool AOUT>
+template <int EPI, bool LNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
             int BN, int mc, const EpiParams ep) {
@@ -596,7 +547,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m_idx = (tile % num_m) * mrows + (int)prank * (2 * BM) + (int)rank * BM;
       const int n_idx = (tile / num_m) * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX);
-      epilogue_warp_tile<EPI, LNF, AOUT>(ep, taddr, m_idx + quarter * 32, n_idx, BN, half, M, N, stage_buf, lane,
+      epilogue_warp_tile<EPI, LNF>(ep, taddr, m_idx + quarter * 32, n_idx, BN, half, M, N, stage_buf, lane,
                                    &tmem_full[acc], acc_phase);
       // release this accumulator buffer to the leader's MMA warp
       tcgen05_fence_before();
@@ -686,13 +637,13 @@ static int pick_tile_n(int M, int N, int K, int kind, int units, int mc) {
   return best_bn;
 }
 
-template <int EPI, bool LNF = false, bool AOUT = false>
+template <int EPI, bool LNF = false>
 static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int tile_n, int cluster_pairs,
                   const EpiParams& ep, cudaStream_t st) {
   static bool configured = false;
   static int max_clusters[2] = {0, 0};     // co-resident clusters of 2 / 4 CTAs (GPC boundaries can strand SMs)
   if (!configured) {
-    TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF, AOUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     for (int i = 0; i < 2; ++i) {
       cudaLaunchConfig_t cfg = {};
       cudaLaunchAttribute at[1];
@@ -701,7 +652,7 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
       cfg.gridDim = dim3((unsigned)(sm_count() / (2 << i) * (2 << i))); cfg.blockDim = dim3(NUM_THREADS);
       cfg.dynamicSmemBytes = SMEM_BYTES; cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
-      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<EPI, LNF, AOUT>, &cfg) != cudaSuccess || n <= 0) {
+      if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<EPI, LNF>, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
         n = sm_count() / (2 << i);
       }
@@ -725,7 +676,7 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
   const int mrows = mc ? 4 * BM : 2 * BM;
   const int tiles = ((M + mrows - 1) / mrows) * ((N + bn - 1) / bn);
   const int units = tiles < max_units ? tiles : max_units;
-  TOC3D_CHECK_CUDA(launch_pdl(gemm_kernel<EPI, LNF, AOUT>, dim3(csize * units), dim3(NUM_THREADS), SMEM_BYTES, st, csize, ta, tb, M,
+  TOC3D_CHECK_CUDA(launch_pdl(gemm_kernel<EPI, LNF>, dim3(csize * units), dim3(NUM_THREADS), SMEM_BYTES, st, csize, ta, tb, M,
                               N, K, bn, mc, ep));
   return 0;
 }
@@ -744,7 +695,6 @@ static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, E
   ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
   ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
   ep.ln_stats = reinterpret_cast<const long long*>(e->ln_stats);
-  ep.a_out = reinterpret_cast<__nv_bfloat16*>(e->a_out); ep.zero_stats = reinterpret_cast<long long*>(e->zero_stats);
   const int tile_n = e->tile_n;
   TOC3D_REQUIRE(e->cluster_pairs >= 0 && e->cluster_pairs <= 2, kErrBadArg, "%s: cluster_pairs must be 0 (auto), 1 or 2", fn);
   TOC3D_REQUIRE(tile_n == 0 || (tile_n >= 64 && tile_n <= BN_MAX && tile_n % 32 == 0 &&
@@ -752,14 +702,9 @@ static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, E
                 "%s: tile_n must be 0 (auto) or a multiple of 32 (64 for SWIGLU) in [64, 256], got %d", fn, tile_n);
   const bool lnf = ep.ln_stats != nullptr;
   if (lnf)
-    TOC3D_REQUIRE((kind == TOC3D_EPI_RESID || kind == TOC3D_EPI_SWIGLU) && ep.ln_u != nullptr && ep.ln_n > 0 &&
+    TOC3D_REQUIRE(kind == TOC3D_EPI_RESID && ep.ln_u != nullptr && ep.ln_n > 0 &&
                   ((uintptr_t)ep.ln_u & 15) == 0 && ((uintptr_t)ep.ln_stats & 15) == 0,
-                  kErrBadArg, "%s: folded LayerNorm (RESID / SWIGLU) needs ln_stats + ln_u (16-byte aligned), ln_n > 0", fn);
-  const bool aout = ep.a_out != nullptr;
-  if (aout)
-    TOC3D_REQUIRE(kind == TOC3D_EPI_RESID && !lnf && ep.row_stats != nullptr && ((uintptr_t)ep.a_out & 15) == 0 &&
-                  ((uintptr_t)ep.row_stats & 15) == 0 && ((uintptr_t)ep.zero_stats & 15) == 0, kErrBadArg,
-                  "%s: a_out needs RESID without ln fold, plus row_stats (16-byte aligned)", fn);
+                  kErrBadArg, "%s: folded LayerNorm (RESID) needs ln_stats + ln_u (16-byte aligned), ln_n > 0", fn);
   TOC3D_REQUIRE(ep.ldo > 0 && ep.ldo % 4 == 0 && N % 4 == 0, kErrBadArg,
                 "%s: N and ldo must be positive multiples of 4 (vector epilogue), got N=%d ldo=%d", fn, N, ep.ldo);
   TOC3D_REQUIRE(((uintptr_t)ep.out & 15) == 0 && ((uintptr_t)ep.bias & 15) == 0 && ((uintptr_t)ep.resid & 15) == 0 &&
@@ -798,17 +743,14 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   const int tile_n = e->tile_n;
   const int cpairs = e->cluster_pairs;
   const bool lnf = ep.ln_stats != nullptr;
-  const bool aout = ep.a_out != nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (kind) {
     case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
     case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
     case TOC3D_EPI_RESID:
-      if (aout) return launch<TOC3D_EPI_RESID, false, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
       return lnf ? launch<TOC3D_EPI_RESID, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st)
                  : launch<TOC3D_EPI_RESID, false>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
     default:
-      return lnf ? launch<TOC3D_EPI_SWIGLU, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st)
-                 : launch<TOC3D_EPI_SWIGLU, false>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
+      return launch<TOC3D_EPI_SWIGLU>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
   }
 }
