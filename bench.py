@@ -160,10 +160,14 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------- reference arm (CPU)
+NECK_CFG = dict(in_channels=[1024], out_channels=256, num_outs=2)      # img_neck of ToC3D_fast.py:70-74
+
+
 def workload_config(name, batch, world):
     """The `config` object of the JSON line - identical in both arms (the driver compares them)."""
     kind, cfg, hw = CONFIGS[name]
-    return {"workload": name, "backbone": kind, "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": batch,
+    return {"workload": name, "backbone": kind, "neck": "CPFPN 1024 -> 256, 2 levels (the multi-scale feature list)",
+            "views": VIEWS, "image_hw": list(hw), "batch_per_gpu": batch,
             "prev_exists": True, "weights": "random-init EVA-ViT-L + ToC3D selectors (seed 0)",
             "parallelism": "dp%d (views x batch sharded, all-gather of the feature list)" % world}
 
@@ -191,31 +195,37 @@ def reference_step_fn(name, views, device="cpu", autocast=False, batch=1):
             m = (ns.ToC3DEVAViT if kind == "ToC3DEVAViT" else ns.EVA_ViT)(**cfg).eval()
         m.load_state_dict(randomize_state_dict(m.state_dict(), seed=0, bias_std=0.02))
         m = m.to(device)
+        with contextlib.redirect_stdout(io.StringIO()):
+            nk = ns.CPFPN(**NECK_CFG).eval()                # the reference's own img_neck (necks/cp_fpn.py), same step as the native arm
+        nk.load_state_dict(randomize_state_dict(nk.state_dict(), seed=0, bias_std=0.02))
+        nk = nk.to(device)
         d = {k: (v.to(device) if torch.is_tensor(v) else v) for k, v in inp.items()}
         gnd = [g.to(device) for g in gn]
 
         def step():
             ns.set_gumbel(gnd)
             with torch.no_grad(), torch.autocast(device_type=torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
-                if kind == "EVA_ViT":
-                    return m(d["x"])["last_feat"]
-                return m(**d).img_feats["last_feat"]
+                feats = m(d["x"]) if kind == "EVA_ViT" else m(**d).img_feats        # petr3d.py:145-179
+                return nk(list(feats.values()))                                       # petr3d.py:188-190
         return step, "reference"
     if device != "cpu":
         raise RuntimeError("the oracle port is a CPU checker; the GPU-eager reference leg needs baseline/_ref (tools/stage_ref.sh)")
     from oracle import toc3d_oracle as O
-    from toc3d_b200 import EVA_ViT, ToC3DEVAViT
+    from toc3d_b200 import CPFPN, EVA_ViT, ToC3DEVAViT
     torch.manual_seed(0)
     model = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
     sd = randomize_state_dict(model.state_dict(), seed=0, bias_std=0.02)
+    sdn = randomize_state_dict(CPFPN(**NECK_CFG).state_dict(), seed=0, bias_std=0.02)
     del model
 
     def step():
         with torch.no_grad():
             if kind == "EVA_ViT":
-                return O.forward_dense(sd, cfg, inp["x"])
-            return O.forward_toc3d(sd, cfg, inp["x"], inp["temp_queries"], inp["temp_ref_points"], inp["temp_vel"],
-                                   inp["temp_timestamp"], inp["temp_ego_pose"], inp["ego_pose_inv"], True, gn)
+                lf = O.forward_dense(sd, cfg, inp["x"])["last_feat"]
+            else:
+                lf = O.forward_toc3d(sd, cfg, inp["x"], inp["temp_queries"], inp["temp_ref_points"], inp["temp_vel"],
+                                     inp["temp_timestamp"], inp["temp_ego_pose"], inp["ego_pose_inv"], True, gn)["last_feat"]
+            return O.neck_cpfpn(sdn, lf)
     return step, "port"
 
 
@@ -241,8 +251,8 @@ def run_reference(args):
     dt = (time.perf_counter() - t0) / args.steps
     scale = VIEWS // views
     value = 1.0 / (dt * scale)
-    what = {"reference": "the reference's own ToC3DEVAViT / EVA_ViT modules (unmodified sources, third-party imports stubbed)",
-            "port": "fp32 oracle port of the reference forward (reference sources not present)"}[rkind]
+    what = {"reference": "the reference's own ToC3DEVAViT / EVA_ViT + CPFPN modules (unmodified sources, third-party imports stubbed)",
+            "port": "fp32 oracle port of the reference forward + neck (reference sources not present)"}[rkind]
     sample = "%d of %d views per step, fp32, torch.no_grad, %d torch threads: %s%s" % (
         views, VIEWS, cores, what, "" if scale == 1 else "; scaled x%d (extrapolated)" % scale)
     line = {
@@ -259,9 +269,26 @@ def run_reference(args):
 
 
 # ------------------------------------------------------------------------------- native arm (B200)
+def build_native(name, dev, view_groups=None):
+    """Backbone + neck plugins with seeded random-init weights; the neck runs inside the backbone's CUDA graph."""
+    from toc3d_b200 import CPFPN, EVA_ViT, ToC3DEVAViT
+    kind, cfg, hw = CONFIGS[name]
+    torch.manual_seed(0)
+    model = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
+    model.load_state_dict(randomize_state_dict(model.state_dict(), seed=0, bias_std=0.02))
+    model = model.eval().to(dev)
+    model.set_image_preprocess(**IMG_NORM)       # row f3: lets forward() take the uint8 camera crops as well
+    if view_groups is not None and hasattr(model, "view_groups"):
+        model.view_groups = view_groups
+    neck = CPFPN(**NECK_CFG)
+    neck.load_state_dict(randomize_state_dict(neck.state_dict(), seed=0, bias_std=0.02))
+    neck = neck.eval().to(dev)
+    model.fuse_neck(neck)
+    return model, neck
+
+
 def run_native(args):
     import torch.distributed as dist
-    from toc3d_b200 import EVA_ViT, ToC3DEVAViT
     from toc3d_b200 import lib as L
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -273,31 +300,10 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-
-    kind, cfg, hw = CONFIGS[args.config]
-    torch.manual_seed(0)
-    model = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
-    model.load_state_dict(randomize_state_dict(model.state_dict(), seed=0, bias_std=0.02))
-    model = model.eval().to(dev)
-    model.set_image_preprocess(**IMG_NORM)       # row f3: lets forward() take the uint8 camera crops as well
-    if args.view_groups is not None and hasattr(model, "view_groups"):
-        model.view_groups = args.view_groups
-    B = args.batch
-    V = B * VIEWS
-    H, W = hw[0] // 16, hw[1] // 16
-    inp = make_inputs(B, VIEWS, hw, seed=rank)
-    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}
-    res = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
-    out_host = torch.empty(V, cfg["embed_dim"], H, W, dtype=torch.float32).pin_memory()
-    gathered = torch.empty(world * V, H, W, cfg["embed_dim"], device=dev) if world > 1 else None
+    if args.strong:
+        return run_strong(args, world, rank, dev)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)        # > 126 MB L2
-
-    def forward(d):
-        out = model(**d)
-        lf = out["last_feat"] if isinstance(out, dict) else out.img_feats["last_feat"]
-        if world > 1:   # all-gather the feature list for the detection head (NHWC storage of last_feat)
-            dist.all_gather_into_tensor(gathered, lf.permute(0, 2, 3, 1))
-        return lf
+    B = args.batch
 
     def barrier():
         if world > 1:
@@ -305,7 +311,7 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        """K steps, each bracketed by CUDA events on the launch stream; L2 flushed between steps."""
+        """K steps, each bracketed by CUDA events on the launch stream; L2 flushed between steps; max over ranks."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         barrier()
         for s, e in ev:
@@ -320,10 +326,53 @@ def run_native(args):
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         return tot.item(), ms
 
-    # --- end to end through the plugin: every step copies ITS inputs from pinned host memory and reads ITS
-    #     last_feat back to pinned host memory.  The copies run on two copy streams, double-buffered, so the H2D of
-    #     step i+1 and the D2H of step i-1 overlap forward(i) (what a streaming deployment does); everything is
-    #     inside the timed region, which ends only when the last D2H has landed.
+    def make_forward(model, neck, V, H, W):
+        """One step through the plugin boundary: img_backbone forward, img_neck on its feature dict (petr3d.py:159-190),
+        and for N > 1 the all-gather of the multi-scale feature list.  Level 1 of the CPFPN is the stride-2 subsample of
+        level 0 (cp_fpn.py:190-191), so gathering level 0 (NHWC, 256 channels) gathers the whole list."""
+        gathered = torch.empty(world * V, H, W, NECK_CFG["out_channels"], device=dev) if world > 1 else None
+
+        def forward(d):
+            out = model(**d)
+            feats = out if isinstance(out, dict) else out.img_feats
+            levels = neck(list(feats.values()))
+            lv0 = levels[0].permute(0, 2, 3, 1)              # contiguous NHWC rows of level 0
+            if world > 1:
+                dist.all_gather_into_tensor(gathered, lv0)
+            return lv0
+        return forward
+
+    def quick_config(name, steps):
+        """Device-resident throughput of another shipped config (same step definition), for the driver's record."""
+        kind, cfg, hw = CONFIGS[name]
+        m, nk = build_native(name, dev)
+        H, W = hw[0] // 16, hw[1] // 16
+        d = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in make_inputs(B, VIEWS, hw, seed=rank).items()}
+        fwd = make_forward(m, nk, B * VIEWS, H, W)
+        for _ in range(3):
+            fwd(d)
+        t, _ = timed(lambda: fwd(d), steps)
+        work = algorithmic_work(cfg, kind, hw, B * VIEWS)
+        r = {"value": world * B * steps / (t * 1e-3), "unit": UNIT, "ms_per_step": t / steps, "steps": steps, "image_hw": list(hw),
+             "whole_step_tflops_per_gpu": work["flops"] / (t / steps * 1e-3) / 1e12}
+        del m, nk, fwd, d
+        torch.cuda.empty_cache()
+        return r
+
+    kind, cfg, hw = CONFIGS[args.config]
+    model, neck = build_native(args.config, dev, args.view_groups)
+    V = B * VIEWS
+    H, W = hw[0] // 16, hw[1] // 16
+    inp = make_inputs(B, VIEWS, hw, seed=rank)
+    host = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in inp.items()}
+    res = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp.items()}
+    out_host = torch.empty(V, H, W, NECK_CFG["out_channels"], dtype=torch.float32).pin_memory()
+    forward = make_forward(model, neck, V, H, W)
+
+    # --- end to end through the plugins: every step copies ITS inputs from pinned host memory and reads ITS result (the
+    #     multi-scale feature list = level 0 of the neck, see make_forward) back to pinned host memory.  The copies run on
+    #     two copy streams, double-buffered, so the H2D of step i+1 and the D2H of step i-1 overlap forward(i) (what a
+    #     streaming deployment does); everything is inside the timed region, which ends only when the last D2H has landed.
     h2d_s, d2h_s = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
     dev_in = [{k: (torch.empty_like(v, device=dev) if torch.is_tensor(v) else v) for k, v in host.items()} for _ in range(2)]
     out_hosts = [out_host, torch.empty_like(out_host).pin_memory()]
@@ -356,14 +405,26 @@ def run_native(args):
             if flush_l2:
                 flush.zero_()
             main.wait_event(ev_in[i])
-            lf = forward(dev_in[i % 2])
+            lv0 = forward(dev_in[i % 2])
             ev_fwd[i].record(main)
             with torch.cuda.stream(d2h_s):
                 d2h_s.wait_event(ev_fwd[i])
-                out_hosts[i % 2].copy_(lf, non_blocking=True)
-                lf.record_stream(d2h_s)
+                out_hosts[i % 2].copy_(lv0, non_blocking=True)
+                lv0.record_stream(d2h_s)
         main.wait_stream(d2h_s)
         main.wait_stream(h2d_s)
+
+    def e2e_timed(steps, host, dev_in):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        e2e_run(steps, True, host, dev_in)
+        e1.record()
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
 
     for _ in range(max(args.warmup, 3)):
         forward(res)
@@ -375,34 +436,46 @@ def run_native(args):
         l0 = L.launch_count
         total_ms, ms = timed(lambda: forward(res), args.steps)
         launches = (L.launch_count - l0) // args.steps
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        e2e_run(args.steps, True)
-        e1.record()
-        barrier()
-        e2e_t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_ms = e2e_t.item()
-        e0.record()
-        e2e_run(args.steps, True, host_u8, dev_in_u8)
-        e1.record()
-        barrier()
-        e2e_t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-        e2e_u8_ms = e2e_t.item()
+        e2e_ms = e2e_timed(args.steps, host, dev_in)
+        e2e_u8_ms = e2e_timed(args.steps, host_u8, dev_in_u8)
     clocks = clk.summary()
-
-    # --- roofline of the dominant kernel (the tcgen05 GEMM) + per-kernel breakdown: one extra instrumented
-    #     eager step after the timed region, CUDA events around every C-ABI launch on the launch stream.  A
-    #     device-side sleep is queued first so the host runs ahead and the events bracket kernels, not launch gaps.
+    step_ms = total_ms / args.steps
     work = algorithmic_work(cfg, kind, hw, V)
+    peaks = load_peaks()
+
+    # --- roofline, method 1 (the figure reported as `achieved`): marginal time of a kernel family under the product's
+    #     own conditions.  The step is re-captured as a CUDA graph with the family's C-ABI calls skipped and timed exactly
+    #     like the headline; family time = step - step without the family.  Launch overlap (programmatic dependent
+    #     launch), side streams and L2 state are those of the real step; events sit outside the replay, as they must.
+    fam = {"gemm": ["gemm"], "attention": ["window_attention"],
+           "token_kernels": ["layernorm_rows", "ln_gather_merge", "fast_token_update", "fill_pad_kv", "window_topk", "compact_rows",
+                             "score_tokens", "topk_split", "motion_queries_fold", "im2col_patch16", "im2col_3x3", "cast_bf16"]}
+    marginal = {}
+    if not args.no_roofline:
+        for fname, names_ in fam.items():
+            saved_ = {n: getattr(L, n) for n in names_}
+            for n in names_:
+                setattr(L, n, lambda *a, **k: k.get("out"))
+            model._graphs = {}
+            try:
+                for _ in range(3):
+                    forward(res)
+                t_wo, _ = timed(lambda: forward(res), 10)
+            finally:
+                for n in names_:
+                    setattr(L, n, saved_[n])
+                model._graphs = {}
+            marginal[fname] = max(step_ms - t_wo / 10, 1e-6)
+        for _ in range(3):
+            forward(res)
+
+    # --- roofline, method 2 (per-kernel split, pessimistic): one instrumented EAGER step, CUDA events around every C-ABI
+    #     launch on the launch stream.  An event between two kernels forbids their programmatic overlap, so every launch
+    #     here also pays the ~3 us of prologue / launch latency that the graph replay hides: the sum exceeds the step.
     recs = []
     names = ["gemm", "window_attention", "layernorm_rows", "ln_gather_merge", "fill_pad_kv", "fill_pad_kv_rope", "compact_rows", "subln", "window_topk", "topk_split", "merge_fast_tokens",
              "fast_token_update", "motion_queries_fold", "score_tokens", "score_finish", "im2col_patch16", "mask_rows",
-             "global_half_mean"]
+             "global_half_mean", "im2col_3x3", "cast_bf16"]
     saved = {n: getattr(L, n) for n in names}
     kind_names = {L.EPI_LINEAR: "linear", L.EPI_QKV_ROPE: "qkv_rope", L.EPI_RESID: "resid", L.EPI_SWIGLU: "swiglu"}
 
@@ -466,23 +539,37 @@ def run_native(args):
     g_ms = sum(s.elapsed_time(e) for s, e, _ in g)
     g_fl = sum(f for _, _, f in g)
     g_by = sum(by for label, _, _, _, by in recs if label.startswith("gemm"))
-    peaks = load_peaks()
-    step_ms = total_ms / args.steps
-    ach = g_fl / (g_ms * 1e-3) / 1e12
+    a_fl = sum(fl for label, _, _, fl, _ in recs if label.startswith("window_attention"))
+    ach_events = g_fl / (g_ms * 1e-3) / 1e12
+    g_marg = marginal.get("gemm")
+    ach = g_fl / (g_marg * 1e-3) / 1e12 if g_marg else ach_events
     traffic, traffic_src = load_ncu_traffic(args.config)
-    hbm_k = [v for k_, v in breakdown.items() if k_ in ("ln_gather_merge", "fast_token_update", "merge_fast_tokens", "layernorm_rows") and "gbs" in v]
+    hbm_names = ("ln_gather_merge", "fast_token_update", "merge_fast_tokens", "layernorm_rows")
+    hbm_k = [v for k_, v in breakdown.items() if k_ in hbm_names and "gbs" in v]
     hbm_ms = sum(v["ms"] for v in hbm_k)
     hbm_gbs = sum(v["gbs"] * v["ms"] for v in hbm_k) / hbm_ms if hbm_ms else None
+    hbm_bytes = sum(by for label, _, _, _, by in recs if label in hbm_names)
     roofline = {"bound": "tensor", "kernel": "toc3d::gemm::gemm_kernel (tcgen05 cta_group::2, all epilogues)",
                 "achieved": ach, "peak": peaks["tf_sust"], "unit": "TFLOP/s", "frac": ach / peaks["tf_sust"],
+                "frac_of_burst_peak": ach / peaks["tf_burst"],
+                "method": ("marginal: FLOPs launched by the GEMM calls of one step / (step time - time of the same CUDA-graph step "
+                           "captured with those calls skipped), CUDA events around the replays" if g_marg else
+                           "per-launch CUDA events of one eager step"),
+                "gemm_ms_per_step": g_marg, "gemm_share_of_step": (g_marg / step_ms) if g_marg else g_ms / step_ms,
                 "traffic": traffic, "traffic_source": traffic_src, "algorithmic_bytes_per_launch": g_by / max(1, len(g)),
-                "peak_source": peaks["src"] + " bf16_tflops_sustained",
-                "hbm_kernels": {"what": "LayerNorm/gather, merge, fast-token update (algorithmic bytes / event time)",
+                "peak_source": peaks["src"] + " bf16_tflops_sustained", "launches_per_step": len(g),
+                "avg_launch_us": (g_marg if g_marg else g_ms) * 1e3 / max(1, len(g)),
+                "attention": {"ms_per_step": marginal.get("attention"), "flops": a_fl,
+                              "achieved_tflops": (a_fl / (marginal["attention"] * 1e-3) / 1e12) if marginal.get("attention") else None,
+                              "note": "MUFU (ex2) bound, not tensor bound: 2 MUFU ops per 256 tensor FLOPs (DESIGN 3.2)"},
+                "hbm_kernels": {"what": "LayerNorm/gather, merge, fast-token update (algorithmic bytes / per-launch event time, eager step)",
                                 "achieved": hbm_gbs, "peak": peaks["hbm"], "unit": "GB/s",
-                                "frac": (hbm_gbs / peaks["hbm"]) if hbm_gbs else None},
-                "launches_per_step": len(g), "avg_launch_us": g_ms * 1e3 / max(1, len(g)),
-                "gemm_share_of_step": g_ms / step_ms, "measured": "one instrumented eager step after the timed region",
-                "whole_step_tflops": work["flops"] / (step_ms * 1e-3) / 1e12, "breakdown": breakdown}
+                                "frac": (hbm_gbs / peaks["hbm"]) if hbm_gbs else None, "algorithmic_bytes_per_step": hbm_bytes},
+                "token_kernels_ms_per_step": marginal.get("token_kernels"),
+                "eager_event_breakdown": {"achieved_gemm_tflops": ach_events, "gemm_ms": g_ms,
+                                          "note": "events between kernels forbid programmatic overlap: ~3 us per launch more than in the graph",
+                                          "kernels": breakdown},
+                "whole_step_tflops": work["flops"] / (step_ms * 1e-3) / 1e12}
 
     value = world * B * args.steps / (total_ms * 1e-3)
     e2e_value = world * B * args.steps / (e2e_ms * 1e-3)
@@ -496,16 +583,17 @@ def run_native(args):
         "config": workload_config(args.config, B, world),
         "native_details": {"l2": "256 MiB buffer zeroed between timed steps (L2 flush)",
                            "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate",
-                           "launch": "whole forward replayed as one CUDA graph per call",
-                           "e2e_pipeline": "per step: pinned-host inputs -> H2D, forward, last_feat -> D2H to pinned host; copies "
-                                           "double-buffered on copy streams (overlap the neighbouring steps' forward); the L2 "
+                           "launch": "backbone + neck replayed as one CUDA graph per call",
+                           "collective": ("ncclAllGather of level 0 of the feature list (NHWC fp32, %d B per rank); level 1 is its stride-2 "
+                                          "subsample" % d2h) if world > 1 else None,
+                           "e2e_pipeline": "per step: pinned-host inputs -> H2D, backbone + neck, feature list (level 0) -> D2H to pinned "
+                                           "host; copies double-buffered on copy streams (overlap the neighbouring steps' forward); the L2 "
                                            "flush between steps is inside the e2e timed region"},
-        # link_gbs = bytes moved per step / step time: when it sits at the host link's rate (6 GB/s both directions
-        # together on the slowest boxes of the pool) the e2e number is bound by the copies, not by the forward
+        # link_gbs = bytes moved per step / step time: when it sits at the host link's rate the e2e number is bound by the copies
         "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "ms_per_step": e2e_ms / args.steps, "link_gbs": (h2d + d2h) / (e2e_ms / args.steps) / 1e6},
-        # row f3 (context, not the headline): same pipeline fed the uint8 HWC camera crops; normalise + pad run fused
-        # in the stem kernel (toc3d_preprocess_patch16_u8), so the H2D copy carries 4x fewer image bytes
+        # row f3 (context): same pipeline fed the uint8 HWC camera crops; normalise + pad run fused in the stem kernel
+        # (toc3d_preprocess_patch16_u8), so the H2D copy carries 4x fewer image bytes
         "e2e_u8_input": {"value": world * B * args.steps / (e2e_u8_ms / 1e3), "unit": UNIT,
                          "h2d_bytes_per_step": sum(v.numel() * v.element_size() for v in host_u8.values() if torch.is_tensor(v)),
                          "d2h_bytes_per_step": d2h, "ms_per_step": e2e_u8_ms / args.steps},
@@ -514,23 +602,23 @@ def run_native(args):
     }
     if world > 1 and args.overlap_gather:
         # experiment (not the headline): the all-gather of step i runs on its own stream behind forward(i) and overlaps
-        # forward(i+1) - what a pipelined deployment would do; the timed region ends when the last gather has landed.
-        # The L2 flushes are inside this region (they are outside the per-step events of `value`).
+        # forward(i+1); the timed region ends when the last gather has landed.  The L2 flushes are inside this region.
         gs = torch.cuda.Stream(device=dev)
-        gbuf = [gathered, torch.empty_like(gathered)]
+        gbuf = [torch.empty(world * V, H, W, NECK_CFG["out_channels"], device=dev) for _ in range(2)]
         main = torch.cuda.current_stream()
 
         def run_overlapped(steps):
             for i in range(steps):
                 flush.zero_()
                 out = model(**res)
-                lf = out["last_feat"] if isinstance(out, dict) else out.img_feats["last_feat"]
+                feats = out if isinstance(out, dict) else out.img_feats
+                lv0 = neck(list(feats.values()))[0].permute(0, 2, 3, 1)
                 ev = torch.cuda.Event()
                 ev.record(main)
                 with torch.cuda.stream(gs):
                     gs.wait_event(ev)
-                    dist.all_gather_into_tensor(gbuf[i % 2], lf.permute(0, 2, 3, 1))
-                    lf.record_stream(gs)
+                    dist.all_gather_into_tensor(gbuf[i % 2], lv0)
+                    lv0.record_stream(gs)
             main.wait_stream(gs)
 
         run_overlapped(3)
@@ -545,17 +633,28 @@ def run_native(args):
         line["overlap_gather"] = {"value": world * B * args.steps / (ot.item() * 1e-3), "unit": UNIT,
                                   "ms_per_step": ot.item() / args.steps,
                                   "note": "all-gather of step i overlaps forward(i+1); L2 flushes inside the region; not the headline"}
+    del forward, model, neck
+    torch.cuda.empty_cache()
+    if not args.no_other_configs:
+        # BASELINE.json's other configs through the same step definition (device-resident inputs), so that they reach the
+        # driver's record: all of them at N = 1, the sharded 1600x800 config (configs[3]) at every N
+        others = ["toc3d_faster", "eva_vit_l", "toc3d_fast_1600", "toc3d_faster_1600", "eva_vit_l_1600"] if world == 1 else ["toc3d_faster_1600"]
+        line["other_configs"] = {n: quick_config(n, 5 if n.endswith("1600") else 10) for n in others if n != args.config}
+        if world == 1 and "eva_vit_l_1600" in line["other_configs"] and "toc3d_faster_1600" in line["other_configs"]:
+            line["other_configs"]["speedup_faster_1600_over_dense_1600"] = (line["other_configs"]["toc3d_faster_1600"]["value"]
+                                                                            / line["other_configs"]["eva_vit_l_1600"]["value"])
     if world == 1 and args.batch == 1 and not args.no_batch4:
-        # context, not the headline: the same forward with 4 samples (24 views) per launch - at batch 1 the 200-odd
-        # kernels of a 5 ms step are latency bound, a serving deployment with several streams would batch them
-        inp4 = make_inputs(4, VIEWS, hw, seed=1)
-        res4 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in inp4.items()}
+        # context, not the headline: the same forward with 4 samples (24 views) per launch
+        m4, n4 = build_native(args.config, dev)
+        res4 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in make_inputs(4, VIEWS, hw, seed=1).items()}
+        f4 = lambda: n4(list(m4(**res4).img_feats.values())) if kind == "ToC3DEVAViT" else n4(list(m4(**res4).values()))
         for _ in range(3):
-            model(**res4)
-        t4, _ = timed(lambda: model(**res4), 10)
+            f4()
+        t4, _ = timed(f4, 10)
         line["throughput_batch4"] = {"value": 4 * 10 / (t4 * 1e-3), "unit": UNIT, "ms_per_step": t4 / 10,
                                      "note": "4 samples per launch, device-resident inputs; not the headline"}
-        del res4
+        del res4, m4, n4, f4
+        torch.cuda.empty_cache()
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         # the reference on the same box: its own modules on the B200 in PyTorch eager, fp32 and bf16
         # autocast - the number the native result should be read against; then on the host cores (cpu_baseline)
@@ -569,8 +668,8 @@ def run_native(args):
                 gpu_ref[label] = {"value": 5 / (t_ms * 1e-3), "unit": UNIT, "ms_per_step": t_ms / 5}
                 del step
                 torch.cuda.empty_cache()
-            gpu_ref["what"] = ("the reference's own module (.cuda(), torch %s eager, ATen/cuBLAS/cuDNN kernels), same weights and "
-                               "inputs, 6 views, batch 1, L2 flushed between steps" % torch.__version__)
+            gpu_ref["what"] = ("the reference's own backbone + neck modules (.cuda(), torch %s eager, ATen/cuBLAS/cuDNN kernels), same "
+                               "weights and inputs, 6 views, batch 1, L2 flushed between steps" % torch.__version__)
             line["reference_gpu_eager"] = gpu_ref
         except Exception as ex:  # reference sources not staged: say so, do not guess
             line["reference_gpu_eager"] = {"unavailable": str(ex)[:200]}
@@ -585,10 +684,54 @@ def run_native(args):
         dt = (time.perf_counter() - t0) / n
         scale = VIEWS // views
         line["cpu_baseline"] = {"value": 1.0 / (dt * scale), "unit": UNIT, "cores": cores, "kind": rkind,
-                                "sample": "%d of 6 views x %d forwards after 1 warm-up, fp32, %d torch threads%s" % (
+                                "sample": "%d of 6 views x %d forwards (backbone + neck) after 1 warm-up, fp32, %d torch threads%s" % (
                                     views, n, cores, "" if scale == 1 else ", scaled x%d (extrapolated)" % scale)}
     if rank == 0:
         emit(line)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_strong(args, world, rank, dev):
+    """Strong scaling: ONE batch of `--batch` samples (6 * batch views) cut into contiguous image chunks over the ranks
+    (toc3d_b200.shard.partition); every rank runs the backbone on its chunk and `last_feat`, the token masks and the
+    keep / drop lists are all-gathered in global image order (ShardedBackbone over NCCL)."""
+    import torch.distributed as dist
+    from toc3d_b200 import shard as S
+    kind, cfg, hw = CONFIGS[args.config]
+    model, neck = build_native(args.config, dev)
+    model.fuse_neck(None)
+    Bt = args.batch
+    inp = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in make_inputs(Bt, VIEWS, hw, seed=0).items()}
+    sb = S.ShardedBackbone(model, views=VIEWS)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+    for _ in range(max(args.warmup, 3)):
+        sb(**inp)
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    with ClockSampler(dev.index, enabled=(rank == 0)) as clk:
+        barrier()
+        for s, e in ev:
+            flush.zero_()
+            s.record()
+            sb(**inp)
+            e.record()
+        barrier()
+    tot = torch.tensor([sum(s.elapsed_time(e) for s, e in ev)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    ms = tot.item() / args.steps
+    if rank == 0:
+        emit({"metric": METRIC, "value": Bt / (ms * 1e-3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+              "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+              "dtype": "bf16", "data": "synthetic", "config": dict(workload_config(args.config, Bt, world), batch_total=Bt,
+              parallelism="%d views of one %d-sample batch per rank (shard.partition), all-gather of last_feat + masks + index lists" % (
+                  Bt * VIEWS // world, Bt)),
+              "clocks": clk.summary()})
     if world > 1:
         dist.destroy_process_group()
 
@@ -625,6 +768,9 @@ def main():
     ap.add_argument("--no-batch4", action="store_true", help="skip the extra batch-4 throughput line")
     ap.add_argument("--view-groups", type=int, default=None, help="override the plugin's view_groups (streams of views)")
     ap.add_argument("--overlap-gather", action="store_true", help="experiment (N > 1): extra line with the all-gather overlapped")
+    ap.add_argument("--no-roofline", action="store_true", help="skip the marginal-time roofline re-captures")
+    ap.add_argument("--no-other-configs", action="store_true", help="skip the extra lines for BASELINE.json's other configs")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: one --batch-sample batch sharded over the ranks (ShardedBackbone)")
     args = ap.parse_args()
     _claim_stdout()
     if args.impl == "reference":

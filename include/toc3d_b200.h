@@ -148,12 +148,13 @@ int toc3d_subln_bf16(const void* h, void* out, const float* gamma, const float* 
  *            representative token, last row of each window),
  *   rope_rows int32 [nW*(k+1)] RoPE table row (slot index; k for the representative token,
  *            toc3d_eva_vit.py:434-435),
- *   fast_map int32 [nW,n-k] image row of each fast token or -1.
+ *   fast_map int32 [nW,n-k] image row of each fast token or -1,
+ *   fast_win int32 [V*H*W] image row -> window in which it is a FAST token | -1 (slow token); every entry is written.
  * nW = V*ceil(H/ws)*ceil(W/ws); window order view-major, row, col (eva_utils.py:108-109).
  */
 int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int32_t W, int32_t ws, int32_t k,
                       int32_t* slow_idx, int32_t* fast_idx, float* fast_score, int32_t* tok_map,
-                      int32_t* rope_rows, int32_t* fast_map, void* stream);
+                      int32_t* rope_rows, int32_t* fast_map, int32_t* fast_win, void* stream);
 
 /* Compact row space of an accelerated block (toc3d_eva_vit.py:421-461): of the selected rows [k slow | rep] of a
  * window, the slow rows that are pad slots (tok_map = -1) are needed as attention keys / values only - norm1, q/k/v,
@@ -217,12 +218,24 @@ typedef struct toc3d_pad_fill {
   int32_t ft;
 } toc3d_pad_fill;
 
+/* Deferred fast-token update (toc3d_eva_vit.py:452-461) of the PREVIOUS accelerated block, applied by
+ * toc3d_ln_gather_merge while it reads the rows anyway (every real row is read exactly once: as a slow row or as a fast
+ * row of the new block): x[r] += packed[rep_row[w]] - rep[w] for w = fast_win[r] >= 0, written back to x.  Same
+ * expression as toc3d_fast_token_update, so the result is bit-identical to calling that in between.  `packed` / `rep`
+ * must not be the buffers the same launch writes (ping-pong them between consecutive blocks). */
+typedef struct toc3d_pending_update {
+  const int32_t* fast_win;   /* [rows of x] previous block: window in which the row was a fast token | -1 (toc3d_window_topk) */
+  const float* packed;       /* previous block's packed / compact rows (representative AFTER the block) */
+  const int32_t* rep_row;    /* previous block: row of `packed` of window w's representative */
+  const float* rep;          /* previous block: representative BEFORE the block, fp32 [nW_prev, C] */
+} toc3d_pending_update;
+
 /* Fused front end of an accelerated block (toc3d_eva_vit.py:421-427 gather + merge_tokens, then norm1 at
  * :371): in ONE launch, (1) rep[w] = sum_j (s_j / sum s) x[fast_map[w,j]] -> rep_out[w] and packed row
  * w*(k+1)+k (fp32), LayerNorm(rep[w]) -> out row w*(k+1)+k; (2) LayerNorm of every gathered slow row
  * m (tok_map[m] >= 0: x row; -1: pad slot = zero vector -> beta; -2: the representative row, see (1)) ->
  * bf16 out [nW*(k+1), C].  C in {128, 256, 512, 1024}.  zero_stats as in toc3d_layernorm_rows. */
-int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t* fast_map, const float* fast_score,
+int toc3d_ln_gather_merge(float* x /* written only with a pending update */, const int32_t* tok_map, const int32_t* fast_map, const float* fast_score,
                           const float* gamma, const float* beta, void* out_bf16, float* rep_out, float* packed,
                           int32_t nW, int32_t k, int32_t n_fast, int32_t C, float eps, int64_t* zero_stats,
                           const int32_t* rep_row /* row of `packed` for the representative; NULL: w*(k+1)+k */,
@@ -232,6 +245,7 @@ int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t*
                           int32_t* counters /* int32 [nW], zeroed once by the caller: the representative token of a window
                                                is merged by C/256 thread blocks (256-channel slices), the last one to
                                                arrive normalises the row and clears the counter; NULL allowed for C = 128 */,
+                          const toc3d_pending_update* pending /* host pointer or NULL */,
                           void* stream);
 
 /* ------------------------------------------------------------------ history-query scorer

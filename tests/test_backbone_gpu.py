@@ -264,3 +264,27 @@ def test_degenerate_scores_below_pad_value():
         assert torch.equal(a.cpu(), b)
     mx, mean, rel = _stats(out.img_feats["last_feat"].cpu(), ref["last_feat"])
     assert torch.isfinite(out.img_feats["last_feat"]).all() and rel < 1.2e-2, rel
+
+
+@pytest.mark.parametrize("name", ["tiny_prev", "tiny_prev_small"])
+def test_deferred_fast_update_is_bit_identical(name):
+    """defer_fast_update (default: the fast-token update of an accelerated block is applied by the next block's first
+    launch) returns exactly what the one-launch-per-block form returns - features, masks, indices - eagerly and through
+    the CUDA graph (same device noise counter)."""
+    fx, kind, cfg, model, sd, inp, gn = case_setup(name)
+    outs = []
+    for defer in (False, True):
+        m = build_model(kind, cfg)
+        m.load_state_dict(sd)
+        m.defer_fast_update = defer
+        m = m.cuda()
+        with torch.no_grad():
+            o = m(**to_cuda(inp), gumbel_noise=gn)
+            m._engine.seed_t.fill_(7)
+            og = m(**to_cuda(inp))                        # graph capture + replay, device-drawn noise with seed counter 8
+            m._engine.seed_t.fill_(7)
+            og2 = m(**to_cuda(inp))
+        outs.append((o, og, og2))
+    for a, b in zip(outs[0], outs[1]):
+        assert torch.equal(a.img_feats["last_feat"], b.img_feats["last_feat"])
+        assert all(torch.equal(x, y) for x, y in zip(a.keep_idx + a.drop_idx + a.token_masks, b.keep_idx + b.drop_idx + b.token_masks))

@@ -480,6 +480,70 @@ def test_compact_rows_and_pad_fill(lib):
     assert (q[[3, 17, 39], :C] == 7).all() and (q[[0, 1, 2, 4]] == 7).all()
 
 
+@pytest.mark.parametrize("ws_prev,ws", [(16, 16), (16, 20), (20, 16)])
+def test_deferred_fast_update_in_gather_merge(lib, ws_prev, ws):
+    """toc3d_ln_gather_merge with a pending update == toc3d_fast_token_update of the previous block followed by the plain
+    launch, bit for bit (residual stream, LayerNorm rows, representative tokens); also window_topk's fast_win table."""
+    g = torch.Generator().manual_seed(ws_prev * 31 + ws)
+    V, H, W, C, ratio = 2, 20, 50, 256, 0.6
+    N = H * W
+    i32 = dict(dtype=torch.int32, device=DEV)
+    s = (-torch.rand(V, H, W, generator=g) * 4).to(DEV)
+
+    def tables(ws_):
+        n, k = ws_ * ws_, int(ws_ * ws_ * ratio)
+        nWh, nWw = -(-H // ws_), -(-W // ws_)
+        nW = V * nWh * nWw
+        real = torch.zeros(nW, dtype=torch.int32)
+        for v in range(V):
+            for a in range(nWh):
+                for b in range(nWw):
+                    real[(v * nWh + a) * nWw + b] = min(ws_, H - a * ws_) * min(ws_, W - b * ws_)
+        rcap = torch.minimum(real, torch.tensor(k, dtype=torch.int32))
+        coff = torch.cumsum(rcap + 1, 0, dtype=torch.int32) - (rcap + 1)
+        Mc = int((rcap + 1).sum())
+        t = dict(n=n, k=k, nf=n - k, nW=nW, Mc=Mc, tok=torch.empty(nW * (k + 1), **i32), rope=torch.empty(nW * (k + 1), **i32),
+                 fmap=torch.empty(nW, n - k, **i32), fsc=torch.empty(nW, n - k, device=DEV), fwin=torch.full((V * N,), -9, **i32),
+                 cmap=torch.empty(nW * (k + 1), **i32), ctok=torch.empty(Mc, **i32), rep_row=torch.empty(nW, **i32))
+        lib.window_topk(s, V, H, W, ws_, k, fast_score=t["fsc"], tok_map=t["tok"], rope_rows=t["rope"], fast_map=t["fmap"], fast_win=t["fwin"])
+        lib.compact_rows(t["tok"], coff.to(DEV), rcap.to(DEV), nW, k, t["cmap"], t["ctok"], t["rep_row"], rope_rows=t["rope"])
+        return t
+    tp, tn = tables(ws_prev), tables(ws)
+    # fast_win: image row -> window of its fast_map entry, -1 for slow rows, every row written
+    fw = tp["fwin"].cpu(); fm = tp["fmap"].cpu()
+    want = torch.full((V * N,), -1, dtype=torch.int32)
+    for w_ in range(tp["nW"]):
+        rows = fm[w_][fm[w_] >= 0].long()
+        want[rows] = w_
+    assert torch.equal(fw, want)
+    x0 = torch.randn(V * N, C, generator=g).to(DEV) * 3
+    T_prev = torch.randn(tp["Mc"], C, generator=g).to(DEV)          # previous block's compact rows after its MLP
+    rep_prev = torch.randn(tp["nW"], C, generator=g).to(DEV)
+    gamma = (1 + 0.1 * torch.randn(C, generator=g)).to(DEV); beta = (0.1 * torch.randn(C, generator=g)).to(DEV)
+    cnt = torch.zeros(tn["nW"], **i32)
+
+    def run(deferred):
+        x = x0.clone()
+        out = torch.zeros(tn["Mc"], C, device=DEV, dtype=torch.bfloat16)
+        rep = torch.zeros(tn["nW"], C, device=DEV); T = torch.zeros(tn["Mc"], C, device=DEV)
+        if not deferred:
+            lib.fast_token_update(x, tp["fmap"], T_prev, rep_prev, tp["nW"], tp["nf"], tp["k"], C, rep_row=tp["rep_row"])
+        lib.ln_gather_merge(x, tn["ctok"], tn["fmap"], tn["fsc"], gamma, beta, out, rep, T, tn["nW"], tn["k"], tn["nf"], C, 1e-6,
+                            rep_row=tn["rep_row"], compact_rows=tn["Mc"], counters=cnt,
+                            pending=(tp["fwin"], T_prev, tp["rep_row"], rep_prev) if deferred else None)
+        torch.cuda.synchronize()
+        return x, out, rep, T
+    a, b = run(False), run(True)
+    assert not torch.equal(a[0], x0)                                  # the update did something
+    for u, v, name in zip(a, b, ("x", "ln rows", "rep", "packed")):
+        assert torch.equal(u, v), name
+    with pytest.raises(RuntimeError, match="ping-pong"):
+        Tn = torch.zeros(max(tn["Mc"], tp["Mc"]), C, device=DEV)
+        lib.ln_gather_merge(x0.clone(), tn["ctok"], tn["fmap"], tn["fsc"], gamma, beta, torch.zeros(tn["Mc"], C, device=DEV, dtype=torch.bfloat16),
+                            torch.zeros(tn["nW"], C, device=DEV), Tn, tn["nW"], tn["k"], tn["nf"], C, 1e-6, rep_row=tn["rep_row"],
+                            compact_rows=tn["Mc"], counters=cnt, pending=(tp["fwin"], Tn, tp["rep_row"], rep_prev))
+
+
 @pytest.mark.parametrize("ft", [16, 20])
 def test_fill_pad_kv_rope_matches_qkv_gemm(lib, ft):
     """Pad rows of an accelerated block (norm1(0) = beta): k / v from the block constants + per-slot rotation equal

@@ -29,7 +29,11 @@ def test_default_sequence_per_block():
     assert seq.count("gemm:%d" % L.EPI_QKV_ROPE) == depth and seq.count("window_attention") == depth
     assert seq.count("gemm:%d" % L.EPI_SWIGLU) == depth
     assert seq.count("gemm:%d" % L.EPI_RESID) == 2 * depth + 1                     # proj + w3 per block, patch embed
-    assert seq.count("ln_gather_merge") == n_acc and seq.count("fast_token_update") == n_acc
+    # fast-token updates are deferred into the next block's first launch inside a stage: one launch per stage remains
+    assert seq.count("ln_gather_merge") == n_acc and seq.count("fast_token_update") == len(m.pruning_loc)
+    m2 = _toc3d()
+    seq2 = dryrun.names(dryrun.run(m2, _inputs(), defer_fast_update=False))
+    assert seq2.count("fast_token_update") == n_acc and len(seq2) == len(seq) + n_acc - len(m.pruning_loc)
     assert seq.count("layernorm_rows") == depth + (depth - n_acc)                 # norm2 everywhere + norm1 of dense blocks
     assert seq.count("motion_queries_fold") == 1                                   # all three stages in one call
     i = seq.index("window_attention")

@@ -11,6 +11,7 @@ nn.Module is used as the parameter container (so reference checkpoints load with
 toc3d_b200.lib (ctypes, raw device pointers).  Inference only.  There is no CPU or
 PyTorch fallback: CPU inputs or a missing library raise.
 """
+import contextlib
 import math
 from functools import partial
 
@@ -244,7 +245,10 @@ class _Workspace:
         self.qkv = torch.zeros(rows, 3 * C, **bf)      # zeroed once: q of pad slots is never written, must stay finite
         self.ao = torch.empty(rows, C, **bf)
         self.hid = torch.empty(rows, eng.Hp, **bf)
-        self.T = torch.empty(rows, C, device=dev, dtype=torch.float32)   # packed slow+rep residual stream
+        # compact slow + rep residual rows of an accelerated block, ping-ponged between consecutive blocks: the deferred
+        # fast-token update of block i reads block i's buffer while block i + 1 already fills the other one
+        self.T2 = [torch.empty(rows, C, device=dev, dtype=torch.float32) for _ in range(2)]
+        self.T = self.T2[0]
         self.stats = torch.zeros(rows, 2, device=dev, dtype=torch.int64)   # sub-LN fixed-point [sum, sum sq] per MLP row
         self.merge_cnt = torch.zeros(max(v["nW"] for v in self.win.values()), device=dev, dtype=torch.int32)
         self.stage = {}                                # (stage, ws) -> selection tables
@@ -407,12 +411,17 @@ class _Engine:
         L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
         self._mlp(bp, wsp, VN, out=X, resid=X)
 
-    def select_windows(self, stage, score, ratio, wsp):
+    def select_windows(self, stage, score, ratio, wsp, first_ws=None):
         """Per-window stable top-k tables for every window size used after this stage.  The reference
         re-sorts inside each of the 6 blocks of a stage (toc3d_eva_vit.py:419); the indices only depend
-        on (stage scores, window size), so they are computed once per (stage, ws)."""
+        on (stage scores, window size), so they are computed once per (stage, ws).  The tables of the window size the
+        next block needs (first_ws) are built on the launch stream, the others on the side stream (they are first
+        needed two blocks later); toc3d_block waits for their event."""
         dev = self.device
-        for ws, w in wsp.win.items():
+        cur = torch.cuda.current_stream()
+        order = sorted(wsp.win.keys(), key=lambda ws: (ws != first_ws, ws))
+        for ws in order:
+            w = wsp.win[ws]
             n, nW = w["n"], w["nW"]
             k = int(n * ratio)                      # toc3d_utils.py:136
             if k >= n:
@@ -428,42 +437,63 @@ class _Engine:
                 Mc = int((rcap + 1).sum())
                 t = dict(k=k, nf=n - k, tok_map=torch.empty(nW * (k + 1), **i32),
                          rope_rows=torch.empty(nW * (k + 1), **i32), fast_map=torch.empty(nW, n - k, **i32),
-                         fast_score=torch.empty(nW, n - k, device=dev), rep=torch.empty(nW, self.C, device=dev),
+                         fast_score=torch.empty(nW, n - k, device=dev),
+                         rep2=[torch.empty(nW, self.C, device=dev) for _ in range(2)],
+                         fast_win=torch.empty(wsp.V * wsp.N, **i32),
                          Mc=Mc, rcap=rcap.to(dev), coff=coff.to(dev), cmap=torch.empty(nW * (k + 1), **i32),
                          ctok=torch.empty(Mc, **i32), rep_row=torch.empty(nW, **i32), cinv=torch.empty(Mc, **i32),
                          crope=torch.empty(Mc, **i32), prope=torch.empty(nW * (k + 1), **i32), q_rows=(rcap + 1).to(dev),
                          item_order=balanced_item_order(rcap + 1, self.heads).to(dev))
                 wsp.stage[(stage, ws)] = t
-            L.window_topk(score, wsp.V, wsp.H, wsp.W, ws, k, fast_score=t["fast_score"], tok_map=t["tok_map"],
-                          rope_rows=t["rope_rows"], fast_map=t["fast_map"])
-            L.compact_rows(t["tok_map"], t["coff"], t["rcap"], nW, k, t["cmap"], t["ctok"], t["rep_row"],
-                           rope_rows=t["rope_rows"], cinv=t["cinv"], crope=t["crope"], prope=t["prope"])
+            on_side = first_ws is not None and ws != first_ws
+            if on_side:
+                self.side.wait_stream(cur)
+            with torch.cuda.stream(self.side) if on_side else contextlib.nullcontext():
+                L.window_topk(score, wsp.V, wsp.H, wsp.W, ws, k, fast_score=t["fast_score"], tok_map=t["tok_map"],
+                              rope_rows=t["rope_rows"], fast_map=t["fast_map"], fast_win=t["fast_win"])
+                L.compact_rows(t["tok_map"], t["coff"], t["rcap"], nW, k, t["cmap"], t["ctok"], t["rep_row"],
+                               rope_rows=t["rope_rows"], cinv=t["cinv"], crope=t["crope"], prope=t["prope"])
+                t["ready"] = None
+                if on_side:
+                    t["ready"] = torch.cuda.Event()
+                    t["ready"].record(self.side)
 
-    def toc3d_block(self, i, X, wsp, stage):
+    def toc3d_block(self, i, X, wsp, stage, pending=None, defer=False):
         """toc3d_eva_vit.py:395-473 (accelerated branch).  The packed set of a window (k slow rows + rep) contains pad
         slots whenever the window holds fewer than k real tokens.  A pad row is norm1(0) = beta: it matters only as an
         attention key / value (block constants up to the RoPE rotation, written by fill_pad_kv_rope); its own
         attention / proj / norm2 / MLP results are cropped by window_unpartition (toc3d_eva_vit.py:459-461).  So
         norm1, q/k/v, proj, norm2 and the MLP run on the COMPACT rows (real slow rows + rep) only; the attention
-        reads the window-packed qkv buffer and writes compact rows."""
+        reads the window-packed qkv buffer and writes compact rows.
+
+        pending: the previous accelerated block's deferred fast-token update (applied by this block's first launch, which
+        reads every real row anyway).  defer=True: leave THIS block's fast-token update (toc3d_eva_vit.py:452-461) to the
+        next block and return its description; else run it here and return None."""
         bp, C = self.blocks[i], self.C
         ws = self.block_ws[i]
         w, t = wsp.win[ws], wsp.stage[(stage, ws)]
+        if t.get("ready") is not None:              # tables built on the side stream (select_windows)
+            torch.cuda.current_stream().wait_event(t["ready"])
+            t["ready"] = None
         nW, k, nf, Mc = w["nW"], t["k"], t["nf"], t["Mc"]
         Mp = nW * (k + 1)
+        T, rep = wsp.T2[i % 2], t["rep2"][i % 2]
         # one launch: representative token (-> T[rep_row]) + norm1 of the compact rows + k / v of the pad rows
-        L.ln_gather_merge(X, t["ctok"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, t["rep"],
-                          wsp.T, nW, k, nf, C, LN_EPS,
+        L.ln_gather_merge(X, t["ctok"], t["fast_map"], t["fast_score"], bp["n1w"], bp["n1b"], wsp.a, rep,
+                          T, nW, k, nf, C, LN_EPS,
                           rep_row=t["rep_row"], compact_rows=Mc,
                           pad_fill=(wsp.qkv, t["cmap"], t["prope"], Mp, bp["kpad"], bp["vpad"], bp["cos"], bp["sin"], bp["ft"]),
-                          counters=wsp.merge_cnt)
+                          counters=wsp.merge_cnt, pending=pending)
         self._qkv_attn(bp, wsp, Mc, nW, k + 1, t["crope"], 0, qkv_out_map=t["cinv"], attn_out_map=t["cmap"],
                        q_rows=t["q_rows"], item_order=t["item_order"])
-        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=wsp.T, ldo=C, resid=X,
-               resid_map=t["ctok"], out_alt=wsp.T)                                      # t1 = t + attn
-        L.layernorm_rows(wsp.T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
-        self._mlp(bp, wsp, Mc, out=X, resid=wsp.T, out_map=t["ctok"], out_alt=wsp.T)     # t2 -> image rows
-        L.fast_token_update(X, t["fast_map"], wsp.T, t["rep"], nW, nf, k, C, rep_row=t["rep_row"])
+        L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=Mc, bias=bp["bproj"], out=T, ldo=C, resid=X,
+               resid_map=t["ctok"], out_alt=T)                                          # t1 = t + attn
+        L.layernorm_rows(T, bp["n2w"], bp["n2b"], wsp.a, Mc, C, LN_EPS, zero_stats=wsp.stats)
+        self._mlp(bp, wsp, Mc, out=X, resid=T, out_map=t["ctok"], out_alt=T)             # t2 -> image rows
+        if defer:
+            return (t["fast_win"], T, t["rep_row"], rep)
+        L.fast_token_update(X, t["fast_map"], T, rep, nW, nf, k, C, rep_row=t["rep_row"])
+        return None
 
     # -- scorers ----------------------------------------------------------------------------
     def fold_all_queries(self, q_kw, V):
@@ -546,6 +576,9 @@ class _EvaBase(nn.Module):
         # views are independent: with G > 1 the forward runs G groups of views on their own streams inside the
         # one CUDA graph, so the tail / epilogue of one group's kernels overlaps the other group's kernels
         self.view_groups = 1
+        # fast-token updates of an accelerated block are applied by the next block's first launch (15 of 18 launches less
+        # in the shipped configs; bit-identical results).  False: one toc3d_fast_token_update launch per block.
+        self.defer_fast_update = True
         self.graph_outputs = "clone"   # "static": return the graph's own buffers (overwritten by the next call)
 
     def _init_weights(self):
@@ -881,6 +914,7 @@ class ToC3DEVAViT(_EvaBase):
         X = eng.stem(x, wsp, X_out, pre=getattr(self, "img_preprocess", None))
         masks, keep_idxes, drop_idxes, scores_l = [], [], [], []
         mask_prev, stage = None, -1
+        pending = None
         if tap is not None:
             tap["stem"] = X.clone()
             tap["block_out"] = []
@@ -906,7 +940,7 @@ class ToC3DEVAViT(_EvaBase):
                 side.wait_stream(cur)
                 with torch.cuda.stream(side):
                     L.topk_split(score, V, N, k, keep, drop)
-                eng.select_windows(stage, score, self.token_ratio[stage], wsp)
+                eng.select_windows(stage, score, self.token_ratio[stage], wsp, first_ws=blk.window_size)
                 mask_prev = mask
                 masks.append(mask)
                 keep_idxes.append(keep)
@@ -915,7 +949,12 @@ class ToC3DEVAViT(_EvaBase):
             if tap is not None and "inject_block_in" in tap:
                 X.copy_(tap["inject_block_in"][i].reshape(X.shape))
             if blk.accelerate:
-                eng.toc3d_block(i, X, wsp, stage)
+                # the fast-token update of this block is left to the next block's first launch when that is an
+                # accelerated block of the same stage (nothing reads the residual stream in between)
+                nxt = i + 1
+                defer = (self.defer_fast_update and tap is None and nxt < len(self.blocks) and self.blocks[nxt].accelerate
+                         and nxt not in self.pruning_loc)
+                pending = eng.toc3d_block(i, X, wsp, stage, pending, defer)
             else:
                 eng.dense_block(i, X, wsp)
             if tap is not None:

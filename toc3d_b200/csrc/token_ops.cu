@@ -163,7 +163,7 @@ __device__ __forceinline__ int rank_of(const uint32_t* __restrict__ keys, int n4
 __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int H, int W, int ws, int k,
                                    int* __restrict__ slow_idx, int* __restrict__ fast_idx,
                                    float* __restrict__ fast_score, int* __restrict__ tok_map,
-                                   int* __restrict__ rope_rows, int* __restrict__ fast_map) {
+                                   int* __restrict__ rope_rows, int* __restrict__ fast_map, int* __restrict__ fast_win) {
   pdl_wait();
   pdl_launch_dependents();
   __shared__ __align__(16) uint32_t s_key[1024];
@@ -199,6 +199,9 @@ __global__ void window_topk_kernel(const float* __restrict__ scores, int V, int 
     if (fast_score) fast_score[f] = sc;
     if (fast_map) fast_map[f] = img_row;
   }
+  // image row -> window whose representative token carries this row through the block (fast token), -1 for slow rows;
+  // every real token belongs to exactly one window, so the whole [V*H*W] table is rewritten by each launch
+  if (fast_win && img_row >= 0) fast_win[img_row] = rank < k ? -1 : w;
   if (i == 0) {
     const size_t m = (size_t)w * (k + 1) + k;
     if (tok_map) tok_map[m] = -2;
@@ -456,20 +459,32 @@ merge_fast_kernel(const float* __restrict__ x, const int* __restrict__ fast_map,
 //   blocks [nW, ...)    : LayerNorm of the gathered slow rows (8 rows per block, warp per row).
 // Merge block: warp q accumulates rows j = q (mod 8) over all C channels (VPL float4 per lane, two rows in
 // flight), the eight partials meet in shared memory in a fixed order (deterministic).
+// Deferred fast-token update of the PREVIOUS accelerated block (toc3d_eva_vit.py:452-461): its fast tokens still
+// miss  x += packed_prev[rep row of their window] - rep_prev[window].  This launch reads every real row exactly once
+// (slow rows in the LayerNorm blocks, fast rows in the merge blocks), so it adds the pending delta on the way and writes
+// the row back - same expression as fast_update_kernel, hence bit-identical to running that kernel in between.
+struct Pending {
+  const int* fast_win;         // [rows of x] window of the previous block in which the row was a fast token | -1; nullptr = none
+  const float* packed;         // previous block's packed / compact residual rows (its representative AFTER the block)
+  const int* rep_row;          // previous block: row of `packed` holding window w's representative
+  const float* rep;            // previous block: representative BEFORE the block, [nW_prev, C]
+};
+
 template <int VPL>
 __global__ void __launch_bounds__(256)
-ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_map, const int* __restrict__ fast_map,
+ln_gather_merge_kernel(float* x, const int* __restrict__ tok_map, const int* __restrict__ fast_map,
                        const float* __restrict__ fast_score, const float* __restrict__ gamma,
                        const float* __restrict__ beta, __nv_bfloat16* __restrict__ out, float* __restrict__ rep_out,
                        float* __restrict__ packed, int nW, int k, int n_fast, float eps, long long* __restrict__ zero_stats,
                        const int* __restrict__ rep_row, int ln_rows, int compact, const PadFill fill,
-                       int* __restrict__ counters) {
+                       int* __restrict__ counters, const Pending pend) {
   constexpr int C = VPL * 128;
   constexpr int MSLICES = C >= 256 ? C / 256 : 1;
   const int mblocks = nW * MSLICES;       // merge blocks come first (they are the long pole), then LN, then pad fill
   __shared__ __align__(16) float s_acc[8][C >= 256 ? 256 : 128];
   __shared__ float s_wgt[1024];
   __shared__ int s_row[1024];
+  __shared__ int s_pw[1024];
   __shared__ float s_red[8];
   pdl_wait();
   pdl_launch_dependents();
@@ -489,14 +504,24 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
     if (zero_stats != nullptr && lane == 0) *reinterpret_cast<longlong2*>(zero_stats + 2 * (size_t)m) = make_longlong2(0, 0);
     const int src = tok_map[m];
     if (src == -2 || (compact && src < 0)) return;
-    const float4* p = src >= 0 ? reinterpret_cast<const float4*>(x + (size_t)src * C) : nullptr;
+    float4* p = src >= 0 ? reinterpret_cast<float4*>(x + (size_t)src * C) : nullptr;
+    const int pw = (pend.fast_win != nullptr && src >= 0) ? pend.fast_win[src] : -1;
     float4 v[VPL];
     float sm = 0.f;
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-      v[i] = p ? p[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
-      sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < VPL; ++i) v[i] = p ? p[lane + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    if (pw >= 0) {                                     // fast token of the previous block: apply its pending update
+      const float4* t2 = reinterpret_cast<const float4*>(pend.packed + (size_t)pend.rep_row[pw] * C) + lane;
+      const float4* t0 = reinterpret_cast<const float4*>(pend.rep + (size_t)pw * C) + lane;
+#pragma unroll
+      for (int i = 0; i < VPL; ++i) {
+        const float4 a = __ldg(t2 + 32 * i), b = __ldg(t0 + 32 * i);
+        v[i].x += a.x - b.x; v[i].y += a.y - b.y; v[i].z += a.z - b.z; v[i].w += a.w - b.w;
+        p[lane + 32 * i] = v[i];
+      }
     }
+#pragma unroll
+    for (int i = 0; i < VPL; ++i) sm += (v[i].x + v[i].y) + (v[i].z + v[i].w);
     const float mean = warp_sum(sm) / (float)C;
     float q = 0.f;
 #pragma unroll
@@ -528,8 +553,10 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
   float part_s = 0.f;
   for (int j = threadIdx.x; j < n_fast; j += 256) {
     const float sc = fs[j];
+    const int r = fm[j];
     s_wgt[j] = sc;
-    s_row[j] = fm[j];
+    s_row[j] = r;
+    s_pw[j] = (pend.fast_win != nullptr && r >= 0) ? pend.fast_win[r] : -1;
     part_s += sc;
   }
   part_s = warp_sum(part_s);
@@ -539,7 +566,7 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
   float4 a[LV];
 #pragma unroll
   for (int i = 0; i < LV; ++i) a[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  const float4* xb = reinterpret_cast<const float4*>(x + part * SW) + lane;
+  float4* xb = reinterpret_cast<float4*>(x + part * SW) + lane;
   for (int j0 = warp; j0 < n_fast; j0 += 32) {            // warp q owns rows j = q (mod 8), four rows in flight
     float4 v[4][LV];
     float wg[4];
@@ -551,6 +578,24 @@ ln_gather_merge_kernel(const float* __restrict__ x, const int* __restrict__ tok_
 #pragma unroll
       for (int i = 0; i < LV; ++i)
         v[u][i] = r >= 0 ? xb[(size_t)r * (C / 4) + 32 * i] : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (pend.fast_win != nullptr) {                        // pending update of the previous block (this slice of the row)
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const int j = j0 + 8 * u;
+        const int pw = j < n_fast ? s_pw[j] : -1;
+        if (pw >= 0) {
+          const int r = s_row[j];
+          const float4* t2 = reinterpret_cast<const float4*>(pend.packed + (size_t)pend.rep_row[pw] * C + part * SW) + lane;
+          const float4* t0 = reinterpret_cast<const float4*>(pend.rep + (size_t)pw * C + part * SW) + lane;
+#pragma unroll
+          for (int i = 0; i < LV; ++i) {
+            const float4 a = __ldg(t2 + 32 * i), b = __ldg(t0 + 32 * i);
+            v[u][i].x += a.x - b.x; v[u][i].y += a.y - b.y; v[u][i].z += a.z - b.z; v[u][i].w += a.w - b.w;
+            xb[(size_t)r * (C / 4) + 32 * i] = v[u][i];
+          }
+        }
+      }
     }
 #pragma unroll
     for (int u = 0; u < 4; ++u)
@@ -908,7 +953,7 @@ extern "C" int toc3d_subln_bf16(const void* h, void* out, const float* gamma, co
 
 extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int32_t W, int32_t ws, int32_t k,
                                  int32_t* slow_idx, int32_t* fast_idx, float* fast_score, int32_t* tok_map,
-                                 int32_t* rope_rows, int32_t* fast_map, void* stream) {
+                                 int32_t* rope_rows, int32_t* fast_map, int32_t* fast_win, void* stream) {
   TOC3D_REQUIRE(scores, kErrBadArg, "toc3d_window_topk: null scores");
   const int n = ws * ws;
   TOC3D_REQUIRE(V > 0 && H > 0 && W > 0 && ws > 0 && n <= 1024 && k >= 0 && k <= n, kErrBadArg,
@@ -916,7 +961,7 @@ extern "C" int toc3d_window_topk(const float* scores, int32_t V, int32_t H, int3
   const int nW = V * ((H + ws - 1) / ws) * ((W + ws - 1) / ws);
   const int threads = ((n + 31) / 32) * 32;
   TOC3D_CHECK_CUDA(launch_pdl(window_topk_kernel, dim3(nW), dim3(threads), 0, ST(stream), 1, scores, V, H, W, ws, k, slow_idx, fast_idx,
-                                                                      fast_score, tok_map, rope_rows, fast_map));
+                                                                      fast_score, tok_map, rope_rows, fast_map, fast_win));
   TOC3D_CHECK_CUDA(cudaGetLastError());
   return 0;
 }
@@ -992,11 +1037,11 @@ extern "C" int toc3d_fast_token_update(float* x, const int32_t* fast_map, const 
   return 0;
 }
 
-extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, const int32_t* fast_map,
+extern "C" int toc3d_ln_gather_merge(float* x, const int32_t* tok_map, const int32_t* fast_map,
                                      const float* fast_score, const float* gamma, const float* beta, void* out,
                                      float* rep_out, float* packed, int32_t nW, int32_t k, int32_t n_fast, int32_t C,
                                      float eps, int64_t* zero_stats, const int32_t* rep_row, int32_t compact_rows,
-                                     const toc3d_pad_fill* pf, int32_t* counters, void* stream) {
+                                     const toc3d_pad_fill* pf, int32_t* counters, const toc3d_pending_update* pu, void* stream) {
   TOC3D_REQUIRE(x && tok_map && fast_map && fast_score && gamma && beta && out && rep_out && packed, kErrBadArg,
                 "toc3d_ln_gather_merge: null pointer");
   TOC3D_REQUIRE(nW > 0 && k >= 0 && n_fast > 0 && n_fast <= 1024, kErrBadArg,
@@ -1014,13 +1059,20 @@ extern "C" int toc3d_ln_gather_merge(const float* x, const int32_t* tok_map, con
                    pf->sin_axis, pf->ft};
     fill_blocks = (pf->Mp + 7) / 8;
   }
+  Pending pend{};
+  if (pu != nullptr && pu->fast_win != nullptr) {
+    TOC3D_REQUIRE(pu->packed && pu->rep_row && pu->rep, kErrBadArg, "toc3d_ln_gather_merge: incomplete pending-update description");
+    TOC3D_REQUIRE(pu->packed != packed && pu->rep != rep_out, kErrBadArg,
+                  "toc3d_ln_gather_merge: the pending update must read buffers this launch does not write (ping-pong packed / rep)");
+    pend = Pending{pu->fast_win, pu->packed, pu->rep_row, pu->rep};
+  }
   const int mslices = C >= 256 ? C / 256 : 1;
   TOC3D_REQUIRE(mslices == 1 || counters != nullptr, kErrBadArg, "toc3d_ln_gather_merge: counters (int32 [nW], zeroed) required for C >= 256");
   dim3 grid(nW * mslices + (M + 7) / 8 + fill_blocks), block(256);
   __nv_bfloat16* o = reinterpret_cast<__nv_bfloat16*>(out);
   long long* zs = reinterpret_cast<long long*>(zero_stats);
 #define LGM_CASE(V)                                                                                                  \
-  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs, rep_row, M, compact, fill, counters)); break;
+  case V: TOC3D_CHECK_CUDA(launch_pdl(ln_gather_merge_kernel<V>, grid, block, 0, ST(stream), 1, x, tok_map, fast_map, fast_score, gamma, beta, o, rep_out, packed, nW, k, n_fast, eps, zs, rep_row, M, compact, fill, counters, pend)); break;
   switch (C % 128 == 0 ? C / 128 : 0) {
     LGM_CASE(1) LGM_CASE(2) LGM_CASE(4) LGM_CASE(6) LGM_CASE(8)
     default: TOC3D_REQUIRE(false, kErrBadArg, "toc3d_ln_gather_merge: C must be 128, 256, 512, 768 or 1024 (got %d)", C);

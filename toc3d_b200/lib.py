@@ -30,6 +30,10 @@ class Epilogue(ctypes.Structure):
     ]
 
 
+class PendingUpdate(ctypes.Structure):
+    _fields_ = [("fast_win", _c_void_p), ("packed", _c_void_p), ("rep_row", _c_void_p), ("rep", _c_void_p)]
+
+
 class PadFill(ctypes.Structure):
     _fields_ = [("qkv", _c_void_p), ("cmap", _c_void_p), ("rope_rows", _c_void_p), ("Mp", _c_int), ("kpad", _c_void_p),
                 ("vpad", _c_void_p), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p), ("ft", _c_int)]
@@ -46,7 +50,7 @@ _SIGS = {
     "toc3d_subln_bf16": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
                          _c_int),
     "toc3d_window_topk": ([_c_void_p, _c_int, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p,
-                           _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+                           _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_compact_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                             _c_void_p, _c_void_p, _c_void_p], _c_int),
     "toc3d_fill_pad_kv_rope": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
@@ -58,7 +62,7 @@ _SIGS = {
     "toc3d_fast_token_update": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int,
                                  _c_void_p, _c_void_p], _c_int),
     "toc3d_ln_gather_merge": ([_c_void_p] * 9 + [_c_int, _c_int, _c_int, _c_int, _c_float, _c_void_p, _c_void_p, _c_int,
-                               ctypes.POINTER(PadFill), _c_void_p, _c_void_p], _c_int),
+                               ctypes.POINTER(PadFill), _c_void_p, ctypes.POINTER(PendingUpdate), _c_void_p], _c_int),
     "toc3d_motion_blob_floats": ([_c_int, _c_int], _c_i64),
     "toc3d_motion_queries_fold": ([_c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
                                    _c_int, _c_void_p, _c_void_p, _c_float, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
@@ -174,10 +178,10 @@ def subln(h, out, gamma, beta, M, Hd, ld, eps):
 
 
 def window_topk(scores, V, H, W, ws, k, slow_idx=None, fast_idx=None, fast_score=None, tok_map=None,
-                rope_rows=None, fast_map=None):
+                rope_rows=None, fast_map=None, fast_win=None):
     _want(scores, torch.float32, "scores")
     _check(load().toc3d_window_topk(_p(scores), V, H, W, ws, k, _p(slow_idx), _p(fast_idx), _p(fast_score),
-                                    _p(tok_map), _p(rope_rows), _p(fast_map), _stream()), "toc3d_window_topk")
+                                    _p(tok_map), _p(rope_rows), _p(fast_map), _p(fast_win), _stream()), "toc3d_window_topk")
 
 
 def topk_split(scores, B, N, k, keep_idx, drop_idx):
@@ -210,8 +214,13 @@ def fast_token_update(x, fast_map, packed, rep, nW, n_fast, k, C, rep_row=None):
 
 
 def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out, packed, nW, k, n_fast, C, eps,
-                    zero_stats=None, rep_row=None, compact_rows=0, pad_fill=None, counters=None):
-    """pad_fill = (qkv, cmap, rope_rows, Mp, kpad, vpad, cos_axis, sin_axis, ft): also write the pad rows' k / v."""
+                    zero_stats=None, rep_row=None, compact_rows=0, pad_fill=None, counters=None, pending=None):
+    """pad_fill = (qkv, cmap, rope_rows, Mp, kpad, vpad, cos_axis, sin_axis, ft): also write the pad rows' k / v.
+    pending = (fast_win, packed, rep_row, rep) of the previous accelerated block: apply its deferred fast-token update."""
+    pu = None
+    if pending is not None:
+        fw, pk, rr_, rp = pending
+        pu = PendingUpdate(_p(fw), _p(pk), _p(rr_), _p(rp))
     pf = None
     if pad_fill is not None:
         q, cm, rr, Mp, kp, vp, ca, sa, ft = pad_fill
@@ -219,7 +228,8 @@ def ln_gather_merge(x, tok_map, fast_map, fast_score, gamma, beta, out, rep_out,
     _want(x, torch.float32, "x"); _want(out, torch.bfloat16, "out")
     _check(load().toc3d_ln_gather_merge(_p(x), _p(tok_map), _p(fast_map), _p(fast_score), _p(gamma), _p(beta), _p(out),
                                         _p(rep_out), _p(packed), nW, k, n_fast, C, eps, _p(zero_stats), _p(rep_row), compact_rows,
-                                        ctypes.byref(pf) if pf is not None else None, _p(counters), _stream()),
+                                        ctypes.byref(pf) if pf is not None else None, _p(counters),
+                                        ctypes.byref(pu) if pu is not None else None, _stream()),
            "toc3d_ln_gather_merge")
 
 

@@ -45,6 +45,9 @@ def local_inputs(inputs, views, rank, world):
     for k in _PER_FRAME:
         if inputs.get(k) is not None:
             out[k] = inputs[k][fa:fb]
+    for k in ("gumbel_noise", "teacher_scores"):          # per-image test / parity hooks of the plugin's forward
+        if inputs.get(k) is not None:
+            out[k] = [t[a:b] for t in inputs[k]]
     return out
 
 
