@@ -572,6 +572,39 @@ def test_fill_pad_kv_rope_matches_qkv_gemm(lib, ft):
     assert (got[pad][:, C:] - want[pad][:, C:]).abs().max().item() <= 2 ** -7 * want[pad][:, C:].abs().max().item()
 
 
+@pytest.mark.parametrize("seq", [129, 130, 180, 256])
+def test_attention_tail_row_129(lib, seq):
+    """Windows that need exactly 128 + 1 query rows (k = 128 slow tokens + representative: the second query tile holds ONE
+    row), mixed with windows needing 1, 128, 130 and all rows, through compact out maps, many items per CTA (ring
+    reuse), with and without the balanced item order, against the fp32 reference."""
+    g = torch.Generator().manual_seed(seq)
+    nW, heads = 40, 4
+    C = heads * 64
+    qkv = bf16_round(torch.randn(nW * seq, 3 * C, generator=g))
+    q, k, v = qkv.reshape(nW, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(nW, seq, C)
+    choices = [129, 129, 129, 1, 128, min(seq, 130), seq, 129]
+    qr = torch.tensor([min(seq, choices[i % len(choices)]) for i in range(nW)], dtype=torch.int32)
+    omap = torch.full((nW * seq,), -1, dtype=torch.int32)
+    n = 0
+    for w in range(nW):                                   # compact destination rows: only the needed query rows
+        for r in range(int(qr[w])):
+            omap[w * seq + r] = n
+            n += 1
+    order = torch.argsort(((qr + 127) // 128).repeat_interleave(heads), descending=True, stable=True).int()
+    for io in (None, order):
+        out = torch.full((n, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+        lib.window_attention(qkv.to(DEV).bfloat16(), out, nW, seq, heads, out_map=omap.to(DEV), q_rows=qr.to(DEV),
+                             item_order=None if io is None else io.to(DEV))
+        got = out.float().cpu()
+        assert torch.isfinite(got).all()
+        for w in range(nW):
+            r = int(qr[w])
+            rows = omap[w * seq: w * seq + r].long()
+            err = (got[rows] - ref[w, :r]).abs().max().item()
+            assert err < 3e-2, (w, r, err)
+
+
 @pytest.mark.parametrize("seq", [77, 180, 256, 300, 401, 500])
 def test_attention_q_rows_prefix(lib, seq):
     """q_rows: only the leading query rows of each window are computed / stored; all rows remain keys."""

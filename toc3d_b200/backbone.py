@@ -251,6 +251,10 @@ class _Workspace:
         self.T = self.T2[0]
         self.stats = torch.zeros(rows, 2, device=dev, dtype=torch.int64)   # sub-LN fixed-point [sum, sum sq] per MLP row
         self.merge_cnt = torch.zeros(max(v["nW"] for v in self.win.values()), device=dev, dtype=torch.int32)
+        # side branches of this group of views (one workspace per view group, so concurrent groups never queue behind each
+        # other): pad-slot k / v constants of the dense blocks; image-level sort + tables of the second window size
+        self.fill_stream = torch.cuda.Stream(device=dev)
+        self.side = torch.cuda.Stream(device=dev)
         self.stage = {}                                # (stage, ws) -> selection tables
 
 
@@ -321,8 +325,7 @@ class _Engine:
             self.sel_scale = preds[0].scale
         self.ws_cache = {}
         self._gstreams = []
-        self.fill_stream = torch.cuda.Stream(device=device)   # dense blocks: pad-slot k / v constants, beside norm1 + q/k/v
-        self.side = torch.cuda.Stream(device=device)      # query folding / image-level top-k overlap the blocks
+        self.side = torch.cuda.Stream(device=device)      # history-query encoding + folding overlaps the stem and the dense blocks
         self.seed_t = torch.zeros(1, device=device, dtype=torch.int64)   # forward counter (Gumbel seed, graph-safe)
 
     # -- helpers ---------------------------------------------------------------------------
@@ -400,7 +403,7 @@ class _Engine:
         VN = wsp.V * wsp.N
         # the pad slots' constants touch only pad rows of the qkv buffer: written on a second stream, concurrently with
         # norm1 and the q/k/v GEMM (which writes the real slots), joined before the attention
-        cur, fs = torch.cuda.current_stream(), self.fill_stream
+        cur, fs = torch.cuda.current_stream(), wsp.fill_stream
         fs.wait_stream(cur)                                  # the previous attention has finished reading qkv
         with torch.cuda.stream(fs):
             L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
@@ -447,8 +450,8 @@ class _Engine:
                 wsp.stage[(stage, ws)] = t
             on_side = first_ws is not None and ws != first_ws
             if on_side:
-                self.side.wait_stream(cur)
-            with torch.cuda.stream(self.side) if on_side else contextlib.nullcontext():
+                wsp.side.wait_stream(cur)
+            with torch.cuda.stream(wsp.side) if on_side else contextlib.nullcontext():
                 L.window_topk(score, wsp.V, wsp.H, wsp.W, ws, k, fast_score=t["fast_score"], tok_map=t["tok_map"],
                               rope_rows=t["rope_rows"], fast_map=t["fast_map"], fast_win=t["fast_win"])
                 L.compact_rows(t["tok_map"], t["coff"], t["rcap"], nW, k, t["cmap"], t["ctok"], t["rep_row"],
@@ -456,7 +459,7 @@ class _Engine:
                 t["ready"] = None
                 if on_side:
                     t["ready"] = torch.cuda.Event()
-                    t["ready"].record(self.side)
+                    t["ready"].record(wsp.side)
 
     def toc3d_block(self, i, X, wsp, stage, pending=None, defer=False):
         """toc3d_eva_vit.py:395-473 (accelerated branch).  The packed set of a window (k slow rows + rep) contains pad
@@ -603,6 +606,16 @@ class _EvaBase(nn.Module):
         self.refresh_weights()
         return super().load_state_dict(*a, **k)
 
+    def _load_from_state_dict(self, *a, **k):
+        # mmcv's load_checkpoint (what the reference uses) calls this on every module directly, bypassing load_state_dict
+        self.refresh_weights()
+        return super()._load_from_state_dict(*a, **k)
+
+    def _option_key(self):
+        """Options that change the captured launch sequence: part of every graph key."""
+        return (self.view_groups, self.defer_fast_update, self.graph_outputs, id(getattr(self, "_fused_neck", None)),
+                tuple(getattr(self, "token_ratio", ()) or ()))
+
     def refresh_weights(self):
         """Call after mutating parameters in place (the engine holds repacked bf16 copies, the captured
         graphs hold pointers into it)."""
@@ -740,7 +753,7 @@ class EVA_ViT(_EvaBase):
 
         GLOBAL_TIMER.event_start("StreamPETR-EVA-ViT/backbone")
         if self.use_cuda_graph and tap is None:
-            X, *extra = self._graphed(("dense", V, Hi, Wi, tuple(x.shape), x.dtype), {"x": x}, core)
+            X, *extra = self._graphed(("dense", V, Hi, Wi, tuple(x.shape), x.dtype, self._option_key()), {"x": x}, core)
         else:
             X, *extra = core({"x": x})
         GLOBAL_TIMER.event_end("StreamPETR-EVA-ViT/backbone")
@@ -789,7 +802,10 @@ class ToC3DEVAViT(_EvaBase):
                 from mmdet3d.models.builder import build_loss
                 self.token_selection_loss = build_loss(token_selection_loss)
             except ImportError:
-                raise RuntimeError("token_selection_loss needs mmdet3d (training only); pass None for inference")
+                # the loss is a training-time consumer (toc3d_eva_vit.py:312-326); the shipped configs always pass it, and
+                # inference never uses it, so a stand-alone (mmdet3d-less) construction keeps going
+                import warnings
+                warnings.warn("token_selection_loss ignored: mmdet3d is not importable (the loss is training-only)")
         self.score_predictor = nn.ModuleList([
             _Selector(embed_dim, pruning_num_queries, token_ratio[i], pc_range) for i in range(len(pruning_loc))])
         hh = embed_dim // num_heads // 2
@@ -837,7 +853,7 @@ class ToC3DEVAViT(_EvaBase):
 
         GLOBAL_TIMER.event_start("ToC3D-StreamPETR-EVAViT/backbone")
         if self.use_cuda_graph and gumbel_noise is None and teacher_scores is None and tap is None:
-            key = ("toc3d", prev) + tuple((k, tuple(v.shape), v.dtype) for k, v in tensors.items())
+            key = ("toc3d", prev, self._option_key()) + tuple((k, tuple(v.shape), v.dtype) for k, v in tensors.items())
             flat = self._graphed(key, tensors, core)
         else:
             flat = core(tensors)
@@ -910,7 +926,7 @@ class ToC3DEVAViT(_EvaBase):
         V = x.shape[0]
         H, W = wsp.H, wsp.W
         N = H * W
-        cur, side = torch.cuda.current_stream(), eng.side
+        cur, side = torch.cuda.current_stream(), wsp.side
         X = eng.stem(x, wsp, X_out, pre=getattr(self, "img_preprocess", None))
         masks, keep_idxes, drop_idxes, scores_l = [], [], [], []
         mask_prev, stage = None, -1
@@ -961,6 +977,7 @@ class ToC3DEVAViT(_EvaBase):
                 tap["block_out"].append(X.clone())
         if tap is not None:
             tap["scores"] = scores_l
+        cur.wait_stream(side)                      # image-level index lists
         return (X, *masks, *keep_idxes, *drop_idxes)
 
     def loss(self, pred_masks, gt_bboxes, *args, **kwargs):

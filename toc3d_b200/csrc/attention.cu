@@ -11,6 +11,9 @@
 //   attn_tc::window_attention_tc2_kernel (256 < seq <= 448): same math, one CTA per (window, head), one slot, two
 //            softmax warps per TMEM lane quarter splitting the key columns.
 //   attn::window_attention_kernel (seq > 448, not reached by any shipped config): flash-style mma.sync fallback.
+// Measured and NOT adopted (round 2, profiles/r02h_attn_bench_tail_warp.txt): an 11th warp computing the 129th query row
+// of 128 + 1 row windows on CUDA cores (so that those windows need one tensor tile instead of two) - correct, but the
+// extra warp slowed every shape (48 x 256 keys: 35.3 -> 41.7 us) and the row itself took longer than the tile it replaced.
 // All take an optional out_map (rows stored in compact order, padding rows skipped) and q_rows (only the leading
 // query rows of a window are needed; the rest is padding that only serves as keys / values).
 //
@@ -21,6 +24,8 @@
 // Replaces eva_vit.py:109-111 / toc3d_eva_vit.py:509-511 (q@k^T, softmax, @v, head merge).
 #include "common.cuh"
 #include "../../include/toc3d_b200.h"
+
+#include <mutex>
 
 namespace toc3d {
 
@@ -219,7 +224,7 @@ constexpr int BOX_ROWS = 64;                    // TMA box: 64 rows x 64 bf16 (1
 constexpr int BOX_BYTES = BOX_ROWS * D * 2;
 constexpr int MAX_SEQ = 448;                    // S (<= 448 fp32 columns) + O (64) fill the 512 TMEM columns
 constexpr int PP_MAX_SEQ = 256;                 // ping-pong kernel: two 256-column slots
-constexpr int PP_THREADS = 352;                 // warp 0 TMA, warp 1 MMA issue, warps 2-5 / 6-9 softmax of slot 0 / 1, warp 10 tail rows
+constexpr int PP_THREADS = 320;                 // warp 0 TMA, warp 1 MMA issue, warps 2-5 / 6-9 softmax of slot 0 / 1
 constexpr float LOG2E = 1.4426950408889634f;
 
 // kind::f16 instruction descriptor: D=f32, A=B=bf16, M=128; b_mn = 1 selects an MN-major B operand
@@ -387,72 +392,6 @@ __device__ __forceinline__ void issue_pv(uint32_t o_addr, uint32_t p_addr, const
 
 enum { BAR_QK = 0, BAR_V, BAR_S, BAR_P, BAR_O, BAR_OFREE, NUM_BARS };
 
-// One query row against all keys of the window on CUDA cores (one warp).  Used for the 129th query row of a window
-// that needs 128 + 1 rows (k = 128 slow tokens + the representative token, ws16 at ratio 0.5): as a second 128-row
-// tensor tile that single row would occupy a TMEM slot and its softmax warps for a whole tile period.
-// sq: the row's 64 bf16 (unswizzled: row 0 of a box); sK / sV: 64-row boxes, 128B-swizzled (16-byte chunk c of row r
-// at chunk position c ^ (r & 7)).  q is already rotated and scaled.  fp32 scores, probabilities and accumulation.
-__device__ __forceinline__ void tail_row_attention(const uint8_t* sq, const uint8_t* sK, const uint8_t* sV, int seq, int lane,
-                                                   __nv_bfloat16* out_row) {
-  float q[D];
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const uint4 u = *reinterpret_cast<const uint4*>(sq + 16 * c);
-    const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), e = unpack_bf16(u.z), f = unpack_bf16(u.w);
-    q[8 * c + 0] = a.x; q[8 * c + 1] = a.y; q[8 * c + 2] = b.x; q[8 * c + 3] = b.y;
-    q[8 * c + 4] = e.x; q[8 * c + 5] = e.y; q[8 * c + 6] = f.x; q[8 * c + 7] = f.y;
-  }
-  float sc[8];                                   // keys lane, lane + 32, ... (seq <= 256)
-  float mx = -INFINITY;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int j = lane + 32 * c;
-    sc[c] = -INFINITY;
-    if (j < seq) {
-      const int r = j & 63;
-      const uint8_t* row = sK + (j >> 6) * BOX_BYTES + r * 128;
-      float acc = 0.f;
-#pragma unroll
-      for (int ch = 0; ch < 8; ++ch) {
-        const uint4 u = *reinterpret_cast<const uint4*>(row + ((ch ^ (r & 7)) << 4));
-        const float2 a = unpack_bf16(u.x), b = unpack_bf16(u.y), e = unpack_bf16(u.z), f = unpack_bf16(u.w);
-        acc = fmaf(q[8 * ch + 0], a.x, acc); acc = fmaf(q[8 * ch + 1], a.y, acc);
-        acc = fmaf(q[8 * ch + 2], b.x, acc); acc = fmaf(q[8 * ch + 3], b.y, acc);
-        acc = fmaf(q[8 * ch + 4], e.x, acc); acc = fmaf(q[8 * ch + 5], e.y, acc);
-        acc = fmaf(q[8 * ch + 6], f.x, acc); acc = fmaf(q[8 * ch + 7], f.y, acc);
-      }
-      sc[c] = acc;
-      mx = fmaxf(mx, acc);
-    }
-  }
-  mx = warp_max(mx);
-  const float mneg = -mx * LOG2E;
-  float sum = 0.f;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    sc[c] = (lane + 32 * c < seq) ? ex2_approx(fmaf(sc[c], LOG2E, mneg)) : 0.f;
-    sum += sc[c];
-  }
-  sum = warp_sum(sum);
-  // O: this lane owns head dims 2 * lane, 2 * lane + 1 (4 bytes of every V row)
-  float o0 = 0.f, o1 = 0.f;
-  const int vch = lane >> 2, voff = (lane & 3) * 4;
-#pragma unroll
-  for (int c = 0; c < 8; ++c) {
-    const int n = min(32, seq - 32 * c);           // warp-uniform
-    for (int jj = 0; jj < n; ++jj) {
-      const float pj = __shfl_sync(0xffffffffu, sc[c], jj);
-      const int j = 32 * c + jj, r = j & 63;
-      const uint32_t u = *reinterpret_cast<const uint32_t*>(sV + (j >> 6) * BOX_BYTES + r * 128 + ((vch ^ (r & 7)) << 4) + voff);
-      const float2 v = unpack_bf16(u);
-      o0 = fmaf(pj, v.x, o0);
-      o1 = fmaf(pj, v.y, o1);
-    }
-  }
-  const float inv = 1.0f / sum;
-  reinterpret_cast<uint32_t*>(out_row)[lane] = pack_bf16(o0 * inv, o1 * inv);
-}
-
 // ---------------------------------------------------------------------------------------------------
 // Ping-pong kernel (seq <= 256): persistent CTAs, one per SM, looping over (window, head) items.
 //   * the Q/K/V boxes of the next items are prefetched by TMA into a ring of item buffers while the
@@ -483,8 +422,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // query tiles of item i: only the leading q_rows[w] query rows of a window are needed afterwards (the rest are
   // window padding, used as keys / values only), so a window may need fewer tiles than its key count suggests
-  // tail: the window needs exactly 128 + 1 query rows -> one tensor tile, row 128 goes to the tail warp (CUDA cores)
-  auto item_tiles = [&](int i, int& w, int& h, bool& tail) {
+  auto item_tiles = [&](int i, int& w, int& h) {
     // item_order (optional): (window, head) items sorted by query-tile count, so that the round-robin deal to the
     // persistent CTAs balances the tile units
     const int idx = (int)blockIdx.x + i * (int)gridDim.x;
@@ -492,15 +430,14 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     w = it / heads;
     h = it - w * heads;
     const int need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;
-    tail = need == 129;
-    return tail ? 1 : (need + 127) >> 7;
+    return (need + 127) >> 7;
   };
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tm);
     for (int b = 0; b < 4; ++b) {
       mbar_init(&bars[PB_FULL + b], 1);
-      mbar_init(&bars[PB_EMPTY + b], 2);           // the MMA thread's commit + the tail warp
+      mbar_init(&bars[PB_EMPTY + b], 1);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&bars[PB_S + s], 1);
@@ -523,9 +460,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       // ------------------------------------------------------------------ TMA producer: ring of item buffers
       for (int i = 0; i < my_items; ++i) {
         int w, h;
-        bool tail;
-        const int Ti = item_tiles(i, w, h, tail);
-        const int qboxes = 2 * Ti + (tail ? 1 : 0);       // the tail row is row 0 of the third Q box
+        const int Ti = item_tiles(i, w, h);
         const int row0 = w * seq;
         const int buf = i % nbuf;
         const uint32_t round = (uint32_t)(i / nbuf);
@@ -533,9 +468,9 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
         uint8_t* base = smem + buf * item_bytes;
         uint8_t* sK = base + 2 * T * BOX_BYTES;
         uint8_t* sV = sK + nb * BOX_BYTES;
-        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)((qboxes + 2 * nb) * BOX_BYTES));
+        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)((2 * Ti + 2 * nb) * BOX_BYTES));
         for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
-        for (int b = 0; b < qboxes; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
+        for (int b = 0; b < 2 * Ti; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
         for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
       }
     }
@@ -558,8 +493,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       int u = 0;
       for (int i = 0; i < my_items; ++i) {
         int w, h;
-        bool tail;
-        const int Ti = item_tiles(i, w, h, tail);
+        const int Ti = item_tiles(i, w, h);
         const int buf = i % nbuf;
         const uint8_t* base = smem + buf * item_bytes;
         const uint8_t* sK = base + 2 * T * BOX_BYTES;
@@ -586,26 +520,6 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       }
       if (have_prev) do_pv(prev);
     }
-  } else if (warp == 10) {
-    // -------------------------------------------------------------------- tail warp: row 128 of 129-row windows
-    // It waits for every item's buffer (so that it can never run a whole ring round ahead of the MMA thread) and
-    // gives its share of the buffer back when it is done with it.
-    for (int i = 0; i < my_items; ++i) {
-      int w, h;
-      bool tail;
-      item_tiles(i, w, h, tail);
-      const int buf = i % nbuf;
-      mbar_wait(&bars[PB_FULL + buf], (uint32_t)((i / nbuf) & 1));
-      if (tail) {
-        const uint8_t* base = smem + buf * item_bytes;
-        const uint8_t* sK = base + 2 * T * BOX_BYTES;
-        int dst = w * seq + 128;
-        if (out_map != nullptr) dst = out_map[dst];
-        if (dst >= 0) tail_row_attention(base + 2 * BOX_BYTES, sK, sK + nb * BOX_BYTES, seq, lane, out + (size_t)dst * C + h * D);
-      }
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&bars[PB_EMPTY + buf]);
-    }
   } else {
     // -------------------------------------------------------------------- softmax warps: slot = (warp - 2) / 4
     const int slot = (warp - 2) >> 2;
@@ -629,8 +543,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     int u = 0;
     for (int i = 0; i < my_items; ++i) {
       int w, h;
-      bool tail;
-      const int Ti = item_tiles(i, w, h, tail);
+      const int Ti = item_tiles(i, w, h);
       for (int t = 0; t < Ti; ++t, ++u) {
         if ((u & 1) != slot) continue;
         const int q = t * 128 + quarter * 32 + lane;
@@ -920,8 +833,17 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
   TOC3D_REQUIRE(n_windows <= 65535, kErrBadArg, "toc3d_window_attention: too many windows (%d)", n_windows);
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   if (seq_len <= attn_tc::MAX_SEQ) {
-    static bool configured = false;
-    static int n_sm = 148;
+    // one-time setup per device ordinal (several GPUs in one process)
+    static bool configured_dev[64] = {};
+    static int n_sm_dev[64] = {};
+    static std::mutex cfg_mutex;
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    if (dev_ < 0 || dev_ >= 64) dev_ = 0;
+    int n_sm = 148;
+    {
+    std::lock_guard<std::mutex> lock(cfg_mutex);
+    bool& configured = configured_dev[dev_];
     if (!configured) {
       TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_tc2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             227 * 1024));
@@ -929,10 +851,12 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       TOC3D_CHECK_CUDA(cudaFuncSetAttribute(attn_tc::window_attention_pp_kernel<true>,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-      int dev = 0;
-      cudaGetDevice(&dev);
-      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+      int v = 0;
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev_);
+      n_sm_dev[dev_] = v > 0 ? v : 148;
       configured = true;
+    }
+    n_sm = n_sm_dev[dev_];
     }
     const int C = heads * attn_tc::D;
     CUtensorMap tm;

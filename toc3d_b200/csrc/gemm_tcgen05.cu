@@ -605,15 +605,24 @@ int make_tmap_bf16_2d(CUtensorMap* tm, const void* base, int64_t rows, int64_t c
 
 namespace gemm {
 
+constexpr int kMaxDevices = 64;       // one-time kernel setup is kept per device ordinal (several GPUs in one process)
+static std::mutex g_cfg_mutex;
+
+static int current_device() {
+  int dev = 0;
+  cudaGetDevice(&dev);
+  return dev >= 0 && dev < kMaxDevices ? dev : 0;
+}
+
 static int sm_count() {
-  static int n = 0;
-  if (n == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
-    if (n <= 0) n = 148;
+  static int n[kMaxDevices] = {};
+  const int dev = current_device();
+  if (n[dev] == 0) {
+    int v = 0;
+    cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev);
+    n[dev] = v > 0 ? v : 148;
   }
-  return n;
+  return n[dev];
 }
 
 // Tile width.  The mainloop is L2 -> SM bandwidth bound (measured: 8192^3 runs at 1.49 PFLOP/s with 256-wide
@@ -640,8 +649,13 @@ static int pick_tile_n(int M, int N, int K, int kind, int units, int mc) {
 template <int EPI, bool LNF = false>
 static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int tile_n, int cluster_pairs,
                   const EpiParams& ep, cudaStream_t st) {
-  static bool configured = false;
-  static int max_clusters[2] = {0, 0};     // co-resident clusters of 2 / 4 CTAs (GPC boundaries can strand SMs)
+  static bool configured_dev[kMaxDevices] = {};
+  static int max_clusters_dev[kMaxDevices][2] = {};     // co-resident clusters of 2 / 4 CTAs (GPC boundaries can strand SMs)
+  const int dev = current_device();
+  int* max_clusters = max_clusters_dev[dev];
+  {
+  std::lock_guard<std::mutex> lock(g_cfg_mutex);
+  bool& configured = configured_dev[dev];
   if (!configured) {
     TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     for (int i = 0; i < 2; ++i) {
@@ -660,9 +674,14 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
     }
     configured = true;
   }
+  }
   // Two pairs per cluster (weight tile multicast) is opt-in: measured on B200 it is 3-10 % SLOWER than one pair on
-  // every shape of this path and on 8192^3 (profiles/r01l_gemm_bench_cluster_pairs.txt) - the mainloop is not
-  // L2 -> SM bandwidth bound, and 4-CTA clusters strand SMs at GPC boundaries.
+  // every shape of this path and on 8192^3 (profiles/r01l_gemm_bench_cluster_pairs.txt) - TMA multicast across <= 4 CTAs
+  // does not reduce the L2 reads on this part (the L2 serves each destination), and 4-CTA clusters strand SMs at GPC
+  // boundaries.  WIDE tiles (one 352 / 512-column accumulator, two MMAs per k-step, single wave for the N = 1024 GEMMs)
+  // were also built and measured (profiles/r02e_gemm_bench_wide_tiles_experiment.txt): bit-identical, but 6 - 10 %
+  // slower than the two balanced waves of 176 / 192-wide tiles the cost model above picks, whose first epilogue hides
+  // behind the second mainloop; removed.
   const int mc = cluster_pairs == 2 ? 1 : 0;
   const int csize = mc ? 4 : 2;
   const int max_units = max_clusters[mc];
