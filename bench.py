@@ -311,26 +311,38 @@ def run_native(args):
         torch.cuda.synchronize()
 
     def timed(fn, steps):
-        """K steps, each bracketed by CUDA events on the launch stream; L2 flushed between steps; max over ranks."""
+        """K steps, each bracketed by CUDA events on the launch stream; L2 flushed between steps; max over ranks.  N > 1:
+        the all-gather of the last step (still running on its own stream) is joined and timed as a tail."""
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        tail = torch.cuda.Event(enable_timing=True)
         barrier()
         for s, e in ev:
             flush.zero_()
             s.record()
             fn()
             e.record()
+        if gather_stream is not None:
+            torch.cuda.current_stream().wait_stream(gather_stream)
+        tail.record()
         barrier()
         ms = [s.elapsed_time(e) for s, e in ev]
+        if gather_stream is not None:
+            ms.append(ev[-1][1].elapsed_time(tail))
         tot = torch.tensor([sum(ms)], device=dev, dtype=torch.float64)
         if world > 1:
             dist.all_reduce(tot, op=dist.ReduceOp.MAX)
         return tot.item(), ms
 
+    gather_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+
     def make_forward(model, neck, V, H, W):
         """One step through the plugin boundary: img_backbone forward, img_neck on its feature dict (petr3d.py:159-190),
         and for N > 1 the all-gather of the multi-scale feature list.  Level 1 of the CPFPN is the stride-2 subsample of
-        level 0 (cp_fpn.py:190-191), so gathering level 0 (NHWC, 256 channels) gathers the whole list."""
-        gathered = torch.empty(world * V, H, W, NECK_CFG["out_channels"], device=dev) if world > 1 else None
+        level 0 (cp_fpn.py:190-191), so gathering level 0 (NHWC, 256 channels) gathers the whole list.  The gather of
+        step i is issued on its own stream behind forward(i) and overlaps forward(i + 1) (double-buffered destination);
+        `timed` joins that stream inside the timed region, so every gather is paid for."""
+        gbuf = [torch.empty(world * V, H, W, NECK_CFG["out_channels"], device=dev) for _ in range(2)] if world > 1 else None
+        state = {"i": 0}
 
         def forward(d):
             out = model(**d)
@@ -338,7 +350,16 @@ def run_native(args):
             levels = neck(list(feats.values()))
             lv0 = levels[0].permute(0, 2, 3, 1)              # contiguous NHWC rows of level 0
             if world > 1:
-                dist.all_gather_into_tensor(gathered, lv0)
+                if args.serial_gather:
+                    dist.all_gather_into_tensor(gbuf[0], lv0)
+                else:
+                    ev = torch.cuda.Event()
+                    ev.record(torch.cuda.current_stream())
+                    with torch.cuda.stream(gather_stream):
+                        gather_stream.wait_event(ev)
+                        dist.all_gather_into_tensor(gbuf[state["i"] % 2], lv0)
+                        lv0.record_stream(gather_stream)
+                    state["i"] += 1
             return lv0
         return forward
 
@@ -413,6 +434,8 @@ def run_native(args):
                 lv0.record_stream(d2h_s)
         main.wait_stream(d2h_s)
         main.wait_stream(h2d_s)
+        if gather_stream is not None:
+            main.wait_stream(gather_stream)
 
     def e2e_timed(steps, host, dev_in):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -584,8 +607,10 @@ def run_native(args):
         "native_details": {"l2": "256 MiB buffer zeroed between timed steps (L2 flush)",
                            "residual_stream": "fp32", "gemm_operands": "bf16, fp32 accumulate",
                            "launch": "backbone + neck replayed as one CUDA graph per call",
-                           "collective": ("ncclAllGather of level 0 of the feature list (NHWC fp32, %d B per rank); level 1 is its stride-2 "
-                                          "subsample" % d2h) if world > 1 else None,
+                           "collective": ("ncclAllGather of level 0 of the feature list (NHWC fp32, %d B per rank; level 1 is its stride-2 "
+                                          "subsample), %s" % (d2h, "after each forward on the launch stream" if args.serial_gather else
+                                                               "on its own stream: the gather of step i overlaps forward(i+1), the last one "
+                                                               "is joined and timed as a tail")) if world > 1 else None,
                            "e2e_pipeline": "per step: pinned-host inputs -> H2D, backbone + neck, feature list (level 0) -> D2H to pinned "
                                            "host; copies double-buffered on copy streams (overlap the neighbouring steps' forward); the L2 "
                                            "flush between steps is inside the e2e timed region"},
@@ -600,39 +625,6 @@ def run_native(args):
         "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches,
         "clocks": clocks, "roofline": roofline,
     }
-    if world > 1 and args.overlap_gather:
-        # experiment (not the headline): the all-gather of step i runs on its own stream behind forward(i) and overlaps
-        # forward(i+1); the timed region ends when the last gather has landed.  The L2 flushes are inside this region.
-        gs = torch.cuda.Stream(device=dev)
-        gbuf = [torch.empty(world * V, H, W, NECK_CFG["out_channels"], device=dev) for _ in range(2)]
-        main = torch.cuda.current_stream()
-
-        def run_overlapped(steps):
-            for i in range(steps):
-                flush.zero_()
-                out = model(**res)
-                feats = out if isinstance(out, dict) else out.img_feats
-                lv0 = neck(list(feats.values()))[0].permute(0, 2, 3, 1)
-                ev = torch.cuda.Event()
-                ev.record(main)
-                with torch.cuda.stream(gs):
-                    gs.wait_event(ev)
-                    dist.all_gather_into_tensor(gbuf[i % 2], lv0)
-                    lv0.record_stream(gs)
-            main.wait_stream(gs)
-
-        run_overlapped(3)
-        barrier()
-        o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        o0.record()
-        run_overlapped(args.steps)
-        o1.record()
-        barrier()
-        ot = torch.tensor([o0.elapsed_time(o1)], device=dev, dtype=torch.float64)
-        dist.all_reduce(ot, op=dist.ReduceOp.MAX)
-        line["overlap_gather"] = {"value": world * B * args.steps / (ot.item() * 1e-3), "unit": UNIT,
-                                  "ms_per_step": ot.item() / args.steps,
-                                  "note": "all-gather of step i overlaps forward(i+1); L2 flushes inside the region; not the headline"}
     del forward, model, neck
     torch.cuda.empty_cache()
     if not args.no_other_configs:
@@ -767,7 +759,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch4", action="store_true", help="skip the extra batch-4 throughput line")
     ap.add_argument("--view-groups", type=int, default=None, help="override the plugin's view_groups (streams of views)")
-    ap.add_argument("--overlap-gather", action="store_true", help="experiment (N > 1): extra line with the all-gather overlapped")
+    ap.add_argument("--serial-gather", action="store_true", help="N > 1: all-gather on the launch stream after each forward (default: own stream, overlapped)")
     ap.add_argument("--no-roofline", action="store_true", help="skip the marginal-time roofline re-captures")
     ap.add_argument("--no-other-configs", action="store_true", help="skip the extra lines for BASELINE.json's other configs")
     ap.add_argument("--strong", action="store_true", help="strong scaling: one --batch-sample batch sharded over the ranks (ShardedBackbone)")

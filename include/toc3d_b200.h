@@ -113,9 +113,17 @@ int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int3
  * put the needed rows first); query tiles beyond them are not computed.  All seq_len rows still act as keys.
  * item_order (optional, int32 [n_windows*heads], a permutation of the (window*heads + head) items): processing
  * order of the persistent kernel, e.g. sorted by query-tile count so that its round-robin deal is balanced.
+ * kv_rows + pad_v (optional, together; seq_len <= 448): ANALYTIC pad keys of the dense blocks.  The reference zero-pads
+ * the normalised map to whole windows (eva_vit.py:249-254), so a pad slot has k = 0 exactly (k_proj has no bias,
+ * RoPE keeps zero) and v = v_bias: its score is 0 for every query and its value is one common vector.  With
+ * kv_rows[w] (int32 [n_windows]) = number of REAL keys of window w (stored first) and pad_v (fp32 [C]) = v_bias, only the
+ * real keys are staged and multiplied; the seq_len - kv_rows[w] pad keys enter the softmax as one closed-form term
+ * (row max includes 0, row sum += n_pad * exp(0 - max), O += n_pad * exp(0 - max) * pad_v).  The pad rows of qkv are
+ * then never read, so nobody has to write them.
  */
 int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
-                           const int32_t* out_map, const int32_t* q_rows, const int32_t* item_order, void* stream);
+                           const int32_t* out_map, const int32_t* q_rows, const int32_t* item_order,
+                           const int32_t* kv_rows, const float* pad_v, void* stream);
 
 /* ------------------------------------------------------------------ LayerNorm over gathered rows
  * out_bf16[m] = LN(row(m)) * gamma + beta over C channels (C % 128 == 0, C <= 4096), m in [0,M).

@@ -46,6 +46,38 @@ def test_first_frame_or_empty_memory_gives_zeros(prev):
         memory_queries(_head(), None, 2, 64, "cpu")
 
 
+REF_PETR3D = "/root/reference/projects/mmdet3d_plugin/models/detectors/petr3d.py"
+
+
+@pytest.mark.skipif(not __import__("os").path.exists(REF_PETR3D), reason="/root/reference not present (GPU box)")
+@pytest.mark.parametrize("prev,empty", [(1.0, False), (0.0, False), (1.0, True)])
+def test_mirror_equals_the_reference_lines_executed(prev, empty):
+    """The reference's OWN statements (the `if self.query_backbone_selection:` block of Petr3D.extract_img_feat,
+    petr3d.py:116-143 - the detector class itself cannot be imported without mmdet3d) are cut out of the source file and
+    executed against a stand-in `self`; the mirror must hand the backbone the very same tensors."""
+    import textwrap
+    src = open(REF_PETR3D).read().split("\n")
+    a = next(i for i, l in enumerate(src) if "if self.query_backbone_selection:" in l)
+    b = next(i for i in range(a, len(src)) if src[i].strip() == "mid_frame = False")
+    block = textwrap.dedent("\n".join(src[a:b + 1]))
+    head = _head()
+    if empty:
+        head.memory_embedding = None
+    me = types.SimpleNamespace(query_backbone_selection=True, pts_bbox_head=head,
+                               img_backbone=types.SimpleNamespace(pruning_num_queries=64))
+    B = 2
+    ns = {"self": me, "torch": torch, "prev_exists": torch.full((B, 1), prev), "B": B, "img": torch.zeros(1)}
+    exec(compile(block, REF_PETR3D, "exec"), ns)
+    kw = memory_queries(head, ns["prev_exists"], B, 64, "cpu")
+    assert kw["prev_exists"] == ns["mid_frame"]
+    for ours, theirs in (("temp_queries", "mem_queries"), ("temp_ref_points", "mem_reference_point"), ("temp_timestamp", "mem_timestamp"),
+                         ("temp_ego_pose", "mem_egopose"), ("temp_vel", "mem_velo")):
+        x, y = kw[ours], ns[theirs]
+        assert x.shape == y.shape and x.dtype == y.dtype and torch.equal(x, y) and x.requires_grad == y.requires_grad, ours
+        if prev and not empty:
+            assert x.data_ptr() == y.data_ptr()            # both are views of the head's memory
+
+
 @pytest.mark.gpu
 def test_backbone_consumes_the_handoff():
     from tests.helpers import build_model

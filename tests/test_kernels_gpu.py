@@ -605,6 +605,37 @@ def test_attention_tail_row_129(lib, seq):
             assert err < 3e-2, (w, r, err)
 
 
+@pytest.mark.parametrize("seq", [64, 180, 256, 400, 448])
+def test_attention_analytic_pad_keys(lib, seq):
+    """Dense-block pad slots (k = 0, v = v_bias, eva_vit.py:249-254) as ONE closed-form softmax term: kv_rows[w] real keys
+    are staged, the seq - kv_rows[w] pads are never read (their qkv rows hold finite garbage here) - against the fp32
+    attention over the explicitly padded window."""
+    g = torch.Generator().manual_seed(seq)
+    nW, heads = 12, 3
+    C = heads * 64
+    vb = torch.randn(C, generator=g) * 0.5
+    kvs = [seq, 1, 8, 32, min(seq, 64), min(seq, 65), seq // 2, seq - 1, min(seq, 200), 17, seq, min(seq, 129)]
+    kv = torch.tensor([max(1, k) for k in kvs], dtype=torch.int32)
+    qkv = bf16_round(torch.randn(nW, seq, 3 * C, generator=g))
+    ref_in = qkv.clone()
+    for w in range(nW):                                    # the reference sees the true pad slots
+        ref_in[w, int(kv[w]):, C:2 * C] = 0.0
+        ref_in[w, int(kv[w]):, 2 * C:] = vb
+        qkv[w, int(kv[w]):, C:] = bf16_round(torch.randn(seq - int(kv[w]), 2 * C, generator=g) * 30)   # garbage: must not matter
+    q, k, v = ref_in.reshape(nW, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(nW, seq, C)
+    out = torch.zeros(nW * seq, C, device=DEV, dtype=torch.bfloat16)
+    lib.window_attention(qkv.reshape(nW * seq, 3 * C).to(DEV).bfloat16(), out, nW, seq, heads, q_rows=kv.to(DEV), kv_rows=kv.to(DEV),
+                         pad_v=vb.to(DEV))
+    got = out.float().cpu().reshape(nW, seq, C)
+    for w in range(nW):
+        r = int(kv[w])
+        err = (got[w, :r] - ref[w, :r]).abs().max().item()
+        assert err < 3e-2, (w, r, err)
+    with pytest.raises(RuntimeError, match="go together"):
+        lib.window_attention(qkv.reshape(nW * seq, 3 * C).to(DEV).bfloat16(), out, nW, seq, heads, kv_rows=kv.to(DEV))
+
+
 @pytest.mark.parametrize("seq", [77, 180, 256, 300, 401, 500])
 def test_attention_q_rows_prefix(lib, seq):
     """q_rows: only the leading query rows of each window are computed / stored; all rows remain keys."""

@@ -13,6 +13,7 @@ PyTorch fallback: CPU inputs or a missing library raise.
 """
 import contextlib
 import math
+import os
 from functools import partial
 
 import torch
@@ -381,7 +382,7 @@ class _Engine:
                ln_n=self.Hd, ln_eps=LN_EPS, **resid_kw)
 
     def _qkv_attn(self, bp, wsp, M, nW, seq, rope_rows, rope_slots, qkv_out_map=None, attn_out_map=None, q_rows=None,
-                  item_order=None, join=None):
+                  item_order=None, join=None, kv_rows=None, pad_v=None):
         """q/k/v for the M rows of wsp.a (scattered to window slots through qkv_out_map when given), then attention
         over nW windows of seq slots; attn_out_map sends the rows that are used afterwards to compact positions."""
         C = self.C
@@ -391,25 +392,31 @@ class _Engine:
         if join is not None:
             torch.cuda.current_stream().wait_stream(join)
         L.window_attention(wsp.qkv, wsp.ao, nW, seq, self.heads, out_map=attn_out_map, q_rows=q_rows,
-                           item_order=item_order)
+                           item_order=item_order, kv_rows=kv_rows, pad_v=pad_v)
 
     def dense_block(self, i, X, wsp):
         """eva_vit.py:247-268.  The reference pads the normalised map to whole windows and runs q/k/v, attention and
         proj on every slot; the pad slots are exact zeros after norm1, so their k is 0 and their v is v_bias, and
         their own outputs are cropped by window_unpartition.  Here q/k/v and proj run over the real tokens only
-        (image-row order); the pad slots of the window layout get their constant k / v from fill_pad_kv."""
+        (image-row order) and the pad slots are never materialised: with k = 0 their score is 0 for every query, so the
+        attention kernel adds them as one closed-form softmax term (analytic pad keys: kv_rows + pad_v).  Windows longer
+        than the tcgen05 kernels take (> 448 slots, no shipped config) fall back to writing the constants (fill_pad_kv)."""
         bp, C = self.blocks[i], self.C
         w = wsp.win[self.block_ws[i]]
         VN = wsp.V * wsp.N
-        # the pad slots' constants touch only pad rows of the qkv buffer: written on a second stream, concurrently with
-        # norm1 and the q/k/v GEMM (which writes the real slots), joined before the attention
-        cur, fs = torch.cuda.current_stream(), wsp.fill_stream
-        fs.wait_stream(cur)                                  # the previous attention has finished reading qkv
-        with torch.cuda.stream(fs):
-            L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
+        analytic = w["n"] <= 448 and not os.environ.get("TOC3D_NO_ANALYTIC_PADS")     # env: A/B diagnostic only (tools/)
+        fs = None
+        if not analytic:
+            # the pad slots' constants touch only pad rows of the qkv buffer: written on a second stream, concurrently with
+            # norm1 and the q/k/v GEMM (which writes the real slots), joined before the attention
+            cur, fs = torch.cuda.current_stream(), wsp.fill_stream
+            fs.wait_stream(cur)                                  # the previous attention has finished reading qkv
+            with torch.cuda.stream(fs):
+                L.fill_pad_kv(wsp.qkv, w["pad_rows"], bp["vb"], C)
         L.layernorm_rows(X, bp["n1w"], bp["n1b"], wsp.a, VN, C, LN_EPS)
         self._qkv_attn(bp, wsp, VN, w["nW"], w["n"], w["rope_slot"], 0, qkv_out_map=w["slot_of_row"], attn_out_map=w["map"],
-                       q_rows=w["q_rows"], item_order=w["item_order"], join=fs)
+                       q_rows=w["q_rows"], item_order=w["item_order"], join=fs,
+                       kv_rows=w["q_rows"] if analytic else None, pad_v=bp["vb"] if analytic else None)
         L.gemm(wsp.ao, bp["wproj"], L.EPI_RESID, M=VN, bias=bp["bproj"], out=X, ldo=C, resid=X)
         L.layernorm_rows(X, bp["n2w"], bp["n2b"], wsp.a, VN, C, LN_EPS, zero_stats=wsp.stats)
         self._mlp(bp, wsp, VN, out=X, resid=X)

@@ -246,7 +246,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
 // tcgen05.wait::ld covers every outstanding load); max and sum run on four / two independent accumulators so
 // the fixed-latency FMNMX / FADD chains do not serialise a warp that shares its scheduler with one other warp.
 // Returns the row sum (0 for warps whose rows are all beyond the window: `active` false, warp-uniform).
-__device__ __forceinline__ float softmax_rows(uint32_t lane_base, int seq, bool active, int tr_role = -1, int tr_unit = 0) {
+// Analytic pad keys (dense blocks, eva_vit.py:249-254): npad further keys of the window have k = 0 exactly (score 0)
+// and one common value vector; they are not staged or multiplied: the row max includes the score 0, the row sum
+// npad * exp(0 - max), and `corr` (= npad * exp(0 - max)) is the factor of that value vector in the O epilogue.
+__device__ __forceinline__ float softmax_rows(uint32_t lane_base, int seq, bool active, float npad, float& corr, int tr_role = -1,
+                                              int tr_unit = 0) {
+  corr = 0.f;
   if (!active) return 0.f;
   const int nchunks = (seq + 31) >> 5;
   float m0 = -INFINITY, m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY;
@@ -277,7 +282,9 @@ __device__ __forceinline__ float softmax_rows(uint32_t lane_base, int seq, bool 
       max_chunk(vb, c + 1);
     }
   }
-  const float mneg = -fmaxf(fmaxf(m0, m1), fmaxf(m2, m3)) * LOG2E;
+  float mrow = fmaxf(fmaxf(m0, m1), fmaxf(m2, m3));
+  if (npad > 0.f) mrow = fmaxf(mrow, 0.f);
+  const float mneg = -mrow * LOG2E;
   ATRACE(tr_role >= 0, tr_role, tr_unit, 2);
   float s0 = 0.f, s1 = 0.f;
   auto exp_chunk = [&](const uint32_t (&v)[32], int c) {
@@ -316,7 +323,8 @@ __device__ __forceinline__ float softmax_rows(uint32_t lane_base, int seq, bool 
     }
   }
   tmem_st_wait();
-  return s0 + s1;
+  if (npad > 0.f) corr = npad * ex2_approx(mneg);
+  return s0 + s1 + corr;
 }
 
 // O epilogue of a tile, in two halves so that the slot can be released between them: read the 64 fp32 O columns
@@ -328,9 +336,25 @@ __device__ __forceinline__ void load_o(uint32_t o_addr, bool active, uint32_t (&
     tmem_ld_wait();
   }
 }
-// ... and store O / sum as 64 bf16 (128 bytes of one output row).
-__device__ __forceinline__ void store_o(const uint32_t (&o0)[32], const uint32_t (&o1)[32], float sum, __nv_bfloat16* out_row) {
+// ... and store (O + corr * pad_v) / sum as 64 bf16 (128 bytes of one output row); pad_v = the pad keys' common value
+// vector for this head (fp32 [64], nullptr / corr = 0: no analytic pad keys).
+__device__ __forceinline__ void store_o(uint32_t (&o0)[32], uint32_t (&o1)[32], float sum, __nv_bfloat16* out_row, float corr,
+                                        const float* __restrict__ pad_v) {
   const float inv = 1.0f / sum;
+  if (pad_v != nullptr && corr != 0.f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pad_v) + j), b = __ldg(reinterpret_cast<const float4*>(pad_v) + 8 + j);
+      o0[4 * j + 0] = __float_as_uint(fmaf(corr, a.x, __uint_as_float(o0[4 * j + 0])));
+      o0[4 * j + 1] = __float_as_uint(fmaf(corr, a.y, __uint_as_float(o0[4 * j + 1])));
+      o0[4 * j + 2] = __float_as_uint(fmaf(corr, a.z, __uint_as_float(o0[4 * j + 2])));
+      o0[4 * j + 3] = __float_as_uint(fmaf(corr, a.w, __uint_as_float(o0[4 * j + 3])));
+      o1[4 * j + 0] = __float_as_uint(fmaf(corr, b.x, __uint_as_float(o1[4 * j + 0])));
+      o1[4 * j + 1] = __float_as_uint(fmaf(corr, b.y, __uint_as_float(o1[4 * j + 1])));
+      o1[4 * j + 2] = __float_as_uint(fmaf(corr, b.z, __uint_as_float(o1[4 * j + 2])));
+      o1[4 * j + 3] = __float_as_uint(fmaf(corr, b.w, __uint_as_float(o1[4 * j + 3])));
+    }
+  }
   uint4* dst = reinterpret_cast<uint4*>(out_row);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -355,7 +379,8 @@ __device__ __forceinline__ void store_o(const uint32_t (&o0)[32], const uint32_t
 // O epilogue of a tile: await O = P V (bar_o), read it, release the O columns (bar_ofree; and bar_p when the caller
 // hands over the next P at the same moment), store the row.
 __device__ __forceinline__ void finish_tile(uint32_t o_addr, bool active, bool store, float sum, __nv_bfloat16* out_row,
-                                            uint64_t* bar_o, uint64_t* bar_ofree, uint64_t* bar_p, uint32_t parity) {
+                                            uint64_t* bar_o, uint64_t* bar_ofree, uint64_t* bar_p, uint32_t parity, float corr,
+                                            const float* __restrict__ pad_v) {
   uint32_t o0[32], o1[32];
   mbar_wait(bar_o, parity);
   tcgen05_fence_after();
@@ -363,7 +388,7 @@ __device__ __forceinline__ void finish_tile(uint32_t o_addr, bool active, bool s
   tcgen05_fence_before();
   mbar_arrive(bar_ofree);
   if (bar_p != nullptr) mbar_arrive(bar_p);
-  if (store) store_o(o0, o1, sum, out_row);
+  if (store) store_o(o0, o1, sum, out_row, corr, pad_v);
 }
 
 // S(tile) = Q_tile K^T into TMEM columns [s_col, s_col + spad): one MMA chain for the first 256 keys, a second
@@ -405,7 +430,7 @@ template <bool deferred>
 __global__ void __launch_bounds__(PP_THREADS, 1)
 window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
                            int n_items, int nbuf, const int* __restrict__ out_map, const int* __restrict__ q_rows,
-                           const int* __restrict__ item_order) {
+                           const int* __restrict__ item_order, const int* __restrict__ kv_rows, const float* __restrict__ pad_v) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int T = (seq + 127) >> 7;               // 1 or 2 query tiles
@@ -431,6 +456,13 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     h = it - w * heads;
     const int need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;
     return (need + 127) >> 7;
+  };
+  // keys of window w that are staged and multiplied: all seq slots, or only the leading kv_rows[w] (the rest are the
+  // analytic pad keys, see softmax_rows)
+  auto item_kv = [&](int w) {
+    if (kv_rows == nullptr) return seq;
+    const int kv = kv_rows[w];
+    return kv >= 1 && kv < seq ? kv : seq;
   };
 
   if (warp == 0 && lane == 0) {
@@ -468,10 +500,11 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
         uint8_t* base = smem + buf * item_bytes;
         uint8_t* sK = base + 2 * T * BOX_BYTES;
         uint8_t* sV = sK + nb * BOX_BYTES;
-        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)((2 * Ti + 2 * nb) * BOX_BYTES));
-        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
+        const int nbi = (item_kv(w) + BOX_ROWS - 1) / BOX_ROWS;      // K / V boxes of this window
+        mbar_arrive_expect_tx(&bars[PB_FULL + buf], (uint32_t)((2 * Ti + 2 * nbi) * BOX_BYTES));
+        for (int b = 0; b < nbi; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
         for (int b = 0; b < 2 * Ti; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], base + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
-        for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
+        for (int b = 0; b < nbi; ++b) tma_load_2d(&tm, &bars[PB_FULL + buf], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
       }
     }
   } else if (warp == 1) {
@@ -479,16 +512,16 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       // ------------------------------------------------------------------ MMA issuer
       // unit u = (item, query tile), enumerated item by item; unit u runs on slot u & 1.  Software pipeline of
       // depth 1: issue S(u), then P V of unit u - 1.
-      struct Unit { int s; uint32_t n; const uint8_t* sV; int last_buf; };   // last_buf >= 0: last tile of its item
+      struct Unit { int s; uint32_t n; const uint8_t* sV; int last_buf; int spad; };   // last_buf >= 0: last tile of its item
       auto do_pv = [&](const Unit& un) {
         mbar_wait(&bars[PB_P + un.s], un.n & 1);
         tcgen05_fence_after();
         ATRACE(true, 2, (int)(2 * un.n) + un.s, 4);        // unit index of `un` = 2 n + slot
-        issue_pv(tmem_base + (uint32_t)(un.s * 256) + o_off, tmem_base + (uint32_t)(un.s * 256), un.sV, spad);
+        issue_pv(tmem_base + (uint32_t)(un.s * 256) + o_off, tmem_base + (uint32_t)(un.s * 256), un.sV, un.spad);
         tcgen05_commit(&bars[PB_O + un.s]);
         if (un.last_buf >= 0) tcgen05_commit(&bars[PB_EMPTY + un.last_buf]);   // all MMAs reading this item are issued
       };
-      Unit prev{0, 0, nullptr, -1};
+      Unit prev{0, 0, nullptr, -1, spad};
       bool have_prev = false;
       int u = 0;
       for (int i = 0; i < my_items; ++i) {
@@ -498,6 +531,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
         const uint8_t* base = smem + buf * item_bytes;
         const uint8_t* sK = base + 2 * T * BOX_BYTES;
         const uint8_t* sV = sK + nb * BOX_BYTES;
+        const int spad_i = (item_kv(w) + 15) & ~15;            // keys of this window, padded to the MMA granularity
         for (int t = 0; t < Ti; ++t, ++u) {
           const int s = u & 1;
           const uint32_t n = (uint32_t)(u >> 1);              // how many units this slot has seen before
@@ -509,12 +543,12 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
           // this thread's MMAs in issue order - and the O columns are guarded by the P barrier (see below)
           if (!deferred && n > 0) mbar_wait(&bars[PB_OFREE + s], (n - 1) & 1);
           tcgen05_fence_after();
-          issue_qk(tmem_base + (uint32_t)(s * 256), base + t * 2 * BOX_BYTES, sK, spad);
+          issue_qk(tmem_base + (uint32_t)(s * 256), base + t * 2 * BOX_BYTES, sK, spad_i);
           tcgen05_commit(&bars[PB_S + s]);
           ATRACE(true, 2, u, 2);
           if (have_prev) do_pv(prev);
           ATRACE(true, 2, u, 3);
-          prev = Unit{s, n, sV, t == Ti - 1 ? buf : -1};
+          prev = Unit{s, n, sV, t == Ti - 1 ? buf : -1, spad_i};
           have_prev = true;
         }
       }
@@ -533,17 +567,19 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     // slot's previous tile runs after the softmax of the current one, so the slot never idles through P V + O read
     // + S(next): it only waits for S, which was issued right behind P V.
     bool pend = false, pend_act = false, pend_ok = false;
-    float pend_sum = 0.f;
+    float pend_sum = 0.f, pend_corr = 0.f;
     __nv_bfloat16* pend_row = out;
+    const float* pend_pv = nullptr;
     uint32_t pend_par = 0;
     auto finish = [&](bool then_p) {
       finish_tile(lane_base + o_off, pend_act, pend_act && pend_ok, pend_sum, pend_row, bar_o, bar_ofree, then_p ? bar_p : nullptr,
-                  pend_par);
+                  pend_par, pend_corr, pend_pv);
     };
     int u = 0;
     for (int i = 0; i < my_items; ++i) {
       int w, h;
       const int Ti = item_tiles(i, w, h);
+      const int kv = item_kv(w);
       for (int t = 0; t < Ti; ++t, ++u) {
         if ((u & 1) != slot) continue;
         const int q = t * 128 + quarter * 32 + lane;
@@ -556,7 +592,8 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
         mbar_wait(bar_s, parity);
         tcgen05_fence_after();
         ATRACE(tr, slot, u >> 1, 1);
-        const float sum = softmax_rows(lane_base, seq, active, tr ? slot : -1, u >> 1);
+        float corr;
+        const float sum = softmax_rows(lane_base, kv, active, (float)(seq - kv), corr, tr ? slot : -1, u >> 1);
         ATRACE(tr, slot, u >> 1, 3);
         if (deferred) {
           if (pend) {
@@ -570,7 +607,8 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
           mbar_arrive(bar_p);
         }
         ATRACE(tr, slot, u >> 1, 4);
-        pend = true; pend_act = active; pend_ok = dst >= 0; pend_sum = sum; pend_par = parity;
+        pend = true; pend_act = active; pend_ok = dst >= 0; pend_sum = sum; pend_par = parity; pend_corr = corr;
+        pend_pv = pad_v != nullptr ? pad_v + h * D : nullptr;
         pend_row = out + (size_t)(dst < 0 ? 0 : dst) * C + h * D;
         if (!deferred) {
           finish(false);
@@ -624,7 +662,8 @@ __device__ __forceinline__ void issue_pv_split(uint32_t o_addr, uint32_t slot_ad
 // combined with the partner warp of the lane quarter through xmax / xsum (indexed [half][lane]) and barrier bar_id.
 // Returns the full row sum.  `active` is the same for both partners (same rows).
 __device__ __forceinline__ float softmax_half(uint32_t lane_base, int seq, int n, int c0, int half, int lane, bool active,
-                                              float* xmax, float* xsum, int bar_id) {
+                                              float* xmax, float* xsum, int bar_id, float npad, float& corr) {
+  corr = 0.f;
   if (!active) return 0.f;
   const int cb = half ? c0 : 0, ce = half ? n : c0;
   uint32_t v[32];
@@ -650,6 +689,7 @@ __device__ __forceinline__ float softmax_half(uint32_t lane_base, int seq, int n
   xmax[half * 32 + lane] = mx;
   named_bar_sync(bar_id, 64);
   mx = fmaxf(mx, xmax[(half ^ 1) * 32 + lane]);          // finite: chunk 0 holds at least one valid key
+  if (npad > 0.f) mx = fmaxf(mx, 0.f);                   // analytic pad keys (score 0), see softmax_rows
   const float mneg = -mx * LOG2E;
   float s0 = 0.f, s1 = 0.f;
   for (int j = cb; j < ce; ++j) {
@@ -683,12 +723,24 @@ __device__ __forceinline__ float softmax_half(uint32_t lane_base, int seq, int n
   const float sum = s0 + s1;
   xsum[half * 32 + lane] = sum;
   named_bar_sync(bar_id, 64);                           // also: both halves of P are in TMEM
-  return sum + xsum[(half ^ 1) * 32 + lane];
+  if (npad > 0.f) corr = npad * ex2_approx(mneg);
+  return sum + xsum[(half ^ 1) * 32 + lane] + corr;
 }
 
 // this warp's 32 of the 64 O columns of a row -> 64 bytes of the output row
-__device__ __forceinline__ void store_o_half(const uint32_t (&o)[32], float sum, __nv_bfloat16* out_half_row) {
+__device__ __forceinline__ void store_o_half(uint32_t (&o)[32], float sum, __nv_bfloat16* out_half_row, float corr,
+                                             const float* __restrict__ pad_v_half) {
   const float inv = 1.0f / sum;
+  if (pad_v_half != nullptr && corr != 0.f) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 a = __ldg(reinterpret_cast<const float4*>(pad_v_half) + j);
+      o[4 * j + 0] = __float_as_uint(fmaf(corr, a.x, __uint_as_float(o[4 * j + 0])));
+      o[4 * j + 1] = __float_as_uint(fmaf(corr, a.y, __uint_as_float(o[4 * j + 1])));
+      o[4 * j + 2] = __float_as_uint(fmaf(corr, a.z, __uint_as_float(o[4 * j + 2])));
+      o[4 * j + 3] = __float_as_uint(fmaf(corr, a.w, __uint_as_float(o[4 * j + 3])));
+    }
+  }
   uint4* dst = reinterpret_cast<uint4*>(out_half_row);
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
@@ -709,7 +761,8 @@ constexpr int TC2_XCH_BYTES = 2 * 4 * 2 * 32 * 4;   // {max, sum} x quarter x ha
 
 __global__ void __launch_bounds__(TC2_THREADS)
 window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16* __restrict__ out, int seq, int heads,
-                            const int* __restrict__ out_map, const int* __restrict__ q_rows) {
+                            const int* __restrict__ out_map, const int* __restrict__ q_rows, const int* __restrict__ kv_rows,
+                            const float* __restrict__ pad_v) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   const int Tmax = (seq + 127) >> 7;
@@ -746,18 +799,26 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat1
   pdl_wait();
   pdl_launch_dependents();
 
-  const int spad = (seq + 15) & ~15;
-  const int n = (seq + 31) >> 5;
+  // keys that are staged and multiplied: all seq slots, or the leading kv_rows[w] (the rest: analytic pad keys)
+  int kv = seq;
+  if (kv_rows != nullptr) {
+    const int r = kv_rows[w];
+    if (r >= 1 && r < seq) kv = r;
+  }
+  const float npad = (float)(seq - kv);
+  const int nbk = (kv + BOX_ROWS - 1) / BOX_ROWS;
+  const int spad = (kv + 15) & ~15;
+  const int n = (kv + 31) >> 5;
   const int c0 = (n + 1) >> 1;
   const uint32_t o_col = (uint32_t)tmem_cols - 64u;          // host: spad <= 448, so O never aliases S / P
 
   if (warp == 0) {
     if (elect_one_sync()) {
-      mbar_arrive_expect_tx(&bars[BAR_QK], (uint32_t)((2 * T + nb) * BOX_BYTES));
-      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_QK], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
+      mbar_arrive_expect_tx(&bars[BAR_QK], (uint32_t)((2 * T + nbk) * BOX_BYTES));
+      for (int b = 0; b < nbk; ++b) tma_load_2d(&tm, &bars[BAR_QK], sK + b * BOX_BYTES, C + h * D, row0 + b * BOX_ROWS);
       for (int b = 0; b < 2 * T; ++b) tma_load_2d(&tm, &bars[BAR_QK], sQ + b * BOX_BYTES, h * D, row0 + b * BOX_ROWS);
-      mbar_arrive_expect_tx(&bars[BAR_V], (uint32_t)(nb * BOX_BYTES));
-      for (int b = 0; b < nb; ++b) tma_load_2d(&tm, &bars[BAR_V], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
+      mbar_arrive_expect_tx(&bars[BAR_V], (uint32_t)(nbk * BOX_BYTES));
+      for (int b = 0; b < nbk; ++b) tma_load_2d(&tm, &bars[BAR_V], sV + b * BOX_BYTES, 2 * C + h * D, row0 + b * BOX_ROWS);
       mbar_wait(&bars[BAR_QK], 0);
       tcgen05_fence_after();
       issue_qk(tmem_base, sQ, sK, spad);
@@ -789,7 +850,8 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat1
       const uint32_t parity = (uint32_t)(t & 1);
       mbar_wait(&bars[BAR_S], parity);
       tcgen05_fence_after();
-      const float sum = softmax_half(lane_base, seq, n, c0, half, lane, active, xmax, xsum, 1 + quarter);
+      float corr;
+      const float sum = softmax_half(lane_base, kv, n, c0, half, lane, active, xmax, xsum, 1 + quarter, npad, corr);
       tcgen05_fence_before();
       mbar_arrive(&bars[BAR_P]);
       mbar_wait(&bars[BAR_O], parity);
@@ -801,7 +863,8 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat1
       }
       tcgen05_fence_before();
       mbar_arrive(&bars[BAR_OFREE]);
-      if (active && dst >= 0) store_o_half(o, sum, out + (size_t)dst * C + h * D + half * 32);
+      if (active && dst >= 0)
+        store_o_half(o, sum, out + (size_t)dst * C + h * D + half * 32, corr, pad_v != nullptr ? pad_v + h * D + half * 32 : nullptr);
     }
   }
 
@@ -825,9 +888,12 @@ extern "C" int toc3d_attn_trace_read(unsigned long long* host, int n) {
 
 extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
                                       const int32_t* out_map, const int32_t* q_rows, const int32_t* item_order,
-                                      void* stream) {
+                                      const int32_t* kv_rows, const float* pad_v, void* stream) {
   using namespace toc3d;
   TOC3D_REQUIRE(qkv && out, kErrBadArg, "toc3d_window_attention: null pointer");
+  TOC3D_REQUIRE((kv_rows == nullptr) == (pad_v == nullptr), kErrBadArg, "toc3d_window_attention: kv_rows and pad_v go together");
+  TOC3D_REQUIRE(kv_rows == nullptr || (seq_len <= attn_tc::MAX_SEQ && ((uintptr_t)pad_v & 15) == 0), kErrBadArg,
+                "toc3d_window_attention: analytic pad keys need seq <= %d and a 16-byte aligned pad_v", attn_tc::MAX_SEQ);
   TOC3D_REQUIRE(n_windows > 0 && seq_len > 0 && seq_len <= 1024 && heads > 0 && heads <= 65535, kErrBadArg,
                 "toc3d_window_attention: bad shape nW=%d seq=%d heads=%d", n_windows, seq_len, heads);
   TOC3D_REQUIRE(n_windows <= 65535, kErrBadArg, "toc3d_window_attention: too many windows (%d)", n_windows);
@@ -874,16 +940,16 @@ extern "C" int toc3d_window_attention(const void* qkv, void* out, int32_t n_wind
       // keys (padded to 16) <= 192: the O columns do not alias S, the epilogue is deferred behind the next softmax
       if (((seq_len + 15) & ~15) <= 192) {
         TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel<true>, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1,
-                                    tm, o, seq_len, heads, n_items, nbuf, out_map, q_rows, item_order));
+                                    tm, o, seq_len, heads, n_items, nbuf, out_map, q_rows, item_order, kv_rows, pad_v));
       } else {
         TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_pp_kernel<false>, dim3(grid), dim3(attn_tc::PP_THREADS), smem, st, 1,
-                                    tm, o, seq_len, heads, n_items, nbuf, out_map, q_rows, item_order));
+                                    tm, o, seq_len, heads, n_items, nbuf, out_map, q_rows, item_order, kv_rows, pad_v));
       }
       return 0;
     }
     const size_t smem2 = (size_t)(2 * T + 2 * nb) * attn_tc::BOX_BYTES + 1024 + 128 + attn_tc::TC2_XCH_BYTES;
     TOC3D_CHECK_CUDA(launch_pdl(attn_tc::window_attention_tc2_kernel, dim3(heads, n_windows), dim3(attn_tc::TC2_THREADS), smem2,
-                                st, 1, tm, o, seq_len, heads, out_map, q_rows));
+                                st, 1, tm, o, seq_len, heads, out_map, q_rows, kv_rows, pad_v));
     return 0;
   }
   dim3 grid((seq_len + attn::BQ - 1) / attn::BQ, heads, n_windows);

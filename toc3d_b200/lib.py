@@ -44,7 +44,8 @@ _SIGS = {
     "toc3d_last_error": ([], ctypes.c_char_p),
     "toc3d_gemm_bf16": ([_c_void_p, _c_i64, _c_void_p, _c_i64, _c_int, _c_int, _c_int, _c_int,
                          ctypes.POINTER(Epilogue), _c_void_p], _c_int),
-    "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p], _c_int),
+    "toc3d_window_attention": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p,
+                                _c_void_p], _c_int),
     "toc3d_layernorm_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int,
                               _c_float, _c_int, _c_void_p, _c_void_p], _c_int),
     "toc3d_subln_bf16": ([_c_void_p, _c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_float, _c_void_p],
@@ -156,10 +157,11 @@ def gemm(A, B, kind, M=None, **epi):
     return out
 
 
-def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None, q_rows=None, item_order=None):
+def window_attention(qkv, out, n_windows, seq_len, heads, out_map=None, q_rows=None, item_order=None, kv_rows=None, pad_v=None):
+    """kv_rows (int32 [n_windows]) + pad_v (fp32 [C]): analytic pad keys of the dense blocks (include/toc3d_b200.h)."""
     _want(qkv, torch.bfloat16, "qkv"); _want(out, torch.bfloat16, "out")
     _check(load().toc3d_window_attention(_p(qkv), _p(out), n_windows, seq_len, heads, _p(out_map), _p(q_rows), _p(item_order),
-                                         _stream()),
+                                         _p(kv_rows), _p(pad_v), _stream()),
            "toc3d_window_attention")
     return out
 

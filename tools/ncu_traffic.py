@@ -30,7 +30,7 @@ for r in csv.DictReader(lines):
     else:
         scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}[u]
         per[i][m] = v * scale
-starts = [n for n, i in enumerate(order) if "im2col" in per[i]["name"]]
+starts = [n for n, i in enumerate(order) if "im2col_patch16" in per[i]["name"]]
 sel = order[starts[-1]:] if starts else order
 fam = defaultdict(lambda: [0, 0.0, 0.0])
 for i in sel:

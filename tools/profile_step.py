@@ -12,7 +12,7 @@ import sys
 import torch
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
-from toc3d_b200 import CONFIGS, EVA_ViT, ToC3DEVAViT  # noqa: E402
+from toc3d_b200 import CONFIGS, CPFPN, EVA_ViT, ToC3DEVAViT  # noqa: E402
 from toc3d_b200.synthetic import make_inputs, randomize_state_dict  # noqa: E402
 
 ap = argparse.ArgumentParser()
@@ -26,6 +26,10 @@ torch.manual_seed(0)
 m = (ToC3DEVAViT if kind == "ToC3DEVAViT" else EVA_ViT)(**cfg)
 m.load_state_dict(randomize_state_dict(m.state_dict(), seed=0, bias_std=0.02))
 m = m.eval().cuda()
+neck = CPFPN(in_channels=[1024], out_channels=256, num_outs=2)          # the step bench.py times: backbone + fused neck
+neck.load_state_dict(randomize_state_dict(neck.state_dict(), seed=0, bias_std=0.02))
+neck = neck.eval().cuda()
+m.fuse_neck(neck)
 if args.eager:
     m.use_cuda_graph = False
 inp = {k: (v.cuda() if torch.is_tensor(v) else v) for k, v in make_inputs(args.batch, 6, hw, seed=0).items()}
@@ -34,6 +38,7 @@ for i in range(args.iters):
     if i == args.iters - 1:
         marker.fill_(1.0)     # marker launch: vectorized fill of 7777 elements
     with torch.no_grad():
-        m(**inp)
+        out = m(**inp)
+        neck(list((out if isinstance(out, dict) else out.img_feats).values()))
 torch.cuda.synchronize()
 print("done")

@@ -19,7 +19,7 @@ for r in rd:
     rows.append((r["Kernel Name"], us, r.get("Grid Size", ""), r.get("Block Size", "")))
 # cut at the marker: the last vectorized fill with grid computed for 7777 elements is hard to spot; use the
 # last occurrence of im2col (start of a forward) instead
-starts = [i for i, r in enumerate(rows) if "im2col" in r[0]]
+starts = [i for i, r in enumerate(rows) if "im2col_patch16" in r[0]]
 cut = starts[-1] if starts else 0
 sel = rows[cut:]
 agg = defaultdict(lambda: [0, 0.0])
