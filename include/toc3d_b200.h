@@ -94,9 +94,6 @@ typedef struct toc3d_epilogue {
   /* Tile width override (tuning / tests): 0 = chosen per launch to minimise wave quantisation on the
    * 74 CTA pairs; else a multiple of 32 (64 for SWIGLU) in [64, 256]. */
   int32_t tile_n;
-  /* CTA pairs per cluster (tuning / tests): 0 or 1 = one pair (default), 2 = two pairs sharing the weight tile by
-   * TMA multicast (needs tile_n % 64 == 0; measured slower on B200, kept as a tested option). */
-  int32_t cluster_pairs;
 } toc3d_epilogue;
 
 int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,

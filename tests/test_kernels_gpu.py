@@ -77,41 +77,6 @@ def test_gemm_back_to_back_stream_order(lib):
     assert rel_err(cur.float().cpu(), ref) < 2e-2
 
 
-@pytest.mark.parametrize("kind", ["linear", "swiglu", "resid"])
-@pytest.mark.parametrize("tile_n", [128, 192, 256])
-@pytest.mark.parametrize("M", [300, 513, 2000])
-def test_gemm_two_pair_cluster_multicast(lib, kind, tile_n, M):
-    """cluster_pairs=2: two CTA pairs share the weight tile through TMA multicast; same numbers as one pair."""
-    from toc3d_b200.backbone import interleave_w12, hidden_pad
-    g = torch.Generator().manual_seed(M + tile_n)
-    K = 192
-    A = bf16_round(torch.randn(M, K, generator=g)).to(DEV).bfloat16()
-    outs = []
-    if kind == "swiglu":
-        Hd = 341; Hp = hidden_pad(Hd)
-        w1 = bf16_round(torch.randn(Hd, K, generator=g) * 0.1); w2 = bf16_round(torch.randn(Hd, K, generator=g) * 0.1)
-        W, b = interleave_w12(w1, torch.randn(Hd, generator=g), w2, torch.randn(Hd, generator=g), Hp)
-        W, b = W.to(DEV).bfloat16(), b.to(DEV)
-        for cp in (1, 2):
-            o = torch.full((M, Hp), float("nan"), device=DEV, dtype=torch.bfloat16)
-            lib.gemm(A, W, lib.EPI_SWIGLU, bias=b, out=o, tile_n=tile_n, cluster_pairs=cp)
-            outs.append(o.float().cpu())
-    else:
-        N = 520
-        W = bf16_round(torch.randn(N, K, generator=g) * 0.05).to(DEV).bfloat16()
-        b = torch.randn(N, generator=g).to(DEV)
-        x = torch.randn(M, N, generator=g).to(DEV)
-        for cp in (1, 2):
-            o = torch.full((M, N), float("nan"), device=DEV)
-            if kind == "linear":
-                lib.gemm(A, W, lib.EPI_LINEAR, bias=b, out=o, out_f32=True, tile_n=tile_n, cluster_pairs=cp)
-            else:
-                lib.gemm(A, W, lib.EPI_RESID, bias=b, out=o, resid=x, tile_n=tile_n, cluster_pairs=cp)
-            outs.append(o.cpu())
-    assert torch.isfinite(outs[1]).all()
-    assert torch.equal(outs[0], outs[1])
-
-
 @pytest.mark.parametrize("act", [1, 2])
 def test_gemm_linear_act(lib, act):
     g = torch.Generator().manual_seed(7)

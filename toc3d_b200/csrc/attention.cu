@@ -447,14 +447,14 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
   const int my_items = (n_items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   // query tiles of item i: only the leading q_rows[w] query rows of a window are needed afterwards (the rest are
   // window padding, used as keys / values only), so a window may need fewer tiles than its key count suggests
-  auto item_tiles = [&](int i, int& w, int& h) {
+  auto item_tiles = [&](int i, int& w, int& h, int& need) {
     // item_order (optional): (window, head) items sorted by query-tile count, so that the round-robin deal to the
     // persistent CTAs balances the tile units
     const int idx = (int)blockIdx.x + i * (int)gridDim.x;
     const int it = item_order != nullptr ? item_order[idx] : idx;
     w = it / heads;
     h = it - w * heads;
-    const int need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;
+    need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;
     return (need + 127) >> 7;
   };
   // keys of window w that are staged and multiplied: all seq slots, or only the leading kv_rows[w] (the rest are the
@@ -491,8 +491,8 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     if (elect_one_sync()) {
       // ------------------------------------------------------------------ TMA producer: ring of item buffers
       for (int i = 0; i < my_items; ++i) {
-        int w, h;
-        const int Ti = item_tiles(i, w, h);
+        int w, h, need;
+        const int Ti = item_tiles(i, w, h, need);
         const int row0 = w * seq;
         const int buf = i % nbuf;
         const uint32_t round = (uint32_t)(i / nbuf);
@@ -525,8 +525,8 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
       bool have_prev = false;
       int u = 0;
       for (int i = 0; i < my_items; ++i) {
-        int w, h;
-        const int Ti = item_tiles(i, w, h);
+        int w, h, need;
+        const int Ti = item_tiles(i, w, h, need);
         const int buf = i % nbuf;
         const uint8_t* base = smem + buf * item_bytes;
         const uint8_t* sK = base + 2 * T * BOX_BYTES;
@@ -577,15 +577,15 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat16
     };
     int u = 0;
     for (int i = 0; i < my_items; ++i) {
-      int w, h;
-      const int Ti = item_tiles(i, w, h);
+      int w, h, need;
+      const int Ti = item_tiles(i, w, h, need);
       const int kv = item_kv(w);
       for (int t = 0; t < Ti; ++t, ++u) {
         if ((u & 1) != slot) continue;
         const int q = t * 128 + quarter * 32 + lane;
-        int dst = q < seq ? w * seq + q : -1;
+        int dst = q < need ? w * seq + q : -1;
         if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
-        const bool active = t * 128 + quarter * 32 < seq;
+        const bool active = t * 128 + quarter * 32 < need;      // a warp whose 32 query rows are all unneeded skips the tile
         const uint32_t parity = (uint32_t)((u >> 1) & 1);
         const bool tr = quarter == 0 && lane == 0;
         ATRACE(tr, slot, u >> 1, 0);
@@ -776,7 +776,8 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat1
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int h = blockIdx.x, w = blockIdx.y;
-  const int T = ((q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq) + 127) >> 7;
+  const int need = q_rows != nullptr ? min(seq, max(1, q_rows[w])) : seq;      // query rows that are used afterwards
+  const int T = (need + 127) >> 7;
   const int C = heads * D;
   const int row0 = w * seq;
   constexpr int tmem_cols = 512;
@@ -844,9 +845,9 @@ window_attention_tc2_kernel(const __grid_constant__ CUtensorMap tm, __nv_bfloat1
     float* xsum = xmax + 4 * 2 * 32;
     for (int t = 0; t < T; ++t) {
       const int q = t * 128 + quarter * 32 + lane;
-      int dst = q < seq ? row0 + q : -1;
+      int dst = q < need ? row0 + q : -1;
       if (dst >= 0 && out_map != nullptr) dst = out_map[dst];
-      const bool active = t * 128 + quarter * 32 < seq;
+      const bool active = t * 128 + quarter * 32 < need;       // warps whose 32 query rows are all unneeded skip the tile
       const uint32_t parity = (uint32_t)(t & 1);
       mbar_wait(&bars[BAR_S], parity);
       tcgen05_fence_after();

@@ -220,16 +220,6 @@ __device__ __forceinline__ void tma_load_2d_2sm(const CUtensorMap* m, uint32_t b
       ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_cluster_addr), "r"(c0), "r"(c1)
       : "memory");
 }
-// Same, multicast: the box is written at the same CTA-relative offset of every CTA in `mask` (cluster ranks) and
-// each destination's bytes are signalled on the barrier at `bar_addr`'s offset in that destination's pair leader.
-__device__ __forceinline__ void tma_load_2d_2sm_mc(const CUtensorMap* m, uint32_t bar_addr, void* dst, int c0, int c1,
-                                                   uint16_t mask) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster"
-      " [%0], [%1, {%4, %5}], [%2], %3;"
-      ::"r"(smem_u32(dst)), "l"(reinterpret_cast<uint64_t>(m)), "r"(bar_addr), "h"(mask), "r"(c0), "r"(c1)
-      : "memory");
-}
 __device__ __forceinline__ void tmem_alloc_2sm(uint32_t* dst_smem, uint32_t ncols) {
   asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                "r"(ncols)

@@ -405,7 +405,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
 template <int EPI, bool LNF>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, int M, int N, int K,
-            int BN, int mc, const EpiParams ep) {
+            int BN, const EpiParams ep) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // 1024-byte alignment for the 128B swizzle; pointer arithmetic (not an integer round trip) keeps the
   // shared address space visible to the compiler (LDS/STS instead of generic loads in the epilogue).
@@ -421,31 +421,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  // mc = 0: cluster = one CTA pair.  mc = 1: cluster = two pairs working on vertically adjacent 256-row tiles of
-  // the same BN columns; every CTA then loads only HALF of its pair-half of the B tile and multicasts it to the
-  // CTA of the same rank in the other pair (L2 -> SM traffic per k-block 24 KB instead of 32 KB per CTA).
-  const uint32_t crank = cluster_ctarank();         // rank in the cluster (0..1 or 0..3)
-  const uint32_t rank = crank & 1u;                 // rank in the pair, 0 = leader
-  const uint32_t prank = crank >> 1;                // which pair of the cluster
-  const uint32_t lead = crank & ~1u;                // cluster rank of this pair's leader
-  const int csize = mc ? 4 : 2;
-  const int pair = blockIdx.x / csize;              // "scheduling unit" index: cluster (mc) or pair
-  const int num_pairs = gridDim.x / csize;
-  const int mrows = mc ? 4 * BM : 2 * BM;           // rows covered by one scheduling unit
+  const uint32_t rank = cluster_ctarank();          // rank in the pair (= cluster), 0 = leader
+  const uint32_t lead = 0u;                         // cluster rank of the pair's leader
+  const int pair = blockIdx.x >> 1;
+  const int num_pairs = gridDim.x >> 1;
+  const int mrows = 2 * BM;                         // rows covered by one pair tile
   const int num_m = (M + mrows - 1) / mrows;
   const int num_n = (N + BN - 1) / BN;
   const int num_tiles = num_m * num_n;
   const int num_k = (K + BK - 1) / BK;
   const int b_rows = BN >> 1;                       // weight rows this CTA feeds to the pair MMA
-  const int b_load = mc ? (b_rows >> 1) : b_rows;   // weight rows this CTA loads itself
-  const uint16_t b_mask = (uint16_t)((1u << rank) | (1u << (2u + rank)));
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     for (int s = 0; s < STAGES; ++s) {
       mbar_init(&full_bar[s], 1);
-      mbar_init(&empty_bar[s], mc ? 2 : 1);           // mc: both pairs' MMAs must have released the slot
+      mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tmem_full[a], 1);
@@ -469,8 +461,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       auto load_b = [&](int stage, int kb, int n_idx) {
         const uint32_t bar = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;             // pair leader's barrier (peer bit cleared)
         uint8_t* sb = smem + stage * STAGE_BYTES + A_BYTES;
-        if (mc) tma_load_2d_2sm_mc(&tmB, bar, sb + prank * b_load * BK * 2, kb * BK, n_idx + (int)prank * b_load, b_mask);
-        else tma_load_2d_2sm(&tmB, bar, sb, kb * BK, n_idx);
+        tma_load_2d_2sm(&tmB, bar, sb, kb * BK, n_idx);
       };
       // The weights (B) do not depend on the previous kernel in the stream: the first ring of B loads
       // is issued before the programmatic-dependency wait and overlaps that kernel's tail.
@@ -485,7 +476,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       }
       pdl_wait();
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-        const int m_idx = (tile % num_m) * mrows + (int)prank * (2 * BM) + (int)rank * BM;
+        const int m_idx = (tile % num_m) * mrows + (int)rank * BM;
         const int n_idx = (tile / num_m) * BN + (int)rank * b_rows;
         for (int kb = 0; kb < num_k; ++kb) {
           const uint32_t lead_full = smem_u32(&full_bar[stage]) & 0xFEFFFFFFu;
@@ -511,7 +502,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       uint32_t acc_phase = 0;
       const uint32_t idesc = make_idesc(BN);
       const uint16_t full_mask = (uint16_t)(3u << lead);
-      const uint16_t empty_mask = mc ? (uint16_t)0xF : full_mask;
+      const uint16_t empty_mask = full_mask;
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1);
         tcgen05_fence_after();
@@ -544,7 +535,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
     uint32_t acc_phase = 0;
     pdl_wait();                            // residual / maps / statistics come from the previous kernels
     for (int tile = pair; tile < num_tiles; tile += num_pairs) {
-      const int m_idx = (tile % num_m) * mrows + (int)prank * (2 * BM) + (int)rank * BM;
+      const int m_idx = (tile % num_m) * mrows + (int)rank * BM;
       const int n_idx = (tile / num_m) * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX);
       epilogue_warp_tile<EPI, LNF>(ep, taddr, m_idx + quarter * 32, n_idx, BN, half, M, N, stage_buf, lane,
@@ -629,74 +620,63 @@ static int sm_count() {
 // tiles and time per tile scales with the A + B bytes staged per k-block), so narrower tiles re-read A more
 // often and only pay off when they remove a mostly empty last wave:
 //   cost(BN) = waves * (k_blocks * (A + B bytes per CTA) + c_tile) + c_epi * BN      (last epilogue is exposed)
-static int pick_tile_n(int M, int N, int K, int kind, int units, int mc) {
-  const int mrows = mc ? 4 * BM : 2 * BM;
+static int pick_tile_n(int M, int N, int K, int kind, int units) {
+  const int mrows = 2 * BM;
   const int num_m = (M + mrows - 1) / mrows;
   const int step = kind == TOC3D_EPI_SWIGLU ? 64 : 32;
   const double kb = (double)((K + BK - 1) / BK);
   double best = 1e30;
   int best_bn = BN_MAX;
   for (int bn = BN_MAX; bn >= 128; bn -= step) {
-    if (mc && bn % 64) continue;                                   // B quarter boxes are whole 8-row swizzle groups
     const long tiles = (long)num_m * ((N + bn - 1) / bn);
     const long waves = (tiles + units - 1) / units;
-    const double cost = (double)waves * (kb * (256.0 + (mc ? bn / 2.0 : (double)bn)) + 1024.0) + 16.0 * bn;
+    const double cost = (double)waves * (kb * (256.0 + (double)bn) + 1024.0) + 16.0 * bn;
     if (cost < best * 0.97) { best = cost; best_bn = bn; }     // prefer the widest tile unless clearly better
   }
   return best_bn;
 }
 
 template <int EPI, bool LNF = false>
-static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int tile_n, int cluster_pairs,
+static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M, int N, int K, int tile_n,
                   const EpiParams& ep, cudaStream_t st) {
   static bool configured_dev[kMaxDevices] = {};
-  static int max_clusters_dev[kMaxDevices][2] = {};     // co-resident clusters of 2 / 4 CTAs (GPC boundaries can strand SMs)
+  static int max_pairs_dev[kMaxDevices] = {};     // co-resident CTA pairs (GPC boundaries can strand SMs)
   const int dev = current_device();
-  int* max_clusters = max_clusters_dev[dev];
   {
-  std::lock_guard<std::mutex> lock(g_cfg_mutex);
-  bool& configured = configured_dev[dev];
-  if (!configured) {
-    TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    for (int i = 0; i < 2; ++i) {
+    std::lock_guard<std::mutex> lock(g_cfg_mutex);
+    if (!configured_dev[dev]) {
+      TOC3D_CHECK_CUDA(cudaFuncSetAttribute(gemm_kernel<EPI, LNF>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
       cudaLaunchConfig_t cfg = {};
       cudaLaunchAttribute at[1];
       at[0].id = cudaLaunchAttributeClusterDimension;
-      at[0].val.clusterDim.x = 2 << i; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-      cfg.gridDim = dim3((unsigned)(sm_count() / (2 << i) * (2 << i))); cfg.blockDim = dim3(NUM_THREADS);
+      at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+      cfg.gridDim = dim3((unsigned)(sm_count() / 2 * 2)); cfg.blockDim = dim3(NUM_THREADS);
       cfg.dynamicSmemBytes = SMEM_BYTES; cfg.attrs = at; cfg.numAttrs = 1;
       int n = 0;
       if (cudaOccupancyMaxActiveClusters(&n, gemm_kernel<EPI, LNF>, &cfg) != cudaSuccess || n <= 0) {
         cudaGetLastError();
-        n = sm_count() / (2 << i);
+        n = sm_count() / 2;
       }
-      max_clusters[i] = n < sm_count() / (2 << i) ? n : sm_count() / (2 << i);
+      max_pairs_dev[dev] = n < sm_count() / 2 ? n : sm_count() / 2;
+      configured_dev[dev] = true;
     }
-    configured = true;
   }
-  }
-  // Two pairs per cluster (weight tile multicast) is opt-in: measured on B200 it is 3-10 % SLOWER than one pair on
-  // every shape of this path and on 8192^3 (profiles/r01l_gemm_bench_cluster_pairs.txt) - TMA multicast across <= 4 CTAs
-  // does not reduce the L2 reads on this part (the L2 serves each destination), and 4-CTA clusters strand SMs at GPC
-  // boundaries.  WIDE tiles (one 352 / 512-column accumulator, two MMAs per k-step, single wave for the N = 1024 GEMMs)
-  // were also built and measured (profiles/r02e_gemm_bench_wide_tiles_experiment.txt): bit-identical, but 6 - 10 %
-  // slower than the two balanced waves of 176 / 192-wide tiles the cost model above picks, whose first epilogue hides
-  // behind the second mainloop; removed.
-  const int mc = cluster_pairs == 2 ? 1 : 0;
-  const int csize = mc ? 4 : 2;
-  const int max_units = max_clusters[mc];
-  const int bn = tile_n > 0 ? tile_n : pick_tile_n(M, N, K, EPI, max_units, mc);
-  TOC3D_REQUIRE(!mc || bn % 64 == 0, kErrBadArg, "toc3d_gemm_bf16: two-pair clusters need tile_n %% 64 == 0 (got %d)", bn);
+  // Built, verified and measured slower on B200, then removed: two pairs per cluster sharing the weight
+  // tile by TMA multicast (3 - 10 % slower: multicast across <= 4 CTAs does not reduce the L2 reads on this part, and
+  // 4-CTA clusters strand SMs at GPC boundaries; profiles/r01l_gemm_bench_cluster_pairs.txt); wide tiles (one 352 / 512
+  // column accumulator, two MMAs per k-step, a single wave for the N = 1024 GEMMs: 6 - 10 % slower than the two balanced
+  // waves of 176 / 192-wide tiles the cost model picks, whose first epilogue hides behind the second mainloop;
+  // profiles/r02e_gemm_bench_wide_tiles_experiment.txt); stream-K; chained launches.
+  const int max_units = max_pairs_dev[dev];
+  const int bn = tile_n > 0 ? tile_n : pick_tile_n(M, N, K, EPI, max_units);
   CUtensorMap ta, tb;
   int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BM);
   if (rc) return rc;
-  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, mc ? bn / 4 : bn / 2);
+  rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, bn / 2);
   if (rc) return rc;
-  const int mrows = mc ? 4 * BM : 2 * BM;
-  const int tiles = ((M + mrows - 1) / mrows) * ((N + bn - 1) / bn);
+  const int tiles = ((M + 2 * BM - 1) / (2 * BM)) * ((N + bn - 1) / bn);
   const int units = tiles < max_units ? tiles : max_units;
-  TOC3D_CHECK_CUDA(launch_pdl(gemm_kernel<EPI, LNF>, dim3(csize * units), dim3(NUM_THREADS), SMEM_BYTES, st, csize, ta, tb, M,
-                              N, K, bn, mc, ep));
+  TOC3D_CHECK_CUDA(launch_pdl(gemm_kernel<EPI, LNF>, dim3(2 * units), dim3(NUM_THREADS), SMEM_BYTES, st, 2, ta, tb, M, N, K, bn, ep));
   return 0;
 }
 
@@ -715,7 +695,6 @@ static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, E
   ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
   ep.ln_stats = reinterpret_cast<const long long*>(e->ln_stats);
   const int tile_n = e->tile_n;
-  TOC3D_REQUIRE(e->cluster_pairs >= 0 && e->cluster_pairs <= 2, kErrBadArg, "%s: cluster_pairs must be 0 (auto), 1 or 2", fn);
   TOC3D_REQUIRE(tile_n == 0 || (tile_n >= 64 && tile_n <= BN_MAX && tile_n % 32 == 0 &&
                                 (kind != TOC3D_EPI_SWIGLU || tile_n % 64 == 0)), kErrBadArg,
                 "%s: tile_n must be 0 (auto) or a multiple of 32 (64 for SWIGLU) in [64, 256], got %d", fn, tile_n);
@@ -760,16 +739,15 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   int rc = to_params("toc3d_gemm_bf16", e, kind, N, ep);
   if (rc) return rc;
   const int tile_n = e->tile_n;
-  const int cpairs = e->cluster_pairs;
   const bool lnf = ep.ln_stats != nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);
   switch (kind) {
-    case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
-    case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
+    case TOC3D_EPI_LINEAR: return launch<TOC3D_EPI_LINEAR>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
+    case TOC3D_EPI_QKV_ROPE: return launch<TOC3D_EPI_QKV_ROPE>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
     case TOC3D_EPI_RESID:
-      return lnf ? launch<TOC3D_EPI_RESID, true>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st)
-                 : launch<TOC3D_EPI_RESID, false>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
+      return lnf ? launch<TOC3D_EPI_RESID, true>(A, lda, B, ldb, M, N, K, tile_n, ep, st)
+                 : launch<TOC3D_EPI_RESID, false>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
     default:
-      return launch<TOC3D_EPI_SWIGLU>(A, lda, B, ldb, M, N, K, tile_n, cpairs, ep, st);
+      return launch<TOC3D_EPI_SWIGLU>(A, lda, B, ldb, M, N, K, tile_n, ep, st);
   }
 }

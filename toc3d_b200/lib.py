@@ -26,7 +26,7 @@ class Epilogue(ctypes.Structure):
         ("out_alt", _c_void_p), ("rope_rows", _c_void_p), ("rope_slots", _c_int), ("rope_ft", _c_int),
         ("rope_cols", _c_int), ("q_scale", _c_float), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p),
         ("row_stats", _c_void_p), ("ln_stats", _c_void_p), ("ln_u", _c_void_p), ("ln_n", _c_int), ("ln_eps", _c_float),
-        ("tile_n", _c_int), ("cluster_pairs", _c_int),
+        ("tile_n", _c_int),
     ]
 
 
@@ -130,7 +130,7 @@ def _want(t, dtype, name):
 def _epilogue(*, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, resid=None,
               resid_map=None, resid_mod=0, out_map=None, out_alt=None, rope_rows=None, rope_slots=0, rope_ft=0,
               rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None, row_stats=None, ln_u=None, ln_n=0, ln_eps=0.0,
-              tile_n=0, cluster_pairs=0, ln_stats=None):
+              tile_n=0, ln_stats=None):
     e = Epilogue()
     e.bias = _p(bias); e.out = _p(out); e.ldo = out.shape[-1] if ldo is None else ldo
     e.out_f32 = int(out_f32); e.act = act
@@ -139,7 +139,7 @@ def _epilogue(*, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, res
     e.rope_rows = _p(rope_rows); e.rope_slots = rope_slots; e.rope_ft = rope_ft; e.rope_cols = rope_cols
     e.q_scale = q_scale; e.cos_axis = _p(cos_axis); e.sin_axis = _p(sin_axis)
     e.row_stats = _p(row_stats); e.ln_stats = _p(ln_stats)
-    e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps; e.tile_n = tile_n; e.cluster_pairs = cluster_pairs
+    e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps; e.tile_n = tile_n
     return e
 
 

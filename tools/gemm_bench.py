@@ -20,7 +20,6 @@ ap.add_argument("--no-flush", action="store_true")
 ap.add_argument("--tiles", default="0", help="comma list of tile_n values to sweep (0 = auto)")
 ap.add_argument("--ms", default="8640,6192,6000,5058,3618,12288,7200")
 ap.add_argument("--square", action="store_true")
-ap.add_argument("--cp", type=int, default=0, help="cluster_pairs override (0 auto, 1, 2)")
 args = ap.parse_args()
 dev = "cuda"
 L.load()
@@ -74,23 +73,23 @@ for M in [int(m) for m in args.ms.split(",")]:
     Wqkv = (rn(3 * C, C) * 0.02).bfloat16(); bq = rn(3 * C)
     qkv = torch.empty(M, 3 * C, device=dev, dtype=torch.bfloat16)
     cos = rn(16, 16); sin = rn(16, 16)
-    report("qkv+rope", M, 3 * C, C, lambda t: L.gemm(A, Wqkv, L.EPI_QKV_ROPE, bias=bq, out=qkv, rope_slots=256, tile_n=t, cluster_pairs=args.cp,
+    report("qkv+rope", M, 3 * C, C, lambda t: L.gemm(A, Wqkv, L.EPI_QKV_ROPE, bias=bq, out=qkv, rope_slots=256, tile_n=t,
                                                      rope_ft=16, rope_cols=2 * C, q_scale=0.125, cos_axis=cos, sin_axis=sin))
     Wp = (rn(C, C) * 0.02).bfloat16(); bp = rn(C)
     X = rn(M, C); T = torch.empty(M, C, device=dev)
-    report("proj+resid", M, C, C, lambda t: L.gemm(A, Wp, L.EPI_RESID, bias=bp, out=T, resid=X, tile_n=t, cluster_pairs=args.cp))
+    report("proj+resid", M, C, C, lambda t: L.gemm(A, Wp, L.EPI_RESID, bias=bp, out=T, resid=X, tile_n=t))
     W12 = (rn(2 * Hp, C) * 0.02).bfloat16(); b12 = rn(2 * Hp)
     hid = torch.empty(M, Hp, device=dev, dtype=torch.bfloat16)
     stats = torch.zeros(M, 2, device=dev, dtype=torch.int64)
-    report("w12 swiglu+stats", M, 2 * Hp, C, lambda t: L.gemm(A, W12, L.EPI_SWIGLU, bias=b12, out=hid, row_stats=stats, tile_n=t, cluster_pairs=args.cp))
+    report("w12 swiglu+stats", M, 2 * Hp, C, lambda t: L.gemm(A, W12, L.EPI_SWIGLU, bias=b12, out=hid, row_stats=stats, tile_n=t))
     W3 = (rn(C, Hp) * 0.02).bfloat16(); u3 = rn(C)
     report("w3 ln-fold+resid", M, C, Hp, lambda t: L.gemm(hid, W3, L.EPI_RESID, bias=bp, out=X, resid=T, ln_stats=stats,
-                                                         ln_u=u3, ln_n=Hd, ln_eps=1e-6, tile_n=t, cluster_pairs=args.cp))
+                                                         ln_u=u3, ln_n=Hd, ln_eps=1e-6, tile_n=t))
     ob = torch.empty(M, C, device=dev, dtype=torch.bfloat16)
-    report("linear bf16 (N=1024)", M, C, C, lambda t: L.gemm(A, Wp, L.EPI_LINEAR, bias=bp, out=ob, tile_n=t, cluster_pairs=args.cp))
+    report("linear bf16 (N=1024)", M, C, C, lambda t: L.gemm(A, Wp, L.EPI_LINEAR, bias=bp, out=ob, tile_n=t))
 for n in ((4096, 8192) if args.square else ()):
     A = rn(n, n).bfloat16(); B = rn(n, n).bfloat16(); o = torch.empty(n, n, device=dev, dtype=torch.bfloat16)
-    report("square linear", n, n, n, lambda t: L.gemm(A, B, L.EPI_LINEAR, out=o, tile_n=t, cluster_pairs=args.cp))
+    report("square linear", n, n, n, lambda t: L.gemm(A, B, L.EPI_LINEAR, out=o, tile_n=t))
     report("torch.matmul (cuBLAS)", n, n, n, lambda t: torch.matmul(A, B.t()))
 clk.__exit__()
 print("clocks:", clk.summary(), flush=True)
