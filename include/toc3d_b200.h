@@ -94,6 +94,14 @@ typedef struct toc3d_epilogue {
   /* Tile width override (tuning / tests): 0 = chosen per launch to minimise wave quantisation on the
    * 74 CTA pairs; else a multiple of 32 (64 for SWIGLU) in [64, 256]. */
   int32_t tile_n;
+  /* Implicit 3 x 3 convolution (LINEAR epilogue; necks/cp_fpn.py:123-133 without a materialised im2col): conv_cin > 0
+   * makes A a [M, conv_cin] matrix of pixels in a spatially ZERO-PADDED NHWC layout (rows of (H+2) x (W+2) pixels per
+   * image, border pixels zero), K = 9 * conv_cin with the weight columns ordered (ky, kx, ci), and the k-blocks of tap
+   * t = 3 ky + kx read the A rows m + conv_row_shift[t] (= (ky-1) * (W+2) + (kx-1)) by TMA - the shifted rows of a
+   * padded layout are again contiguous.  Rows outside A read zeros.  Border rows of the output are garbage: drop them
+   * with out_map = -1.  conv_cin % 64 == 0. */
+  int32_t conv_cin;
+  int32_t conv_row_shift[9];
 } toc3d_epilogue;
 
 int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int32_t M, int32_t N, int32_t K,

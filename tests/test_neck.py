@@ -123,3 +123,37 @@ def test_fused_neck_matches_separate_call_and_keeps_state_dict():
     d.fuse_neck(neck)
     b = neck([d(x)["last_feat"]])
     assert all(torch.equal(u, v) for u, v in zip(a, b))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,H,W,ci,co", [(1, 5, 7, 64, 64), (3, 20, 50, 256, 256), (2, 13, 9, 128, 72)])
+def test_implicit_conv3x3_gemm(V, H, W, ci, co):
+    """The GEMM's implicit 3x3 convolution mode (toc3d_epilogue.conv_*: nine row-shifted TMA views of a zero-padded NHWC
+    matrix, no im2col buffer) against F.conv2d on the same bf16-rounded operands, fp32 accumulation."""
+    import torch.nn.functional as F
+    from toc3d_b200 import lib as L
+    g = torch.Generator().manual_seed(V * H * W + ci)
+    x = (torch.randn(V, H, W, ci, generator=g) * 2).to(torch.bfloat16).float()
+    w = (torch.randn(co, ci, 3, 3, generator=g) * 0.05).to(torch.bfloat16).float()
+    b = torch.randn(co, generator=g)
+    ref = F.conv2d(x.permute(0, 3, 1, 2), w, b, padding=1).permute(0, 2, 3, 1).reshape(-1, co)
+    Hp, Wp = H + 2, W + 2
+    pad = torch.zeros(V, Hp, Wp, ci)
+    pad[:, 1:-1, 1:-1] = x
+    vv, yy, xx = torch.meshgrid(torch.arange(V), torch.arange(H), torch.arange(W), indexing="ij")
+    to_pad = ((vv * Hp + yy + 1) * Wp + xx + 1).reshape(-1)
+    from_pad = torch.full((V * Hp * Wp,), -1, dtype=torch.int32)
+    from_pad[to_pad] = torch.arange(V * H * W, dtype=torch.int32)
+    A = pad.reshape(-1, ci).cuda().bfloat16()
+    Bw = w.permute(0, 2, 3, 1).reshape(co, 9 * ci).cuda().bfloat16().contiguous()
+    out = torch.full((V * H * W, co), float("nan"), device="cuda")
+    shifts = [(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)]
+    if co % 8:
+        pytest.skip("N must be a multiple of 8")
+    L.gemm(A, Bw, L.EPI_LINEAR, M=A.shape[0], bias=b.cuda(), out=out, out_f32=True, out_map=from_pad.cuda(), conv_cin=ci,
+           conv_row_shift=shifts)
+    got = out.cpu()
+    assert torch.isfinite(got).all()
+    assert (got - ref).abs().max().item() < 2e-3 * max(1.0, ref.abs().max().item())
+    with pytest.raises(RuntimeError, match="9 \\* conv_cin"):
+        L.gemm(A, Bw[:, : 8 * ci].contiguous(), L.EPI_LINEAR, M=A.shape[0], out=out, out_f32=True, conv_cin=ci, conv_row_shift=shifts)

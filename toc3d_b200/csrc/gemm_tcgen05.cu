@@ -63,6 +63,10 @@ struct EpiParams {
   const float* ln_u;
   int ln_n;
   float ln_eps;
+  // implicit 3 x 3 convolution (A operand addressing only): k-block kb reads A columns (kb % conv_kmod) * BK of the rows
+  // m + conv_shift[kb / conv_kmod]; conv_kmod = 0: plain GEMM
+  int conv_kmod;
+  int conv_shift[9];
 };
 
 // Folded-LayerNorm row statistics are accumulated as int64 fixed point: sum * 2^30 (|sum| < 8.6e9,
@@ -488,7 +492,12 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
             if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], stage_tx);
             load_b(stage, kb, n_idx);
           }
-          tma_load_2d_2sm(&tmA, lead_full, sa, kb * BK, m_idx);
+          if (ep.conv_kmod > 0) {    // tap (ky, kx) of an implicit 3 x 3 convolution: the same rows, shifted (OOB rows read 0)
+            const int tap = kb / ep.conv_kmod;
+            tma_load_2d_2sm(&tmA, lead_full, sa, (kb - tap * ep.conv_kmod) * BK, m_idx + ep.conv_shift[tap]);
+          } else {
+            tma_load_2d_2sm(&tmA, lead_full, sa, kb * BK, m_idx);
+          }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -670,7 +679,7 @@ static int launch(const void* A, int64_t lda, const void* B, int64_t ldb, int M,
   const int max_units = max_pairs_dev[dev];
   const int bn = tile_n > 0 ? tile_n : pick_tile_n(M, N, K, EPI, max_units);
   CUtensorMap ta, tb;
-  int rc = make_tmap_bf16_2d(&ta, A, M, K, lda, BM);
+  int rc = make_tmap_bf16_2d(&ta, A, M, ep.conv_kmod > 0 ? ep.conv_kmod * BK : K, lda, BM);
   if (rc) return rc;
   rc = make_tmap_bf16_2d(&tb, B, N, K, ldb, bn / 2);
   if (rc) return rc;
@@ -694,6 +703,14 @@ static int to_params(const char* fn, const toc3d_epilogue* e, int kind, int N, E
   ep.rope_cols = e->rope_cols; ep.q_scale = e->q_scale; ep.cos_axis = e->cos_axis; ep.sin_axis = e->sin_axis;
   ep.row_stats = reinterpret_cast<long long*>(e->row_stats); ep.ln_u = e->ln_u; ep.ln_n = e->ln_n; ep.ln_eps = e->ln_eps;
   ep.ln_stats = reinterpret_cast<const long long*>(e->ln_stats);
+  ep.conv_kmod = 0;
+  for (int i = 0; i < 9; ++i) ep.conv_shift[i] = 0;
+  if (e->conv_cin > 0) {
+    TOC3D_REQUIRE(kind == TOC3D_EPI_LINEAR && e->conv_cin % BK == 0, kErrBadArg,
+                  "%s: implicit 3x3 convolution needs a LINEAR epilogue and conv_cin %% 64 == 0 (got %d)", fn, e->conv_cin);
+    ep.conv_kmod = e->conv_cin / BK;
+    for (int i = 0; i < 9; ++i) ep.conv_shift[i] = e->conv_row_shift[i];
+  }
   const int tile_n = e->tile_n;
   TOC3D_REQUIRE(tile_n == 0 || (tile_n >= 64 && tile_n <= BN_MAX && tile_n % 32 == 0 &&
                                 (kind != TOC3D_EPI_SWIGLU || tile_n % 64 == 0)), kErrBadArg,
@@ -738,6 +755,8 @@ extern "C" int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_
   EpiParams ep;
   int rc = to_params("toc3d_gemm_bf16", e, kind, N, ep);
   if (rc) return rc;
+  TOC3D_REQUIRE(ep.conv_kmod == 0 || K == 9 * e->conv_cin, kErrBadArg,
+                "toc3d_gemm_bf16: implicit 3x3 convolution needs K == 9 * conv_cin (K=%d, conv_cin=%d)", K, e->conv_cin);
   const int tile_n = e->tile_n;
   const bool lnf = ep.ln_stats != nullptr;
   cudaStream_t st = reinterpret_cast<cudaStream_t>(stream);

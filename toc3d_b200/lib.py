@@ -26,7 +26,7 @@ class Epilogue(ctypes.Structure):
         ("out_alt", _c_void_p), ("rope_rows", _c_void_p), ("rope_slots", _c_int), ("rope_ft", _c_int),
         ("rope_cols", _c_int), ("q_scale", _c_float), ("cos_axis", _c_void_p), ("sin_axis", _c_void_p),
         ("row_stats", _c_void_p), ("ln_stats", _c_void_p), ("ln_u", _c_void_p), ("ln_n", _c_int), ("ln_eps", _c_float),
-        ("tile_n", _c_int),
+        ("tile_n", _c_int), ("conv_cin", _c_int), ("conv_row_shift", _c_int * 9),
     ]
 
 
@@ -130,7 +130,7 @@ def _want(t, dtype, name):
 def _epilogue(*, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, resid=None,
               resid_map=None, resid_mod=0, out_map=None, out_alt=None, rope_rows=None, rope_slots=0, rope_ft=0,
               rope_cols=0, q_scale=1.0, cos_axis=None, sin_axis=None, row_stats=None, ln_u=None, ln_n=0, ln_eps=0.0,
-              tile_n=0, ln_stats=None):
+              tile_n=0, ln_stats=None, conv_cin=0, conv_row_shift=None):
     e = Epilogue()
     e.bias = _p(bias); e.out = _p(out); e.ldo = out.shape[-1] if ldo is None else ldo
     e.out_f32 = int(out_f32); e.act = act
@@ -140,6 +140,11 @@ def _epilogue(*, bias=None, out=None, ldo=None, out_f32=False, act=ACT_NONE, res
     e.q_scale = q_scale; e.cos_axis = _p(cos_axis); e.sin_axis = _p(sin_axis)
     e.row_stats = _p(row_stats); e.ln_stats = _p(ln_stats)
     e.ln_u = _p(ln_u); e.ln_n = ln_n; e.ln_eps = ln_eps; e.tile_n = tile_n
+    e.conv_cin = conv_cin
+    if conv_cin:
+        assert len(conv_row_shift) == 9
+        for i, v in enumerate(conv_row_shift):
+            e.conv_row_shift[i] = int(v)
     return e
 
 
@@ -148,7 +153,7 @@ def gemm(A, B, kind, M=None, **epi):
     _want(A, torch.bfloat16, "A"); _want(B, torch.bfloat16, "B")
     M = A.shape[0] if M is None else M
     N, K = B.shape
-    assert A.shape[1] == K and A.stride(1) == 1 and B.stride(1) == 1
+    assert (A.shape[1] == K or epi.get("conv_cin")) and A.stride(1) == 1 and B.stride(1) == 1
     e = _epilogue(**epi)
     out = epi.get("out")
     rc = load().toc3d_gemm_bf16(A.data_ptr(), A.stride(0), B.data_ptr(), B.stride(0), M, N, K, kind,

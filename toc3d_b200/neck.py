@@ -44,13 +44,14 @@ class CPFPN(nn.Module):
                 or act_cfg or num_outs < 1):
             raise NotImplementedError("only the shipped CPFPN configuration (one input level, no norm / activation / "
                                       "extra convs) is implemented")
-        if in_channels[0] % 64 or out_channels % 8:
-            raise NotImplementedError("channel counts must fit the GEMM tiles (in %% 64 == 0, out %% 8 == 0)")
+        if in_channels[0] % 64 or out_channels % 64:
+            raise NotImplementedError("channel counts must fit the GEMM k-blocks (in %% 64 == 0, out %% 64 == 0)")
         self.in_channels, self.out_channels, self.num_outs = in_channels, out_channels, num_outs
         self.fp16_enabled = False
         self.lateral_convs = nn.ModuleList([_ConvModule(in_channels[0], out_channels, 1)])
         self.fpn_convs = nn.ModuleList([_ConvModule(out_channels, out_channels, 3, padding=1)])
         self._packed = None
+        self._layouts = {}
 
     def _invalidate(self):
         self._packed = None
@@ -78,25 +79,44 @@ class CPFPN(nn.Module):
                                 b3=self.fpn_convs[0].conv.bias.detach().to(dev).float().contiguous())
         return self._packed
 
+    def _conv_layout(self, dev, V, H, W):
+        """Spatially zero-padded NHWC layout of the lateral map ((H+2) x (W+2) pixels per image) for the implicit 3x3
+        convolution: row maps between the V*H*W pixel rows and the padded rows, the tap row shifts, and the padded
+        bf16 buffer itself (borders are zero and never written).  Cached per (device, V, H, W)."""
+        key = (str(dev), V, H, W)
+        c = self._layouts.get(key)
+        if c is None:
+            Hp, Wp = H + 2, W + 2
+            v, y, x = torch.meshgrid(torch.arange(V), torch.arange(H), torch.arange(W), indexing="ij")
+            to_pad = ((v * Hp + y + 1) * Wp + x + 1).reshape(-1).to(torch.int32)
+            from_pad = torch.full((V * Hp * Wp,), -1, dtype=torch.int32)
+            from_pad[to_pad.long()] = torch.arange(V * H * W, dtype=torch.int32)
+            c = dict(Mp=V * Hp * Wp, to_pad=to_pad.to(dev), from_pad=from_pad.to(dev),
+                     shifts=[(ky - 1) * Wp + (kx - 1) for ky in range(3) for kx in range(3)],
+                     lat=torch.zeros(V * Hp * Wp, self.out_channels, device=dev, dtype=torch.bfloat16))
+            self._layouts[key] = c
+        return c
+
     def launch(self, x2d, V, H, W):
         """The neck's launch sequence on the residual-stream buffer itself: x2d = fp32 (or bf16) [V*H*W, C] NHWC rows.
         -> level-0 output, fp32 [V*H*W, out_channels] (NHWC rows).  Stream-ordered, allocation-only host work, so the
-        backbone can run it inside its own CUDA graph (ToC3DEVAViT.fuse_neck)."""
+        backbone can run it inside its own CUDA graph (ToC3DEVAViT.fuse_neck).
+        Lateral 1x1 conv (cp_fpn.py:163-166) = GEMM whose epilogue scatters the rows into the zero-padded layout; 3x3 conv
+        (cp_fpn.py:182-184) = IMPLICIT GEMM over that layout: the nine taps are nine row-shifted TMA views of the same
+        matrix (toc3d_epilogue.conv_*), no im2col buffer; border rows of the result are dropped by the output map."""
         M, C = x2d.shape
         co = self.out_channels
         p = self._weights(x2d.device)
-        bf = dict(device=x2d.device, dtype=torch.bfloat16)
+        lay = self._conv_layout(x2d.device, V, H, W)
         if x2d.dtype == torch.bfloat16:
             a = x2d
         else:
-            a = torch.empty(M, C, **bf)
+            a = torch.empty(M, C, device=x2d.device, dtype=torch.bfloat16)
             L.cast_bf16(x2d, a)
-        lat = torch.empty(M, co, **bf)
-        L.gemm(a, p["w1"], L.EPI_LINEAR, bias=p["b1"], out=lat)                            # lateral 1x1 (cp_fpn.py:163-166)
-        cols = torch.empty(M, 9 * co, **bf)
-        L.im2col_3x3(lat, cols, V, H, W, co)
+        L.gemm(a, p["w1"], L.EPI_LINEAR, bias=p["b1"], out=lay["lat"], out_map=lay["to_pad"])
         out0 = torch.empty(M, co, device=x2d.device, dtype=torch.float32)
-        L.gemm(cols, p["w3"], L.EPI_LINEAR, bias=p["b3"], out=out0, out_f32=True)          # fpn 3x3 (cp_fpn.py:182-184)
+        L.gemm(lay["lat"], p["w3"], L.EPI_LINEAR, M=lay["Mp"], bias=p["b3"], out=out0, out_f32=True, out_map=lay["from_pad"],
+               conv_cin=co, conv_row_shift=lay["shifts"])
         return out0
 
     def levels(self, out0, V, H, W):

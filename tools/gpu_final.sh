@@ -8,10 +8,12 @@ echo "gpu suite rc=$?"; grep -E "passed|failed|error" gpurun_out/gpu_suite_$tag.
 grep -E "ISOLATED|score max-abs|last_feat|overlap|motion queries|first-frame" gpurun_out/gpu_suite_$tag.log | cut -c1-400 > gpurun_out/parity_table_$tag.txt
 timeout 300 python __graft_entry__.py smoke > gpurun_out/smoke_$tag.log 2>&1
 echo "smoke rc=$?"; tail -2 gpurun_out/smoke_$tag.log | cut -c1-300
-/usr/bin/time -f "reference arm wall %e s" timeout 1200 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_${tag}_reference.json 2> gpurun_out/bench_${tag}_reference.err
-echo "reference rc=$?"; tail -1 gpurun_out/bench_${tag}_reference.err; cut -c1-300 gpurun_out/bench_${tag}_reference.json
-/usr/bin/time -f "native arm wall %e s" timeout 1200 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
-echo "bench rc=$?"; tail -2 gpurun_out/bench_$tag.err
+t0=$SECONDS
+timeout 1200 python bench.py --impl reference --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_${tag}_reference.json 2> gpurun_out/bench_${tag}_reference.err
+echo "reference rc=$? wall $((SECONDS - t0)) s"; cut -c1-300 gpurun_out/bench_${tag}_reference.json
+t0=$SECONDS
+timeout 1200 python bench.py --gpus 1 --steps 20 --warmup 5 > gpurun_out/bench_$tag.json 2> gpurun_out/bench_$tag.err
+echo "bench rc=$? wall $((SECONDS - t0)) s"; tail -2 gpurun_out/bench_$tag.err
 python - <<PY
 import json
 d = json.load(open("gpurun_out/bench_$tag.json"))
