@@ -473,7 +473,7 @@ def run_native(args):
     fam = {"gemm": ["gemm"], "attention": ["window_attention"],
            "hbm_kernels": ["layernorm_rows", "ln_gather_merge", "fast_token_update"],
            "token_kernels": ["layernorm_rows", "ln_gather_merge", "fast_token_update", "fill_pad_kv", "window_topk", "compact_rows",
-                             "score_tokens", "topk_split", "motion_queries_fold", "im2col_patch16", "im2col_3x3", "cast_bf16"]}
+                             "score_tokens", "topk_split", "motion_queries_fold", "im2col_patch16", "cast_bf16"]}
     marginal = {}
     if not args.no_roofline:
         for fname, names_ in fam.items():
@@ -499,7 +499,7 @@ def run_native(args):
     recs = []
     names = ["gemm", "window_attention", "layernorm_rows", "ln_gather_merge", "fill_pad_kv", "fill_pad_kv_rope", "compact_rows", "subln", "window_topk", "topk_split", "merge_fast_tokens",
              "fast_token_update", "motion_queries_fold", "score_tokens", "score_finish", "im2col_patch16", "mask_rows",
-             "global_half_mean", "im2col_3x3", "cast_bf16"]
+             "global_half_mean", "cast_bf16"]
     saved = {n: getattr(L, n) for n in names}
     kind_names = {L.EPI_LINEAR: "linear", L.EPI_QKV_ROPE: "qkv_rope", L.EPI_RESID: "resid", L.EPI_SWIGLU: "swiglu"}
 

@@ -317,13 +317,11 @@ int toc3d_im2col_patch16(const float* img, void* out_bf16, int32_t V, int32_t Hi
 int toc3d_preprocess_patch16_u8(const uint8_t* img, const float* lut, void* out_bf16, int32_t V, int32_t Hs,
                                 int32_t Ws, int32_t Hi, int32_t Wi, int32_t to_rgb, void* stream);
 
-/* ------------------------------------------------------------------ neck (next row: CPFPN, necks/cp_fpn.py:157-208)
- * im2col for the 3x3 / stride 1 / pad 1 fpn conv (cp_fpn.py:123-133,182-184) over an NHWC bf16 map
- * [V,H,W,C] -> bf16 [V*H*W, 9*C], column = (ky*3+kx)*C + c, zeros outside the image.  C % 8 == 0.
- * The 1x1 lateral conv (cp_fpn.py:114-122) and the 3x3 conv are toc3d_gemm_bf16 calls (LINEAR). */
-int toc3d_im2col_3x3(const void* in_bf16, void* out_bf16, int32_t V, int32_t H, int32_t W, int32_t C, void* stream);
-
-/* Row-wise helpers used by the first-frame scorer and weight repacking. */
+/* Neck (next row: CPFPN, necks/cp_fpn.py:157-208): the 1x1 lateral conv (cp_fpn.py:114-122) is a toc3d_gemm_bf16 call
+ * (LINEAR) whose out_map scatters the rows into a zero-padded NHWC layout, the 3x3 fpn conv (cp_fpn.py:123-133,182-184)
+ * a toc3d_gemm_bf16 call in implicit-convolution mode over that layout (toc3d_epilogue.conv_*); no im2col buffer.
+ *
+ * Row-wise helpers used by the neck, the first-frame scorer and weight repacking. */
 int toc3d_cast_f32_to_bf16(const float* in, void* out_bf16, int64_t n, void* stream);
 /* x[m,:] * mask[m] -> LN -> bf16 is toc3d_layernorm_rows on a pre-masked buffer; this masks. */
 int toc3d_mask_rows(const float* x, const float* mask, float* out, int32_t M, int32_t C, void* stream);

@@ -844,29 +844,6 @@ preprocess_patch16_u8_kernel(const uint8_t* __restrict__ img, const float* __res
   }
 }
 
-// im2col for a 3x3 / stride 1 / pad 1 convolution over an NHWC bf16 map: out[(v,y,x), (ky*3+kx)*C + c] =
-// in[v, y+ky-1, x+kx-1, c] (zero outside the image).  Thread = 8 channels (16 bytes) of one tap.
-__global__ void __launch_bounds__(256)
-im2col3x3_kernel(const __nv_bfloat16* __restrict__ in, __nv_bfloat16* __restrict__ out, int V, int H, int W, int C) {
-  pdl_wait();
-  pdl_launch_dependents();
-  const int cv = C >> 3;                                  // 16-byte vectors per pixel
-  const size_t total = (size_t)V * H * W * 9 * cv;
-  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= total) return;
-  const int c8 = (int)(idx % cv);
-  size_t r = idx / cv;
-  const int tap = (int)(r % 9); r /= 9;
-  const int x = (int)(r % W); r /= W;
-  const int y = (int)(r % H);
-  const int v = (int)(r / H);
-  const int yy = y + tap / 3 - 1, xx = x + tap % 3 - 1;
-  uint4 val = make_uint4(0u, 0u, 0u, 0u);
-  if (yy >= 0 && yy < H && xx >= 0 && xx < W)
-    val = *reinterpret_cast<const uint4*>(in + (((size_t)v * H + yy) * W + xx) * C + c8 * 8);
-  *reinterpret_cast<uint4*>(out + (((size_t)v * H + y) * W + x) * (size_t)(9 * C) + (size_t)tap * C + c8 * 8) = val;
-}
-
 __global__ void cast_bf16_kernel(const float* __restrict__ in, __nv_bfloat16* __restrict__ out, long long n) {
   pdl_wait();
   pdl_launch_dependents();
@@ -1121,15 +1098,6 @@ extern "C" int toc3d_preprocess_patch16_u8(const uint8_t* img, const float* lut,
   TOC3D_CHECK_CUDA(launch_pdl(preprocess_patch16_u8_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), 1,
                               img, lut, reinterpret_cast<__nv_bfloat16*>(out), V, Hs, Ws, Hi, Wi, to_rgb));
   TOC3D_CHECK_CUDA(cudaGetLastError());
-  return 0;
-}
-
-extern "C" int toc3d_im2col_3x3(const void* in, void* out, int32_t V, int32_t H, int32_t W, int32_t C, void* stream) {
-  TOC3D_REQUIRE(in && out, kErrBadArg, "toc3d_im2col_3x3: null pointer");
-  TOC3D_REQUIRE(V > 0 && H > 0 && W > 0 && C > 0 && C % 8 == 0, kErrBadArg, "toc3d_im2col_3x3: bad shape V=%d H=%d W=%d C=%d", V, H, W, C);
-  const size_t total = (size_t)V * H * W * 9 * (C / 8);
-  TOC3D_CHECK_CUDA(launch_pdl(im2col3x3_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), 0, ST(stream), 1,
-                              reinterpret_cast<const __nv_bfloat16*>(in), reinterpret_cast<__nv_bfloat16*>(out), V, H, W, C));
   return 0;
 }
 

@@ -73,7 +73,6 @@ _SIGS = {
                             _c_void_p], _c_int),
     "toc3d_im2col_patch16": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_preprocess_patch16_u8": ([_c_void_p, _c_void_p, _c_void_p] + [_c_int] * 6 + [_c_void_p], _c_int),
-    "toc3d_im2col_3x3": ([_c_void_p, _c_void_p, _c_int, _c_int, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_cast_f32_to_bf16": ([_c_void_p, _c_void_p, _c_i64, _c_void_p], _c_int),
     "toc3d_mask_rows": ([_c_void_p, _c_void_p, _c_void_p, _c_int, _c_int, _c_void_p], _c_int),
     "toc3d_global_half_mean": ([_c_void_p, _c_int, _c_int, _c_int, _c_void_p], _c_int),
@@ -288,11 +287,6 @@ def preprocess_patch16_u8(img, lut, out, V, Hs, Ws, Hi, Wi, to_rgb):
     _want(img, torch.uint8, "img"); _want(lut, torch.float32, "lut"); _want(out, torch.bfloat16, "out")
     _check(load().toc3d_preprocess_patch16_u8(_p(img), _p(lut), _p(out), V, Hs, Ws, Hi, Wi, int(bool(to_rgb)), _stream()),
            "toc3d_preprocess_patch16_u8")
-
-
-def im2col_3x3(x, out, V, H, W, C):
-    _want(x, torch.bfloat16, "x"); _want(out, torch.bfloat16, "out")
-    _check(load().toc3d_im2col_3x3(_p(x), _p(out), V, H, W, C, _stream()), "toc3d_im2col_3x3")
 
 
 def cast_bf16(src, dst):

@@ -72,7 +72,7 @@ class CPFPN(nn.Module):
         if self._packed is None or self._packed["dev"] != dev:
             co = self.out_channels
             w1 = self.lateral_convs[0].conv.weight.detach().to(dev).float().reshape(co, -1)
-            # [co, ci, ky, kx] -> [co, (ky, kx, ci)]: the column order toc3d_im2col_3x3 produces
+            # [co, ci, ky, kx] -> [co, (ky, kx, ci)]: tap-major weight columns of the implicit 3x3 GEMM
             w3 = self.fpn_convs[0].conv.weight.detach().to(dev).float().permute(0, 2, 3, 1).reshape(co, -1)
             self._packed = dict(dev=dev, w1=w1.to(torch.bfloat16).contiguous(), w3=w3.to(torch.bfloat16).contiguous(),
                                 b1=self.lateral_convs[0].conv.bias.detach().to(dev).float().contiguous(),
