@@ -125,6 +125,10 @@ int toc3d_gemm_bf16(const void* A, int64_t lda, const void* B, int64_t ldb, int3
  * real keys are staged and multiplied; the seq_len - kv_rows[w] pad keys enter the softmax as one closed-form term
  * (row max includes 0, row sum += n_pad * exp(0 - max), O += n_pad * exp(0 - max) * pad_v).  The pad rows of qkv are
  * then never read, so nobody has to write them.
+ * The index tables q_rows, item_order and kv_rows are launch parameters in device memory, not data of the stream: the
+ * kernel reads them before its grid dependency on the preceding kernel resolves (programmatic dependent launch), so they
+ * must not be written by the kernel launched immediately before this call on the same stream (copies and earlier
+ * kernels are fine).  qkv, out_map and pad_v have no such restriction.
  */
 int toc3d_window_attention(const void* qkv, void* out, int32_t n_windows, int32_t seq_len, int32_t heads,
                            const int32_t* out_map, const int32_t* q_rows, const int32_t* item_order,

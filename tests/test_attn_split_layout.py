@@ -44,3 +44,38 @@ def test_split_layout_is_hazard_free(seq):
             c, off = p_cols[base + j]
             key0 = 32 * c + 2 * off                            # column `off` of chunk c packs keys (2 off, 2 off + 1)
             assert key0 == 16 * kk + 2 * j
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Ping-pong kernel (seq <= 256, attention.cu: window_attention_pp_kernel / row_chunks / row_exp): one warp per lane quarter
+# and slot walks the 32-column chunks upwards with the load of the NEXT chunk in flight, packs P chunk c at columns
+# [16 c, 16 c + 16); a last chunk of <= 16 keys is read with a 16-column load AFTER the others and its P stored as 8
+# columns; O sits at columns [192, 256) of the 256-column slot and S(u) waits for the epilogue of unit u - 2 iff its key
+# columns reach them.
+@pytest.mark.parametrize("kv", list(range(1, 257)))
+def test_pp_layout_is_hazard_free(kv):
+    spad = (kv + 15) // 16 * 16
+    n = (kv + 31) // 32
+    tl = kv - 32 * (n - 1)
+    narrow = tl <= 16
+    wide = n - 1 if narrow else n
+    order = list(range(wide)) + ([n - 1] if narrow else [])       # exp-pass order
+    width = lambda c: 16 if (narrow and c == n - 1) else 32
+    unread = set(col for c in order for col in range(32 * c, 32 * c + width(c)))
+    assert set(range(spad)) <= unread                              # every score column S = Q K^T wrote is read
+    p_cols = {}
+    for j, c in enumerate(order):
+        unread -= set(range(32 * c, 32 * c + width(c)))            # chunk c is in registers
+        pw = 8 if width(c) == 16 else 16
+        w = set(range(16 * c, 16 * c + pw))
+        # (the load of the next chunk is in flight when P(c) is stored: it must not be hit either - it is still `unread`)
+        assert w.isdisjoint(unread), "P chunk %d overwrites unread scores" % c
+        assert max(w) < 192 or spad > 192                          # P never reaches the O columns unless S does too
+        for col in w:
+            assert col not in p_cols
+            p_cols[col] = (c, col - 16 * c)
+    assert max(p_cols) < 128                                       # P (<= 256 keys) stays below the O columns in any case
+    for kk in range(spad // 16):                                   # P V: k-step kk = keys [16 kk, 16 kk + 16) = columns [8 kk, 8 kk + 8)
+        for j in range(8):
+            c, off = p_cols[8 * kk + j]
+            assert 32 * c + 2 * off == 16 * kk + 2 * j

@@ -570,6 +570,41 @@ def test_attention_tail_row_129(lib, seq):
             assert err < 3e-2, (w, r, err)
 
 
+@pytest.mark.parametrize("analytic", [False, True])
+@pytest.mark.parametrize("seq", [103, 129, 144, 180, 192, 201, 224, 256])
+def test_attention_many_items_per_cta(lib, seq, analytic):
+    """Persistent kernel under load: ~6 (window, head) items per CTA (ring of item buffers reused several times, both
+    TMEM buffers alternating through units of different key counts and tile counts), ragged q_rows / kv_rows, balanced
+    item order - against the fp32 reference (computed on the GPU in fp32)."""
+    g = torch.Generator().manual_seed(seq + 1000 * analytic)
+    nW, heads = 150, 6
+    C = heads * 64
+    rows = [seq, 1, 33, min(seq, 65), seq, min(seq, 129), 9, seq, min(seq, 128), min(seq, 17), seq, min(seq, 161)]
+    qr = torch.tensor([rows[i % len(rows)] for i in range(nW)], dtype=torch.int32)
+    qkv = bf16_round(torch.randn(nW, seq, 3 * C, generator=g))
+    ref_in = qkv.clone()
+    vb = torch.randn(C, generator=g) * 0.5
+    if analytic:                                           # keys beyond kv = q_rows are pad slots: k = 0, v = v_bias
+        for w in range(nW):
+            ref_in[w, int(qr[w]):, C:2 * C] = 0.0
+            ref_in[w, int(qr[w]):, 2 * C:] = vb
+            qkv[w, int(qr[w]):, C:] = 7.0                  # finite garbage that must not be read
+    q, k, v = ref_in.to(DEV).reshape(nW, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(nW, seq, C).cpu()
+    order = torch.argsort(((qr + 127) // 128).repeat_interleave(heads), descending=True, stable=True).int()
+    kw = dict(kv_rows=qr.to(DEV), pad_v=vb.to(DEV)) if analytic else {}
+    for io in (None, order):
+        out = torch.full((nW * seq, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+        lib.window_attention(qkv.reshape(nW * seq, 3 * C).to(DEV).bfloat16(), out, nW, seq, heads, q_rows=qr.to(DEV),
+                             item_order=None if io is None else io.to(DEV), **kw)
+        got = out.float().cpu().view(nW, seq, C)
+        for w in range(nW):
+            r = int(qr[w])
+            assert torch.isfinite(got[w, :r]).all(), (w, r)
+            err = (got[w, :r] - ref[w, :r]).abs().max().item()
+            assert err < 3e-2, (w, r, err)
+
+
 @pytest.mark.parametrize("seq", [64, 180, 256, 400, 448])
 def test_attention_analytic_pad_keys(lib, seq):
     """Dense-block pad slots (k = 0, v = v_bias, eva_vit.py:249-254) as ONE closed-form softmax term: kv_rows[w] real keys

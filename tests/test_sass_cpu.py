@@ -52,7 +52,7 @@ def test_gemm_kernels_use_tcgen05_and_tma(sass):
 
 def test_attention_kernels_use_tcgen05_with_tmem_operands(sass):
     tc = {k: v for k, v in sass.items() if "attn_tc" in k}
-    assert len(tc) >= 3
+    assert len(tc) >= 2             # persistent ping-pong kernel (<= 256 keys), single-slot split-softmax kernel (<= 448)
     for name, body in tc.items():
         assert _count(body, "UTCHMMA") >= 8, name
         assert _count(body, "UTMALDG") >= 3 and _count(body, "LDTM") >= 2 and _count(body, "STTM") >= 1, name
