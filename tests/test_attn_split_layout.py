@@ -79,3 +79,42 @@ def test_pp_layout_is_hazard_free(kv):
         for j in range(8):
             c, off = p_cols[8 * kk + j]
             assert 32 * c + 2 * off == 16 * kk + 2 * j
+
+
+# TMA boxes of one of Q / K / V of an item (attention.cu: pp_row_bytes / pp_load_rows): all seq rows -> one box of
+# ceil16(seq) rows; fewer -> 64-row boxes, then 16-row boxes (or one 64-row box when the tail needs more than 48 rows).
+def pp_boxes(rows, seq):
+    if rows == seq:
+        return [(0, (seq + 15) // 16 * 16)]
+    nfull, rem = rows // 64, rows % 64
+    boxes = [(64 * b, 64) for b in range(nfull)]
+    r = 64 * nfull
+    if rem > 48:
+        boxes.append((r, 64))
+    else:
+        while r < rows:
+            boxes.append((r, 16))
+            r += 16
+    return boxes
+
+
+def pp_row_bytes(rows, seq):
+    if rows == seq:
+        return (seq + 15) // 16 * 16 * 128
+    nfull, rem = rows // 64, rows % 64
+    if rem > 48:
+        return (nfull + 1) * 8192
+    return nfull * 8192 + (rem + 15) // 16 * 2048
+
+
+@pytest.mark.parametrize("seq", [1, 16, 33, 103, 129, 180, 192, 201, 256])
+def test_pp_tma_boxes_cover_the_rows_and_stay_inside_the_item(seq):
+    region = (seq + 15) // 16 * 16                                # rows of K / V in an item buffer (Q: whole 128-row tiles)
+    for rows in range(1, seq + 1):
+        boxes = pp_boxes(rows, seq)
+        assert sum(n for _, n in boxes) * 128 == pp_row_bytes(rows, seq)      # expect_tx == bytes that arrive
+        covered = set(r for r0, n in boxes for r in range(r0, r0 + n))
+        assert set(range(rows)) <= covered
+        assert max(covered) < region
+        assert all(r0 % 16 == 0 for r0, _ in boxes)                # 2 KB-aligned destinations keep the 128-byte swizzle phase
+        assert len(boxes) <= 6

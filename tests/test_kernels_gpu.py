@@ -605,6 +605,24 @@ def test_attention_many_items_per_cta(lib, seq, analytic):
             assert err < 3e-2, (w, r, err)
 
 
+def test_attention_more_items_than_the_smem_item_list(lib):
+    """> 64 (window, head) items per CTA: the persistent kernel stages the metadata of a CTA's first 64 items in shared
+    memory and fetches the rest from the index tables on the fly."""
+    g = torch.Generator().manual_seed(7)
+    seq, nW, heads = 33, 1700, 6                           # 10 200 items: 69 per CTA on 148 SMs
+    C = heads * 64
+    qr = torch.tensor([(1, 33, 17, 32)[i % 4] for i in range(nW)], dtype=torch.int32)
+    qkv = bf16_round(torch.randn(nW, seq, 3 * C, generator=g))
+    q, k, v = qkv.to(DEV).reshape(nW, seq, 3, heads, 64).permute(2, 0, 3, 1, 4)
+    ref = ((q @ k.transpose(-1, -2)).softmax(-1) @ v).transpose(1, 2).reshape(nW, seq, C).cpu()
+    out = torch.full((nW * seq, C), float("nan"), device=DEV, dtype=torch.bfloat16)
+    lib.window_attention(qkv.reshape(nW * seq, 3 * C).to(DEV).bfloat16(), out, nW, seq, heads, q_rows=qr.to(DEV))
+    got = out.float().cpu().view(nW, seq, C)
+    mask = torch.arange(seq)[None, :] < qr[:, None]
+    assert torch.isfinite(got[mask]).all()
+    assert (got[mask] - ref[mask]).abs().max().item() < 3e-2
+
+
 @pytest.mark.parametrize("seq", [64, 180, 256, 400, 448])
 def test_attention_analytic_pad_keys(lib, seq):
     """Dense-block pad slots (k = 0, v = v_bias, eva_vit.py:249-254) as ONE closed-form softmax term: kv_rows[w] real keys
