@@ -585,7 +585,8 @@ def run_native(args):
                 "avg_launch_us": (g_marg if g_marg else g_ms) * 1e3 / max(1, len(g)),
                 "attention": {"ms_per_step": marginal.get("attention"), "flops": a_fl,
                               "achieved_tflops": (a_fl / (marginal["attention"] * 1e-3) / 1e12) if marginal.get("attention") else None,
-                              "note": "MUFU (ex2) bound, not tensor bound: 2 MUFU ops per 256 tensor FLOPs (DESIGN 3.2)"},
+                              "note": "not tensor bound: 2 MUFU (ex2) ops per 256 tensor FLOPs make the MUFU pipe the throughput floor, and thread = row on "
+                                      "128-row tiles with 129- / 52- / 33-row windows leaves the launches latency-bound (DESIGN 3.2)"},
                 "hbm_kernels": {"what": "LayerNorm / gather + merge (+ deferred fast-token update) / fast-token update launches: algorithmic "
                                         "bytes of one step / their marginal time (same method as `achieved`); the per-launch event "
                                         "figure of the eager step is kept as achieved_events",
