@@ -1,6 +1,7 @@
 """The attention launches of one ToC3D_fast / dense step with their REAL arguments (q_rows, item_order, analytic pad
 keys), timed per shape in trains of launches (CUDA events, clocks recorded), and - with `trace` - the clock64 timeline of
-CTA 0 of the ping-pong kernel from the -DTOC3D_ATTN_TRACE build (tools/probes/attn_trace.py build).  Diagnostic only.
+CTA 0 of the persistent kernel (<= 256 keys) from the -DTOC3D_ATTN_TRACE build (tools/probes/attn_trace.py build; the
+stamps themselves cost 50-150 clk each in the traced warps).  Diagnostic only.
 
     python tools/attn_instep.py                 # per-shape timing, product library
     python tools/attn_instep.py trace 48 129    # timeline of one shape, trace library
@@ -78,28 +79,27 @@ def main():
             t0 = min(x for r in t for u in r for x in u if x)
             rel = lambda x: (x - t0) if x else -1
             print("%s nW=%d seq=%d  (clock64 relative to the first stamp)" % (name, nW, seq))
-            print("softmax warps: unit | wait S | S ready | own max published | exp done | P arrived | partner max seen | [before FULL wait]")
+            print("softmax warps (lane quarter 0): slot, unit of the slot | wait S | S ready | max pass done | exp pass done | P arrived")
             for slot in range(2):
                 for n in range(12):
                     if t[slot][n][0]:
-                        print("slot %d n=%d  " % (slot, n) + "  ".join("%7d" % rel(t[slot][n][k]) for k in range(7)))
+                        print("slot %d n=%d  " % (slot, n) + "  ".join("%7d" % rel(t[slot][n][k]) for k in range(5)))
             print("TMA producer: item | before EMPTY wait | EMPTY ok | loads issued")
             for n in range(12):
                 if t[3][n][0]:
                     print("i=%2d  " % n + "  ".join("%7d" % rel(t[3][n][k]) for k in range(3)))
-            print("MMA thread: unit | top | FULL ok | QK committed | after PV(prev) | [P ready of this unit (stamp 4)]")
+            print("MMA thread: unit | top | FULL / OFREE ok | QK committed | after preparing the next unit and P V (previous unit)")
             for u in range(24):
                 if t[2][u][0]:
-                    print("u=%2d  " % u + "  ".join("%7d" % rel(t[2][u][k]) for k in range(5)))
+                    print("u=%2d  " % u + "  ".join("%7d" % rel(t[2][u][k]) for k in range(4)))
             fb = (ctypes.c_ulonglong * 512)()
             so.toc3d_attn_trace_fin.argtypes = [ctypes.c_void_p]
             assert so.toc3d_attn_trace_fin(fb) == 0
             print("epilogue warp (quarter 0), unit n: start | O ready | O loaded | OFREE arrived | staged | stored")
-            for slot in range(2):
-                for n in range(8):
-                    st = [fb[(slot * 32 + n) * 8 + k] for k in range(7)]
-                    if st[0]:
-                        print("half %d n=%d  " % (slot, n) + "  ".join("%7d" % rel(x) for x in st))
+            for n in range(16):
+                st = [fb[n * 8 + k] for k in range(6)]
+                if st[0]:
+                    print("u=%2d  " % n + "  ".join("%7d" % rel(x) for x in st))
             for slot in range(2):
                 for ps in range(2):
                     st = [cb[(slot * 2 + ps) * 16 + c] for c in range(16)]
