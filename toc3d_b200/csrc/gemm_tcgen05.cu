@@ -77,6 +77,28 @@ constexpr double STAT_SQ_SCALE = 67108864.0;
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ float silu(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
+// Diagnostic build only (-DTOC3D_GEMM_TRACE, tools/probes/gemm_trace.py): %globaltimer stamps (ns) of pair 0 / CTA 0 of the
+// last 8 launches, [launch & 7][8 stamps]: 0 kernel entry, 1 prologue done, 2 dependency resolved (producer), 3 first
+// operands landed (MMA thread), 4 last MMA issued, 5 last accumulator complete (epilogue warp 2), 6 last epilogue done,
+// 7 before exit.  Compiled out of the product library.
+#ifdef TOC3D_GEMM_TRACE
+__device__ unsigned long long g_gemm_trace[8 * 8];
+__device__ unsigned int g_gemm_launch;
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+// [launch & 7][16]: inside the last epilogue of warp 2: 0 entry, 1 maps / residual prefetch issued, 2 accumulator seen,
+// 3 + c: chunk c done
+__device__ unsigned long long g_epi_trace[8 * 16];
+#define GTRACE(cond, k) do { if ((cond) && blockIdx.x == 0) g_gemm_trace[(trace_slot & 7) * 8 + (k)] = gtime(); } while (0)
+#define ETRACE(tr, k) do { if ((tr) >= 0 && lane == 0 && (k) < 16) g_epi_trace[((tr) & 7) * 16 + (k)] = gtime(); } while (0)
+#else
+#define GTRACE(cond, k) do {} while (0)
+#define ETRACE(tr, k) do {} while (0)
+#endif
+
 // ---------------------------------------------------------------------------------------------
 // Epilogue: 8 warps; warp w owns TMEM lane quarter (w % 4) = 32 rows of this CTA's 128 x BN
 // accumulator and the 32-column chunks ch = half, half + 2, ... (half = (w - 2) / 4).  Each chunk
@@ -126,7 +148,8 @@ __device__ __forceinline__ void ln_fold_coeffs(const long long* stats_row, int n
 template <int EPI, bool LNF>
 __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t taddr, int m0, int nt0, int bn, int half,
                                                    int M, int N, float* stage, int lane, uint64_t* full_bar,
-                                                   uint32_t parity) {
+                                                   uint32_t parity, int tr = -1) {
+  ETRACE(tr, 0);
   // coalesced-domain coordinates: rows {rin, rin+4, ..., rin+28}, columns 4*cseg..4*cseg+3 of the chunk
   const int rin = lane >> 3;
   const int cseg = lane & 7;
@@ -262,8 +285,10 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       load_resid(r_cur, nt0 + ch0 + 4 * cseg);
       load_cols(b, u4, nt0 + ch0 + 4 * cseg);
     }
+    ETRACE(tr, 1);
     mbar_wait(full_bar, parity);
     tcgen05_fence_after();
+    ETRACE(tr, 2);
     if (ch0 >= bn || nt0 + ch0 >= N) return;                      // warp-uniform
     float f[32];
     tmem_ld_f32x32(taddr + ch0, f);
@@ -295,6 +320,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         }
       }
       __syncwarp();
+      ETRACE(tr, 3 + (c - ch0) / (2 * CHUNK));
       if (more) {
 #pragma unroll
         for (int it = 0; it < 8; ++it) r_cur[it] = r_nxt[it];
@@ -343,8 +369,10 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
     bias4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     if (ep.bias != nullptr && ch0 + i * 2 * CHUNK < bn && col < N) bias4[i] = __ldg(reinterpret_cast<const float4*>(ep.bias + col));
   }
+  ETRACE(tr, 1);
   mbar_wait(full_bar, parity);
   tcgen05_fence_after();
+  ETRACE(tr, 2);
   if (ch0 >= bn || nt0 + ch0 >= N) return;                        // warp-uniform
   float f[32];
   tmem_ld_f32x32(taddr + ch0, f);
@@ -402,6 +430,7 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       }
     }
     __syncwarp();
+    ETRACE(tr, 3 + i);
   }
 }
 
@@ -425,6 +454,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+#ifdef TOC3D_GEMM_TRACE
+  __shared__ unsigned int s_trace_slot;
+  if (threadIdx.x == 0 && blockIdx.x == 0) s_trace_slot = atomicAdd(&g_gemm_launch, 1u);
+  const unsigned long long t_entry = gtime();
+#endif
   const uint32_t rank = cluster_ctarank();          // rank in the pair (= cluster), 0 = leader
   const uint32_t lead = 0u;                         // cluster rank of the pair's leader
   const int pair = blockIdx.x >> 1;
@@ -455,6 +489,11 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   pdl_launch_dependents();            // the next kernel may start its prologue; it waits for this grid itself
+#ifdef TOC3D_GEMM_TRACE
+  const unsigned int trace_slot = blockIdx.x == 0 ? s_trace_slot : 0u;
+  if (threadIdx.x == 0 && blockIdx.x == 0) g_gemm_trace[(trace_slot & 7) * 8 + 0] = t_entry;
+  GTRACE(threadIdx.x == 0, 1);
+#endif
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -479,6 +518,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         }
       }
       pdl_wait();
+      GTRACE(true, 2);
       for (int tile = pair; tile < num_tiles; tile += num_pairs) {
         const int m_idx = (tile % num_m) * mrows + (int)rank * BM;
         const int n_idx = (tile / num_m) * BN + (int)rank * b_rows;
@@ -519,6 +559,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
         for (int kb = 0; kb < num_k; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           tcgen05_fence_after();
+          GTRACE(tile == pair && kb == 0, 3);
           const uint32_t sa = smem_u32(smem + stage * STAGE_BYTES);
           const uint64_t a_desc = umma_desc_k_sw128(sa);
           const uint64_t b_desc = umma_desc_k_sw128(sa + A_BYTES);
@@ -532,6 +573,7 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         tcgen05_commit_2sm(&tmem_full[acc], full_mask);      // accumulator complete -> both epilogues of the pair
+        GTRACE(tile + num_pairs >= num_tiles, 4);
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
@@ -547,8 +589,13 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
       const int m_idx = (tile % num_m) * mrows + (int)rank * BM;
       const int n_idx = (tile / num_m) * BN;
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN_MAX);
+      int tr = -1;
+#ifdef TOC3D_GEMM_TRACE
+      if (warp == 2 && tile + num_pairs >= num_tiles && blockIdx.x == 0) tr = (int)(trace_slot & 7);
+#endif
       epilogue_warp_tile<EPI, LNF>(ep, taddr, m_idx + quarter * 32, n_idx, BN, half, M, N, stage_buf, lane,
-                                   &tmem_full[acc], acc_phase);
+                                   &tmem_full[acc], acc_phase, tr);
+      GTRACE(warp == 2 && lane == 0 && tile + num_pairs >= num_tiles, 6);
       // release this accumulator buffer to the leader's MMA warp
       tcgen05_fence_before();
       __syncwarp();
@@ -559,11 +606,23 @@ gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUt
 
   tcgen05_fence_before();
   cluster_sync_all();                      // nobody may still signal a barrier / read TMEM of an exited peer
+  GTRACE(threadIdx.x == 0, 7);
   if (warp == 1) {
     tcgen05_fence_after();
     tmem_dealloc_2sm(tmem_base, TMEM_COLS);
   }
 }
+
+#ifdef TOC3D_GEMM_TRACE
+extern "C" int toc3d_gemm_trace_read(unsigned long long* host) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, g_gemm_trace, sizeof(unsigned long long) * 64);
+}
+extern "C" int toc3d_gemm_epi_trace_read(unsigned long long* host) {
+  cudaDeviceSynchronize();
+  return (int)cudaMemcpyFromSymbol(host, g_epi_trace, sizeof(unsigned long long) * 128);
+}
+#endif
 
 
 // ---------------------------------------------------------------------------- host side

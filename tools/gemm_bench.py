@@ -22,6 +22,8 @@ ap.add_argument("--ms", default="8640,6192,6000,5058,3618,12288,7200")
 ap.add_argument("--square", action="store_true")
 args = ap.parse_args()
 dev = "cuda"
+if os.environ.get("TOC3D_LIB"):                # A/B of two builds of the library
+    L.LIB_PATH = os.environ["TOC3D_LIB"]
 L.load()
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
