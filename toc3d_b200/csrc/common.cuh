@@ -58,6 +58,34 @@ __device__ __forceinline__ float2 unpack_bf16(uint32_t u) {
   return __bfloat1622float2(h);
 }
 
+// Predicated global stores.  `if (ok) *p = v;` in an unrolled loop compiles to one convergence region (BSSY / BSYNC) per
+// iteration, which keeps ptxas from overlapping the iterations (the GEMM epilogue's store loop ran at ~100 clk per
+// iteration that way); a predicated store leaves the loop body branch-free.  The address may be anything when !ok.
+__device__ __forceinline__ void st_global_if(float4* p, float4 v, bool ok) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_cg_if(float4* p, float4 v, bool ok) {      // cache-global: one-shot data, skip L1
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q st.global.cg.v4.f32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok)
+      : "memory");
+}
+__device__ __forceinline__ void st_global_if(uint2* p, uint2 v, bool ok) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %3, 0;\n\t"
+      "@q st.global.v2.b32 [%0], {%1, %2};\n\t}"
+      ::"l"(p), "r"(v.x), "r"(v.y), "r"((int)ok)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

@@ -200,18 +200,15 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       stage_rows32(stage, lane, h);
       __syncwarp();
       const int hcol = (col1 >> 1) + 4 * cseg;            // hidden column of this lane
-      if (hcol < ep.ldo) {
+      const bool hcol_ok = hcol < ep.ldo;
 #pragma unroll
-        for (int it = 0; it < 8; ++it) {
-          const int row = it * 4 + rin;
-          const float4 a = stage_read(stage, row, cseg);
-          if (m0 + row < M) {
-            uint2 u;
-            u.x = pack_bf16(a.x, a.y);
-            u.y = pack_bf16(a.z, a.w);
-            *reinterpret_cast<uint2*>(out + (size_t)(m0 + row) * ep.ldo + hcol) = u;
-          }
-        }
+      for (int it = 0; it < 8; ++it) {                    // branch-free body (st_global_if): the iterations overlap
+        const int row = it * 4 + rin;
+        const float4 a = stage_read(stage, row, cseg);
+        uint2 u;
+        u.x = pack_bf16(a.x, a.y);
+        u.y = pack_bf16(a.z, a.w);
+        st_global_if(reinterpret_cast<uint2*>(out + (size_t)(m0 + row) * ep.ldo + hcol), u, hcol_ok && m0 + row < M);
       }
       __syncwarp();
     }
@@ -307,17 +304,15 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       const int col = col0 + 4 * cseg;
       const bool col_ok = col < N;                        // N % 4 == 0
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
+      for (int it = 0; it < 8; ++it) {                    // branch-free body (st_global_cg_if): the iterations overlap
         const float4 a = stage_read(stage, it * 4 + rin, cseg);
-        if (col_ok && ((o_ok >> it) & 1u)) {
-          float4 o;
-          o.x = r_cur[it].x + (fmaf(la[it], a.x, lb[it] * u4.x) + b.x);
-          o.y = r_cur[it].y + (fmaf(la[it], a.y, lb[it] * u4.y) + b.y);
-          o.z = r_cur[it].z + (fmaf(la[it], a.z, lb[it] * u4.z) + b.z);
-          o.w = r_cur[it].w + (fmaf(la[it], a.w, lb[it] * u4.w) + b.w);
-          float* base = ((o_alt >> it) & 1u) ? ep.out_alt : reinterpret_cast<float*>(ep.out);
-          __stcg(reinterpret_cast<float4*>(base + (size_t)o_row[it] * ep.ldo + col), o);
-        }
+        float4 o;
+        o.x = r_cur[it].x + (fmaf(la[it], a.x, lb[it] * u4.x) + b.x);
+        o.y = r_cur[it].y + (fmaf(la[it], a.y, lb[it] * u4.y) + b.y);
+        o.z = r_cur[it].z + (fmaf(la[it], a.z, lb[it] * u4.z) + b.z);
+        o.w = r_cur[it].w + (fmaf(la[it], a.w, lb[it] * u4.w) + b.w);
+        float* base = ((o_alt >> it) & 1u) ? ep.out_alt : reinterpret_cast<float*>(ep.out);
+        st_global_cg_if(reinterpret_cast<float4*>(base + (size_t)o_row[it] * ep.ldo + col), o, col_ok && ((o_ok >> it) & 1u));
       }
       __syncwarp();
       ETRACE(tr, 3 + (c - ch0) / (2 * CHUNK));
@@ -391,22 +386,31 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
       const bool rot = col0 < ep.rope_cols;               // warp-uniform (rope_cols % 128 == 0)
       const float sc_q = (col0 < (ep.rope_cols >> 1)) ? ep.q_scale : 1.0f;
       __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(ep.out);
+      // the warp-uniform `rot` is decided once per chunk and the stores are predicated: branch-free loop bodies, so the
+      // eight iterations overlap instead of running as eight convergence regions
+      if (rot) {
 #pragma unroll
-      for (int it = 0; it < 8; ++it) {
-        const int row = it * 4 + rin;
-        float4 a = stage_read(stage, row, cseg);
-        a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
-        if (rot) {
+        for (int it = 0; it < 8; ++it) {
+          float4 a = stage_read(stage, it * 4 + rin, cseg);
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
           const float2 c2 = rc[it], sn = rs[it];
           const float x0 = a.x, x1 = a.y, x2 = a.z, x3 = a.w;
           a.x = (x0 * c2.x - x1 * sn.x) * sc_q; a.y = (x1 * c2.x + x0 * sn.x) * sc_q;
           a.z = (x2 * c2.y - x3 * sn.y) * sc_q; a.w = (x3 * c2.y + x2 * sn.y) * sc_q;
-        }
-        if (col_ok && d_row[it] >= 0) {
           uint2 u;
           u.x = pack_bf16(a.x, a.y);
           u.y = pack_bf16(a.z, a.w);
-          *reinterpret_cast<uint2*>(out + (size_t)d_row[it] * ep.ldo + col) = u;
+          st_global_if(reinterpret_cast<uint2*>(out + (size_t)d_row[it] * ep.ldo + col), u, col_ok && d_row[it] >= 0);
+        }
+      } else {
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          float4 a = stage_read(stage, it * 4 + rin, cseg);
+          a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
+          uint2 u;
+          u.x = pack_bf16(a.x, a.y);
+          u.y = pack_bf16(a.z, a.w);
+          st_global_if(reinterpret_cast<uint2*>(out + (size_t)d_row[it] * ep.ldo + col), u, col_ok && d_row[it] >= 0);
         }
       }
     } else {  // TOC3D_EPI_LINEAR
@@ -417,16 +421,12 @@ __device__ __forceinline__ void epilogue_warp_tile(const EpiParams& ep, uint32_t
         a.x += b.x; a.y += b.y; a.z += b.z; a.w += b.w;
         if (ep.act == 1) { a.x = gelu_erf(a.x); a.y = gelu_erf(a.y); a.z = gelu_erf(a.z); a.w = gelu_erf(a.w); }
         else if (ep.act == 2) { a.x = fmaxf(a.x, 0.f); a.y = fmaxf(a.y, 0.f); a.z = fmaxf(a.z, 0.f); a.w = fmaxf(a.w, 0.f); }
-        if (col_ok && d_row[it] >= 0) {
-          if (ep.out_f32) {
-            *reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)d_row[it] * ep.ldo + col) = a;
-          } else {
-            uint2 u;
-            u.x = pack_bf16(a.x, a.y);
-            u.y = pack_bf16(a.z, a.w);
-            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)d_row[it] * ep.ldo + col) = u;
-          }
-        }
+        const bool ok = col_ok && d_row[it] >= 0;
+        uint2 u;
+        u.x = pack_bf16(a.x, a.y);
+        u.y = pack_bf16(a.z, a.w);
+        st_global_if(reinterpret_cast<float4*>(reinterpret_cast<float*>(ep.out) + (size_t)d_row[it] * ep.ldo + col), a, ok && ep.out_f32);
+        st_global_if(reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(ep.out) + (size_t)d_row[it] * ep.ldo + col), u, ok && !ep.out_f32);
       }
     }
     __syncwarp();
