@@ -881,7 +881,7 @@ window_attention_pp_kernel(const __grid_constant__ CUtensorMap tm, const __grid_
             const int r = (lane >> 3) + 4 * k, c = lane & 7;
             const int d = __shfl_sync(0xffffffffu, dst, r);
             const uint4 v = *reinterpret_cast<const uint4*>(stage + r * 128 + ((c ^ (r & 7)) << 4));
-            if (d >= 0) *reinterpret_cast<uint4*>(obase + (size_t)d * C + c * 8) = v;
+            st_global_if(reinterpret_cast<uint4*>(obase + (size_t)d * C + c * 8), v, d >= 0);     // branch-free loop body
           }
           __syncwarp();
           ATRACE_FIN(tr, 0, u, 5);

@@ -77,6 +77,14 @@ __device__ __forceinline__ void st_global_cg_if(float4* p, float4 v, bool ok) { 
       ::"l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w), "r"((int)ok)
       : "memory");
 }
+__device__ __forceinline__ void st_global_if(uint4* p, uint4 v, bool ok) {
+  asm volatile(
+      "{\n\t.reg .pred q;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q st.global.v4.b32 [%0], {%1, %2, %3, %4};\n\t}"
+      ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "r"((int)ok)
+      : "memory");
+}
 __device__ __forceinline__ void st_global_if(uint2* p, uint2 v, bool ok) {
   asm volatile(
       "{\n\t.reg .pred q;\n\t"
